@@ -1,0 +1,653 @@
+// engine.cu -- host side of libdualar.so: weight arena, KV caches, CUDA-graph step, the C-ABI.
+// See include/dualar.h for the contract of every entry point and the reference interface it replaces.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dualar.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "misc_kernels.cuh"
+
+using namespace da;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(DUALAR_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct LayerW {
+  bf16 *wqkv = nullptr, *bqkv = nullptr, *wo = nullptr, *bo = nullptr, *qn = nullptr, *kn = nullptr;
+  bf16 *w13 = nullptr, *w2 = nullptr, *ffn_norm = nullptr, *attn_norm = nullptr;
+  bf16 *kc = nullptr, *vc = nullptr; bool kv_external = false;
+};
+struct Slot { bf16 *dst; int64_t n; int rows, cols, pitch_rows; bool loaded; };  // pitch_rows: 2 => interleaved halves
+
+struct dualar_engine {
+  dualar_config c;
+  int device = 0, sms = 0;
+  bool finalized = false, request_open = false;
+  char *arena = nullptr; size_t arena_bytes = 0, fast_off = 0, fast_bytes = 0;
+  std::map<std::string, Slot> slots;
+  std::vector<LayerW> slow, fast;
+  bf16 *emb = nullptr, *cb_emb = nullptr, *norm = nullptr, *out_w = nullptr, *fast_emb = nullptr, *fast_norm = nullptr, *fast_out = nullptr;
+  bf16 *rope = nullptr, *fast_rope = nullptr; bool rope_loaded = false, fast_rope_loaded = false;
+  // activations
+  bf16 *x = nullptr, *h = nullptr, *qkv = nullptr, *y = nullptr, *act = nullptr, *logits = nullptr, *logits_raw = nullptr;
+  bf16 *fin = nullptr, *fbuf[2] = {nullptr, nullptr}, *fh = nullptr, *fqkv = nullptr, *fact = nullptr, *flogits = nullptr, *flogits_raw = nullptr;
+  float *part_o = nullptr, *part_ml = nullptr; float2 *partials = nullptr; unsigned long long *cand = nullptr;
+  DAState *st = nullptr; int *seq = nullptr; int *h_seq = nullptr; DAState *h_st = nullptr;
+  void *kv_arena = nullptr;
+  int nsplit = 1, fv = 0, gemv_grid = 0;
+  float delta = 6.0f; int cpu_sem = 0;
+  uint64_t seed = 0; const bf16 *noise = nullptr; int64_t noise_steps = 0;
+  cudaStream_t cap_stream = nullptr;
+  cudaGraphExec_t g_step = nullptr, g_prefill = nullptr;
+  int launches_step = 0, launches_prefill = 0;
+  int prompt_len = 0, max_gen = 0;
+  std::vector<void *> owned;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- arena planning ------------------------------------------------------------------------------
+static void plan_layer(dualar_engine *e, const std::string &pre, LayerW &L, int dim, int nh, int nkv, int hd, int inter,
+                       bool qkv_bias, bool o_bias, bool qk_norm, size_t &off, bool assign) {
+  auto take = [&](bf16 *&ptr, const std::string &key, int rows, int cols, int pitch_rows, bf16 *alias_base, size_t alias_off) {
+    if (alias_base) { if (assign) e->slots[key] = Slot{alias_base + alias_off, (int64_t)rows * cols, rows, cols, pitch_rows, false}; return; }
+    size_t bytes = (size_t)rows * cols * pitch_rows * sizeof(bf16);
+    if (assign) { ptr = (bf16 *)(e->arena + off); e->slots[key] = Slot{ptr, (int64_t)rows * cols, rows, cols, pitch_rows, false}; }
+    off = align_up(off + bytes, 256);
+  };
+  take(L.wqkv, pre + ".attention.wqkv.weight", (nh + 2 * nkv) * hd, dim, 1, nullptr, 0);
+  if (qkv_bias) take(L.bqkv, pre + ".attention.wqkv.bias", 1, (nh + 2 * nkv) * hd, 1, nullptr, 0);
+  take(L.wo, pre + ".attention.wo.weight", dim, nh * hd, 1, nullptr, 0);
+  if (o_bias) take(L.bo, pre + ".attention.wo.bias", 1, dim, 1, nullptr, 0);
+  if (qk_norm) { take(L.qn, pre + ".attention.q_norm.weight", 1, hd, 1, nullptr, 0); take(L.kn, pre + ".attention.k_norm.weight", 1, hd, 1, nullptr, 0); }
+  // w1 / w3 share one row-interleaved matrix: row 2j = w1[j], row 2j+1 = w3[j]
+  take(L.w13, pre + ".feed_forward.w1.weight", inter, dim, 2, nullptr, 0);
+  { bf16 *dummy = nullptr; take(dummy, pre + ".feed_forward.w3.weight", inter, dim, 2, assign ? L.w13 : (bf16 *)1, (size_t)dim); }
+  take(L.w2, pre + ".feed_forward.w2.weight", dim, inter, 1, nullptr, 0);
+  take(L.ffn_norm, pre + ".ffn_norm.weight", 1, dim, 1, nullptr, 0);
+  take(L.attn_norm, pre + ".attention_norm.weight", 1, dim, 1, nullptr, 0);
+}
+
+static size_t plan(dualar_engine *e, bool assign) {
+  const dualar_config &c = e->c;
+  size_t off = 0;
+  auto take = [&](bf16 *&ptr, const char *key, int64_t rows, int64_t cols) {
+    size_t bytes = (size_t)rows * cols * sizeof(bf16);
+    if (assign) { ptr = (bf16 *)(e->arena + off); e->slots[key] = Slot{ptr, rows * cols, (int)rows, (int)cols, 1, false}; }
+    off = align_up(off + bytes, 256);
+  };
+  take(e->emb, "embeddings.weight", c.vocab_size, c.dim);
+  take(e->cb_emb, "codebook_embeddings.weight", (int64_t)c.codebook_size * c.num_codebooks, c.dim);
+  if (assign) e->slow.resize(c.n_layer);
+  for (int i = 0; i < c.n_layer; ++i) {
+    LayerW tmp; LayerW &L = assign ? e->slow[i] : tmp;
+    plan_layer(e, "layers." + std::to_string(i), L, c.dim, c.n_head, c.n_local_heads, c.head_dim, c.intermediate_size,
+               c.attention_qkv_bias, c.attention_o_bias, c.attention_qk_norm, off, assign);
+  }
+  take(e->norm, "norm.weight", 1, c.dim);
+  if (!c.tie_word_embeddings) take(e->out_w, "output.weight", c.vocab_size, c.dim);
+  take(e->rope, "freqs_cis", c.max_seq_len, c.head_dim);
+  off = align_up(off, 2u << 20);
+  if (assign) e->fast_off = off;
+  take(e->fast_emb, "fast_embeddings.weight", c.codebook_size, c.fast_dim);
+  if (assign) e->fast.resize(c.n_fast_layer);
+  for (int i = 0; i < c.n_fast_layer; ++i) {
+    LayerW tmp; LayerW &L = assign ? e->fast[i] : tmp;
+    plan_layer(e, "fast_layers." + std::to_string(i), L, c.fast_dim, c.fast_n_head, c.fast_n_local_heads, c.fast_head_dim,
+               c.fast_intermediate_size, c.fast_attention_qkv_bias, c.fast_attention_o_bias, c.fast_attention_qk_norm, off, assign);
+  }
+  take(e->fast_norm, "fast_norm.weight", 1, c.fast_dim);
+  take(e->fast_out, "fast_output.weight", c.codebook_size, c.fast_dim);
+  take(e->fast_rope, "fast_freqs_cis", c.num_codebooks, c.fast_head_dim);
+  if (assign) e->fast_bytes = off - e->fast_off;
+  return align_up(off, 2u << 20);
+}
+
+static int check_config(const dualar_config &c) {
+  if (c.abi_version != DUALAR_ABI_VERSION) return fail(DUALAR_EINVAL, "abi_version %d != %d", c.abi_version, DUALAR_ABI_VERSION);
+  if (c.fast_dim != c.dim) return fail(DUALAR_EINVAL, "fast_dim != dim (fast_project_in) is not supported");
+  if (c.dim % 256 || c.intermediate_size % 256 || (c.n_head * c.head_dim) % 256 || c.fast_intermediate_size % 256 ||
+      (c.fast_n_head * c.fast_head_dim) % 256)
+    return fail(DUALAR_EINVAL, "dim, intermediate_size and n_head*head_dim must be multiples of 256");
+  if (c.head_dim % 8 || c.fast_head_dim % 8 || c.head_dim > 128 || c.head_dim < 8 || (c.head_dim & (c.head_dim - 1)))
+    return fail(DUALAR_EINVAL, "head_dim must be a power of two in [8, 128]");
+  if (c.n_head % c.n_local_heads || c.fast_n_head % c.fast_n_local_heads) return fail(DUALAR_EINVAL, "n_head %% n_local_heads != 0");
+  int G = c.n_head / c.n_local_heads;
+  if (G > DA_MAX_G || G * c.head_dim > DA_MAX_G * 128) return fail(DUALAR_EINVAL, "GQA group too large");
+  if (c.n_local_heads > DA_MAX_KV_HEADS) return fail(DUALAR_EINVAL, "too many kv heads");
+  if (c.num_codebooks + 1 > DA_MAX_ROWS || c.num_codebooks < 2) return fail(DUALAR_EINVAL, "num_codebooks out of range");
+  if (c.vocab_size <= 0 || c.max_seq_len <= 0 || c.n_layer <= 0 || c.n_fast_layer <= 0) return fail(DUALAR_EINVAL, "bad sizes");
+  if (c.semantic_begin_id < 0 || c.semantic_end_id >= c.vocab_size || c.semantic_end_id < c.semantic_begin_id)
+    return fail(DUALAR_EINVAL, "semantic id range outside the vocabulary");
+  return 0;
+}
+
+extern "C" int dualar_abi_version(void) { return DUALAR_ABI_VERSION; }
+extern "C" const char *dualar_last_error(void) { return g_err; }
+
+extern "C" int dualar_create(const dualar_config *cfg, int device, dualar_engine **out) {
+  if (!cfg || !out) return fail(DUALAR_EINVAL, "null argument");
+  int rc = check_config(*cfg); if (rc) return rc;
+  int ndev = 0; CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DUALAR_EINVAL, "device %d not present (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(DUALAR_EINVAL, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  dualar_engine *e = new dualar_engine();
+  e->c = *cfg; e->device = device; e->sms = prop.multiProcessorCount;
+  e->fv = cfg->codebook_size < 1024 ? cfg->codebook_size : 1024;   // logits[:, :, :1024]  (inference.py:134)
+  e->arena_bytes = plan(e, false);
+  cudaError_t ce = cudaMalloc((void **)&e->arena, e->arena_bytes);
+  if (ce != cudaSuccess) { delete e; return fail(DUALAR_ECUDA, "cudaMalloc(%zu) failed: %s", e->arena_bytes, cudaGetErrorString(ce)); }
+  cudaMemset(e->arena, 0, e->arena_bytes);
+  plan(e, true);
+  *out = e;
+  return 0;
+}
+
+extern "C" int dualar_load_weight(dualar_engine *e, const char *key, const void *data, int64_t n, int on_device) {
+  if (!e || !key || !data) return fail(DUALAR_EINVAL, "null argument");
+  if (e->finalized) return fail(DUALAR_ESTATE, "weights are frozen after dualar_finalize");
+  auto it = e->slots.find(key);
+  if (it == e->slots.end()) return fail(DUALAR_EINVAL, "unknown weight key '%s'", key);
+  Slot &s = it->second;
+  if (n != s.n) return fail(DUALAR_EINVAL, "weight '%s': %lld elements given, %lld expected", key, (long long)n, (long long)s.n);
+  CU(cudaSetDevice(e->device));
+  cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  size_t row = (size_t)s.cols * sizeof(bf16);
+  if (s.pitch_rows == 1) CU(cudaMemcpy(s.dst, data, (size_t)s.n * sizeof(bf16), kind));
+  else CU(cudaMemcpy2D(s.dst, row * s.pitch_rows, data, row, row, s.rows, kind));
+  s.loaded = true;
+  if (!strcmp(key, "freqs_cis")) e->rope_loaded = true;
+  if (!strcmp(key, "fast_freqs_cis")) e->fast_rope_loaded = true;
+  return 0;
+}
+
+extern "C" int dualar_bind_kv(dualar_engine *e, int is_fast, int layer, void *k, void *v) {
+  if (!e || !k || !v) return fail(DUALAR_EINVAL, "null argument");
+  if (e->finalized) return fail(DUALAR_ESTATE, "bind KV before dualar_finalize");
+  std::vector<LayerW> &Ls = is_fast ? e->fast : e->slow;
+  if (layer < 0 || layer >= (int)Ls.size()) return fail(DUALAR_EINVAL, "layer %d out of range", layer);
+  Ls[layer].kc = (bf16 *)k; Ls[layer].vc = (bf16 *)v; Ls[layer].kv_external = true;
+  return 0;
+}
+
+// llama.py:594-603 restated on the host (used only when the caller does not hand the table over)
+static void host_rope(std::vector<uint16_t> &out, int seq, int n_elem, float base) {
+  out.resize((size_t)seq * n_elem);
+  for (int i = 0; i < n_elem / 2; ++i) {
+    float ex = (float)(2 * i) / (float)n_elem;
+    float freq = 1.0f / (float)pow((double)base, (double)ex);
+    for (int t = 0; t < seq; ++t) {
+      float ang = (float)t * freq;
+      float cs[2] = {(float)cos((double)ang), (float)sin((double)ang)};
+      for (int k = 0; k < 2; ++k) {
+        uint32_t u; memcpy(&u, &cs[k], 4);
+        uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+        out[((size_t)t * (n_elem / 2) + i) * 2 + k] = (uint16_t)(r >> 16);
+      }
+    }
+  }
+}
+
+template <typename T> static int dev_alloc(dualar_engine *e, T *&p, size_t n) {
+  CU(cudaMalloc((void **)&p, n * sizeof(T)));
+  CU(cudaMemset(p, 0, n * sizeof(T)));
+  e->owned.push_back((void *)p);
+  return 0;
+}
+
+// ---- kernel launch plumbing ---------------------------------------------------------------------------
+template <int PRO, int EPI> static size_t gemv_smem(const dualar_engine *e, const GemvArgs &a) {
+  size_t f = ((size_t)a.K + 80) * sizeof(float);
+  size_t work = 0;
+  if (PRO == PRO_FASTATTN) work = ((size_t)a.fa.nh * a.fa.hd + 2 * (size_t)a.fa.ncb * a.fa.nkv * a.fa.hd + (size_t)a.fa.nh * a.fa.ncb) * sizeof(float);
+  if (EPI == EPI_LOGITS && a.head > 0) { size_t n2 = 1; while ((int)n2 < a.rows) n2 <<= 1; size_t w2 = n2 * 8 + 34 * 8 + 80 * 4 + 64; if (w2 > work) work = w2; }
+  (void)e;
+  return f + work + 16;
+}
+template <int PRO, int EPI> static int launch_gemv(dualar_engine *e, GemvArgs a, cudaStream_t s, int &count) {
+  static size_t configured = 0;
+  size_t smem = gemv_smem<PRO, EPI>(e, a);
+  if (smem > configured) {
+    CU(cudaFuncSetAttribute(gemv_kernel<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 200 * 1024 ? smem : 200 * 1024)));
+    configured = 200 * 1024 > smem ? 200 * 1024 : smem;
+  }
+  int npairs = (a.rows + 1) / 2;
+  int grid = npairs < e->sms ? npairs : e->sms;
+  a.st = e->st;
+  gemv_kernel<PRO, EPI><<<grid, 512, smem, s>>>(a);
+  CU(cudaGetLastError());
+  ++count;
+  return grid;
+}
+
+static GemvArgs base_args(const bf16 *W, const bf16 *bias, int rows, int K, int evict_last) {
+  GemvArgs a; memset(&a, 0, sizeof(a));
+  a.W = W; a.bias = bias; a.rows = rows; a.K = K; a.evict_last = evict_last;
+  return a;
+}
+
+// one transformer block on the slow stack (llama.py:322-331)
+static int enqueue_slow_layer(dualar_engine *e, int li, cudaStream_t s, int &count) {
+  const dualar_config &c = e->c; LayerW &L = e->slow[li];
+  const int qkv_rows = (c.n_head + 2 * c.n_local_heads) * c.head_dim, qd = c.n_head * c.head_dim;
+  int rc;
+  { GemvArgs a = base_args(L.wqkv, L.bqkv, qkv_rows, c.dim, 0); a.x = e->x; a.norm_w = L.attn_norm; a.eps = c.norm_eps; a.out = e->qkv;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_STORE>(e, a, s, count)) < 0) return rc; }
+  { AttnArgs t; memset(&t, 0, sizeof(t));
+    t.qkv = e->qkv; t.kc = L.kc; t.vc = L.vc; t.rope = e->rope; t.qn = L.qn; t.kn = L.kn;
+    t.nh = c.n_head; t.nkv = c.n_local_heads; t.hd = c.head_dim; t.S = c.max_seq_len; t.eps = c.norm_eps;
+    t.sf = (float)sqrt(1.0 / sqrt((double)c.head_dim));
+    t.part_o = e->part_o; t.part_ml = e->part_ml; t.y = e->y; t.nsplit_max = e->nsplit; t.st = e->st;
+    size_t smem = attn_smem_bytes(c.n_head / c.n_local_heads, c.head_dim);
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(attn_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    attn_slow_kernel<<<dim3(e->nsplit, c.n_local_heads), DA_ATTN_THREADS, smem, s>>>(t);
+    CU(cudaGetLastError()); ++count; }
+  { GemvArgs a = base_args(L.wo, L.bo, c.dim, qd, 0); a.x = e->y; a.res = e->x; a.out = e->h;
+    if ((rc = launch_gemv<PRO_PLAIN, EPI_RESIDUAL>(e, a, s, count)) < 0) return rc; }
+  { GemvArgs a = base_args(L.w13, nullptr, 2 * c.intermediate_size, c.dim, 0); a.x = e->h; a.norm_w = L.ffn_norm; a.eps = c.norm_eps; a.out = e->act;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_SWIGLU>(e, a, s, count)) < 0) return rc; }
+  { GemvArgs a = base_args(L.w2, nullptr, c.dim, c.intermediate_size, 0); a.x = e->act; a.res = e->h; a.out = e->x;
+    if ((rc = launch_gemv<PRO_PLAIN, EPI_RESIDUAL>(e, a, s, count)) < 0) return rc; }
+  return 0;
+}
+
+// one fast block for codebook position `p` (llama.py:561-580 via :322-331, use_sdpa=False)
+static int enqueue_fast_layer(dualar_engine *e, int li, int p, const bf16 *in, bf16 *out, cudaStream_t s, int &count) {
+  const dualar_config &c = e->c; LayerW &L = e->fast[li];
+  const int qkv_rows = (c.fast_n_head + 2 * c.fast_n_local_heads) * c.fast_head_dim, qd = c.fast_n_head * c.fast_head_dim;
+  int rc;
+  { GemvArgs a = base_args(L.wqkv, L.bqkv, qkv_rows, c.fast_dim, 1); a.x = in; a.norm_w = L.attn_norm; a.eps = c.norm_eps; a.out = e->fqkv;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_STORE>(e, a, s, count)) < 0) return rc; }
+  { GemvArgs a = base_args(L.wo, L.bo, c.fast_dim, qd, 1); a.res = in; a.out = e->fh;
+    a.fa.qkv = e->fqkv; a.fa.kc = L.kc; a.fa.vc = L.vc; a.fa.rope = e->fast_rope; a.fa.qn = L.qn; a.fa.kn = L.kn;
+    a.fa.nh = c.fast_n_head; a.fa.nkv = c.fast_n_local_heads; a.fa.hd = c.fast_head_dim; a.fa.ncb = c.num_codebooks; a.fa.pos = p;
+    a.fa.eps = c.norm_eps; a.fa.scale = (float)(1.0 / sqrt((double)c.fast_head_dim));
+    if ((rc = launch_gemv<PRO_FASTATTN, EPI_RESIDUAL>(e, a, s, count)) < 0) return rc; }
+  { GemvArgs a = base_args(L.w13, nullptr, 2 * c.fast_intermediate_size, c.fast_dim, 1); a.x = e->fh; a.norm_w = L.ffn_norm; a.eps = c.norm_eps; a.out = e->fact;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_SWIGLU>(e, a, s, count)) < 0) return rc; }
+  { GemvArgs a = base_args(L.w2, nullptr, c.fast_dim, c.fast_intermediate_size, 1); a.x = e->fact; a.res = e->fh; a.out = out;
+    if ((rc = launch_gemv<PRO_PLAIN, EPI_RESIDUAL>(e, a, s, count)) < 0) return rc; }
+  return 0;
+}
+
+// the decode step of decode_one_token_ar (inference.py:83-155); slow_only = one prefill position
+static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &count) {
+  const dualar_config &c = e->c;
+  int rc;
+  { EmbedArgs a; memset(&a, 0, sizeof(a));
+    a.emb = e->emb; a.cb_emb = e->cb_emb; a.x = e->x; a.dim = c.dim; a.vocab = c.vocab_size; a.codebook_size = c.codebook_size;
+    a.num_codebooks = c.num_codebooks; a.sem_begin = c.semantic_begin_id; a.sem_end = c.semantic_end_id; a.scale_cb = c.scale_codebook_embeddings;
+    a.inv_sqrt = (float)(1.0 / sqrt((double)(c.num_codebooks + 1))); a.sqrt_c = (float)sqrt((double)(c.num_codebooks + 1)); a.st = e->st;
+    embed_kernel<<<(c.dim + 255) / 256, 256, 0, s>>>(a); CU(cudaGetLastError()); ++count; }
+  for (int i = 0; i < c.n_layer; ++i) if ((rc = enqueue_slow_layer(e, i, s, count)) < 0) return rc;
+  if (slow_only) {
+    PrefillColArgs a{e->seq, c.max_seq_len, c.num_codebooks + 1, e->st};
+    prefill_col_kernel<<<1, 32, 0, s>>>(a, 1); CU(cudaGetLastError()); ++count;
+    return 0;
+  }
+  // LM head + sampler (llama.py:446-451, inference.py:103-113)
+  int head_grid;
+  { GemvArgs a = base_args(c.tie_word_embeddings ? e->emb : e->out_w, nullptr, c.vocab_size, c.dim, 0);
+    a.x = e->x; a.norm_w = e->norm; a.eps = c.norm_eps; a.out = e->logits; a.logits_raw = e->logits_raw; a.partials = e->partials;
+    a.head = 0; a.n_rows_tok = c.num_codebooks + 1;
+    if ((head_grid = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(e, a, s, count)) < 0) return head_grid; }
+  { SelectArgs a; memset(&a, 0, sizeof(a));
+    a.logits = e->logits; a.partials = e->partials; a.n_partials = head_grid; a.V = c.vocab_size; a.delta = e->delta; a.cand = e->cand;
+    a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.sem_begin = c.semantic_begin_id; a.st = e->st;
+    size_t smem = (size_t)DA_CAND_CAP * 8 + 34 * 8 + 80 * 4 + 64;
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    select_sample_kernel<<<e->sms, 512, smem, s>>>(a); CU(cudaGetLastError()); ++count; }
+  // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
+  for (int p = 0; p < c.num_codebooks; ++p) {
+    const bf16 *in = p == 0 ? e->x : e->fin;
+    for (int l = 0; l < c.n_fast_layer; ++l) {
+      bf16 *out = e->fbuf[l & 1];
+      if ((rc = enqueue_fast_layer(e, l, p, in, out, s, count)) < 0) return rc;
+      in = out;
+    }
+    if (p == 0) continue;   // logits of pass 0 are discarded by the reference (inference.py:122)
+    GemvArgs a = base_args(e->fast_out, nullptr, e->fv, c.fast_dim, 1);
+    a.x = in; a.norm_w = e->fast_norm; a.eps = c.norm_eps;
+    a.out = e->flogits + (size_t)(p - 1) * e->fv; a.logits_raw = e->flogits_raw + (size_t)(p - 1) * e->fv;
+    a.head = p; a.noise_off = (long long)c.vocab_size + (long long)(p - 1) * e->fv;
+    a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size;
+    a.last_head = (p == c.num_codebooks - 1);
+    a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.n_rows_tok = c.num_codebooks + 1;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(e, a, s, count)) < 0) return rc;
+  }
+  return 0;
+}
+
+static int capture(dualar_engine *e, bool slow_only, cudaGraphExec_t *out, int *count) {
+  // dry run first: configures kernel attributes outside capture and surfaces launch errors eagerly
+  int n = 0;
+  int rc = enqueue_step(e, e->cap_stream, slow_only, n);
+  if (rc < 0) return rc;
+  CU(cudaStreamSynchronize(e->cap_stream));
+  cudaGraph_t g;
+  CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  n = 0;
+  rc = enqueue_step(e, e->cap_stream, slow_only, n);
+  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
+  if (rc < 0) return rc;
+  if (ce != cudaSuccess) return fail(DUALAR_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+  CU(cudaGraphInstantiate(out, g, 0));
+  CU(cudaGraphDestroy(g));
+  *count = n;
+  return 0;
+}
+
+extern "C" int dualar_finalize(dualar_engine *e) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  if (e->finalized) return 0;
+  const dualar_config &c = e->c;
+  CU(cudaSetDevice(e->device));
+  if (!e->rope_loaded) {
+    std::vector<uint16_t> t; host_rope(t, c.max_seq_len, c.head_dim, c.rope_base);
+    CU(cudaMemcpy(e->rope, t.data(), t.size() * 2, cudaMemcpyHostToDevice)); e->slots["freqs_cis"].loaded = true;
+  }
+  if (!e->fast_rope_loaded) {
+    std::vector<uint16_t> t; host_rope(t, c.num_codebooks, c.fast_head_dim, c.rope_base);
+    CU(cudaMemcpy(e->fast_rope, t.data(), t.size() * 2, cudaMemcpyHostToDevice)); e->slots["fast_freqs_cis"].loaded = true;
+  }
+  for (auto &kv : e->slots) if (!kv.second.loaded) return fail(DUALAR_EMISSING, "weight '%s' was never loaded", kv.first.c_str());
+  // KV caches (llama.py:126-149 layout) unless the caller bound its own
+  for (auto &L : e->slow) if (!L.kv_external) {
+    size_t n = (size_t)c.n_local_heads * c.max_seq_len * c.head_dim; int rc;
+    if ((rc = dev_alloc(e, L.kc, n))) return rc; if ((rc = dev_alloc(e, L.vc, n))) return rc;
+  }
+  for (auto &L : e->fast) if (!L.kv_external) {
+    size_t n = (size_t)c.fast_n_local_heads * c.num_codebooks * c.fast_head_dim; int rc;
+    if ((rc = dev_alloc(e, L.kc, n))) return rc; if ((rc = dev_alloc(e, L.vc, n))) return rc;
+  }
+  int rc;
+  const int G = c.n_head / c.n_local_heads;
+  e->nsplit = e->sms / c.n_local_heads; if (e->nsplit < 1) e->nsplit = 1; if (e->nsplit > 64) e->nsplit = 64;
+  const int qkv_rows = (c.n_head + 2 * c.n_local_heads) * c.head_dim, fqkv_rows = (c.fast_n_head + 2 * c.fast_n_local_heads) * c.fast_head_dim;
+  if ((rc = dev_alloc(e, e->x, c.dim)) || (rc = dev_alloc(e, e->h, c.dim)) || (rc = dev_alloc(e, e->qkv, qkv_rows)) ||
+      (rc = dev_alloc(e, e->y, c.n_head * c.head_dim)) || (rc = dev_alloc(e, e->act, c.intermediate_size)) ||
+      (rc = dev_alloc(e, e->logits, c.vocab_size)) || (rc = dev_alloc(e, e->logits_raw, c.vocab_size)) ||
+      (rc = dev_alloc(e, e->fin, c.fast_dim)) || (rc = dev_alloc(e, e->fbuf[0], c.fast_dim)) || (rc = dev_alloc(e, e->fbuf[1], c.fast_dim)) ||
+      (rc = dev_alloc(e, e->fh, c.fast_dim)) || (rc = dev_alloc(e, e->fqkv, fqkv_rows)) || (rc = dev_alloc(e, e->fact, c.fast_intermediate_size)) ||
+      (rc = dev_alloc(e, e->flogits, (size_t)c.num_codebooks * e->fv)) || (rc = dev_alloc(e, e->flogits_raw, (size_t)c.num_codebooks * e->fv)) ||
+      (rc = dev_alloc(e, e->part_o, (size_t)c.n_local_heads * e->nsplit * G * c.head_dim)) ||
+      (rc = dev_alloc(e, e->part_ml, (size_t)c.n_local_heads * e->nsplit * G * 2)) ||
+      (rc = dev_alloc(e, e->partials, (size_t)e->sms)) || (rc = dev_alloc(e, e->cand, (size_t)DA_CAND_CAP)) ||
+      (rc = dev_alloc(e, e->st, 1)) || (rc = dev_alloc(e, e->seq, (size_t)(c.num_codebooks + 1) * c.max_seq_len)))
+    return rc;
+  CU(cudaMallocHost((void **)&e->h_seq, (size_t)(c.num_codebooks + 1) * c.max_seq_len * sizeof(int)));
+  CU(cudaMallocHost((void **)&e->h_st, sizeof(DAState)));
+  CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
+  { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+    if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp); cudaGetLastError(); }
+  // a benign state for the dry runs inside capture()
+  DAState init; memset(&init, 0, sizeof(init)); init.temperature = 0.7f; init.top_p = 0.8f; init.rep_penalty = 1.1f;
+  init.tok_in[0] = c.semantic_begin_id; init.seed = e->seed; init.cpu_sem = e->cpu_sem;
+  CU(cudaMemcpy(e->st, &init, sizeof(init), cudaMemcpyHostToDevice));
+  if ((rc = capture(e, false, &e->g_step, &e->launches_step))) return rc;
+  if ((rc = capture(e, true, &e->g_prefill, &e->launches_prefill))) return rc;
+  CU(cudaMemcpy(e->st, &init, sizeof(init), cudaMemcpyHostToDevice));
+  // the dry runs wrote KV position 0 / 1 of caches we own; clear them again
+  for (auto &L : e->slow) if (!L.kv_external) {
+    size_t n = (size_t)c.n_local_heads * c.max_seq_len * c.head_dim * sizeof(bf16);
+    CU(cudaMemset(L.kc, 0, n)); CU(cudaMemset(L.vc, 0, n));
+  }
+  CU(cudaDeviceSynchronize());
+  e->finalized = true;
+  return 0;
+}
+
+extern "C" void dualar_destroy(dualar_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (e->g_step) cudaGraphExecDestroy(e->g_step);
+  if (e->g_prefill) cudaGraphExecDestroy(e->g_prefill);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (void *p : e->owned) cudaFree(p);
+  if (e->h_seq) cudaFreeHost(e->h_seq);
+  if (e->h_st) cudaFreeHost(e->h_st);
+  if (e->arena) cudaFree(e->arena);
+  delete e;
+}
+
+extern "C" int dualar_seed(dualar_engine *e, uint64_t seed) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  e->seed = seed;
+  if (e->finalized) {
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpy(&e->st->seed, &seed, sizeof(seed), cudaMemcpyHostToDevice));
+    unsigned zero = 0; CU(cudaMemcpy(&e->st->step_ctr, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+extern "C" int dualar_set_option(dualar_engine *e, const char *name, double value) {
+  if (!e || !name) return fail(DUALAR_EINVAL, "null argument");
+  if (!strcmp(name, "cpu_scalar_semantics")) {
+    e->cpu_sem = value != 0.0;
+    if (e->finalized) { CU(cudaSetDevice(e->device)); CU(cudaMemcpy(&e->st->cpu_sem, &e->cpu_sem, sizeof(int), cudaMemcpyHostToDevice)); }
+    return 0;
+  }
+  if (!strcmp(name, "candidate_delta")) {
+    if (e->finalized) return fail(DUALAR_ESTATE, "candidate_delta must be set before dualar_finalize");
+    if (!(value > 0.0)) return fail(DUALAR_EINVAL, "candidate_delta must be positive");
+    e->delta = (float)value; return 0;
+  }
+  return fail(DUALAR_EINVAL, "unknown option '%s'", name);
+}
+
+extern "C" int dualar_set_noise(dualar_engine *e, const void *noise, int64_t n_steps) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  e->noise = (const bf16 *)noise; e->noise_steps = noise ? n_steps : 0;
+  return 0;
+}
+
+extern "C" int dualar_fill_noise(dualar_engine *e, uint64_t seed, uint32_t step, uint32_t head, void *out, int64_t n, void *stream) {
+  if (!e || !out || n < 0) return fail(DUALAR_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  if (n == 0) return 0;
+  int grid = (int)((n + 255) / 256); if (grid > 4 * e->sms) grid = 4 * e->sms;
+  fill_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((bf16 *)out, n, seed, step, head);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ---- step mode (decode_one_token_ar, inference.py:83-155) --------------------------------------------
+extern "C" int dualar_step(dualar_engine *e, const int32_t *x, const int32_t *input_pos, const int32_t *prev, int64_t prev_stride,
+                           const float *temperature, const float *top_p, const float *rep, const void *noise, int32_t *out, void *stream) {
+  if (!e || !x || !input_pos || !temperature || !top_p || !rep || !out) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->finalized) return fail(DUALAR_ESTATE, "dualar_finalize has not been called");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  LoadStepArgs a{x, input_pos, prev, prev_stride, temperature, top_p, rep, (const bf16 *)noise, e->c.num_codebooks + 1, e->st};
+  load_step_kernel<<<1, 256, 0, s>>>(a); CU(cudaGetLastError());
+  CU(cudaGraphLaunch(e->g_step, s));
+  store_step_kernel<<<1, 32, 0, s>>>(e->st, out, e->c.num_codebooks + 1); CU(cudaGetLastError());
+  e->request_open = false;
+  return 0;
+}
+
+// ---- test hook: the sampler alone on caller-supplied logits ------------------------------------------------
+namespace da {
+__global__ void __launch_bounds__(512, 1) debug_fast_sample_kernel(const GemvArgs a, const bf16 *in) {
+  extern __shared__ __align__(16) float smem_dbg[];
+  DAState *st = a.st;
+  const float rp_bf = eff_rep_penalty(st);
+  for (int i = threadIdx.x; i < a.rows; i += blockDim.x) {
+    float z = bf2f(in[i]);
+    if (st->use_penalty) for (int c = 0; c < DA_WIN; ++c) if (st->win[(a.head + 1) * DA_WIN + c] == i) { z = penalise(z, rp_bf); break; }
+    a.out[i] = f2bf(z);
+  }
+  __threadfence();
+  __syncthreads();
+  fast_head_sample(a, smem_dbg);
+}
+}  // namespace da
+
+extern "C" int dualar_debug_sample(dualar_engine *e, int head, const void *logits, const int32_t *prev, int64_t prev_stride,
+                                   const float *temperature, const float *top_p, const float *rep, const void *noise,
+                                   int32_t *out_token, void *stream) {
+  if (!e || !logits || !temperature || !top_p || !rep || !out_token) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->finalized) return fail(DUALAR_ESTATE, "dualar_finalize has not been called");
+  const dualar_config &c = e->c;
+  if (head < 0 || head >= c.num_codebooks) return fail(DUALAR_EINVAL, "head out of range");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  LoadStepArgs la{e->st->tok_in, &e->st->pos, prev, prev_stride, temperature, top_p, rep, (const bf16 *)noise, c.num_codebooks + 1, e->st};
+  load_step_kernel<<<1, 256, 0, s>>>(la); CU(cudaGetLastError());
+  if (head == 0) {
+    debug_stats_kernel<<<e->sms, 512, 0, s>>>((const bf16 *)logits, e->logits, e->partials, c.vocab_size, c.num_codebooks + 1, e->st); CU(cudaGetLastError());
+    SelectArgs a; memset(&a, 0, sizeof(a));
+    a.logits = e->logits; a.partials = e->partials; a.n_partials = e->sms; a.V = c.vocab_size; a.delta = e->delta; a.cand = e->cand;
+    a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.sem_begin = c.semantic_begin_id; a.st = e->st;
+    size_t smem = (size_t)DA_CAND_CAP * 8 + 34 * 8 + 80 * 4 + 64;
+    select_sample_kernel<<<e->sms, 512, smem, s>>>(a); CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_token, &e->st->tok_out[0], sizeof(int), cudaMemcpyDeviceToDevice, s));
+  } else {
+    GemvArgs a = base_args(e->fast_out, nullptr, e->fv, c.fast_dim, 1);
+    a.out = e->flogits + (size_t)(head - 1) * e->fv; a.head = head; a.noise_off = (long long)c.vocab_size + (long long)(head - 1) * e->fv;
+    a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.last_head = 0;
+    a.n_rows_tok = c.num_codebooks + 1; a.st = e->st;
+    size_t n2 = 1; while ((int)n2 < e->fv) n2 <<= 1;
+    size_t smem = n2 * 8 + 34 * 8 + 80 * 4 + 64;
+    debug_fast_sample_kernel<<<1, 512, smem, s>>>(a, (const bf16 *)logits); CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_token, &e->st->tok_out[head + 1], sizeof(int), cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+// ---- loop mode (generate / generate_streaming, inference.py:279-384, 643-738) ---------------------------
+extern "C" int dualar_prefill(dualar_engine *e, const int32_t *prompt, int T, int max_new, float temperature, float top_p, float rep, void *stream) {
+  if (!e || !prompt) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->finalized) return fail(DUALAR_ESTATE, "dualar_finalize has not been called");
+  const dualar_config &c = e->c;
+  const int R = c.num_codebooks + 1;
+  if (T < 1) return fail(DUALAR_EINVAL, "empty prompt");
+  if (T >= c.max_seq_len) return fail(DUALAR_EINVAL, "Input sequence length %d exceeds max_seq_len %d", T, c.max_seq_len);   // inference.py:296-299
+  if (max_new <= 0 || T + max_new > c.max_seq_len) max_new = c.max_seq_len - T;                                              // inference.py:301-307
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaStreamSynchronize(s));   // h_seq / h_st staging buffers are reused
+  for (int r = 0; r < R; ++r) memcpy(e->h_seq + (size_t)r * T, prompt + (size_t)r * T, (size_t)T * sizeof(int));
+  CU(cudaMemcpy2DAsync(e->seq, (size_t)c.max_seq_len * sizeof(int), e->h_seq, (size_t)T * sizeof(int), (size_t)T * sizeof(int), R, cudaMemcpyHostToDevice, s));
+  DAState *h = e->h_st; memset(h, 0, sizeof(*h));
+  h->pos = 0; h->n_gen = 0; h->max_gen = max_new; h->prompt_len = T; h->loop_mode = 1; h->use_penalty = 0;
+  h->temperature = temperature; h->top_p = top_p; h->rep_penalty = rep; h->seed = e->seed; h->step_ctr = 0;
+  h->cpu_sem = e->cpu_sem;
+  h->noise = e->noise; h->noise_stride = (long long)c.vocab_size + (long long)(c.num_codebooks - 1) * e->fv;
+  for (int r = 0; r < R; ++r) h->tok_in[r] = prompt[(size_t)r * T];
+  CU(cudaMemcpyAsync(e->st, h, sizeof(*h), cudaMemcpyHostToDevice, s));
+  for (int t = 0; t + 1 < T; ++t) CU(cudaGraphLaunch(e->g_prefill, s));
+  CU(cudaGraphLaunch(e->g_step, s));
+  e->prompt_len = T; e->max_gen = max_new; e->request_open = true;
+  return 0;
+}
+
+extern "C" int dualar_decode(dualar_engine *e, int n_steps, void *stream) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  if (!e->request_open) return fail(DUALAR_ESTATE, "dualar_decode without a prefilled request");
+  CU(cudaSetDevice(e->device));
+  for (int i = 0; i < n_steps; ++i) CU(cudaGraphLaunch(e->g_step, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dualar_collect(dualar_engine *e, int32_t *out, int cap, int *n_tokens, int *finished, void *stream) {
+  if (!e || !n_tokens) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->request_open) return fail(DUALAR_ESTATE, "dualar_collect without a prefilled request");
+  const dualar_config &c = e->c; const int R = c.num_codebooks + 1;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(e->h_st, e->st, sizeof(DAState), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (e->h_st->err) return fail(DUALAR_EDEVICE, "device fault flag %d (1: token id out of range, 2: bulk-copy wait timed out, 3: code >= codebook_size)", e->h_st->err);
+  int n = e->h_st->n_gen;
+  *n_tokens = n;
+  if (finished) *finished = e->h_st->done;
+  if (out && n > 0) {
+    if (cap < n) return fail(DUALAR_EINVAL, "output capacity %d < %d generated columns", cap, n);
+    CU(cudaMemcpy2DAsync(e->h_seq, (size_t)n * sizeof(int), e->seq + e->prompt_len, (size_t)c.max_seq_len * sizeof(int), (size_t)n * sizeof(int), R, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int r = 0; r < R; ++r) memcpy(out + (size_t)r * cap, e->h_seq + (size_t)r * n, (size_t)n * sizeof(int));
+  }
+  return 0;
+}
+
+extern "C" int dualar_generate(dualar_engine *e, const int32_t *prompt, int T, int max_new, float temperature, float top_p, float rep,
+                               int32_t *out, int cap, int *n_tokens, void *stream) {
+  int rc = dualar_prefill(e, prompt, T, max_new, temperature, top_p, rep, stream);
+  if (rc) return rc;
+  // every replay after <|im_end|> is a no-op, so the whole budget can be enqueued without a host round trip;
+  // checking in on the device flag every 64 steps keeps the wasted launches bounded
+  int remaining = e->max_gen - 1, n = 0, fin = 0;
+  while (remaining > 0) {
+    int chunk = remaining < 64 ? remaining : 64;
+    if ((rc = dualar_decode(e, chunk, stream))) return rc;
+    remaining -= chunk;
+    if (remaining > 0) {
+      CU(cudaMemcpyAsync(e->h_st, e->st, sizeof(DAState), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+      CU(cudaStreamSynchronize((cudaStream_t)stream));
+      if (e->h_st->done) break;
+    }
+  }
+  rc = dualar_collect(e, out, cap, &n, &fin, stream);
+  if (n_tokens) *n_tokens = n;
+  return rc;
+}
+
+extern "C" int dualar_read_buffer(dualar_engine *e, const char *name, void *dst, int64_t nbytes, void *stream) {
+  if (!e || !name || !dst) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->finalized) return fail(DUALAR_ESTATE, "dualar_finalize has not been called");
+  const dualar_config &c = e->c;
+  const void *src = nullptr; int64_t avail = 0;
+  if (!strcmp(name, "slow_logits")) { src = e->logits; avail = (int64_t)c.vocab_size * 2; }
+  else if (!strcmp(name, "slow_logits_raw")) { src = e->logits_raw; avail = (int64_t)c.vocab_size * 2; }
+  else if (!strcmp(name, "hidden")) { src = e->x; avail = (int64_t)c.dim * 2; }
+  else if (!strcmp(name, "fast_logits")) { src = e->flogits_raw; avail = (int64_t)(c.num_codebooks - 1) * e->fv * 2; }
+  else if (!strcmp(name, "tokens")) { src = e->st->tok_out; avail = (int64_t)(c.num_codebooks + 1) * 4; }
+  else if (!strcmp(name, "nucleus")) { src = e->st->nucleus; avail = (int64_t)c.num_codebooks * 4; }
+  else if (!strcmp(name, "qkv")) { src = e->qkv; avail = (int64_t)(c.n_head + 2 * c.n_local_heads) * c.head_dim * 2; }
+  else if (!strcmp(name, "y")) { src = e->y; avail = (int64_t)c.n_head * c.head_dim * 2; }
+  else if (!strcmp(name, "h")) { src = e->h; avail = (int64_t)c.dim * 2; }
+  else if (!strcmp(name, "act")) { src = e->act; avail = (int64_t)c.intermediate_size * 2; }
+  else if (!strcmp(name, "fast_x")) { src = e->fbuf[(c.n_fast_layer - 1) & 1]; avail = (int64_t)c.fast_dim * 2; }
+  else if (!strcmp(name, "fast_in")) { src = e->fin; avail = (int64_t)c.fast_dim * 2; }
+  else return fail(DUALAR_EINVAL, "unknown buffer '%s'", name);
+  if (nbytes > avail) return fail(DUALAR_EINVAL, "buffer '%s' holds %lld bytes, %lld requested", name, (long long)avail, (long long)nbytes);
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dualar_launches_per_step(const dualar_engine *e, int *decode_step, int *prefill_position) {
+  if (!e || !e->finalized) return fail(DUALAR_ESTATE, "engine not finalized");
+  if (decode_step) *decode_step = e->launches_step;
+  if (prefill_position) *prefill_position = e->launches_prefill;
+  return 0;
+}
+
+extern "C" int dualar_weight_bytes(const dualar_engine *e, int64_t *total, int64_t *fast) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  if (total) *total = (int64_t)e->arena_bytes;
+  if (fast) *fast = (int64_t)e->fast_bytes;
+  return 0;
+}

@@ -1,0 +1,347 @@
+// gemv.cuh -- the weight-streaming bf16 GEMV family: every nn.Linear of the decode step at batch 1.
+//
+// Replaces (reference fish_tts/models/llama.py): wqkv :240, wo :283, w1/w3/w2 :190, the LM head
+// :446-451 and fast_output :577-578, fused with what surrounds them:
+//   prologue  PLAIN     x -> fp32 in shared memory
+//             RMSNORM   the custom RMSNorm :172-177 (fp32 normalise, round to bf16, THEN * weight)
+//             FASTATTN  the whole fast-layer attention :246-251, 285-309 (RoPE, KV write, bf16
+//                       scores/softmax/PV over <= num_codebooks positions), recomputed per CTA
+//   epilogue  STORE     bf16(acc + bias)
+//             RESIDUAL  bf16(res + bf16(acc + bias))                                   :329-330
+//             SWIGLU    rows come interleaved (w1_j, w3_j): bf16(bf16(silu(a)) * b)    :190
+//             LOGITS    repetition penalty on the penalised ids, logits to L2-resident global
+//                       memory, per-CTA (max, sum exp) partials; the fast heads finish the whole
+//                       sampling step in the last CTA to arrive.
+//
+// Work split: rows are dealt to warps in adjacent PAIRS, pair p -> CTA p % grid, warp p / grid, so
+// all SMs stream equal shares; a warp owns whole rows, lane l of segment s holds the 8 weights
+// [s*256 + l*8, +8) as one 128-bit load (L1 bypassed, explicit L2 eviction policy); K is reduced
+// inside the warp (fp32 fma chain per lane, then a butterfly) -- one canonical order for every
+// caller, so the multi-kernel path and any later persistent kernel agree bit for bit.
+#pragma once
+#include "common.cuh"
+#include "sampler.cuh"
+
+namespace da {
+
+enum { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_FASTATTN = 2 };
+enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
+
+struct FastAttnArgs {
+  const bf16 *qkv;        // [(nh + 2 nkv) * hd], output of this pass's wqkv
+  bf16 *kc, *vc;          // [nkv][ncb][hd]
+  const bf16 *rope;       // [ncb][hd/2][2] bf16 (llama.py:537-541)
+  const bf16 *qn, *kn;    // optional qk-norm weights [hd]
+  int nh, nkv, hd, ncb, pos;
+  float eps, scale;       // scale = 1/sqrt(hd)
+};
+
+struct GemvArgs {
+  const bf16 *W;          // [rows][K] row-major
+  const bf16 *bias;       // [rows] or null
+  int rows, K;
+  int evict_last;         // L2 policy for W: 1 = keep (fast stack), 0 = stream
+  const bf16 *x;          // prologue input [K]
+  const bf16 *norm_w;     // RMSNORM weight [K]
+  float eps;
+  FastAttnArgs fa;
+  const bf16 *res;        // RESIDUAL input [rows]
+  bf16 *out;              // STORE/RESIDUAL: [rows]; SWIGLU: [rows/2]; LOGITS: logits [rows]
+  // LOGITS
+  bf16 *logits_raw;       // optional copy before the penalty
+  float2 *partials;       // [grid] (max, sumexp)
+  int head;               // 0 = slow head, k >= 1 = fast head of codebook k
+  long long noise_off;    // offset of this head inside one step's noise block
+  const bf16 *fast_emb;   // [codebook_size][fast_dim]
+  bf16 *fast_x;           // next fast pass input [fast_dim]
+  int fast_dim, last_head, codebook_size;
+  int *seq; int seq_stride; int im_end_id; int n_rows_tok;  // finish_step
+  DAState *st;
+};
+
+// one warp applies (optional) nn.RMSNorm and RoPE to one head vector held as fp32 in shared memory
+// llama.py:246-251 + 606-618.  nn.RMSNorm rounds once, after the weight multiply.
+__device__ __forceinline__ void head_norm_rope(float *v, int hd, const bf16 *nw, float eps, const bf16 *rope_row, int lane) {
+  if (nw) {
+    float ss = 0.f;
+    for (int d = lane; d < hd; d += 32) ss = fmaf(v[d], v[d], ss);
+    ss = warp_sum(ss);
+    float rstd = rsqrtf(ss * (1.0f / (float)hd) + eps);
+    for (int d = lane; d < hd; d += 32) v[d] = rbf(__fmul_rn(__fmul_rn(v[d], rstd), bf2f(nw[d])));
+    __syncwarp();
+  }
+  for (int i = lane; i < (hd >> 1); i += 32) {
+    float x0 = v[2 * i], x1 = v[2 * i + 1];
+    float c = bf2f(rope_row[2 * i]), s = bf2f(rope_row[2 * i + 1]);
+    // separate mul / mul / add kernels in the reference: no fma contraction
+    float o0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+    float o1 = __fadd_rn(__fmul_rn(x1, c), __fmul_rn(x0, s));
+    v[2 * i] = rbf(o0); v[2 * i + 1] = rbf(o1);
+  }
+  __syncwarp();
+}
+
+// ---- prologues: fill xs (fp32, xs_index layout) ------------------------------------------------
+__device__ __forceinline__ void prologue_plain(const GemvArgs &a, float *xs) {
+  for (int e = threadIdx.x; e < a.K; e += blockDim.x) xs[xs_index(e)] = bf2f(a.x[e]);
+}
+
+__device__ __forceinline__ void prologue_rmsnorm(const GemvArgs &a, float *xs, float *scratch) {
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < a.K; e += blockDim.x) { float v = bf2f(a.x[e]); ss = fmaf(v, v, ss); }
+  ss = block_sum(ss, scratch);
+  float inv = rsqrtf(ss * (1.0f / (float)a.K) + a.eps);
+  for (int e = threadIdx.x; e < a.K; e += blockDim.x) {
+    float v = rbf(__fmul_rn(bf2f(a.x[e]), inv));          // .type_as(x)
+    xs[xs_index(e)] = rbf(__fmul_rn(v, bf2f(a.norm_w[e])));   // * weight
+  }
+}
+
+// fast-layer attention for ONE query position, every CTA recomputes it (<= 16 heads x 10 positions)
+// work: [q | k_all | v_all | p] floats after xs
+__device__ __forceinline__ void prologue_fastattn(const GemvArgs &a, float *xs, float *work) {
+  const FastAttnArgs &f = a.fa;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int qd = f.nh * f.hd, kd = f.nkv * f.hd, P = f.pos + 1, G = f.nh / f.nkv;
+  float *q = work, *ka = q + qd, *va = ka + f.ncb * kd, *pr = va + f.ncb * kd;   // pr: [nh][ncb]
+  // this position's q, k, v
+  for (int e = threadIdx.x; e < qd + 2 * kd; e += blockDim.x) {
+    float v = bf2f(f.qkv[e]);
+    if (e < qd) q[e] = v;
+    else if (e < qd + kd) ka[f.pos * kd + (e - qd)] = v;
+    else va[f.pos * kd + (e - qd - kd)] = v;
+  }
+  // earlier positions from the (tiny, L2-resident) fast KV cache: layout [nkv][ncb][hd]
+  for (int e = threadIdx.x; e < f.pos * kd; e += blockDim.x) {
+    int j = e / kd, r = e - j * kd, g = r / f.hd, d = r - g * f.hd;
+    size_t src = ((size_t)g * f.ncb + j) * f.hd + d;
+    ka[e] = bf2f(f.kc[src]); va[e] = bf2f(f.vc[src]);
+  }
+  __syncthreads();
+  const bf16 *rope_row = f.rope + (size_t)f.pos * f.hd;
+  for (int h = w; h < f.nh + f.nkv; h += nw) {
+    if (h < f.nh) head_norm_rope(q + h * f.hd, f.hd, f.qn, f.eps, rope_row, lane);
+    else head_norm_rope(ka + f.pos * kd + (h - f.nh) * f.hd, f.hd, f.kn, f.eps, rope_row, lane);
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {   // KVCache.update (llama.py:142-149) -- one writer
+    for (int e = threadIdx.x; e < kd; e += blockDim.x) {
+      int g = e / f.hd, d = e - g * f.hd;
+      size_t dst = ((size_t)g * f.ncb + f.pos) * f.hd + d;
+      f.kc[dst] = f2bf(ka[f.pos * kd + e]); f.vc[dst] = f2bf(va[f.pos * kd + e]);
+    }
+  }
+  // scores: bf16(q @ k^T) then bf16(* scale)   (llama.py:304)
+  for (int t = threadIdx.x; t < f.nh * P; t += blockDim.x) {
+    int h = t / P, j = t - h * P, g = h / G;
+    const float *qq = q + h * f.hd, *kk = ka + j * kd + g * f.hd;
+    float acc = 0.f;
+    for (int d = 0; d < f.hd; ++d) acc = fmaf(qq[d], kk[d], acc);
+    pr[h * f.ncb + j] = rbf(__fmul_rn(rbf(acc), f.scale));
+  }
+  __syncthreads();
+  // softmax over j <= pos in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf)=0)
+  for (int h = threadIdx.x; h < f.nh; h += blockDim.x) {
+    float m = -INFINITY;
+    for (int j = 0; j < P; ++j) m = fmaxf(m, pr[h * f.ncb + j]);
+    float s = 0.f;
+    for (int j = 0; j < P; ++j) s += expf(pr[h * f.ncb + j] - m);
+    for (int j = 0; j < P; ++j) pr[h * f.ncb + j] = rbf(expf(pr[h * f.ncb + j] - m) / s);
+  }
+  __syncthreads();
+  // y = bf16(p @ v)  (llama.py:309), laid out [h*hd + d] = the wo input
+  for (int e = threadIdx.x; e < qd; e += blockDim.x) {
+    int h = e / f.hd, d = e - h * f.hd, g = h / G;
+    float acc = 0.f;
+    for (int j = 0; j < P; ++j) acc = fmaf(pr[h * f.ncb + j], va[j * kd + g * f.hd + d], acc);
+    xs[xs_index(e)] = rbf(acc);
+  }
+}
+
+// ---- the dot core: two adjacent rows per warp iteration -----------------------------------------
+__device__ __forceinline__ void fma8(const uint4 &wv, const float4 &x0, const float4 &x1, float &acc) {
+  float f[8]; unpack8(wv, f);
+  acc = fmaf(f[0], x0.x, acc); acc = fmaf(f[1], x0.y, acc); acc = fmaf(f[2], x0.z, acc); acc = fmaf(f[3], x0.w, acc);
+  acc = fmaf(f[4], x1.x, acc); acc = fmaf(f[5], x1.y, acc); acc = fmaf(f[6], x1.z, acc); acc = fmaf(f[7], x1.w, acc);
+}
+
+#define DA_CH 4   // segments (of 256 elements) fetched per batch: 8 x 128-bit loads in flight per lane
+
+__device__ __forceinline__ void warp_dot_pair(const bf16 *__restrict__ w0, const bf16 *__restrict__ w1, bool has1,
+                                              int nseg, const float *xs, int lane, uint64_t pol, float &r0, float &r1) {
+  float a0 = 0.f, a1 = 0.f;
+  const uint4 *p0 = reinterpret_cast<const uint4 *>(w0) + lane;
+  const uint4 *p1 = reinterpret_cast<const uint4 *>(w1) + lane;
+  const float4 *xv = reinterpret_cast<const float4 *>(xs) + lane;
+  for (int s0 = 0; s0 < nseg; s0 += DA_CH) {
+    uint4 u0[DA_CH], u1[DA_CH];
+#pragma unroll
+    for (int c = 0; c < DA_CH; ++c) {
+      if (s0 + c < nseg) {
+        u0[c] = ldg_w(p0 + (s0 + c) * 32, pol);
+        u1[c] = has1 ? ldg_w(p1 + (s0 + c) * 32, pol) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < DA_CH; ++c) {
+      if (s0 + c < nseg) {
+        float4 x0 = xv[((s0 + c) * 2 + 0) * 32], x1 = xv[((s0 + c) * 2 + 1) * 32];
+        fma8(u0[c], x0, x1, a0);
+        fma8(u1[c], x0, x1, a1);
+      }
+    }
+  }
+  r0 = warp_sum(a0); r1 = warp_sum(a1);
+}
+
+// ---- end of a decode step (loop mode): what decode_n_tokens does between calls -------------------
+// inference.py:186-211: record the column, advance input_pos, rebuild the 16-wide window, EOS test.
+__device__ __forceinline__ void finish_step(const GemvArgs &a) {
+  DAState *st = a.st;
+  if (!st->loop_mode) return;
+  const int R = a.n_rows_tok;
+  int pos = st->pos + 1, n_gen = st->n_gen + 1;
+  for (int r = 0; r < R; ++r) { a.seq[(size_t)r * a.seq_stride + pos] = st->tok_out[r]; st->tok_in[r] = st->tok_out[r]; }
+  st->pos = pos; st->n_gen = n_gen; st->step_ctr += 1; st->use_penalty = 1;
+  if (st->noise) st->noise += st->noise_stride;
+  if (st->tok_out[0] == a.im_end_id || n_gen >= st->max_gen) st->done = 1;
+  // previous_tokens[:, j] = generated column j+1 (the prefill-produced column 0 is never recorded)
+  int i = n_gen - 1, T = st->prompt_len;
+  for (int c = 0; c < DA_WIN; ++c) {
+    int j = i < DA_WIN ? c : i - DA_WIN + c;
+    for (int r = 0; r < R; ++r)
+      st->win[r * DA_WIN + c] = (j < i) ? a.seq[(size_t)r * a.seq_stride + T + 1 + j] : 0;
+  }
+}
+
+// the fast heads (<= 1024 logits): one CTA samples and prepares the next pass
+__device__ void fast_head_sample(const GemvArgs &a, float *smem) {
+  DAState *st = a.st;
+  const int V = a.rows;
+  unsigned long long *cand = reinterpret_cast<unsigned long long *>(smem);
+  int n2 = 1; while (n2 < V) n2 <<= 1;
+  unsigned long long *scr64 = cand + n2;
+  float *scrf = reinterpret_cast<float *>(scr64 + 34);
+  const volatile uint16_t *lg = reinterpret_cast<const volatile uint16_t *>(a.out);
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    if (i < V) { uint16_t b = lg[i]; cand[i] = make_sortkey(b, (uint32_t)i); mx = fmaxf(mx, bits2f(b)); }
+    else cand[i] = ~0ull;
+  }
+  SampleParams sp;
+  sp.m = block_max(mx, scrf);
+  float es = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) es += expf(sortkey_logit(cand[i]) - sp.m);
+  sp.S = block_sum(es, scrf);
+  sp.T_bf = eff_temperature(st);
+  sp.c_max = cmax_from_top_p(st->top_p);
+  uint32_t idx = sample_sorted(cand, V, n2, true, sp, st, (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], scr64, scrf);
+  if (idx >= (uint32_t)a.codebook_size) { idx = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
+  for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[d] = a.fast_emb[(size_t)idx * a.fast_dim + d];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->tok_out[a.head + 1] = (int)idx;
+    if (a.last_head) finish_step(a);
+  }
+}
+
+// the last CTA of the fast-head GEMV to arrive runs it
+__device__ void fast_head_tail(const GemvArgs &a, float *smem) {
+  DAState *st = a.st;
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->fast_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) st->fast_ticket = 0;
+  fast_head_sample(a, smem);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+// dynamic shared memory: xs[K] floats | 80 floats scratch | prologue / sampler workspace
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(512, 1) gemv_kernel(const GemvArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  if (a.st->done) return;
+  float *xs = smem;
+  float *scratch = smem + a.K;
+  float *work = scratch + 80;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  if (PRO == PRO_PLAIN) prologue_plain(a, xs);
+  else if (PRO == PRO_RMSNORM) prologue_rmsnorm(a, xs, scratch);
+  else prologue_fastattn(a, xs, work);
+  __syncthreads();
+
+  const uint64_t pol = a.evict_last ? policy_evict_last() : policy_evict_first();
+  const int nseg = a.K >> 8;
+  const int npairs = (a.rows + 1) >> 1;
+
+  // LOGITS: penalised ids and the online (max, sumexp) of this warp's rows
+  int pen_id = -1; float rp_bf = 1.f; float wm = -INFINITY, wl = 0.f;
+  if (EPI == EPI_LOGITS) {
+    const DAState *st = a.st;
+    if (st->use_penalty) {
+      rp_bf = eff_rep_penalty(st);
+      if (a.head == 0) { if (lane < a.n_rows_tok) pen_id = st->win[lane * DA_WIN]; }       // previous_tokens[:, 0]  (inference.py:109-111)
+      else if (lane < DA_WIN) pen_id = st->win[(a.head + 1) * DA_WIN + lane];               // previous_tokens[k+1]   (inference.py:141-145)
+    }
+  }
+
+  for (int p = w * gridDim.x + blockIdx.x; p < npairs; p += nw * gridDim.x) {
+    const int r0 = 2 * p, r1 = r0 + 1;
+    const bool has1 = r1 < a.rows;
+    float d0, d1;
+    warp_dot_pair(a.W + (size_t)r0 * a.K, a.W + (size_t)(has1 ? r1 : r0) * a.K, has1, nseg, xs, lane, pol, d0, d1);
+    if (a.bias) { d0 += bf2f(a.bias[r0]); if (has1) d1 += bf2f(a.bias[r1]); }
+    if (EPI == EPI_STORE) {
+      if (lane == 0) { a.out[r0] = f2bf(d0); if (has1) a.out[r1] = f2bf(d1); }
+    } else if (EPI == EPI_RESIDUAL) {
+      if (lane == 0) {
+        a.out[r0] = f2bf(bf2f(a.res[r0]) + rbf(d0));
+        if (has1) a.out[r1] = f2bf(bf2f(a.res[r1]) + rbf(d1));
+      }
+    } else if (EPI == EPI_SWIGLU) {
+      if (lane == 0) {
+        float g = rbf(d0), u = rbf(d1);
+        float s = rbf(g / (1.0f + expf(-g)));       // F.silu in fp32, rounded
+        a.out[p] = f2bf(__fmul_rn(s, u));
+      }
+    } else {
+      float z0 = rbf(d0), z1 = rbf(d1);
+      if (a.logits_raw && lane == 0) { a.logits_raw[r0] = f2bf(z0); if (has1) a.logits_raw[r1] = f2bf(z1); }
+      unsigned hit0 = __ballot_sync(0xffffffffu, pen_id == r0), hit1 = __ballot_sync(0xffffffffu, pen_id == r1);
+      if (hit0) z0 = penalise(z0, rp_bf);
+      if (hit1) z1 = penalise(z1, rp_bf);
+      if (lane == 0) {
+        a.out[r0] = f2bf(z0);
+        float mn = fmaxf(wm, z0); wl = wl * expf(wm - mn) + expf(z0 - mn); wm = mn;
+        if (has1) {
+          a.out[r1] = f2bf(z1);
+          mn = fmaxf(wm, z1); wl = wl * expf(wm - mn) + expf(z1 - mn); wm = mn;
+        }
+      }
+    }
+  }
+
+  if (EPI == EPI_LOGITS) {
+    if (a.head == 0) {
+      // per-CTA partial of the softmax statistics; combined by the select kernel
+      __syncthreads();
+      if (lane == 0) { scratch[w] = wm; scratch[40 + w] = wl; }
+      __syncthreads();
+      if (w == 0) {
+        float mi = lane < nw ? scratch[lane] : -INFINITY, li = lane < nw ? scratch[40 + lane] : 0.f;
+        float m = warp_max(mi);
+        float l = warp_sum(li > 0.f ? li * expf(mi - m) : 0.f);
+        if (lane == 0) a.partials[blockIdx.x] = make_float2(m, l);
+      }
+    } else {
+      fast_head_tail(a, work);
+    }
+  }
+}
+
+}  // namespace da

@@ -1,0 +1,188 @@
+// misc_kernels.cuh -- the small kernels around the GEMVs: token embedding, the slow-head
+// candidate selection + sampler, step-input loading and the noise generator.
+#pragma once
+#include "common.cuh"
+#include "sampler.cuh"
+
+namespace da {
+
+// ---- K1: token + codebook embedding (llama.py:409-429) -------------------------------------------
+struct EmbedArgs {
+  const bf16 *emb;        // [vocab][dim]
+  const bf16 *cb_emb;     // [codebook_size * num_codebooks][dim]
+  bf16 *x;                // [dim]
+  int dim, vocab, codebook_size, num_codebooks;
+  int sem_begin, sem_end, scale_cb;
+  float inv_sqrt;         // float(1 / sqrt(num_codebooks + 1)): CUDA `tensor / python_scalar` multiplies by the reciprocal
+  float sqrt_c;           // float(sqrt(num_codebooks + 1)): the CPU kernel divides
+  DAState *st;
+};
+
+__global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
+  DAState *st = a.st;
+  if (st->done) return;
+  int tok = st->tok_in[0];
+  if (tok < 0 || tok >= a.vocab) { tok = 0; if (threadIdx.x == 0) st->err = 1; }
+  const bool is_sem = tok >= a.sem_begin && tok <= a.sem_end;
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < a.dim; d += gridDim.x * blockDim.x) {
+    float vq = 0.f;
+    if (is_sem) {
+      for (int i = 0; i < a.num_codebooks; ++i) {       // stack(...).sum(dim=1): fp32 accumulate, one rounding
+        int c = st->tok_in[i + 1];
+        if (c < 0 || c >= a.codebook_size) { c = 0; st->err = 1; }
+        vq += bf2f(a.cb_emb[((size_t)c + (size_t)i * a.codebook_size) * a.dim + d]);
+      }
+      vq = rbf(vq);
+    }
+    float x = rbf(bf2f(a.emb[(size_t)tok * a.dim + d]) + vq);
+    if (a.scale_cb && is_sem) x = st->cpu_sem ? rbf(__fdiv_rn(x, a.sqrt_c)) : rbf(__fmul_rn(x, a.inv_sqrt));
+    a.x[d] = f2bf(x);
+  }
+}
+
+// ---- slow head, stage 2: candidate selection on all SMs, sampling in the last CTA -----------------
+struct SelectArgs {
+  const bf16 *logits;     // [V] penalised
+  const float2 *partials; int n_partials;
+  int V;
+  float delta;            // candidates: z >= max - delta
+  unsigned long long *cand;   // [DA_CAND_CAP] global
+  const bf16 *fast_emb; bf16 *fast_x; int fast_dim, codebook_size, sem_begin;
+  DAState *st;
+};
+
+// dynamic smem: cand[DA_CAND_CAP] u64 | scr64[34] | scrf[80]
+__global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw_sel[];
+  DAState *st = a.st;
+  if (st->done) return;
+  unsigned long long *cand = reinterpret_cast<unsigned long long *>(smraw_sel);
+  unsigned long long *scr64 = cand + DA_CAND_CAP;
+  float *scrf = reinterpret_cast<float *>(scr64 + 34);
+  __shared__ float s_m, s_S;
+  // softmax statistics from the head kernel's per-CTA partials (fixed order)
+  if (threadIdx.x < 32) {   // warp 0: exact max, then per-lane strided sums + butterfly (fixed order)
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < a.n_partials; i += 32) m = fmaxf(m, a.partials[i].x);
+    m = warp_max(m);
+    float S = 0.f;
+    for (int i = threadIdx.x; i < a.n_partials; i += 32) if (a.partials[i].y > 0.f) S += a.partials[i].y * expf(a.partials[i].x - m);
+    S = warp_sum(S);
+    if (threadIdx.x == 0) { s_m = m; s_S = S; }
+  }
+  __syncthreads();
+  const float m = s_m, thr = m - a.delta;
+  const uint16_t *lb = reinterpret_cast<const uint16_t *>(a.logits);
+  const int chunk = (a.V + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * chunk, i1 = min(a.V, i0 + chunk);
+  const int lane = threadIdx.x & 31;
+  for (int base = i0; base < i1; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    uint16_t b = 0; bool c = false;
+    if (i < i1) { b = lb[i]; c = bits2f(b) >= thr; }
+    unsigned mask = __ballot_sync(0xffffffffu, c);
+    if (mask) {
+      unsigned basei = 0;
+      if (lane == 0) basei = atomicAdd(&st->n_cand, (unsigned)__popc(mask));
+      basei = __shfl_sync(0xffffffffu, basei, 0);
+      if (c) {
+        unsigned slot = basei + __popc(mask & ((1u << lane) - 1));
+        if (slot < DA_CAND_CAP) a.cand[slot] = make_sortkey(b, (uint32_t)i);
+      }
+    }
+  }
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->sel_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  SampleParams sp;
+  sp.m = m; sp.S = s_S;
+  sp.T_bf = eff_temperature(st);
+  sp.c_max = cmax_from_top_p(st->top_p);
+  const unsigned n_cand = *((volatile unsigned *)&st->n_cand);
+  uint32_t idx = 0xFFFFFFFFu;
+  if (n_cand >= 1 && n_cand <= DA_CAND_CAP) {
+    int n = (int)n_cand, n2 = 1; while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) cand[i] = i < n ? __ldcg(a.cand + i) : ~0ull;
+    __syncthreads();
+    idx = sample_sorted(cand, n, n2, n == a.V, sp, st, 0u, 0ll, &st->nucleus[0], scr64, scrf);
+  }
+  if (idx == 0xFFFFFFFFu) idx = sample_fallback(a.logits, a.V, sp, st, 0u, 0ll, &st->nucleus[0], scr64, scrf);
+  // inference.py:123-126: first codebook = semantic id - semantic_begin (clamped at 0); next input = its fast embedding
+  int cb0 = (int)idx - a.sem_begin; if (cb0 < 0) cb0 = 0;
+  if (cb0 >= a.codebook_size) { cb0 = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
+  for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[d] = a.fast_emb[(size_t)cb0 * a.fast_dim + d];
+  if (threadIdx.x == 0) {
+    st->tok_out[0] = (int)idx; st->tok_out[1] = cb0;
+    st->n_cand = 0; st->sel_ticket = 0;
+  }
+}
+
+// ---- step-mode input loading: what the reference passes to decode_one_token (inference.py:194-204)
+struct LoadStepArgs {
+  const int *x; const int *input_pos; const int *prev; long long prev_stride;
+  const float *temperature, *top_p, *rep_penalty; const bf16 *noise;
+  int n_rows;
+  DAState *st;
+};
+__global__ void load_step_kernel(const LoadStepArgs a) {
+  DAState *st = a.st;
+  int t = threadIdx.x;
+  if (t < a.n_rows) st->tok_in[t] = a.x[t];
+  if (a.prev) for (int i = t; i < a.n_rows * DA_WIN; i += blockDim.x) st->win[i] = a.prev[(size_t)(i / DA_WIN) * a.prev_stride + (i % DA_WIN)];
+  if (t == 0) {
+    st->pos = a.input_pos[0];
+    st->temperature = a.temperature[0]; st->top_p = a.top_p[0]; st->rep_penalty = a.rep_penalty[0];
+    st->use_penalty = a.prev ? 1 : 0;
+    st->noise = a.noise; st->loop_mode = 0; st->done = 0;
+    st->n_cand = 0; st->sel_ticket = 0; st->fast_ticket = 0; st->head_ticket = 0;
+    for (int g = 0; g < DA_MAX_KV_HEADS; ++g) st->attn_ticket[g] = 0;
+  }
+}
+__global__ void store_step_kernel(const DAState *st, int *out, int n_rows) {
+  if (threadIdx.x < n_rows) out[threadIdx.x] = st->tok_out[threadIdx.x];
+  if (threadIdx.x == 0) const_cast<DAState *>(st)->step_ctr += 1;
+}
+
+// ---- loop-mode prefill bookkeeping -----------------------------------------------------------------
+// loads column `pos` of the prompt as the step input; on the last prompt position arms the sampler
+struct PrefillColArgs { const int *seq; int seq_stride; int n_rows; DAState *st; };
+__global__ void prefill_col_kernel(const PrefillColArgs a, int advance) {
+  DAState *st = a.st;
+  if (advance) { if (threadIdx.x == 0) st->pos += 1; }
+  __syncthreads();
+  int pos = st->pos;
+  if (threadIdx.x < a.n_rows) st->tok_in[threadIdx.x] = a.seq[(size_t)threadIdx.x * a.seq_stride + pos];
+}
+
+// ---- test hook: run the sampler alone on caller-supplied logits (dualar_debug_sample) ------------------
+// slow head: penalty + per-CTA softmax partials, exactly what the LOGITS epilogue leaves behind
+__global__ void __launch_bounds__(512) debug_stats_kernel(const bf16 *in, bf16 *out, float2 *partials, int V, int n_rows_tok, DAState *st) {
+  __shared__ float scratch[80];
+  const int chunk = (V + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * chunk, i1 = min(V, i0 + chunk);
+  const float rp_bf = eff_rep_penalty(st);
+  float m = -INFINITY;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    float z = bf2f(in[i]);
+    if (st->use_penalty) for (int r = 0; r < n_rows_tok; ++r) if (st->win[r * DA_WIN] == i) { z = penalise(z, rp_bf); break; }
+    out[i] = f2bf(z);
+    m = fmaxf(m, z);
+  }
+  m = block_max(m, scratch);
+  float l = 0.f;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) l += expf(bf2f(out[i]) - m);
+  l = block_sum(l, scratch);
+  if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(m, l);
+}
+
+__global__ void fill_noise_kernel(bf16 *out, long long n, unsigned long long seed, unsigned step, unsigned head) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = f2bf(exp1_noise(seed, step, head, (uint32_t)i));
+}
+
+}  // namespace da

@@ -1,0 +1,265 @@
+// sampler.cuh -- repetition penalty / top-p / temperature / Exp(1)-race sampling, sort-free for the
+// 155,776-way slow head.  Restates fish_tts/models/inference.py:24-80 with the reference's own
+// rounding points (the whole sampler is bf16 there):
+//   score<0 ? score*rp : score/rp      (rp rounded to bf16, result rounded to bf16)      :38-45
+//   p_i   = bf16(exp(z_i - max) / sum)                     softmax over the sorted logits :48-51
+//   cum_j = running sum of p in sorted order; remove_j = bf16(cum_j) > bf16(top_p); keep j=0 :49-53
+//   z'_i  = bf16(z_i / bf16(clip(T,1e-5))) for kept, -inf otherwise                        :57-58
+//   p'_i  = bf16(exp(z'_i - max') / sum');  r_i = bf16(p'_i / q_i);  argmax (first index on ties) :60, 26-27
+//
+// Where the reference is implementation-defined we fix a definition (DESIGN.md "sampler"):
+//   * equal logits are ordered by ascending index (torch.sort leaves it unspecified);
+//   * the running sum is exact: probabilities are bf16 values, summed as 2^-44 fixed point in
+//     u64, so the nucleus does not depend on summation order (the reference's CPU path runs a
+//     sequential fp32 sum, its CUDA path a bf16 tree scan -- they already disagree with each other).
+#pragma once
+#include "common.cuh"
+
+namespace da {
+
+#define DA_FIX_SCALE 17592186044416.0f   // 2^44
+
+struct SampleParams {
+  float m, S;        // max and sum(exp(z-m)) over the (penalised) logits
+  float T_bf;        // bf16(clip(temperature, 1e-5)) as float
+  unsigned long long c_max;  // largest fixed-point cumulative sum that still rounds to <= bf16(top_p)
+};
+
+__device__ __forceinline__ unsigned long long pweight(float z, float m, float S) {
+  float p = rbf(expf(z - m) / S);
+  return (unsigned long long)(p * DA_FIX_SCALE);
+}
+
+__device__ __forceinline__ unsigned long long cmax_from_top_p(float top_p) {
+  // bf16(cum) <= t  <=>  cum < mid, or cum == mid when t's mantissa is even (round-half-even)
+  uint16_t tb = f2bits(top_p);
+  float t = bits2f(tb), nxt = bits2f((uint16_t)(tb + 1));
+  float mid = 0.5f * t + 0.5f * nxt;             // exact: 9 significant bits
+  unsigned long long M = (unsigned long long)(mid * DA_FIX_SCALE);
+  return (tb & 1u) ? (M ? M - 1 : 0) : M;
+}
+
+__device__ __forceinline__ float penalise(float z, float rp_bf) {
+  return z < 0.f ? rbf(z * rp_bf) : rbf(z / rp_bf);
+}
+// torch keeps a 0-dim fp32 operand of a bf16 op in fp32 on the CPU but casts it to bf16 inside CUDA kernels
+// (TensorIterator dynamic casting): `logits / temperature`, `score * repetition_penalty` (inference.py:42-44, 58)
+__device__ __forceinline__ float eff_rep_penalty(const DAState *st) { return st->cpu_sem ? st->rep_penalty : rbf(st->rep_penalty); }
+__device__ __forceinline__ float eff_temperature(const DAState *st) {
+  float t = fmaxf(st->temperature, 1e-5f);
+  return st->cpu_sem ? t : rbf(t);
+}
+
+__device__ __forceinline__ float noise_at(const DAState *st, uint32_t head, long long head_off, uint32_t idx) {
+  if (st->noise) return bf2f(st->noise[head_off + idx]);
+  return exp1_noise(st->seed, st->step_ctr, head, idx);
+}
+
+// ascending bitonic sort of n2 (power of two) u64 keys in shared memory; whole block participates
+__device__ __forceinline__ void bitonic_sort(unsigned long long *a, int n2) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        int i = 2 * t - (t & (j - 1));
+        int l = i + j;
+        unsigned long long x = a[i], y = a[l];
+        bool up = ((i & k) == 0);
+        if ((x > y) == up) { a[i] = y; a[l] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long make_sortkey(uint16_t zbits, uint32_t idx) {
+  return ((unsigned long long)(0xFFFFu - bf16_key(zbits)) << 32) | idx;   // ascending = logit desc, idx asc
+}
+__device__ __forceinline__ float sortkey_logit(unsigned long long k) {
+  return bits2f(key_bf16(0xFFFFu - (uint32_t)(k >> 32)));
+}
+
+// block-wide exclusive scan of one u64 per thread (blockDim <= 1024); scratch >= 33 u64
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long *scratch,
+                                                                  unsigned long long *total) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long x = lane < nw ? scratch[lane] : 0ull, xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += t;
+    }
+    scratch[lane] = xi - x;            // exclusive warp offsets
+    if (lane == 31) scratch[32] = xi;  // grand total
+  }
+  __syncthreads();
+  if (total) *total = scratch[32];
+  return scratch[w] + inc - v;
+}
+
+struct ArgBest { float r; uint32_t idx; };
+__device__ __forceinline__ ArgBest better(ArgBest a, ArgBest b) {   // larger r, then smaller idx
+  if (b.r > a.r || (b.r == a.r && b.idx < a.idx)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgBest block_argbest(ArgBest v, float *fs, uint32_t *is) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgBest t; t.r = __shfl_xor_sync(0xffffffffu, v.r, o); t.idx = __shfl_xor_sync(0xffffffffu, v.idx, o);
+    v = better(v, t);
+  }
+  __syncthreads();
+  if (lane == 0) { fs[w] = v.r; is[w] = v.idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ArgBest b = {fs[0], is[0]};
+    for (int i = 1; i < nw; ++i) { ArgBest t = {fs[i], is[i]}; b = better(b, t); }
+    fs[32] = b.r; is[32] = b.idx;
+  }
+  __syncthreads();
+  ArgBest out = {fs[32], is[32]};
+  return out;
+}
+
+// ---- fast path: candidates already in shared memory ---------------------------------------------
+// cand[0..n) unsorted sort keys, n2 = next pow2 (padding filled with ~0).  Returns the sampled index,
+// or 0xFFFFFFFF when the nucleus is not proven to lie inside the candidate set (caller falls back).
+// `all_present`: the candidate set is the whole vocabulary.
+__device__ uint32_t sample_sorted(unsigned long long *cand, int n, int n2, bool all_present, const SampleParams &sp,
+                                  const DAState *st, uint32_t head, long long head_off, int *nucleus_out,
+                                  unsigned long long *scr64, float *scrf) {
+  bitonic_sort(cand, n2);
+  // each thread owns a contiguous chunk of the sorted list
+  int per = (n + blockDim.x - 1) / blockDim.x;
+  int j0 = threadIdx.x * per, j1 = min(n, j0 + per);
+  unsigned long long local = 0;
+  for (int j = j0; j < j1; ++j) local += pweight(sortkey_logit(cand[j]), sp.m, sp.S);
+  unsigned long long run = block_excl_scan_u64(local, scr64, nullptr);
+  int kept = 0;
+  for (int j = j0; j < j1; ++j) {
+    run += pweight(sortkey_logit(cand[j]), sp.m, sp.S);
+    if (run <= sp.c_max) ++kept;
+  }
+  int n_keep = (int)(block_sum((float)kept, scrf) + 0.5f);   // counts <= 8192: exact in fp32
+  if (n_keep < 1) n_keep = 1;
+  if (n_keep == n && !all_present) return 0xFFFFFFFFu;
+  if (threadIdx.x == 0 && nucleus_out) *nucleus_out = n_keep;
+  // second softmax over the kept prefix, then the Exp(1) race
+  float mz = rbf(sortkey_logit(cand[0]) / sp.T_bf);
+  float es = 0.f;
+  for (int j = j0; j < min(j1, n_keep); ++j) es += expf(rbf(sortkey_logit(cand[j]) / sp.T_bf) - mz);
+  float S2 = block_sum(es, scrf);
+  ArgBest best = {0.f, 0u};   // removed tokens have probability 0 -> r = 0; argmax ties go to index 0
+  for (int j = j0; j < min(j1, n_keep); ++j) {
+    uint32_t idx = (uint32_t)cand[j];
+    float p2 = rbf(expf(rbf(sortkey_logit(cand[j]) / sp.T_bf) - mz) / S2);
+    float q = noise_at(st, head, head_off, idx);
+    ArgBest c = {rbf(p2 / q), idx};
+    best = better(best, c);
+  }
+  best = block_argbest(best, scrf, (uint32_t *)(scrf + 40));
+  return best.idx;
+}
+
+// ---- fallback: nucleus wider than the candidate list (flat distributions) ------------------------
+// One CTA walks the whole logits vector from global memory; all sums are u64, so order-free.
+__device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParams &sp, const DAState *st,
+                                    uint32_t head, long long head_off, int *nucleus_out,
+                                    unsigned long long *scr64, float *scrf) {
+  const uint16_t *lb = reinterpret_cast<const uint16_t *>(logits);
+  __shared__ int sh_i[4];
+  // (1) lowest key kappa such that G(kappa) = sum_{key >= kappa} w <= c_max
+  auto G_of = [&](uint32_t key) {
+    unsigned long long g = 0;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      uint16_t b = lb[i];
+      if (bf16_key(b) >= key) g += pweight(bits2f(b), sp.m, sp.S);
+    }
+    unsigned long long tot;
+    block_excl_scan_u64(g, scr64, &tot);
+    return tot;
+  };
+  uint32_t lo = 0, hi = 65536;   // invariant: G(hi) <= c_max (G(65536) = 0), G(lo) > c_max
+  if (G_of(0) <= sp.c_max) hi = 0;
+  else while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (G_of(mid) <= sp.c_max) hi = mid; else lo = mid;
+  }
+  uint32_t kappa = hi;
+  // (2) G(kappa), count of fully kept, and the next lower present key
+  unsigned long long g = 0; int cnt = 0; uint32_t below = 0; bool has_below = false;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    uint16_t b = lb[i]; uint32_t k = bf16_key(b);
+    if (k >= kappa) { g += pweight(bits2f(b), sp.m, sp.S); ++cnt; }
+    else if (!has_below || k > below) { below = k; has_below = true; }
+  }
+  unsigned long long G;
+  block_excl_scan_u64(g, scr64, &G);
+  int n_full = (int)(block_sum((float)cnt, scrf) + 0.5f);
+  float bmax = block_max(has_below ? (float)below : -1.f, scrf);   // keys < 65536: exact in fp32
+  int tau = (int)bmax;   // -1: nothing below
+  // (3) partial group: how many members of key tau are kept, and up to which index
+  int c_part = 0, i_cut = -1;
+  if (tau >= 0) {
+    int n_tau = 0;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) n_tau += (bf16_key(lb[i]) == (uint32_t)tau);
+    n_tau = (int)(block_sum((float)n_tau, scrf) + 0.5f);
+    unsigned long long w = pweight(bits2f(key_bf16((uint32_t)tau)), sp.m, sp.S);
+    unsigned long long room = sp.c_max >= G ? sp.c_max - G : 0ull;
+    unsigned long long c = w ? room / w : (unsigned long long)n_tau;
+    c_part = (int)(c < (unsigned long long)n_tau ? c : (unsigned long long)n_tau);
+    if (n_full == 0 && c_part < 1) c_part = 1;          // always keep the top-1 (inference.py:53)
+    if (c_part > 0) {
+      // index of the c_part-th member in index order: ordered block scan, chunk by chunk
+      if (threadIdx.x == 0) { sh_i[0] = 0; sh_i[1] = -1; }
+      __syncthreads();
+      for (int base = 0; base < V; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        unsigned long long f = (i < V && bf16_key(lb[i]) == (uint32_t)tau) ? 1ull : 0ull;
+        unsigned long long tot;
+        unsigned long long ex = block_excl_scan_u64(f, scr64, &tot);
+        int before = sh_i[0];
+        if (f && before + (int)ex + 1 == c_part) sh_i[1] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) sh_i[0] = before + (int)tot;
+        __syncthreads();
+        if (sh_i[1] >= 0) break;
+      }
+      i_cut = sh_i[1];
+    }
+  }
+  if (threadIdx.x == 0 && nucleus_out) *nucleus_out = n_full + c_part;
+  // (4) second softmax + race over the kept set
+  float mz = rbf(sp.m / sp.T_bf);   // the top logit is always kept
+  float es = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    uint16_t b = lb[i]; uint32_t k = bf16_key(b);
+    bool keep = k >= kappa || ((int)k == tau && i <= i_cut);
+    if (keep) es += expf(rbf(bits2f(b) / sp.T_bf) - mz);
+  }
+  float S2 = block_sum(es, scrf);
+  ArgBest best = {0.f, 0u};
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    uint16_t b = lb[i]; uint32_t k = bf16_key(b);
+    bool keep = k >= kappa || ((int)k == tau && i <= i_cut);
+    if (keep) {
+      float p2 = rbf(expf(rbf(bits2f(b) / sp.T_bf) - mz) / S2);
+      ArgBest c = {rbf(p2 / noise_at(st, head, head_off, (uint32_t)i)), (uint32_t)i};
+      best = better(best, c);
+    }
+  }
+  best = block_argbest(best, scrf, (uint32_t *)(scrf + 40));
+  return best.idx;
+}
+
+}  // namespace da

@@ -1,0 +1,73 @@
+"""GPU-side helpers shared by the parity tests and the diagnostic script (oracle = checker only)."""
+from __future__ import annotations
+
+import torch
+from torch.nn.attention import SDPBackend, sdpa_kernel
+
+from fish_tts_b200.engine import DualAREngine
+from fish_tts_b200.synthetic import make_state_dict
+from oracle import dualar_oracle as orc
+
+
+def build_pair(cfg, seed=0, bind_kv=True, options=None, sd=None, **sd_kw):
+    """oracle on cuda:0 + engine; with bind_kv the engine runs on the oracle's KV tensors (phase A)."""
+    sd = sd or make_state_dict(cfg, seed=seed, **sd_kw)
+    m = orc.OracleModel.build(cfg, sd, device="cuda:0")
+    m.setup_caches(cfg.max_seq_len)
+    kv = None
+    if bind_kv:
+        kv = {"slow": [(k, v) for k, v in m.kv], "fast": [(k, v) for k, v in m.fast_kv]}
+    eng = DualAREngine(cfg, sd, device=0, kv=kv, options=options)
+    return m, eng, sd
+
+
+def block_noise_source(cfg, block: torch.Tensor) -> orc.NoiseSource:
+    """feed one step's engine-layout noise block to the oracle in its sampling order"""
+    fv = min(1024, cfg.codebook_size)
+
+    def fn(call, n):
+        off = 0 if call == 0 else cfg.vocab_size + (call - 1) * fv
+        return block[off: off + n]
+
+    return orc.NoiseSource(fn)
+
+
+class TeacherForced:
+    """Runs oracle and engine side by side on the ORACLE's trajectory and KV state, one step at a time."""
+
+    def __init__(self, cfg, m, eng, prompt, T, p, rp, noise_seed=11):
+        self.cfg, self.m, self.eng = cfg, m, eng
+        dev = m.device
+        self.t = [torch.tensor(v, device=dev, dtype=torch.float) for v in (T, p, rp)]
+        self.C1 = cfg.num_codebooks + 1
+        self.noise_seed = noise_seed
+        Tlen = prompt.size(1)
+        self.prev = torch.zeros((self.C1, cfg.max_seq_len), dtype=torch.int32, device=dev)
+        blk = eng.step_noise(noise_seed, 0)
+        with torch.inference_mode(), sdpa_kernel(SDPBackend.MATH):
+            first = orc.decode_one_token_ar(m, prompt.view(1, self.C1, -1).to(dev), torch.arange(Tlen, device=dev),
+                                            *self.t, None, noise=block_noise_source(cfg, blk), stable_ties=True)
+        self.cur = first.view(1, self.C1, -1).clone()
+        self.input_pos = torch.tensor([Tlen], device=dev, dtype=torch.int32)
+        self.i = 0
+
+    def step(self):
+        """-> dict(mine tokens, ref tokens, my/ref logits...)"""
+        cfg, m, eng, i = self.cfg, self.m, self.eng, self.i
+        window = self.prev[:, :16] if i < 16 else self.prev[:, i - 16: i]
+        blk = eng.step_noise(self.noise_seed, i + 1)
+        mine = eng.step(self.cur, self.input_pos, window, *self.t, noise=blk).clone()
+        torch.cuda.synchronize()
+        out = {"mine": mine[:, 0].cpu(), "my_slow": eng.read("slow_logits_raw"), "my_fast": eng.read("fast_logits"),
+               "my_hidden": eng.read("hidden"), "nucleus": eng.read("nucleus")}
+        tr = []
+        with torch.inference_mode(), sdpa_kernel(SDPBackend.MATH):
+            ref = orc.decode_one_token_ar(m, self.cur, self.input_pos, *self.t, window,
+                                          noise=block_noise_source(cfg, blk), stable_ties=True, trace=tr)
+        out.update(ref=ref[:, 0].cpu(), ref_slow=tr[0].slow_logits.cpu(), ref_fast=torch.stack(tr[0].fast_logits).cpu(),
+                   ref_hidden=tr[0].hidden.cpu(), window=window.clone().cpu(), noise=blk)
+        self.input_pos += 1
+        self.cur = ref.view(1, self.C1, -1).clone()
+        self.prev[:, i: i + 1] = ref
+        self.i += 1
+        return out
