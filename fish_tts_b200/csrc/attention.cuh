@@ -34,6 +34,7 @@ struct AttnArgs {
   bf16 *y;                // [nh * hd]
   int nsplit_max;
   DAState *st;
+  Timeline tl;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,7 +62,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
 __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) attn_slow_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   DAState *st = a.st;
-  if (st->done) return;
+  tl_stamp(a.tl, 0);
+  pdl_launch_dependents();
+  // st->pos / st->done only change in the LAST kernel of a graph launch, and graph launches serialise, so they
+  // may be read before the dependency wait; that lets the first K/V tile stream in while the wqkv GEMV finishes
+  if (st->done) { pdl_wait(); return; }
   const int g = blockIdx.y, split = blockIdx.x;
   const int G = a.nh / a.nkv, hd = a.hd;
   const int pos = st->pos, L = pos + 1;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) attn_slow_kernel(const Att
   const int nsplit = min(a.nsplit_max, n_tiles);
   const int tps = (n_tiles + nsplit - 1) / nsplit;
   const int nsplit_eff = (n_tiles + tps - 1) / tps;
-  if (split >= nsplit_eff) return;
+  if (split >= nsplit_eff) { pdl_wait(); return; }
   const int t0 = split * tps, t1 = min(n_tiles, t0 + tps);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = DA_ATTN_THREADS / 32;
 
@@ -105,6 +110,8 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) attn_slow_kernel(const Att
     }
   };
   if (threadIdx.x == 0) issue(t0, 0);
+  pdl_wait();
+  tl_stamp(a.tl, 1);
 
   // q heads of this group (and, in the split that owns `pos`, the new k / v row)
   const int qd = a.nh * hd, kd = a.nkv * hd;
@@ -217,6 +224,7 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) attn_slow_kernel(const Att
     __syncthreads();
   }
   if (!ok && threadIdx.x == 0) st->err = 2;
+  tl_stamp(a.tl, 2);
 
   // partials out
   float *po = a.part_o + (((size_t)g * a.nsplit_max + split) * G) * hd;
@@ -232,6 +240,7 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) attn_slow_kernel(const Att
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&st->attn_ticket[g], 1u) == (unsigned)nsplit_eff - 1);
   __syncthreads();
+  tl_stamp(a.tl, 3);
   if (!s_last) return;
   __threadfence();
   // merge in split order

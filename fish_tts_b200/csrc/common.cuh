@@ -132,6 +132,16 @@ __device__ __forceinline__ float exp1_noise(uint64_t seed, uint32_t step, uint32
   return rbf(-logf(u));
 }
 
+// ---- optional in-kernel timeline (DUALAR_TIMELINE=1): block 0 / thread 0 of every kernel of the step graph
+// stamps %globaltimer and clock64 at entry, after the dependency wait, after the prologue and at exit
+struct Timeline { unsigned long long *buf; int slot; };   // buf[slot*8 + {0..3}] = globaltimer ns, {4..7} = clock64
+__device__ __forceinline__ void tl_stamp(const Timeline &t, int k) {
+  if (t.buf && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    t.buf[t.slot * 8 + k] = g; t.buf[t.slot * 8 + 4 + k] = (unsigned long long)clock64();
+  }
+}
+
 }  // namespace da
 
 // ---- device-resident request state: everything a graph replay needs lives here ------------------

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -55,6 +56,7 @@ struct dualar_engine {
   int launches_step = 0, launches_prefill = 0;
   int prompt_len = 0, max_gen = 0;
   std::vector<void *> owned;
+  unsigned long long *tl = nullptr; int tl_slots = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -203,6 +205,20 @@ static void host_rope(std::vector<uint16_t> &out, int seq, int n_elem, float bas
   }
 }
 
+// every kernel of the step graph is launched with programmatic stream serialization (PDL): it starts while its
+// predecessor still runs, prefetches weights, and blocks in griddepcontrol.wait until the predecessor has finished
+static bool g_use_pdl = true;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <typename T> static int dev_alloc(dualar_engine *e, T *&p, size_t n) {
   CU(cudaMalloc((void **)&p, n * sizeof(T)));
   CU(cudaMemset(p, 0, n * sizeof(T)));
@@ -227,10 +243,9 @@ template <int PRO, int EPI> static int launch_gemv(dualar_engine *e, GemvArgs a,
     configured = 200 * 1024 > smem ? 200 * 1024 : smem;
   }
   int npairs = (a.rows + 1) / 2;
-  int grid = npairs < e->sms ? npairs : e->sms;
-  a.st = e->st;
-  gemv_kernel<PRO, EPI><<<grid, 512, smem, s>>>(a);
-  CU(cudaGetLastError());
+  int grid = npairs < 2 * e->sms ? npairs : 2 * e->sms;
+  a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
+  CU(launch_k(gemv_kernel<PRO, EPI>, dim3(grid), dim3(DA_GEMV_THREADS), smem, s, a));
   ++count;
   return grid;
 }
@@ -252,12 +267,11 @@ static int enqueue_slow_layer(dualar_engine *e, int li, cudaStream_t s, int &cou
     t.qkv = e->qkv; t.kc = L.kc; t.vc = L.vc; t.rope = e->rope; t.qn = L.qn; t.kn = L.kn;
     t.nh = c.n_head; t.nkv = c.n_local_heads; t.hd = c.head_dim; t.S = c.max_seq_len; t.eps = c.norm_eps;
     t.sf = (float)sqrt(1.0 / sqrt((double)c.head_dim));
-    t.part_o = e->part_o; t.part_ml = e->part_ml; t.y = e->y; t.nsplit_max = e->nsplit; t.st = e->st;
+    t.part_o = e->part_o; t.part_ml = e->part_ml; t.y = e->y; t.nsplit_max = e->nsplit; t.st = e->st; t.tl.buf = e->tl; t.tl.slot = count;
     size_t smem = attn_smem_bytes(c.n_head / c.n_local_heads, c.head_dim);
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(attn_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-    attn_slow_kernel<<<dim3(e->nsplit, c.n_local_heads), DA_ATTN_THREADS, smem, s>>>(t);
-    CU(cudaGetLastError()); ++count; }
+    CU(launch_k(attn_slow_kernel, dim3(e->nsplit, c.n_local_heads), dim3(DA_ATTN_THREADS), smem, s, t)); ++count; }
   { GemvArgs a = base_args(L.wo, L.bo, c.dim, qd, 0); a.x = e->y; a.res = e->x; a.out = e->h;
     if ((rc = launch_gemv<PRO_PLAIN, EPI_RESIDUAL>(e, a, s, count)) < 0) return rc; }
   { GemvArgs a = base_args(L.w13, nullptr, 2 * c.intermediate_size, c.dim, 0); a.x = e->h; a.norm_w = L.ffn_norm; a.eps = c.norm_eps; a.out = e->act;
@@ -293,12 +307,12 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
   { EmbedArgs a; memset(&a, 0, sizeof(a));
     a.emb = e->emb; a.cb_emb = e->cb_emb; a.x = e->x; a.dim = c.dim; a.vocab = c.vocab_size; a.codebook_size = c.codebook_size;
     a.num_codebooks = c.num_codebooks; a.sem_begin = c.semantic_begin_id; a.sem_end = c.semantic_end_id; a.scale_cb = c.scale_codebook_embeddings;
-    a.inv_sqrt = (float)(1.0 / sqrt((double)(c.num_codebooks + 1))); a.sqrt_c = (float)sqrt((double)(c.num_codebooks + 1)); a.st = e->st;
-    embed_kernel<<<(c.dim + 255) / 256, 256, 0, s>>>(a); CU(cudaGetLastError()); ++count; }
+    a.inv_sqrt = (float)(1.0 / sqrt((double)(c.num_codebooks + 1))); a.sqrt_c = (float)sqrt((double)(c.num_codebooks + 1)); a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
+    CU(launch_k(embed_kernel, dim3((c.dim + 255) / 256), dim3(256), 0, s, a)); ++count; }
   for (int i = 0; i < c.n_layer; ++i) if ((rc = enqueue_slow_layer(e, i, s, count)) < 0) return rc;
   if (slow_only) {
     PrefillColArgs a{e->seq, c.max_seq_len, c.num_codebooks + 1, e->st};
-    prefill_col_kernel<<<1, 32, 0, s>>>(a, 1); CU(cudaGetLastError()); ++count;
+    CU(launch_k(prefill_col_kernel, dim3(1), dim3(32), 0, s, a, 1)); ++count;
     return 0;
   }
   // LM head + sampler (llama.py:446-451, inference.py:103-113)
@@ -309,11 +323,11 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
     if ((head_grid = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(e, a, s, count)) < 0) return head_grid; }
   { SelectArgs a; memset(&a, 0, sizeof(a));
     a.logits = e->logits; a.partials = e->partials; a.n_partials = head_grid; a.V = c.vocab_size; a.delta = e->delta; a.cand = e->cand;
-    a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.sem_begin = c.semantic_begin_id; a.st = e->st;
+    a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.sem_begin = c.semantic_begin_id; a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
     size_t smem = (size_t)DA_CAND_CAP * 8 + 34 * 8 + 80 * 4 + 64;
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-    select_sample_kernel<<<e->sms, 512, smem, s>>>(a); CU(cudaGetLastError()); ++count; }
+    CU(launch_k(select_sample_kernel, dim3(e->sms), dim3(512), smem, s, a)); ++count; }
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
   for (int p = 0; p < c.num_codebooks; ++p) {
     const bf16 *in = p == 0 ? e->x : e->fin;
@@ -389,12 +403,14 @@ extern "C" int dualar_finalize(dualar_engine *e) {
       (rc = dev_alloc(e, e->flogits, (size_t)c.num_codebooks * e->fv)) || (rc = dev_alloc(e, e->flogits_raw, (size_t)c.num_codebooks * e->fv)) ||
       (rc = dev_alloc(e, e->part_o, (size_t)c.n_local_heads * e->nsplit * G * c.head_dim)) ||
       (rc = dev_alloc(e, e->part_ml, (size_t)c.n_local_heads * e->nsplit * G * 2)) ||
-      (rc = dev_alloc(e, e->partials, (size_t)e->sms)) || (rc = dev_alloc(e, e->cand, (size_t)DA_CAND_CAP)) ||
+      (rc = dev_alloc(e, e->partials, (size_t)2 * e->sms)) || (rc = dev_alloc(e, e->cand, (size_t)DA_CAND_CAP)) ||
       (rc = dev_alloc(e, e->st, 1)) || (rc = dev_alloc(e, e->seq, (size_t)(c.num_codebooks + 1) * c.max_seq_len)))
     return rc;
   CU(cudaMallocHost((void **)&e->h_seq, (size_t)(c.num_codebooks + 1) * c.max_seq_len * sizeof(int)));
   CU(cudaMallocHost((void **)&e->h_st, sizeof(DAState)));
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  { const char *v = getenv("DUALAR_PDL"); if (v && v[0] == '0') g_use_pdl = false; }
+  { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 512; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc; } }
   // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
   { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);
     if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp); cudaGetLastError(); }
@@ -629,6 +645,7 @@ extern "C" int dualar_read_buffer(dualar_engine *e, const char *name, void *dst,
   else if (!strcmp(name, "h")) { src = e->h; avail = (int64_t)c.dim * 2; }
   else if (!strcmp(name, "act")) { src = e->act; avail = (int64_t)c.intermediate_size * 2; }
   else if (!strcmp(name, "fast_x")) { src = e->fbuf[(c.n_fast_layer - 1) & 1]; avail = (int64_t)c.fast_dim * 2; }
+  else if (!strcmp(name, "timeline")) { if (!e->tl) return fail(DUALAR_ESTATE, "run with DUALAR_TIMELINE=1"); src = e->tl; avail = (int64_t)e->tl_slots * 64; }
   else if (!strcmp(name, "fast_in")) { src = e->fin; avail = (int64_t)c.fast_dim * 2; }
   else return fail(DUALAR_EINVAL, "unknown buffer '%s'", name);
   if (nbytes > avail) return fail(DUALAR_EINVAL, "buffer '%s' holds %lld bytes, %lld requested", name, (long long)avail, (long long)nbytes);

@@ -57,6 +57,7 @@ struct GemvArgs {
   int fast_dim, last_head, codebook_size;
   int *seq; int seq_stride; int im_end_id; int n_rows_tok;  // finish_step
   DAState *st;
+  Timeline tl;
 };
 
 // one warp applies (optional) nn.RMSNorm and RoPE to one head vector held as fp32 in shared memory
@@ -158,41 +159,47 @@ __device__ __forceinline__ void prologue_fastattn(const GemvArgs &a, float *xs, 
   }
 }
 
-// ---- the dot core: two adjacent rows per warp iteration -----------------------------------------
+// ---- the dot core: two adjacent rows per warp, DA_CH segments (of 256 elements) per batch ------------
 __device__ __forceinline__ void fma8(const uint4 &wv, const float4 &x0, const float4 &x1, float &acc) {
   float f[8]; unpack8(wv, f);
   acc = fmaf(f[0], x0.x, acc); acc = fmaf(f[1], x0.y, acc); acc = fmaf(f[2], x0.z, acc); acc = fmaf(f[3], x0.w, acc);
   acc = fmaf(f[4], x1.x, acc); acc = fmaf(f[5], x1.y, acc); acc = fmaf(f[6], x1.z, acc); acc = fmaf(f[7], x1.w, acc);
 }
 
-#define DA_CH 4   // segments (of 256 elements) fetched per batch: 8 x 128-bit loads in flight per lane
+#define DA_CH 4   // 8 x 128-bit loads in flight per lane per batch; two batches are kept in flight (ping-pong)
 
-__device__ __forceinline__ void warp_dot_pair(const bf16 *__restrict__ w0, const bf16 *__restrict__ w1, bool has1,
-                                              int nseg, const float *xs, int lane, uint64_t pol, float &r0, float &r1) {
-  float a0 = 0.f, a1 = 0.f;
-  const uint4 *p0 = reinterpret_cast<const uint4 *>(w0) + lane;
-  const uint4 *p1 = reinterpret_cast<const uint4 *>(w1) + lane;
+struct PairRegs { uint4 u0[DA_CH], u1[DA_CH]; };
+
+// batch b of row pair p: segments [b*DA_CH, +DA_CH) of rows 2p and 2p+1
+__device__ __forceinline__ void load_batch(PairRegs &r, const bf16 *__restrict__ W, int K, int rows, int p, int b, int nseg,
+                                           int lane, uint64_t pol) {
+  const int r0 = 2 * p;
+  const bool has1 = r0 + 1 < rows;
+  const uint4 *p0 = reinterpret_cast<const uint4 *>(W + (size_t)r0 * K) + lane;
+  const uint4 *p1 = reinterpret_cast<const uint4 *>(W + (size_t)(has1 ? r0 + 1 : r0) * K) + lane;
+#pragma unroll
+  for (int c = 0; c < DA_CH; ++c) {
+    const int sgm = b * DA_CH + c;
+    if (sgm < nseg) { r.u0[c] = ldg_w(p0 + sgm * 32, pol); r.u1[c] = ldg_w(p1 + sgm * 32, pol); }
+  }
+}
+__device__ __forceinline__ void fma_batch(const PairRegs &r, const float *xs, int b, int nseg, int lane, float &a0, float &a1) {
   const float4 *xv = reinterpret_cast<const float4 *>(xs) + lane;
-  for (int s0 = 0; s0 < nseg; s0 += DA_CH) {
-    uint4 u0[DA_CH], u1[DA_CH];
 #pragma unroll
-    for (int c = 0; c < DA_CH; ++c) {
-      if (s0 + c < nseg) {
-        u0[c] = ldg_w(p0 + (s0 + c) * 32, pol);
-        u1[c] = has1 ? ldg_w(p1 + (s0 + c) * 32, pol) : make_uint4(0, 0, 0, 0);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < DA_CH; ++c) {
-      if (s0 + c < nseg) {
-        float4 x0 = xv[((s0 + c) * 2 + 0) * 32], x1 = xv[((s0 + c) * 2 + 1) * 32];
-        fma8(u0[c], x0, x1, a0);
-        fma8(u1[c], x0, x1, a1);
-      }
+  for (int c = 0; c < DA_CH; ++c) {
+    const int sgm = b * DA_CH + c;
+    if (sgm < nseg) {
+      float4 x0 = xv[(sgm * 2 + 0) * 32], x1 = xv[(sgm * 2 + 1) * 32];
+      fma8(r.u0[c], x0, x1, a0);
+      fma8(r.u1[c], x0, x1, a1);
     }
   }
-  r0 = warp_sum(a0); r1 = warp_sum(a1);
 }
+
+// programmatic dependent launch (guide: Guideline 9): the next kernel of the step graph is launched while this one
+// runs; it may only touch weights until griddepcontrol.wait returns (= every earlier kernel has completed).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- end of a decode step (loop mode): what decode_n_tokens does between calls -------------------
 // inference.py:186-211: record the column, advance input_pos, rebuild the 16-wide window, EOS test.
@@ -261,23 +268,38 @@ __device__ void fast_head_tail(const GemvArgs &a, float *smem) {
 
 // ---- the kernel ------------------------------------------------------------------------------
 // dynamic shared memory: xs[K] floats | 80 floats scratch | prologue / sampler workspace
+// A warp walks "units" = (row pair, batch of DA_CH segments); unit u+1 is in flight while unit u is consumed, and the
+// first unit is fetched BEFORE the dependency wait, so the weight stream of kernel N+1 overlaps the tail of kernel N.
+#define DA_GEMV_THREADS 256
 template <int PRO, int EPI>
-__global__ void __launch_bounds__(512, 1) gemv_kernel(const GemvArgs a) {
+__global__ void __launch_bounds__(DA_GEMV_THREADS, 2) gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(16) float smem[];
-  if (a.st->done) return;
+  tl_stamp(a.tl, 0);
+  pdl_launch_dependents();
   float *xs = smem;
   float *scratch = smem + a.K;
   float *work = scratch + 80;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const uint64_t pol = a.evict_last ? policy_evict_last() : policy_evict_first();
+  const int nseg = a.K >> 8;
+  const int nb = (nseg + DA_CH - 1) / DA_CH;
+  const int npairs = (a.rows + 1) >> 1;
+  const int first = w * gridDim.x + blockIdx.x, stride = nw * gridDim.x;
+  const int my_pairs = first < npairs ? (npairs - first + stride - 1) / stride : 0;
+  const int nu = my_pairs * nb;
+
+  PairRegs ra, rb;
+  if (nu > 0) load_batch(ra, a.W, a.K, a.rows, first, 0, nseg, lane, pol);
+
+  pdl_wait();
+  tl_stamp(a.tl, 1);
+  if (a.st->done) return;
 
   if (PRO == PRO_PLAIN) prologue_plain(a, xs);
   else if (PRO == PRO_RMSNORM) prologue_rmsnorm(a, xs, scratch);
   else prologue_fastattn(a, xs, work);
   __syncthreads();
-
-  const uint64_t pol = a.evict_last ? policy_evict_last() : policy_evict_first();
-  const int nseg = a.K >> 8;
-  const int npairs = (a.rows + 1) >> 1;
+  tl_stamp(a.tl, 2);
 
   // LOGITS: penalised ids and the online (max, sumexp) of this warp's rows
   int pen_id = -1; float rp_bf = 1.f; float wm = -INFINITY, wl = 0.f;
@@ -290,42 +312,58 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const GemvArgs a) {
     }
   }
 
-  for (int p = w * gridDim.x + blockIdx.x; p < npairs; p += nw * gridDim.x) {
-    const int r0 = 2 * p, r1 = r0 + 1;
-    const bool has1 = r1 < a.rows;
-    float d0, d1;
-    warp_dot_pair(a.W + (size_t)r0 * a.K, a.W + (size_t)(has1 ? r1 : r0) * a.K, has1, nseg, xs, lane, pol, d0, d1);
-    if (a.bias) { d0 += bf2f(a.bias[r0]); if (has1) d1 += bf2f(a.bias[r1]); }
-    if (EPI == EPI_STORE) {
-      if (lane == 0) { a.out[r0] = f2bf(d0); if (has1) a.out[r1] = f2bf(d1); }
-    } else if (EPI == EPI_RESIDUAL) {
-      if (lane == 0) {
-        a.out[r0] = f2bf(bf2f(a.res[r0]) + rbf(d0));
-        if (has1) a.out[r1] = f2bf(bf2f(a.res[r1]) + rbf(d1));
-      }
-    } else if (EPI == EPI_SWIGLU) {
-      if (lane == 0) {
-        float g = rbf(d0), u = rbf(d1);
-        float s = rbf(g / (1.0f + expf(-g)));       // F.silu in fp32, rounded
-        a.out[p] = f2bf(__fmul_rn(s, u));
-      }
-    } else {
-      float z0 = rbf(d0), z1 = rbf(d1);
-      if (a.logits_raw && lane == 0) { a.logits_raw[r0] = f2bf(z0); if (has1) a.logits_raw[r1] = f2bf(z1); }
-      unsigned hit0 = __ballot_sync(0xffffffffu, pen_id == r0), hit1 = __ballot_sync(0xffffffffu, pen_id == r1);
-      if (hit0) z0 = penalise(z0, rp_bf);
-      if (hit1) z1 = penalise(z1, rp_bf);
-      if (lane == 0) {
-        a.out[r0] = f2bf(z0);
-        float mn = fmaxf(wm, z0); wl = wl * expf(wm - mn) + expf(z0 - mn); wm = mn;
-        if (has1) {
-          a.out[r1] = f2bf(z1);
-          mn = fmaxf(wm, z1); wl = wl * expf(wm - mn) + expf(z1 - mn); wm = mn;
+  float a0 = 0.f, a1 = 0.f;
+  int pi = 0, b = 0;   // unit u = (pair index pi, batch b)
+  auto step = [&](PairRegs &cur, PairRegs &nxt, int u) {
+    // prefetch unit u+1 into the other register set
+    int pin = pi, bn = b + 1;
+    if (bn == nb) { bn = 0; ++pin; }
+    if (u + 1 < nu) load_batch(nxt, a.W, a.K, a.rows, first + pin * stride, bn, nseg, lane, pol);
+    fma_batch(cur, xs, b, nseg, lane, a0, a1);
+    if (b == nb - 1) {
+      const int p = first + pi * stride;
+      const int r0 = 2 * p, r1 = r0 + 1;
+      const bool has1 = r1 < a.rows;
+      float d0 = warp_sum(a0), d1 = warp_sum(a1);
+      a0 = 0.f; a1 = 0.f;
+      if (a.bias) { d0 += bf2f(a.bias[r0]); if (has1) d1 += bf2f(a.bias[r1]); }
+      if (EPI == EPI_STORE) {
+        if (lane == 0) { a.out[r0] = f2bf(d0); if (has1) a.out[r1] = f2bf(d1); }
+      } else if (EPI == EPI_RESIDUAL) {
+        if (lane == 0) {
+          a.out[r0] = f2bf(bf2f(a.res[r0]) + rbf(d0));
+          if (has1) a.out[r1] = f2bf(bf2f(a.res[r1]) + rbf(d1));
+        }
+      } else if (EPI == EPI_SWIGLU) {
+        if (lane == 0) {
+          float g = rbf(d0), up = rbf(d1);
+          float sg = rbf(g / (1.0f + expf(-g)));       // F.silu in fp32, rounded
+          a.out[p] = f2bf(__fmul_rn(sg, up));
+        }
+      } else {
+        float z0 = rbf(d0), z1 = rbf(d1);
+        if (a.logits_raw && lane == 0) { a.logits_raw[r0] = f2bf(z0); if (has1) a.logits_raw[r1] = f2bf(z1); }
+        unsigned hit0 = __ballot_sync(0xffffffffu, pen_id == r0), hit1 = __ballot_sync(0xffffffffu, pen_id == r1);
+        if (hit0) z0 = penalise(z0, rp_bf);
+        if (hit1) z1 = penalise(z1, rp_bf);
+        if (lane == 0) {
+          a.out[r0] = f2bf(z0);
+          float mn = fmaxf(wm, z0); wl = wl * expf(wm - mn) + expf(z0 - mn); wm = mn;
+          if (has1) {
+            a.out[r1] = f2bf(z1);
+            mn = fmaxf(wm, z1); wl = wl * expf(wm - mn) + expf(z1 - mn); wm = mn;
+          }
         }
       }
     }
+    pi = pin; b = bn;
+  };
+  for (int u = 0; u < nu; u += 2) {   // ping-pong with static register sets
+    step(ra, rb, u);
+    if (u + 1 < nu) step(rb, ra, u + 1);
   }
 
+  tl_stamp(a.tl, 3);
   if (EPI == EPI_LOGITS) {
     if (a.head == 0) {
       // per-CTA partial of the softmax statistics; combined by the select kernel

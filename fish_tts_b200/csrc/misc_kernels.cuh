@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "sampler.cuh"
+#include "gemv.cuh"
 
 namespace da {
 
@@ -16,10 +17,15 @@ struct EmbedArgs {
   float inv_sqrt;         // float(1 / sqrt(num_codebooks + 1)): CUDA `tensor / python_scalar` multiplies by the reciprocal
   float sqrt_c;           // float(sqrt(num_codebooks + 1)): the CPU kernel divides
   DAState *st;
+  Timeline tl;
 };
 
 __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
   DAState *st = a.st;
+  tl_stamp(a.tl, 0);
+  pdl_launch_dependents();
+  pdl_wait();
+  tl_stamp(a.tl, 1);
   if (st->done) return;
   int tok = st->tok_in[0];
   if (tok < 0 || tok >= a.vocab) { tok = 0; if (threadIdx.x == 0) st->err = 1; }
@@ -38,6 +44,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
     if (a.scale_cb && is_sem) x = st->cpu_sem ? rbf(__fdiv_rn(x, a.sqrt_c)) : rbf(__fmul_rn(x, a.inv_sqrt));
     a.x[d] = f2bf(x);
   }
+  tl_stamp(a.tl, 3);
 }
 
 // ---- slow head, stage 2: candidate selection on all SMs, sampling in the last CTA -----------------
@@ -49,12 +56,17 @@ struct SelectArgs {
   unsigned long long *cand;   // [DA_CAND_CAP] global
   const bf16 *fast_emb; bf16 *fast_x; int fast_dim, codebook_size, sem_begin;
   DAState *st;
+  Timeline tl;
 };
 
 // dynamic smem: cand[DA_CAND_CAP] u64 | scr64[34] | scrf[80]
 __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs a) {
   extern __shared__ __align__(16) unsigned char smraw_sel[];
   DAState *st = a.st;
+  tl_stamp(a.tl, 0);
+  pdl_launch_dependents();
+  pdl_wait();
+  tl_stamp(a.tl, 1);
   if (st->done) return;
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(smraw_sel);
   unsigned long long *scr64 = cand + DA_CAND_CAP;
@@ -96,6 +108,7 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&st->sel_ticket, 1u) == gridDim.x - 1);
   __syncthreads();
+  tl_stamp(a.tl, 2);
   if (!s_last) return;
   __threadfence();
 
@@ -119,6 +132,7 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
   if (threadIdx.x == 0) {
     st->tok_out[0] = (int)idx; st->tok_out[1] = cb0;
     st->n_cand = 0; st->sel_ticket = 0;
+    if (a.tl.buf) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); a.tl.buf[a.tl.slot * 8 + 3] = g; }
   }
 }
 
@@ -153,6 +167,8 @@ __global__ void store_step_kernel(const DAState *st, int *out, int n_rows) {
 struct PrefillColArgs { const int *seq; int seq_stride; int n_rows; DAState *st; };
 __global__ void prefill_col_kernel(const PrefillColArgs a, int advance) {
   DAState *st = a.st;
+  pdl_launch_dependents();
+  pdl_wait();
   if (advance) { if (threadIdx.x == 0) st->pos += 1; }
   __syncthreads();
   int pos = st->pos;

@@ -35,8 +35,10 @@ def block_noise_source(cfg, block: torch.Tensor) -> orc.NoiseSource:
 class TeacherForced:
     """Runs oracle and engine side by side on the ORACLE's trajectory and KV state, one step at a time."""
 
-    def __init__(self, cfg, m, eng, prompt, T, p, rp, noise_seed=11):
-        self.cfg, self.m, self.eng = cfg, m, eng
+    def __init__(self, cfg, m, eng, prompt, T, p, rp, noise_seed=11, alt=None):
+        """alt: a second OracleModel (e.g. on the CPU) stepped along the same trajectory -- the yardstick for how far
+        two of the reference's own backends are from each other."""
+        self.cfg, self.m, self.eng, self.alt = cfg, m, eng, alt
         dev = m.device
         self.t = [torch.tensor(v, device=dev, dtype=torch.float) for v in (T, p, rp)]
         self.C1 = cfg.num_codebooks + 1
@@ -47,6 +49,12 @@ class TeacherForced:
         with torch.inference_mode(), sdpa_kernel(SDPBackend.MATH):
             first = orc.decode_one_token_ar(m, prompt.view(1, self.C1, -1).to(dev), torch.arange(Tlen, device=dev),
                                             *self.t, None, noise=block_noise_source(cfg, blk), stable_ties=True)
+        if alt is not None:
+            alt.setup_caches(cfg.max_seq_len)
+            ta = [x.to(alt.device) for x in self.t]
+            with torch.inference_mode(), sdpa_kernel(SDPBackend.MATH):
+                orc.decode_one_token_ar(alt, prompt.view(1, self.C1, -1).to(alt.device), torch.arange(Tlen, device=alt.device),
+                                        *ta, None, noise=block_noise_source(cfg, blk.to(alt.device)), stable_ties=True)
         self.cur = first.view(1, self.C1, -1).clone()
         self.input_pos = torch.tensor([Tlen], device=dev, dtype=torch.int32)
         self.i = 0
@@ -66,6 +74,14 @@ class TeacherForced:
                                           noise=block_noise_source(cfg, blk), stable_ties=True, trace=tr)
         out.update(ref=ref[:, 0].cpu(), ref_slow=tr[0].slow_logits.cpu(), ref_fast=torch.stack(tr[0].fast_logits).cpu(),
                    ref_hidden=tr[0].hidden.cpu(), window=window.clone().cpu(), noise=blk)
+        if self.alt is not None:
+            alt, tra = self.alt, []
+            ta = [x.to(alt.device) for x in self.t]
+            with torch.inference_mode(), sdpa_kernel(SDPBackend.MATH):
+                ra = orc.decode_one_token_ar(alt, self.cur.to(alt.device), self.input_pos.to(alt.device), *ta, window.to(alt.device),
+                                             noise=block_noise_source(cfg, blk.to(alt.device)), stable_ties=True, trace=tra)
+            out.update(alt=ra[:, 0].cpu(), alt_slow=tra[0].slow_logits.cpu(), alt_fast=torch.stack(tra[0].fast_logits).cpu(),
+                       alt_hidden=tra[0].hidden.cpu())
         self.input_pos += 1
         self.cur = ref.view(1, self.C1, -1).clone()
         self.prev[:, i: i + 1] = ref

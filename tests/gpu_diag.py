@@ -24,19 +24,33 @@ def cmp(name, a, b):
           f"ref_absmax={b.abs().max().item():.3f} nan={int(torch.isnan(a).sum())}", flush=True)
 
 
-def run(cfg, label, n_steps, modes):
+def run(cfg, label, n_steps, modes, with_alt=False):
     print(f"=== {label}", flush=True)
     t0 = time.time()
     m, eng, sd = build_pair(cfg)
+    alt = None
+    if with_alt:
+        from oracle import dualar_oracle as orc
+        alt = orc.OracleModel.build(cfg, sd, device="cpu")
     print(f"   built in {time.time() - t0:.1f}s; launches/step {eng.launches_per_step()} weight bytes {eng.weight_bytes()}", flush=True)
     prompt = synthetic_prompt(cfg, 5, 12, 4, seed=1)
     for (T, p, rp) in modes:
-        tf = TeacherForced(cfg, m, eng, prompt, T, p, rp)
+        tf = TeacherForced(cfg, m, eng, prompt, T, p, rp, alt=alt)
         agree = 0
+        agree_alt = 0
         for s in range(n_steps):
             o = tf.step()
             same = torch.equal(o["mine"], o["ref"])
             agree += same
+            if alt is not None:
+                agree_alt += torch.equal(o["alt"], o["ref"])
+                sem = slice(cfg.semantic_begin_id, cfg.semantic_end_id + 1)
+                dm = (o["my_slow"].float() - o["ref_slow"].float()).abs()
+                da = (o["alt_slow"].float() - o["ref_slow"].float()).abs()
+                top2 = o["ref_slow"].float()[sem].topk(2).values
+                print(f"  step {s}: |mine-cuda| sem max {dm[sem].max():.4f} mean {dm[sem].mean():.5f} all max {dm.max():.4f} | |cpu-cuda| sem max {da[sem].max():.4f} "
+                      f"mean {da[sem].mean():.5f} all max {da.max():.4f} | hidden mine {(o['my_hidden'].float()-o['ref_hidden'].float()).abs().max():.3f} "
+                      f"cpu {(o['alt_hidden'].float()-o['ref_hidden'].float()).abs().max():.3f} | top2 gap {top2[0]-top2[1]:.4f} | tok mine==cuda {same} cpu==cuda {torch.equal(o['alt'], o['ref'])}", flush=True)
             if s < 3 or not same:
                 print(f"  step {s} T={T} p={p} rp={rp} tokens {'==' if same else '!='} mine {o['mine'].tolist()} ref {o['ref'].tolist()} nucleus {o['nucleus'].tolist()}")
                 cmp("hidden", o["my_hidden"], o["ref_hidden"])
@@ -45,7 +59,7 @@ def run(cfg, label, n_steps, modes):
                 while k < cfg.num_codebooks - 1 and o["mine"][k + 1] == o["ref"][k + 1]:
                     k += 1
                 cmp("fast_logits", o["my_fast"][: max(k, 1)], o["ref_fast"][: max(k, 1)])
-        print(f"  T={T} p={p} rp={rp}: {agree}/{n_steps} steps token-identical", flush=True)
+        print(f"  T={T} p={p} rp={rp}: {agree}/{n_steps} steps token-identical (cpu oracle vs cuda oracle: {agree_alt}/{n_steps})", flush=True)
     # one-layer intermediates
     eng.close()
 
@@ -72,4 +86,4 @@ if __name__ == "__main__":
         for name, cfg in variant_configs().items():
             run(cfg, f"tiny/{name}", 24, modes)
     else:
-        run(s1_mini_config(), "s1-mini", 12, modes)
+        run(s1_mini_config(), "s1-mini", 10, modes, with_alt=True)
