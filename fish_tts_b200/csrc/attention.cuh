@@ -115,12 +115,19 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) attn_slow_kernel(const Att
 
   // q heads of this group (and, in the split that owns `pos`, the new k / v row)
   const int qd = a.nh * hd, kd = a.nkv * hd;
-  for (int e = threadIdx.x; e < G * hd; e += DA_ATTN_THREADS) q[e] = bf2f(a.qkv[(size_t)g * G * hd + e]);
-  if (owns_new)
-    for (int e = threadIdx.x; e < hd; e += DA_ATTN_THREADS) {
-      knew[e] = bf2f(a.qkv[qd + g * hd + e]);
-      vnew[e] = bf2f(a.qkv[qd + kd + g * hd + e]);
+  {   // one 16-byte chunk per thread: G*hd/8 chunks of q, then hd/8 of the new k and of the new v
+    const int nq = (G * hd) >> 3, nk = owns_new ? (hd >> 3) : 0;
+    const int c = threadIdx.x;
+    if (c < nq + 2 * nk) {
+      const bf16 *src; float *dst;
+      if (c < nq) { src = a.qkv + (size_t)g * G * hd + (size_t)c * 8; dst = q + c * 8; }
+      else if (c < nq + nk) { src = a.qkv + qd + (size_t)g * hd + (size_t)(c - nq) * 8; dst = knew + (c - nq) * 8; }
+      else { src = a.qkv + qd + kd + (size_t)g * hd + (size_t)(c - nq - nk) * 8; dst = vnew + (c - nq - nk) * 8; }
+      float t[8]; unpack8(*reinterpret_cast<const uint4 *>(src), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = t[j];
     }
+  }
   __syncthreads();
   const bf16 *rope_row = a.rope + (size_t)pos * hd;
   for (int h = w; h < G + (owns_new ? 1 : 0); h += nw) {

@@ -131,6 +131,10 @@ static int check_config(const dualar_config &c) {
   if (G > DA_MAX_G || G * c.head_dim > DA_MAX_G * 128) return fail(DUALAR_EINVAL, "GQA group too large");
   if (c.n_local_heads > DA_MAX_KV_HEADS) return fail(DUALAR_EINVAL, "too many kv heads");
   if (c.num_codebooks + 1 > DA_MAX_ROWS || c.num_codebooks < 2) return fail(DUALAR_EINVAL, "num_codebooks out of range");
+  if (c.fast_n_head * c.num_codebooks > 256 || c.num_codebooks * c.fast_n_local_heads * c.fast_head_dim > 8192 ||
+      (c.fast_n_head + 2 * c.fast_n_local_heads) * c.fast_head_dim > 4096 || c.dim > 4096 || c.intermediate_size > 4096 ||
+      c.fast_intermediate_size > 4096 || c.n_head * c.head_dim > 4096)
+    return fail(DUALAR_EINVAL, "shape exceeds the per-CTA staging limits of the GEMV prologues (K <= 4096, fast attention <= 256 (head, position) pairs)");
   if (c.vocab_size <= 0 || c.max_seq_len <= 0 || c.n_layer <= 0 || c.n_fast_layer <= 0) return fail(DUALAR_EINVAL, "bad sizes");
   if (c.semantic_begin_id < 0 || c.semantic_end_id >= c.vocab_size || c.semantic_end_id < c.semantic_begin_id)
     return fail(DUALAR_EINVAL, "semantic id range outside the vocabulary");
@@ -231,7 +235,7 @@ template <int PRO, int EPI> static size_t gemv_smem(const dualar_engine *e, cons
   size_t f = ((size_t)a.K + 80) * sizeof(float);
   size_t work = 0;
   if (PRO == PRO_FASTATTN) work = ((size_t)a.fa.nh * a.fa.hd + 2 * (size_t)a.fa.ncb * a.fa.nkv * a.fa.hd + (size_t)a.fa.nh * a.fa.ncb) * sizeof(float);
-  if (EPI == EPI_LOGITS && a.head > 0) { size_t n2 = 1; while ((int)n2 < a.rows) n2 <<= 1; size_t w2 = n2 * 8 + 34 * 8 + 80 * 4 + 64; if (w2 > work) work = w2; }
+  if (EPI == EPI_LOGITS && a.head > 0) { size_t w2 = 192 * 8 + 80 * 4 + 64; if (w2 > work) work = w2; }
   (void)e;
   return f + work + 16;
 }
@@ -324,7 +328,7 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
   { SelectArgs a; memset(&a, 0, sizeof(a));
     a.logits = e->logits; a.partials = e->partials; a.n_partials = head_grid; a.V = c.vocab_size; a.delta = e->delta; a.cand = e->cand;
     a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.sem_begin = c.semantic_begin_id; a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
-    size_t smem = (size_t)DA_CAND_CAP * 8 + 34 * 8 + 80 * 4 + 64;
+    size_t smem = 192 * 8 + 34 * 8 + 80 * 4 + 64;
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     CU(launch_k(select_sample_kernel, dim3(e->sms), dim3(512), smem, s, a)); ++count; }
@@ -504,7 +508,7 @@ extern "C" int dualar_step(dualar_engine *e, const int32_t *x, const int32_t *in
 
 // ---- test hook: the sampler alone on caller-supplied logits ------------------------------------------------
 namespace da {
-__global__ void __launch_bounds__(512, 1) debug_fast_sample_kernel(const GemvArgs a, const bf16 *in) {
+__global__ void __launch_bounds__(DA_GEMV_THREADS, 1) debug_fast_sample_kernel(const GemvArgs a, const bf16 *in) {
   extern __shared__ __align__(16) float smem_dbg[];
   DAState *st = a.st;
   const float rp_bf = eff_rep_penalty(st);
@@ -535,7 +539,7 @@ extern "C" int dualar_debug_sample(dualar_engine *e, int head, const void *logit
     SelectArgs a; memset(&a, 0, sizeof(a));
     a.logits = e->logits; a.partials = e->partials; a.n_partials = e->sms; a.V = c.vocab_size; a.delta = e->delta; a.cand = e->cand;
     a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.sem_begin = c.semantic_begin_id; a.st = e->st;
-    size_t smem = (size_t)DA_CAND_CAP * 8 + 34 * 8 + 80 * 4 + 64;
+    size_t smem = 192 * 8 + 34 * 8 + 80 * 4 + 64;
     select_sample_kernel<<<e->sms, 512, smem, s>>>(a); CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_token, &e->st->tok_out[0], sizeof(int), cudaMemcpyDeviceToDevice, s));
   } else {
@@ -543,9 +547,8 @@ extern "C" int dualar_debug_sample(dualar_engine *e, int head, const void *logit
     a.out = e->flogits + (size_t)(head - 1) * e->fv; a.head = head; a.noise_off = (long long)c.vocab_size + (long long)(head - 1) * e->fv;
     a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.last_head = 0;
     a.n_rows_tok = c.num_codebooks + 1; a.st = e->st;
-    size_t n2 = 1; while ((int)n2 < e->fv) n2 <<= 1;
-    size_t smem = n2 * 8 + 34 * 8 + 80 * 4 + 64;
-    debug_fast_sample_kernel<<<1, 512, smem, s>>>(a, (const bf16 *)logits); CU(cudaGetLastError());
+    size_t smem = 192 * 8 + 80 * 4 + 64;
+    debug_fast_sample_kernel<<<1, DA_GEMV_THREADS, smem, s>>>(a, (const bf16 *)logits); CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_token, &e->st->tok_out[head + 1], sizeof(int), cudaMemcpyDeviceToDevice, s));
   }
   return 0;

@@ -83,40 +83,105 @@ __device__ __forceinline__ void head_norm_rope(float *v, int hd, const bf16 *nw,
 }
 
 // ---- prologues: fill xs (fp32, xs_index layout) ------------------------------------------------
-__device__ __forceinline__ void prologue_plain(const GemvArgs &a, float *xs) {
-  for (int e = threadIdx.x; e < a.K; e += blockDim.x) xs[xs_index(e)] = bf2f(a.x[e]);
+// Activation vectors are moved as 16-byte chunks (8 bf16), every load of a phase issued before the first use, so a
+// prologue costs ONE L2 round trip instead of K/256 dependent ones.  Chunk c -> thread c % blockDim, slot c / blockDim.
+#define DA_XCH 2   // chunks per thread: K <= 8 * 256 * DA_XCH = 4096 with 256 threads
+struct XRegs { uint4 v[DA_XCH]; };
+
+__device__ __forceinline__ void load_chunks(XRegs &r, const bf16 *x, int K) {
+#pragma unroll
+  for (int i = 0; i < DA_XCH; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c * 8 < K) r.v[i] = *reinterpret_cast<const uint4 *>(x + (size_t)c * 8);
+  }
+}
+// chunk c (elements 8c..8c+7) in the xs_index layout: two conflict-free float4 stores
+__device__ __forceinline__ void store_chunk_xs(float *xs, int c, const float *f) {
+  float4 *dst = reinterpret_cast<float4 *>(xs);
+  const int sgm = c >> 5, lane = c & 31;
+  dst[(sgm * 2 + 0) * 32 + lane] = make_float4(f[0], f[1], f[2], f[3]);
+  dst[(sgm * 2 + 1) * 32 + lane] = make_float4(f[4], f[5], f[6], f[7]);
 }
 
-__device__ __forceinline__ void prologue_rmsnorm(const GemvArgs &a, float *xs, float *scratch) {
-  float ss = 0.f;
-  for (int e = threadIdx.x; e < a.K; e += blockDim.x) { float v = bf2f(a.x[e]); ss = fmaf(v, v, ss); }
-  ss = block_sum(ss, scratch);
-  float inv = rsqrtf(ss * (1.0f / (float)a.K) + a.eps);
-  for (int e = threadIdx.x; e < a.K; e += blockDim.x) {
-    float v = rbf(__fmul_rn(bf2f(a.x[e]), inv));          // .type_as(x)
-    xs[xs_index(e)] = rbf(__fmul_rn(v, bf2f(a.norm_w[e])));   // * weight
+__device__ __forceinline__ void prologue_plain(const GemvArgs &a, float *xs, const XRegs &xr) {
+#pragma unroll
+  for (int i = 0; i < DA_XCH; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c * 8 < a.K) { float f[8]; unpack8(xr.v[i], f); store_chunk_xs(xs, c, f); }
   }
 }
 
-// fast-layer attention for ONE query position, every CTA recomputes it (<= 16 heads x 10 positions)
+// wn: the norm weight chunks (a weight: fetched before the dependency wait); xr: the activation chunks
+__device__ __forceinline__ void prologue_rmsnorm(const GemvArgs &a, float *xs, float *scratch, const XRegs &xr, const XRegs &wn) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < DA_XCH; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c * 8 < a.K) {
+      float f[8]; unpack8(xr.v[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+    }
+  }
+  ss = block_sum(ss, scratch);
+  const float inv = rsqrtf(ss * (1.0f / (float)a.K) + a.eps);
+#pragma unroll
+  for (int i = 0; i < DA_XCH; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c * 8 < a.K) {
+      float f[8], g[8]; unpack8(xr.v[i], f); unpack8(wn.v[i], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = rbf(__fmul_rn(rbf(__fmul_rn(f[j], inv)), g[j]));   // .type_as(x), then * weight
+      store_chunk_xs(xs, c, f);
+    }
+  }
+}
+
+// fast-layer attention for ONE query position, every CTA recomputes it (<= 16 heads x <= 15 positions)
 // work: [q | k_all | v_all | p] floats after xs
+#define DA_FKV 4   // chunks of earlier K (and V) rows per thread: pos * nkv * hd <= 8 * 256 * DA_FKV
 __device__ __forceinline__ void prologue_fastattn(const GemvArgs &a, float *xs, float *work) {
   const FastAttnArgs &f = a.fa;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int qd = f.nh * f.hd, kd = f.nkv * f.hd, P = f.pos + 1, G = f.nh / f.nkv;
   float *q = work, *ka = q + qd, *va = ka + f.ncb * kd, *pr = va + f.ncb * kd;   // pr: [nh][ncb]
-  // this position's q, k, v
-  for (int e = threadIdx.x; e < qd + 2 * kd; e += blockDim.x) {
-    float v = bf2f(f.qkv[e]);
-    if (e < qd) q[e] = v;
-    else if (e < qd + kd) ka[f.pos * kd + (e - qd)] = v;
-    else va[f.pos * kd + (e - qd - kd)] = v;
+  // one round trip: this position's q|k|v and every earlier K/V row (cache layout [nkv][ncb][hd], tiny, L2-resident)
+  XRegs cur; load_chunks(cur, f.qkv, qd + 2 * kd);
+  uint4 pk[DA_FKV], pv[DA_FKV];
+  const int hd8 = f.hd >> 3, kd8 = kd >> 3, nprev = f.pos * kd8;
+#pragma unroll
+  for (int i = 0; i < DA_FKV; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < nprev) {
+      const int j = c / kd8, r = c - j * kd8, g = r / hd8, d8 = r - g * hd8;
+      const size_t src = ((size_t)g * f.ncb + j) * f.hd + (size_t)d8 * 8;
+      pk[i] = *reinterpret_cast<const uint4 *>(f.kc + src);
+      pv[i] = *reinterpret_cast<const uint4 *>(f.vc + src);
+    }
   }
-  // earlier positions from the (tiny, L2-resident) fast KV cache: layout [nkv][ncb][hd]
-  for (int e = threadIdx.x; e < f.pos * kd; e += blockDim.x) {
-    int j = e / kd, r = e - j * kd, g = r / f.hd, d = r - g * f.hd;
-    size_t src = ((size_t)g * f.ncb + j) * f.hd + d;
-    ka[e] = bf2f(f.kc[src]); va[e] = bf2f(f.vc[src]);
+#pragma unroll
+  for (int i = 0; i < DA_XCH; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c * 8 < qd + 2 * kd) {
+      float t[8]; unpack8(cur.v[i], t);
+      const int e = c * 8;
+      float *dst = e < qd ? q + e : (e < qd + kd ? ka + f.pos * kd + (e - qd) : va + f.pos * kd + (e - qd - kd));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = t[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DA_FKV; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < nprev) {
+      float t[8];
+      unpack8(pk[i], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ka[c * 8 + j] = t[j];
+      unpack8(pv[i], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) va[c * 8 + j] = t[j];
+    }
   }
   __syncthreads();
   const bf16 *rope_row = f.rope + (size_t)f.pos * f.hd;
@@ -135,27 +200,45 @@ __device__ __forceinline__ void prologue_fastattn(const GemvArgs &a, float *xs, 
   // scores: bf16(q @ k^T) then bf16(* scale)   (llama.py:304)
   for (int t = threadIdx.x; t < f.nh * P; t += blockDim.x) {
     int h = t / P, j = t - h * P, g = h / G;
-    const float *qq = q + h * f.hd, *kk = ka + j * kd + g * f.hd;
+    const float4 *qq = reinterpret_cast<const float4 *>(q + h * f.hd), *kk = reinterpret_cast<const float4 *>(ka + j * kd + g * f.hd);
     float acc = 0.f;
-    for (int d = 0; d < f.hd; ++d) acc = fmaf(qq[d], kk[d], acc);
+    for (int d = 0; d < (f.hd >> 2); ++d) {
+      float4 x = qq[d], y = kk[d];
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
     pr[h * f.ncb + j] = rbf(__fmul_rn(rbf(acc), f.scale));
   }
   __syncthreads();
-  // softmax over j <= pos in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf)=0)
-  for (int h = threadIdx.x; h < f.nh; h += blockDim.x) {
+  // softmax over j <= pos in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf)=0).
+  // one thread per (h, j); every thread of a row walks it in the same order, so the row sum is identical
+  float pval = 0.f;
+  const int t = threadIdx.x;
+  if (t < f.nh * P) {
+    const int h = t / P, j = t - h * P;
     float m = -INFINITY;
-    for (int j = 0; j < P; ++j) m = fmaxf(m, pr[h * f.ncb + j]);
-    float s = 0.f;
-    for (int j = 0; j < P; ++j) s += expf(pr[h * f.ncb + j] - m);
-    for (int j = 0; j < P; ++j) pr[h * f.ncb + j] = rbf(expf(pr[h * f.ncb + j] - m) / s);
+    for (int jj = 0; jj < P; ++jj) m = fmaxf(m, pr[h * f.ncb + jj]);
+    float sum = 0.f;
+    for (int jj = 0; jj < P; ++jj) sum += expf(pr[h * f.ncb + jj] - m);
+    pval = rbf(expf(pr[h * f.ncb + j] - m) / sum);
   }
   __syncthreads();
-  // y = bf16(p @ v)  (llama.py:309), laid out [h*hd + d] = the wo input
-  for (int e = threadIdx.x; e < qd; e += blockDim.x) {
-    int h = e / f.hd, d = e - h * f.hd, g = h / G;
-    float acc = 0.f;
-    for (int j = 0; j < P; ++j) acc = fmaf(pr[h * f.ncb + j], va[j * kd + g * f.hd + d], acc);
-    xs[xs_index(e)] = rbf(acc);
+  if (t < f.nh * P) { const int h = t / P, j = t - h * P; pr[h * f.ncb + j] = pval; }
+  __syncthreads();
+  // y = bf16(p @ v)  (llama.py:309), laid out [h*hd + d] = the wo input; one 8-element chunk per thread
+  for (int c = threadIdx.x; c * 8 < qd; c += blockDim.x) {
+    const int e = c * 8, h = e / f.hd, d = e - h * f.hd, g = h / G;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int jj = 0; jj < P; ++jj) {
+      const float pj = pr[h * f.ncb + jj];
+      const float *vv = va + jj * kd + g * f.hd + d;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(pj, vv[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = rbf(acc[j]);
+    store_chunk_xs(xs, c, acc);
   }
 }
 
@@ -222,32 +305,35 @@ __device__ __forceinline__ void finish_step(const GemvArgs &a) {
 }
 
 // the fast heads (<= 1024 logits): one CTA samples and prepares the next pass
+#define DA_FAST_IPT 4   // 256 threads x 4 items
 __device__ void fast_head_sample(const GemvArgs &a, float *smem) {
   DAState *st = a.st;
   const int V = a.rows;
-  unsigned long long *cand = reinterpret_cast<unsigned long long *>(smem);
-  int n2 = 1; while (n2 < V) n2 <<= 1;
-  unsigned long long *scr64 = cand + n2;
-  float *scrf = reinterpret_cast<float *>(scr64 + 34);
+  unsigned long long *scr = reinterpret_cast<unsigned long long *>(smem);   // 192 u64
+  float *scrf = reinterpret_cast<float *>(scr + 192);
   const volatile uint16_t *lg = reinterpret_cast<const volatile uint16_t *>(a.out);
+  uint32_t key[DA_FAST_IPT], idx[DA_FAST_IPT], valid = 0;
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-    if (i < V) { uint16_t b = lg[i]; cand[i] = make_sortkey(b, (uint32_t)i); mx = fmaxf(mx, bits2f(b)); }
-    else cand[i] = ~0ull;
+#pragma unroll
+  for (int i = 0; i < DA_FAST_IPT; ++i) {
+    const int e = threadIdx.x * DA_FAST_IPT + i;
+    idx[i] = (uint32_t)e; key[i] = 0;
+    if (e < V) { const uint16_t b = lg[e]; key[i] = bf16_key(b); valid |= 1u << i; mx = fmaxf(mx, bits2f(b)); }
   }
   SampleParams sp;
   sp.m = block_max(mx, scrf);
   float es = 0.f;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) es += expf(sortkey_logit(cand[i]) - sp.m);
+#pragma unroll
+  for (int i = 0; i < DA_FAST_IPT; ++i) if ((valid >> i) & 1u) es += expf(bits2f(key_bf16(key[i])) - sp.m);
   sp.S = block_sum(es, scrf);
   sp.T_bf = eff_temperature(st);
   sp.c_max = cmax_from_top_p(st->top_p);
-  uint32_t idx = sample_sorted(cand, V, n2, true, sp, st, (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], scr64, scrf);
-  if (idx >= (uint32_t)a.codebook_size) { idx = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
-  for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[d] = a.fast_emb[(size_t)idx * a.fast_dim + d];
+  uint32_t tok = sample_items<DA_FAST_IPT>(key, idx, valid, (uint32_t)V, true, sp, st, (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], scr);
+  if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
+  for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[d] = a.fast_emb[(size_t)tok * a.fast_dim + d];
   __syncthreads();
   if (threadIdx.x == 0) {
-    st->tok_out[a.head + 1] = (int)idx;
+    st->tok_out[a.head + 1] = (int)tok;
     if (a.last_head) finish_step(a);
   }
 }
@@ -290,13 +376,24 @@ __global__ void __launch_bounds__(DA_GEMV_THREADS, 2) gemv_kernel(const GemvArgs
 
   PairRegs ra, rb;
   if (nu > 0) load_batch(ra, a.W, a.K, a.rows, first, 0, nseg, lane, pol);
+  XRegs wn, xr;
+  if (PRO == PRO_RMSNORM) load_chunks(wn, a.norm_w, a.K);
 
   pdl_wait();
   tl_stamp(a.tl, 1);
-  if (a.st->done) return;
+  // everything this kernel needs from its predecessors is requested in one go: the done flag, the activation
+  // vector and (RESIDUAL) the residual values of this warp's first row pair
+  const int done = *reinterpret_cast<const volatile int *>(&a.st->done);
+  if (PRO != PRO_FASTATTN) load_chunks(xr, a.x, a.K);
+  float res0 = 0.f, res1 = 0.f;
+  if (EPI == EPI_RESIDUAL && nu > 0 && lane == 0) {
+    res0 = bf2f(a.res[2 * first]);
+    if (2 * first + 1 < a.rows) res1 = bf2f(a.res[2 * first + 1]);
+  }
+  if (done) return;
 
-  if (PRO == PRO_PLAIN) prologue_plain(a, xs);
-  else if (PRO == PRO_RMSNORM) prologue_rmsnorm(a, xs, scratch);
+  if (PRO == PRO_PLAIN) prologue_plain(a, xs, xr);
+  else if (PRO == PRO_RMSNORM) prologue_rmsnorm(a, xs, scratch, xr, wn);
   else prologue_fastattn(a, xs, work);
   __syncthreads();
   tl_stamp(a.tl, 2);
@@ -331,8 +428,9 @@ __global__ void __launch_bounds__(DA_GEMV_THREADS, 2) gemv_kernel(const GemvArgs
         if (lane == 0) { a.out[r0] = f2bf(d0); if (has1) a.out[r1] = f2bf(d1); }
       } else if (EPI == EPI_RESIDUAL) {
         if (lane == 0) {
-          a.out[r0] = f2bf(bf2f(a.res[r0]) + rbf(d0));
-          if (has1) a.out[r1] = f2bf(bf2f(a.res[r1]) + rbf(d1));
+          if (pi > 0) { res0 = bf2f(a.res[r0]); if (has1) res1 = bf2f(a.res[r1]); }
+          a.out[r0] = f2bf(res0 + rbf(d0));
+          if (has1) a.out[r1] = f2bf(res1 + rbf(d1));
         }
       } else if (EPI == EPI_SWIGLU) {
         if (lane == 0) {

@@ -59,7 +59,8 @@ struct SelectArgs {
   Timeline tl;
 };
 
-// dynamic smem: cand[DA_CAND_CAP] u64 | scr64[34] | scrf[80]
+#define DA_SEL_IPT 16   // 512 threads x 16 items = DA_CAND_CAP
+// dynamic smem: scr[192] u64 | scr64[34] | scrf[80]
 __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs a) {
   extern __shared__ __align__(16) unsigned char smraw_sel[];
   DAState *st = a.st;
@@ -68,8 +69,8 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
   pdl_wait();
   tl_stamp(a.tl, 1);
   if (st->done) return;
-  unsigned long long *cand = reinterpret_cast<unsigned long long *>(smraw_sel);
-  unsigned long long *scr64 = cand + DA_CAND_CAP;
+  unsigned long long *scr = reinterpret_cast<unsigned long long *>(smraw_sel);
+  unsigned long long *scr64 = scr + 192;
   float *scrf = reinterpret_cast<float *>(scr64 + 34);
   __shared__ float s_m, s_S;
   // softmax statistics from the head kernel's per-CTA partials (fixed order)
@@ -119,10 +120,15 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
   const unsigned n_cand = *((volatile unsigned *)&st->n_cand);
   uint32_t idx = 0xFFFFFFFFu;
   if (n_cand >= 1 && n_cand <= DA_CAND_CAP) {
-    int n = (int)n_cand, n2 = 1; while (n2 < n) n2 <<= 1;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) cand[i] = i < n ? __ldcg(a.cand + i) : ~0ull;
+    uint32_t key[DA_SEL_IPT], ix[DA_SEL_IPT], valid = 0;
+#pragma unroll
+    for (int i = 0; i < DA_SEL_IPT; ++i) {
+      const unsigned e = threadIdx.x + i * blockDim.x;   // coalesced reads of the (unordered) candidate list
+      key[i] = 0; ix[i] = 0;
+      if (e < n_cand) { const unsigned long long k = __ldcg(a.cand + e); key[i] = 0xFFFFu - (uint32_t)(k >> 32); ix[i] = (uint32_t)k; valid |= 1u << i; }
+    }
+    idx = sample_items<DA_SEL_IPT>(key, ix, valid, (uint32_t)a.V, (int)n_cand == a.V, sp, st, 0u, 0ll, &st->nucleus[0], scr);
     __syncthreads();
-    idx = sample_sorted(cand, n, n2, n == a.V, sp, st, 0u, 0ll, &st->nucleus[0], scr64, scrf);
   }
   if (idx == 0xFFFFFFFFu) idx = sample_fallback(a.logits, a.V, sp, st, 0u, 0ll, &st->nucleus[0], scr64, scrf);
   // inference.py:123-126: first codebook = semantic id - semantic_begin (clamped at 0); next input = its fast embedding

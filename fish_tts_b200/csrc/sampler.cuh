@@ -13,6 +13,8 @@
 //     u64, so the nucleus does not depend on summation order (the reference's CPU path runs a
 //     sequential fp32 sum, its CUDA path a bf16 tree scan -- they already disagree with each other).
 #pragma once
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace da {
@@ -53,22 +55,6 @@ __device__ __forceinline__ float eff_temperature(const DAState *st) {
 __device__ __forceinline__ float noise_at(const DAState *st, uint32_t head, long long head_off, uint32_t idx) {
   if (st->noise) return bf2f(st->noise[head_off + idx]);
   return exp1_noise(st->seed, st->step_ctr, head, idx);
-}
-
-// ascending bitonic sort of n2 (power of two) u64 keys in shared memory; whole block participates
-__device__ __forceinline__ void bitonic_sort(unsigned long long *a, int n2) {
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-        int i = 2 * t - (t & (j - 1));
-        int l = i + j;
-        unsigned long long x = a[i], y = a[l];
-        bool up = ((i & k) == 0);
-        if ((x > y) == up) { a[i] = y; a[l] = x; }
-      }
-      __syncthreads();
-    }
-  }
 }
 
 __device__ __forceinline__ unsigned long long make_sortkey(uint16_t zbits, uint32_t idx) {
@@ -131,43 +117,116 @@ __device__ __forceinline__ ArgBest block_argbest(ArgBest v, float *fs, uint32_t 
   return out;
 }
 
-// ---- fast path: candidates already in shared memory ---------------------------------------------
-// cand[0..n) unsorted sort keys, n2 = next pow2 (padding filled with ~0).  Returns the sampled index,
-// or 0xFFFFFFFF when the nucleus is not proven to lie inside the candidate set (caller falls back).
-// `all_present`: the candidate set is the whole vocabulary.
-__device__ uint32_t sample_sorted(unsigned long long *cand, int n, int n2, bool all_present, const SampleParams &sp,
-                                  const DAState *st, uint32_t head, long long head_off, int *nucleus_out,
-                                  unsigned long long *scr64, float *scrf) {
-  bitonic_sort(cand, n2);
-  // each thread owns a contiguous chunk of the sorted list
-  int per = (n + blockDim.x - 1) / blockDim.x;
-  int j0 = threadIdx.x * per, j1 = min(n, j0 + per);
-  unsigned long long local = 0;
-  for (int j = j0; j < j1; ++j) local += pweight(sortkey_logit(cand[j]), sp.m, sp.S);
-  unsigned long long run = block_excl_scan_u64(local, scr64, nullptr);
-  int kept = 0;
-  for (int j = j0; j < j1; ++j) {
-    run += pweight(sortkey_logit(cand[j]), sp.m, sp.S);
-    if (run <= sp.c_max) ++kept;
+// ---- block reduction of (u64 sum, int sum, int max) with ONE barrier per call ------------------------
+// scratch: 2 x 3 x 32 u64 (ping-pong by call parity, see DESIGN.md "sampler"); all threads get the result
+struct Red { unsigned long long s; int c; int m; };
+__device__ __forceinline__ Red block_reduce(Red v, unsigned long long *scr, int &parity) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.s += __shfl_xor_sync(0xffffffffu, v.s, o);
+    v.c += __shfl_xor_sync(0xffffffffu, v.c, o);
+    v.m = max(v.m, __shfl_xor_sync(0xffffffffu, v.m, o));
   }
-  int n_keep = (int)(block_sum((float)kept, scrf) + 0.5f);   // counts <= 8192: exact in fp32
-  if (n_keep < 1) n_keep = 1;
+  unsigned long long *b = scr + parity * 96;
+  parity ^= 1;
+  if (lane == 0) { b[w] = v.s; b[32 + w] = (unsigned long long)(long long)v.c; b[64 + w] = (unsigned long long)(long long)v.m; }
+  __syncthreads();
+  Red r = {0ull, 0, INT_MIN};
+  for (int i = 0; i < nw; ++i) { r.s += b[i]; r.c += (int)(long long)b[32 + i]; r.m = max(r.m, (int)(long long)b[64 + i]); }
+  return r;
+}
+
+#define DA_FIX2_SCALE 1099511627776.0f   // 2^40: fixed point of the second softmax's exp terms
+
+// ---- selection over register-resident items: no sort ----------------------------------------------------
+// Each thread holds IPT items (16-bit monotone logit key, vocabulary index).  The nucleus {j : cum_j <= c_max} of the
+// (logit desc, index asc) order is found by bisection on the key (all sums exact u64 => order-free), a partially
+// kept tie group by a second bisection on the index.  Returns the sampled index, or 0xFFFFFFFF when the nucleus is
+// not proven to lie inside the item set (caller falls back); `all_present`: the items are the whole vocabulary.
+template <int IPT>
+__device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&idx)[IPT], uint32_t valid_mask, uint32_t idx_limit,
+                                 bool all_present, const SampleParams &sp, const DAState *st, uint32_t head, long long head_off,
+                                 int *nucleus_out, unsigned long long *scr) {
+  int parity = 0;
+  unsigned long long w[IPT];
+  Red t = {0ull, 0, -1};
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const bool v = (valid_mask >> i) & 1u;
+    w[i] = v ? pweight(bits2f(key_bf16(key[i])), sp.m, sp.S) : 0ull;
+    t.s += w[i]; t.c += v; if (v) t.m = max(t.m, (int)key[i]);
+  }
+  const Red tot = block_reduce(t, scr, parity);      // total mass, item count, top key
+  const int n = tot.c, top_key = tot.m;
+  // (1) lowest key kappa with G(kappa) = sum_{key >= kappa} w <= c_max
+  uint32_t lo = 0, hi = 65536;
+  if (tot.s <= sp.c_max) hi = 0;
+  else while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    Red g = {0ull, 0, -1};
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) if (((valid_mask >> i) & 1u) && key[i] >= mid) g.s += w[i];
+    if (block_reduce(g, scr, parity).s <= sp.c_max) hi = mid; else lo = mid;
+  }
+  const uint32_t kappa = hi;
+  // (2) mass and count of the fully kept groups, next lower present key
+  Red g = {0ull, 0, -1};
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) if ((valid_mask >> i) & 1u) {
+    if (key[i] >= kappa) { g.s += w[i]; g.c += 1; } else g.m = max(g.m, (int)key[i]);
+  }
+  g = block_reduce(g, scr, parity);
+  const int n_full = g.c, tau = g.m;
+  // (3) partially kept tie group
+  int c_part = 0; long long i_cut = -1;
+  if (tau >= 0) {
+    Red q = {0ull, 0, -1};
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) if (((valid_mask >> i) & 1u) && (int)key[i] == tau) q.c += 1;
+    const int n_tau = block_reduce(q, scr, parity).c;
+    const unsigned long long wt = pweight(bits2f(key_bf16((uint32_t)tau)), sp.m, sp.S);
+    const unsigned long long room = sp.c_max >= g.s ? sp.c_max - g.s : 0ull;
+    const unsigned long long c = wt ? room / wt : (unsigned long long)n_tau;
+    c_part = (int)(c < (unsigned long long)n_tau ? c : (unsigned long long)n_tau);
+    if (n_full == 0 && c_part < 1) c_part = 1;        // always keep the top-1 (inference.py:53)
+    if (c_part == n_tau) i_cut = (long long)idx_limit;
+    else if (c_part > 0) {                             // index of the c_part-th member in index order
+      long long l = -1, h = (long long)idx_limit;
+      while (h - l > 1) {
+        const long long mid = (l + h) >> 1;
+        Red z = {0ull, 0, -1};
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) if (((valid_mask >> i) & 1u) && (int)key[i] == tau && (long long)idx[i] <= mid) z.c += 1;
+        if (block_reduce(z, scr, parity).c >= c_part) h = mid; else l = mid;
+      }
+      i_cut = h;
+    }
+  }
+  const int n_keep = n_full + c_part;
   if (n_keep == n && !all_present) return 0xFFFFFFFFu;
   if (threadIdx.x == 0 && nucleus_out) *nucleus_out = n_keep;
-  // second softmax over the kept prefix, then the Exp(1) race
-  float mz = rbf(sortkey_logit(cand[0]) / sp.T_bf);
-  float es = 0.f;
-  for (int j = j0; j < min(j1, n_keep); ++j) es += expf(rbf(sortkey_logit(cand[j]) / sp.T_bf) - mz);
-  float S2 = block_sum(es, scrf);
-  ArgBest best = {0.f, 0u};   // removed tokens have probability 0 -> r = 0; argmax ties go to index 0
-  for (int j = j0; j < min(j1, n_keep); ++j) {
-    uint32_t idx = (uint32_t)cand[j];
-    float p2 = rbf(expf(rbf(sortkey_logit(cand[j]) / sp.T_bf) - mz) / S2);
-    float q = noise_at(st, head, head_off, idx);
-    ArgBest c = {rbf(p2 / q), idx};
-    best = better(best, c);
+  // (4) second softmax over the kept set (exp terms summed as 2^-40 fixed point => order-free), then the Exp(1) race
+  const float mz = rbf(bits2f(key_bf16((uint32_t)top_key)) / sp.T_bf);
+  float e2[IPT]; uint32_t keep = 0;
+  Red s2 = {0ull, 0, -1};
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const bool k = ((valid_mask >> i) & 1u) && (key[i] >= kappa || ((int)key[i] == tau && (long long)idx[i] <= i_cut));
+    e2[i] = 0.f;
+    if (k) { keep |= 1u << i; e2[i] = expf(rbf(bits2f(key_bf16(key[i])) / sp.T_bf) - mz); s2.s += (unsigned long long)(e2[i] * DA_FIX2_SCALE); }
   }
-  best = block_argbest(best, scrf, (uint32_t *)(scrf + 40));
+  const float S2 = __ull2float_rn(block_reduce(s2, scr, parity).s) * (1.0f / DA_FIX2_SCALE);
+  ArgBest best = {0.f, 0u};   // removed tokens have probability 0 -> r = 0; argmax ties go to index 0
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) if ((keep >> i) & 1u) {
+    const float p2 = rbf(e2[i] / S2);
+    ArgBest cnd = {rbf(p2 / noise_at(st, head, head_off, idx[i])), idx[i]};
+    best = better(best, cnd);
+  }
+  __syncthreads();
+  float *fs = reinterpret_cast<float *>(scr);
+  best = block_argbest(best, fs, reinterpret_cast<uint32_t *>(fs + 40));
   return best.idx;
 }
 
@@ -241,13 +300,15 @@ __device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParam
   if (threadIdx.x == 0 && nucleus_out) *nucleus_out = n_full + c_part;
   // (4) second softmax + race over the kept set
   float mz = rbf(sp.m / sp.T_bf);   // the top logit is always kept
-  float es = 0.f;
+  unsigned long long es = 0;
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
     uint16_t b = lb[i]; uint32_t k = bf16_key(b);
     bool keep = k >= kappa || ((int)k == tau && i <= i_cut);
-    if (keep) es += expf(rbf(bits2f(b) / sp.T_bf) - mz);
+    if (keep) es += (unsigned long long)(expf(rbf(bits2f(b) / sp.T_bf) - mz) * DA_FIX2_SCALE);
   }
-  float S2 = block_sum(es, scrf);
+  unsigned long long es_tot;
+  block_excl_scan_u64(es, scr64, &es_tot);
+  float S2 = __ull2float_rn(es_tot) * (1.0f / DA_FIX2_SCALE);
   ArgBest best = {0.f, 0u};
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
     uint16_t b = lb[i]; uint32_t k = bf16_key(b);
