@@ -128,7 +128,7 @@ __device__ __host__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
 __device__ __forceinline__ float exp1_noise(uint64_t seed, uint32_t step, uint32_t head, uint32_t elem) {
   uint32_t c[4] = {elem, head, step, 0u};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  float u = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), exact in fp32
+  float u = ((float)(c[0] >> 9) + 0.5f) * (1.0f / 8388608.0f);   // 23 bits + 1/2: strictly inside (0,1) and exact in fp32, so q > 0
   return rbf(-logf(u));
 }
 

@@ -273,8 +273,8 @@ static int enqueue_slow_layer(dualar_engine *e, int li, cudaStream_t s, int &cou
     t.sf = (float)sqrt(1.0 / sqrt((double)c.head_dim));
     t.part_o = e->part_o; t.part_ml = e->part_ml; t.y = e->y; t.nsplit_max = e->nsplit; t.st = e->st; t.tl.buf = e->tl; t.tl.slot = count;
     size_t smem = attn_smem_bytes(c.n_head / c.n_local_heads, c.head_dim);
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(attn_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    static size_t configured = 0;   // per process: grow the opt-in limit when a bigger shape comes along
+    if (smem > configured) { CU(cudaFuncSetAttribute(attn_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
     CU(launch_k(attn_slow_kernel, dim3(e->nsplit, c.n_local_heads), dim3(DA_ATTN_THREADS), smem, s, t)); ++count; }
   { GemvArgs a = base_args(L.wo, L.bo, c.dim, qd, 0); a.x = e->y; a.res = e->x; a.out = e->h;
     if ((rc = launch_gemv<PRO_PLAIN, EPI_RESIDUAL>(e, a, s, count)) < 0) return rc; }

@@ -294,7 +294,9 @@ __device__ __forceinline__ void finish_step(const GemvArgs &a) {
   for (int r = 0; r < R; ++r) { a.seq[(size_t)r * a.seq_stride + pos] = st->tok_out[r]; st->tok_in[r] = st->tok_out[r]; }
   st->pos = pos; st->n_gen = n_gen; st->step_ctr += 1; st->use_penalty = 1;
   if (st->noise) st->noise += st->noise_stride;
-  if (st->tok_out[0] == a.im_end_id || n_gen >= st->max_gen) st->done = 1;
+  // the reference tests for <|im_end|> only inside decode_n_tokens (inference.py:210): the column produced by the
+  // prefill call is never checked, so an EOS there is followed by one more step
+  if ((n_gen > 1 && st->tok_out[0] == a.im_end_id) || n_gen >= st->max_gen) st->done = 1;
   // previous_tokens[:, j] = generated column j+1 (the prefill-produced column 0 is never recorded)
   int i = n_gen - 1, T = st->prompt_len;
   for (int c = 0; c < DA_WIN; ++c) {

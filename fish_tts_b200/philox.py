@@ -3,7 +3,7 @@
 The sampler's Exp(1) draws (``multinomial_sample_one_no_sync``, fish_tts/models/inference.py:24-27) come
 from a counter-based stream keyed by (seed, step, head, element), so a host, the oracle and the kernels
 can all reproduce them: counter = (element, head, step, 0), key = (seed_lo, seed_hi),
-u = ((x0 >> 8) + 0.5) * 2^-24, q = bf16(-log(u)).
+u = ((x0 >> 9) + 0.5) * 2^-23 (exact in fp32, strictly inside (0,1), so q > 0), q = bf16(-log(u)).
 """
 
 from __future__ import annotations
@@ -26,16 +26,16 @@ def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
     return c0, c1, c2, c3
 
 
-def uniform24(seed: int, step: int, head: int, n: int) -> np.ndarray:
+def uniform23(seed: int, step: int, head: int, n: int) -> np.ndarray:
     elem = np.arange(n, dtype=np.uint64)
     z = np.zeros(n, dtype=np.uint64)
     x0, _, _, _ = philox4x32_10(elem, z + np.uint64(head), z + np.uint64(step), z, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    return ((x0 >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    return ((x0 >> np.uint64(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
 
 
 def exp1_noise(seed: int, step: int, head: int, n: int) -> torch.Tensor:
     """bf16 Exp(1) draws for one head of one step (what dualar_fill_noise produces on the device)."""
-    u = uniform24(seed, step, head, n)
+    u = uniform23(seed, step, head, n)
     q = (-np.log(u.astype(np.float64))).astype(np.float32)
     return torch.from_numpy(q).to(torch.bfloat16)
 

@@ -87,3 +87,24 @@ class TeacherForced:
         self.prev[:, i: i + 1] = ref
         self.i += 1
         return out
+
+
+def oracle_generate_tokenwise_prefill(m, prompt, n_new, T, p, rp, noise_fn):
+    """`generate` of the oracle, except that the prompt is pushed through the model one position at a time -- the
+    engine's round-1 prefill does the same (every GEMM is then the M=1 case on both sides), so the two KV states
+    agree and the test isolates the loop machinery (window, position, EOS, noise bookkeeping)."""
+    cfg, dev = m.cfg, m.device
+    C1 = cfg.num_codebooks + 1
+    m.setup_caches(cfg.max_seq_len)
+    t = [torch.tensor(v, device=dev, dtype=torch.float) for v in (T, p, rp)]
+    prompt = prompt.to(dev)
+    Tlen = prompt.size(1)
+    noise = orc.NoiseSource(noise_fn)
+    with torch.inference_mode(), sdpa_kernel(SDPBackend.MATH):
+        for i in range(Tlen - 1):
+            orc.forward_generate(m, prompt[:, i:i + 1].view(1, C1, 1), torch.tensor([i], device=dev))
+        first = orc.decode_one_token_ar(m, prompt[:, -1:].view(1, C1, 1), torch.tensor([Tlen - 1], device=dev), *t, None,
+                                        noise=noise, stable_ties=True)
+        rest = orc.decode_n_tokens(m, first.view(1, C1, -1), torch.tensor([Tlen], device=dev, dtype=torch.int), n_new - 1, *t,
+                                   noise=noise, stable_ties=True)
+    return torch.cat([first, rest], dim=1)
