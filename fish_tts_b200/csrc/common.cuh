@@ -157,6 +157,7 @@ struct DAState {
   int cpu_sem;      // scalar-operand semantics of the reference's CPU path instead of its CUDA path (see dualar_set_option)
   float temperature, top_p, rep_penalty;
   unsigned int step_ctr;           // Philox step counter
+  unsigned int phase_ctr;          // running phase counter of the persistent kernels: source of the unit tags
   unsigned long long seed;
   const bf16 *noise;               // explicit noise for this step or nullptr
   long long noise_stride;          // elements per step (loop mode advances `noise`)

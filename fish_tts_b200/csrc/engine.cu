@@ -14,6 +14,7 @@
 #include "../../include/dualar.h"
 #include "attention.cuh"
 #include "common.cuh"
+#include "fast_ar.cuh"
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
 
@@ -57,6 +58,8 @@ struct dualar_engine {
   int prompt_len = 0, max_gen = 0;
   std::vector<void *> owned;
   unsigned long long *tl = nullptr; int tl_slots = 0;
+  uint32_t *u_qkv = nullptr, *u_h = nullptr, *u_act = nullptr, *u_x0 = nullptr, *u_x1 = nullptr, *u_fin = nullptr, *u_logits = nullptr;
+  bool use_fast_ar = false;   // persistent fast-AR kernel: opt-in until it beats the per-phase kernels (option fast_ar_kernel / DUALAR_FAST_AR)
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -332,6 +335,31 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     CU(launch_k(select_sample_kernel, dim3(e->sms), dim3(512), smem, s, a)); ++count; }
+  if (e->use_fast_ar) {
+    // fast AR as ONE persistent cooperative kernel (fast_ar.cuh)
+    FastArArgs a; memset(&a, 0, sizeof(a));
+    for (int l = 0; l < c.n_fast_layer; ++l) {
+      LayerW &L = e->fast[l];
+      a.L[l] = FastLayerW{L.wqkv, L.bqkv, L.wo, L.bo, L.qn, L.kn, L.w13, L.w2, L.ffn_norm, L.attn_norm};
+    }
+    a.n_layer = c.n_fast_layer; a.fast_norm = e->fast_norm; a.fast_out = e->fast_out; a.fast_emb = e->fast_emb; a.rope = e->fast_rope;
+    a.dim = c.fast_dim; a.nh = c.fast_n_head; a.nkv = c.fast_n_local_heads; a.hd = c.fast_head_dim; a.inter = c.fast_intermediate_size;
+    a.ncb = c.num_codebooks; a.fv = e->fv; a.codebook_size = c.codebook_size; a.eps = c.norm_eps; a.scale = (float)(1.0 / sqrt((double)c.fast_head_dim));
+    a.x_slow = e->x; a.fin_plain = e->fin;
+    a.u_qkv = e->u_qkv; a.u_h = e->u_h; a.u_act = e->u_act; a.u_x0 = e->u_x0; a.u_x1 = e->u_x1; a.u_fin = e->u_fin; a.u_logits = e->u_logits;
+    a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
+    a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.n_rows_tok = c.num_codebooks + 1;
+    a.noise_off0 = (long long)c.vocab_size; a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
+    size_t smem = far_smem_bytes(c.n_fast_layer, c.fast_n_head, c.fast_n_local_heads, c.fast_head_dim, c.num_codebooks);
+    static size_t configured = 0;
+    if (smem > configured) { CU(cudaFuncSetAttribute(fast_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_FAR_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, fast_ar_kernel, a)); ++count;
+    return 0;
+  }
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
   for (int p = 0; p < c.num_codebooks; ++p) {
     const bf16 *in = p == 0 ? e->x : e->fin;
@@ -414,6 +442,12 @@ extern "C" int dualar_finalize(dualar_engine *e) {
   CU(cudaMallocHost((void **)&e->h_st, sizeof(DAState)));
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   { const char *v = getenv("DUALAR_PDL"); if (v && v[0] == '0') g_use_pdl = false; }
+  { const char *v = getenv("DUALAR_FAST_AR"); if (v) e->use_fast_ar = v[0] == '1'; }
+  if (c.n_fast_layer > DA_MAX_FAST_LAYERS || c.fast_dim > 4096 || c.fast_intermediate_size > 4096) e->use_fast_ar = false;
+  { const int fqkv = (c.fast_n_head + 2 * c.fast_n_local_heads) * c.fast_head_dim;
+    if ((rc = dev_alloc(e, e->u_qkv, (size_t)fqkv)) || (rc = dev_alloc(e, e->u_h, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_act, (size_t)c.fast_intermediate_size)) ||
+        (rc = dev_alloc(e, e->u_x0, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_x1, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_fin, (size_t)c.fast_dim)) ||
+        (rc = dev_alloc(e, e->u_logits, (size_t)e->fv))) return rc; }
   { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 512; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc; } }
   // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
   { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);
@@ -466,6 +500,10 @@ extern "C" int dualar_set_option(dualar_engine *e, const char *name, double valu
     e->cpu_sem = value != 0.0;
     if (e->finalized) { CU(cudaSetDevice(e->device)); CU(cudaMemcpy(&e->st->cpu_sem, &e->cpu_sem, sizeof(int), cudaMemcpyHostToDevice)); }
     return 0;
+  }
+  if (!strcmp(name, "fast_ar_kernel")) {
+    if (e->finalized) return fail(DUALAR_ESTATE, "fast_ar_kernel must be set before dualar_finalize");
+    e->use_fast_ar = value != 0.0; return 0;
   }
   if (!strcmp(name, "candidate_delta")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "candidate_delta must be set before dualar_finalize");

@@ -98,6 +98,24 @@ def test_long_context_multi_tile_attention():
     assert agree >= 5 and mine.shape[1] == 4 and torch.isfinite(logits.float()).all()
 
 
+@pytest.mark.parametrize("name", list(variant_configs().keys()) + ["s1mini"])
+def test_fast_ar_kernel_bitexact(name):
+    """the persistent fast-AR kernel and the one-kernel-per-phase path share one canonical dot-product order:
+    identical logits and ids, bit for bit"""
+    cfg = s1_mini_config() if name == "s1mini" else variant_configs()[name]
+    sd = make_state_dict(cfg, seed=0)
+    prompt = synthetic_prompt(cfg, 5, 12, 4, seed=1)
+    outs = []
+    for flag in (1, 0):
+        eng = DualAREngine(cfg, sd, device=0, seed=5, options={"fast_ar_kernel": flag})
+        toks = eng.generate(prompt, 24, 0.7, 0.8, 1.1)
+        outs.append((toks, eng.read("fast_logits").clone(), eng.read("slow_logits_raw").clone(), eng.launches_per_step()))
+        eng.close()
+    assert outs[0][3][0] < outs[1][3][0]
+    assert (outs[0][0] == outs[1][0]).all()
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
 @pytest.fixture(scope="module")
 def s1():
     cfg = s1_mini_config()
