@@ -110,14 +110,14 @@ class DualARConfig:
 
     # weight bytes streamed per decode step (bf16), SURVEY.md section 8(d)
     def weight_bytes(self) -> dict:
-        def layer(dim, n_head, n_kv, hd, inter):
-            return 2 * ((n_head + 2 * n_kv) * hd * dim + dim * n_head * hd + 3 * dim * inter)
+        def layer(dim, n_head, n_kv, hd, inter, qk_norm):
+            return 2 * ((n_head + 2 * n_kv) * hd * dim + dim * n_head * hd + 3 * dim * inter + 2 * dim + (2 * hd if qk_norm else 0))
 
         slow = self.n_layer * layer(self.dim, self.n_head, self.n_local_heads, self.head_dim,
-                                    self.intermediate_size)
+                                    self.intermediate_size, self.attention_qk_norm)
         head = 2 * self.vocab_size * self.dim
         fast = self.n_fast_layer * layer(self.fast_dim, self.fast_n_head, self.fast_n_local_heads,
-                                         self.fast_head_dim, self.fast_intermediate_size)
+                                         self.fast_head_dim, self.fast_intermediate_size, self.fast_attention_qk_norm)
         fast_head = 2 * self.codebook_size * self.fast_dim
         kv_per_pos = self.n_layer * 2 * self.n_local_heads * self.head_dim * 2
         return {"slow_layers": slow, "lm_head": head, "fast_layers": fast,

@@ -87,11 +87,11 @@ def fabricate_model_dir(cfg, state_dict: dict, path: str | Path) -> Path:
     (path / "tokenizer.tiktoken").write_text("\n".join(lines) + "\n")
     n_sem = cfg.semantic_end_id - cfg.semantic_begin_id + 1
     if n_sem != 4096:
-        sys.path.insert(0, str(REFERENCE_ROOT))
-        _install_stubs()
-        from fish_tts.models import tokenizer as tk
-        specials = [t for t in tk.ALL_SPECIAL_TOKENS if not t.startswith("<|semantic:")]
-        specials += [tk.SEMANTIC_TOKEN_TEMPLATE.format(i=i) for i in range(n_sem)]
+        # the 15 control tokens of tokenizer.py:52-66, then the semantic tokens
+        specials = ["<|begin_of_text|>", "<|end_of_text|>", "<|pad|>", "<|im_start|>", "<|im_end|>", "<|phoneme_start|>",
+                    "<|phoneme_end|>", "<|tool_call_start|>", "<|tool_call_end|>", "<|text|>", "<|voice|>", "<|interleave|>",
+                    "<|audio_start|>", "<|audio_end|>", "<|audio|>"]
+        specials += [f"<|semantic:{i}|>" for i in range(n_sem)]
         with open(path / "special_tokens.json", "w") as f:
             json.dump(specials, f)
     torch.save(state_dict, path / "model.pth")
