@@ -14,7 +14,7 @@
 #include "../../include/dualar.h"
 #include "attention.cuh"
 #include "common.cuh"
-#include "fast_ar.cuh"
+#include "persistent.cuh"
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
 
@@ -59,6 +59,7 @@ struct dualar_engine {
   std::vector<void *> owned;
   unsigned long long *tl = nullptr; int tl_slots = 0;
   uint32_t *u_qkv = nullptr, *u_h = nullptr, *u_act = nullptr, *u_x0 = nullptr, *u_x1 = nullptr, *u_fin = nullptr, *u_logits = nullptr;
+  PhaseDesc *d_table = nullptr; int n_phases = 0;
   bool use_fast_ar = false;   // persistent fast-AR kernel: opt-in until it beats the per-phase kernels (option fast_ar_kernel / DUALAR_FAST_AR)
 };
 
@@ -336,28 +337,25 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
     if (!configured) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     CU(launch_k(select_sample_kernel, dim3(e->sms), dim3(512), smem, s, a)); ++count; }
   if (e->use_fast_ar) {
-    // fast AR as ONE persistent cooperative kernel (fast_ar.cuh)
-    FastArArgs a; memset(&a, 0, sizeof(a));
-    for (int l = 0; l < c.n_fast_layer; ++l) {
-      LayerW &L = e->fast[l];
-      a.L[l] = FastLayerW{L.wqkv, L.bqkv, L.wo, L.bo, L.qn, L.kn, L.w13, L.w2, L.ffn_norm, L.attn_norm};
-    }
-    a.n_layer = c.n_fast_layer; a.fast_norm = e->fast_norm; a.fast_out = e->fast_out; a.fast_emb = e->fast_emb; a.rope = e->fast_rope;
-    a.dim = c.fast_dim; a.nh = c.fast_n_head; a.nkv = c.fast_n_local_heads; a.hd = c.fast_head_dim; a.inter = c.fast_intermediate_size;
-    a.ncb = c.num_codebooks; a.fv = e->fv; a.codebook_size = c.codebook_size; a.eps = c.norm_eps; a.scale = (float)(1.0 / sqrt((double)c.fast_head_dim));
-    a.x_slow = e->x; a.fin_plain = e->fin;
-    a.u_qkv = e->u_qkv; a.u_h = e->u_h; a.u_act = e->u_act; a.u_x0 = e->u_x0; a.u_x1 = e->u_x1; a.u_fin = e->u_fin; a.u_logits = e->u_logits;
-    a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
+    // fast AR as ONE persistent cooperative kernel (persistent.cuh); the phase table was built at finalize
+    PersistArgs a; memset(&a, 0, sizeof(a));
+    a.table = e->d_table; a.n_phases = e->n_phases;
+    a.rope = e->fast_rope;
+    for (int l = 0; l < c.n_fast_layer; ++l) { a.qn[l] = e->fast[l].qn; a.kn[l] = e->fast[l].kn; }
+    a.n_layer = c.n_fast_layer; a.nh = c.fast_n_head; a.nkv = c.fast_n_local_heads; a.hd = c.fast_head_dim; a.ncb = c.num_codebooks;
+    a.eps = c.norm_eps; a.scale = (float)(1.0 / sqrt((double)c.fast_head_dim));
+    a.fast_emb = e->fast_emb; a.dim = c.fast_dim; a.fv = e->fv; a.codebook_size = c.codebook_size;
+    a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits; a.noise_off0 = (long long)c.vocab_size;
     a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.n_rows_tok = c.num_codebooks + 1;
-    a.noise_off0 = (long long)c.vocab_size; a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
-    size_t smem = far_smem_bytes(c.n_fast_layer, c.fast_n_head, c.fast_n_local_heads, c.fast_head_dim, c.num_codebooks);
+    a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
+    size_t smem = persist_smem_bytes(e->n_phases, c.n_fast_layer, c.fast_n_head, c.fast_n_local_heads, c.fast_head_dim, c.num_codebooks);
     static size_t configured = 0;
-    if (smem > configured) { CU(cudaFuncSetAttribute(fast_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+    if (smem > configured) { CU(cudaFuncSetAttribute(persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_FAR_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_P_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, fast_ar_kernel, a)); ++count;
+    CU(cudaLaunchKernelEx(&cfg, persistent_kernel, a)); ++count;
     return 0;
   }
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
@@ -448,6 +446,50 @@ extern "C" int dualar_finalize(dualar_engine *e) {
     if ((rc = dev_alloc(e, e->u_qkv, (size_t)fqkv)) || (rc = dev_alloc(e, e->u_h, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_act, (size_t)c.fast_intermediate_size)) ||
         (rc = dev_alloc(e, e->u_x0, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_x1, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_fin, (size_t)c.fast_dim)) ||
         (rc = dev_alloc(e, e->u_logits, (size_t)e->fv))) return rc; }
+  if (e->use_fast_ar) {   // the static schedule of the persistent fast-AR kernel
+    std::vector<PhaseDesc> tab;
+    const int L = c.n_fast_layer, qd = c.fast_n_head * c.fast_head_dim, kd = c.fast_n_local_heads * c.fast_head_dim;
+    int last_head_ph = -1;
+    bool fits = true;
+    for (int p = 0; p < c.num_codebooks; ++p) {
+      for (int l = 0; l < L; ++l) {
+        LayerW &W = e->fast[l];
+        const void *lin; int lin_units, lin_ph;
+        if (l == 0) {
+          if (p == 0) { lin = e->x; lin_units = 0; lin_ph = 0; }
+          else if (p == 1) { lin = e->fin; lin_units = 0; lin_ph = 0; }
+          else { lin = e->u_fin; lin_units = 1; lin_ph = last_head_ph; }
+        } else { lin = ((l - 1) & 1) ? e->u_x1 : e->u_x0; lin_units = 1; lin_ph = (int)tab.size() - 1; }
+        PhaseDesc d; memset(&d, 0, sizeof(d));
+        d.layer = (short)l; d.pos = (short)p; d.evict_last = 1;
+        PhaseDesc q = d; q.W = W.wqkv; q.bias = W.bqkv; q.norm_w = W.attn_norm; q.in = lin; q.in_units = (short)lin_units; q.in_ph = lin_ph;
+        q.out = e->u_qkv; q.rows = qd + 2 * kd; q.K = c.fast_dim; q.pro = PP_RMSNORM; q.epi = PE_STORE; tab.push_back(q);
+        PhaseDesc o = d; o.W = W.wo; o.bias = W.bo; o.in = e->u_qkv; o.in_units = 1; o.in_ph = (int)tab.size() - 1; o.res = lin; o.res_units = (short)lin_units;
+        o.out = e->u_h; o.rows = c.fast_dim; o.K = qd; o.pro = PP_FASTATTN; o.epi = PE_RESIDUAL; tab.push_back(o);
+        PhaseDesc f = d; f.W = W.w13; f.norm_w = W.ffn_norm; f.in = e->u_h; f.in_units = 1; f.in_ph = (int)tab.size() - 1;
+        f.out = e->u_act; f.rows = 2 * c.fast_intermediate_size; f.K = c.fast_dim; f.pro = PP_RMSNORM; f.epi = PE_SWIGLU; tab.push_back(f);
+        PhaseDesc g = d; g.W = W.w2; g.in = e->u_act; g.in_units = 1; g.in_ph = (int)tab.size() - 1; g.res = e->u_h; g.res_units = 1;
+        g.out = (l & 1) ? e->u_x1 : e->u_x0; g.rows = c.fast_dim; g.K = c.fast_intermediate_size; g.pro = PP_PLAIN; g.epi = PE_RESIDUAL; tab.push_back(g);
+      }
+      if (p >= 1) {
+        PhaseDesc h; memset(&h, 0, sizeof(h));
+        h.layer = (short)(L - 1); h.pos = (short)p; h.evict_last = 1;
+        h.W = e->fast_out; h.norm_w = e->fast_norm; h.in = ((L - 1) & 1) ? e->u_x1 : e->u_x0; h.in_units = 1; h.in_ph = (int)tab.size() - 1;
+        h.out = e->u_logits; h.rows = e->fv; h.K = c.fast_dim; h.pro = PP_RMSNORM; h.epi = PE_FASTLOGITS;
+        last_head_ph = (int)tab.size(); tab.push_back(h);
+      }
+    }
+    for (auto &d : tab) {
+      int nb = ((d.K >> 8) + DA_CH - 1) / DA_CH, npc = (((d.rows + 1) / 2) + e->sms - 1) / e->sms;
+      if (nb > 1 && npc * nb > DA_PART_UNITS) fits = false;
+    }
+    if (!fits || e->fv > 1024 || tab.size() + 192 > 512 * 4) e->use_fast_ar = false;
+    else {
+      e->n_phases = (int)tab.size();
+      if ((rc = dev_alloc(e, e->d_table, tab.size()))) return rc;
+      CU(cudaMemcpy(e->d_table, tab.data(), tab.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice));
+    }
+  }
   { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 512; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc; } }
   // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
   { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);

@@ -14,10 +14,10 @@
 //                       sampling step in the last CTA to arrive.
 //
 // Work split: rows are dealt to warps in adjacent PAIRS, pair p -> CTA p % grid, warp p / grid, so
-// all SMs stream equal shares; a warp owns whole rows, lane l of segment s holds the 8 weights
-// [s*256 + l*8, +8) as one 128-bit load (L1 bypassed, explicit L2 eviction policy); K is reduced
-// inside the warp (fp32 fma chain per lane, then a butterfly) -- one canonical order for every
-// caller, so the multi-kernel path and any later persistent kernel agree bit for bit.
+// all SMs stream equal shares; lane l of segment s holds the 8 weights [s*256 + l*8, +8) as one 128-bit
+// load (L1 bypassed, explicit L2 eviction policy).  CANONICAL ORDER of a row's dot product, shared by
+// every kernel so that all paths agree bit for bit: per lane, each batch of DA_CH=4 segments is an fp32
+// fma chain starting from zero; the batch partials are added in batch order; then a 5-step butterfly.
 #pragma once
 #include "common.cuh"
 #include "sampler.cuh"
@@ -324,10 +324,13 @@ __device__ void fast_head_sample(const GemvArgs &a, float *smem) {
   }
   SampleParams sp;
   sp.m = block_max(mx, scrf);
-  float es = 0.f;
+  {   // sum of exp terms as 2^-40 fixed point: order-free, so every path computes the same S
+    Red es = {0ull, 0, -1}; int par = 0;
 #pragma unroll
-  for (int i = 0; i < DA_FAST_IPT; ++i) if ((valid >> i) & 1u) es += expf(bits2f(key_bf16(key[i])) - sp.m);
-  sp.S = block_sum(es, scrf);
+    for (int i = 0; i < DA_FAST_IPT; ++i) if ((valid >> i) & 1u) es.s += (unsigned long long)(expf(bits2f(key_bf16(key[i])) - sp.m) * DA_FIX2_SCALE);
+    sp.S = __ull2float_rn(block_reduce(es, scr, par).s) * (1.0f / DA_FIX2_SCALE);
+    __syncthreads();
+  }
   sp.T_bf = eff_temperature(st);
   sp.c_max = cmax_from_top_p(st->top_p);
   uint32_t tok = sample_items<DA_FAST_IPT>(key, idx, valid, (uint32_t)V, true, sp, st, (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], scr);
@@ -418,7 +421,11 @@ __global__ void __launch_bounds__(DA_GEMV_THREADS, 2) gemv_kernel(const GemvArgs
     int pin = pi, bn = b + 1;
     if (bn == nb) { bn = 0; ++pin; }
     if (u + 1 < nu) load_batch(nxt, a.W, a.K, a.rows, first + pin * stride, bn, nseg, lane, pol);
-    fma_batch(cur, xs, b, nseg, lane, a0, a1);
+    {   // canonical order: each batch of DA_CH segments is a chain from zero; batch partials fold in batch order
+      float p0 = 0.f, p1 = 0.f;
+      fma_batch(cur, xs, b, nseg, lane, p0, p1);
+      a0 += p0; a1 += p1;
+    }
     if (b == nb - 1) {
       const int p = first + pi * stride;
       const int r0 = 2 * p, r1 = r0 + 1;
