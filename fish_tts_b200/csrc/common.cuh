@@ -61,33 +61,47 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// all threads get the result; `scratch` holds >= 33 floats; blockDim multiple of 32
+// ---- block scope of a collective: the whole CTA (barrier 0) or a named barrier over the first N threads ----------
+// The persistent decode kernel keeps a producer warp outside its 512 compute threads, so its block-wide
+// reductions run on a named barrier; the per-phase kernels use the whole CTA.
+struct BlockAll {
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+  static __device__ __forceinline__ int nthreads() { return blockDim.x; }
+};
+template <int ID, int N> struct BlockNamed {
+  static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+  static __device__ __forceinline__ int nthreads() { return N; }
+};
+
+// all threads get the result; `scratch` holds >= 33 floats; thread count multiple of 32
+template <class B = BlockAll>
 __device__ __forceinline__ float block_sum(float v, float *scratch) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
   v = warp_sum(v);
-  __syncthreads();
+  B::sync();
   if (lane == 0) scratch[w] = v;
-  __syncthreads();
+  B::sync();
   if (w == 0) {
     float t = 0.f;
     for (int i = 0; i < nw; ++i) t += scratch[i];   // sequential, fixed order
     if (lane == 0) scratch[32] = t;
   }
-  __syncthreads();
+  B::sync();
   return scratch[32];
 }
+template <class B = BlockAll>
 __device__ __forceinline__ float block_max(float v, float *scratch) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
   v = warp_max(v);
-  __syncthreads();
+  B::sync();
   if (lane == 0) scratch[w] = v;
-  __syncthreads();
+  B::sync();
   if (w == 0) {
     float t = -INFINITY;
     for (int i = 0; i < nw; ++i) t = fmaxf(t, scratch[i]);
     if (lane == 0) scratch[32] = t;
   }
-  __syncthreads();
+  B::sync();
   return scratch[32];
 }
 
@@ -171,4 +185,5 @@ struct DAState {
   unsigned int sel_ticket;
   unsigned int n_cand;
   unsigned int fast_ticket;
+  unsigned long long s_fix;        // slow head: sum of exp(z - max) over the vocabulary, 2^-40 fixed point (order-free)
 };

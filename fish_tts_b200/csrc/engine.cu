@@ -14,9 +14,9 @@
 #include "../../include/dualar.h"
 #include "attention.cuh"
 #include "common.cuh"
-#include "persistent.cuh"
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
+#include "mega.cuh"
 
 using namespace da;
 
@@ -58,9 +58,12 @@ struct dualar_engine {
   int prompt_len = 0, max_gen = 0;
   std::vector<void *> owned;
   unsigned long long *tl = nullptr; int tl_slots = 0;
-  uint32_t *u_qkv = nullptr, *u_h = nullptr, *u_act = nullptr, *u_x0 = nullptr, *u_x1 = nullptr, *u_fin = nullptr, *u_logits = nullptr;
-  PhaseDesc *d_table = nullptr; int n_phases = 0;
-  bool use_fast_ar = false;   // persistent fast-AR kernel: opt-in until it beats the per-phase kernels (option fast_ar_kernel / DUALAR_FAST_AR)
+  // persistent whole-step kernel (mega.cuh): unit buffers, the two phase tables (decode step / one prefill position)
+  uint32_t *u_x = nullptr, *u_qkv = nullptr, *u_y = nullptr, *u_h = nullptr, *u_act = nullptr;
+  uint32_t *u_fqkv = nullptr, *u_fh = nullptr, *u_fact = nullptr, *u_fx0 = nullptr, *u_fx1 = nullptr, *u_fin = nullptr, *u_flogits = nullptr;
+  unsigned long long *m_part_o = nullptr, *m_part_ml = nullptr, *m_hmax = nullptr, *m_hcs = nullptr, *m_cand = nullptr;
+  MegaArgs *ma_step = nullptr, *ma_prefill = nullptr; size_t mega_smem = 0; unsigned int *m_phase = nullptr; unsigned char *u_arena = nullptr; size_t u_arena_bytes = 0;
+  bool use_mega = true;   // option mega_kernel / DUALAR_MEGA: 0 = one kernel per phase (the cross-check path)
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -312,6 +315,17 @@ static int enqueue_fast_layer(dualar_engine *e, int li, int p, const bf16 *in, b
 static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &count) {
   const dualar_config &c = e->c;
   int rc;
+  if (e->use_mega) {
+    // the whole step as ONE persistent cooperative kernel (mega.cuh); the phase tables were built at finalize
+    MegaArgs *a = slow_only ? e->ma_prefill : e->ma_step;
+    a->tl = e->tl; a->tl_slots = e->tl_slots;
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_M_THREADS); cfg.dynamicSmemBytes = e->mega_smem; cfg.stream = s;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, mega_kernel, *a)); ++count;
+    return 0;
+  }
   { EmbedArgs a; memset(&a, 0, sizeof(a));
     a.emb = e->emb; a.cb_emb = e->cb_emb; a.x = e->x; a.dim = c.dim; a.vocab = c.vocab_size; a.codebook_size = c.codebook_size;
     a.num_codebooks = c.num_codebooks; a.sem_begin = c.semantic_begin_id; a.sem_end = c.semantic_end_id; a.scale_cb = c.scale_codebook_embeddings;
@@ -336,28 +350,6 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     CU(launch_k(select_sample_kernel, dim3(e->sms), dim3(512), smem, s, a)); ++count; }
-  if (e->use_fast_ar) {
-    // fast AR as ONE persistent cooperative kernel (persistent.cuh); the phase table was built at finalize
-    PersistArgs a; memset(&a, 0, sizeof(a));
-    a.table = e->d_table; a.n_phases = e->n_phases;
-    a.rope = e->fast_rope;
-    for (int l = 0; l < c.n_fast_layer; ++l) { a.qn[l] = e->fast[l].qn; a.kn[l] = e->fast[l].kn; }
-    a.n_layer = c.n_fast_layer; a.nh = c.fast_n_head; a.nkv = c.fast_n_local_heads; a.hd = c.fast_head_dim; a.ncb = c.num_codebooks;
-    a.eps = c.norm_eps; a.scale = (float)(1.0 / sqrt((double)c.fast_head_dim));
-    a.fast_emb = e->fast_emb; a.dim = c.fast_dim; a.fv = e->fv; a.codebook_size = c.codebook_size;
-    a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits; a.noise_off0 = (long long)c.vocab_size;
-    a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.n_rows_tok = c.num_codebooks + 1;
-    a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
-    size_t smem = persist_smem_bytes(e->n_phases, c.n_fast_layer, c.fast_n_head, c.fast_n_local_heads, c.fast_head_dim, c.num_codebooks);
-    static size_t configured = 0;
-    if (smem > configured) { CU(cudaFuncSetAttribute(persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_P_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, persistent_kernel, a)); ++count;
-    return 0;
-  }
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
   for (int p = 0; p < c.num_codebooks; ++p) {
     const bf16 *in = p == 0 ? e->x : e->fin;
@@ -395,6 +387,142 @@ static int capture(dualar_engine *e, bool slow_only, cudaGraphExec_t *out, int *
   CU(cudaGraphInstantiate(out, g, 0));
   CU(cudaGraphDestroy(g));
   *count = n;
+  return 0;
+}
+
+// ---- the static schedule of the persistent whole-step kernel (mega.cuh) ------------------------------------------------
+// Falls back to one kernel per phase (use_mega = false) when a shape does not fit the kernel's limits.
+static int build_mega(dualar_engine *e) {
+  const dualar_config &c = e->c;
+  const int grid = e->sms;
+  const int qd = c.n_head * c.head_dim, kd = c.n_local_heads * c.head_dim, qkv_rows = qd + 2 * kd;
+  const int fqd = c.fast_n_head * c.fast_head_dim, fkd = c.fast_n_local_heads * c.fast_head_dim, fqkv_rows = fqd + 2 * fkd;
+  const int G = c.n_head / c.n_local_heads;
+  const int n_slow = 6 * c.n_layer, n_step = n_slow + 3 + c.num_codebooks * 4 * c.n_fast_layer + (c.num_codebooks - 1);
+  auto pairs = [](int rows) { return (rows + 1) / 2; };
+  if (n_step > DA_M_MAX_PHASES || c.n_layer > DA_M_MAXL || c.n_fast_layer > DA_M_MAXFL || grid > 160 || e->fv > 1024 ||
+      pairs(qkv_rows) < grid || pairs(2 * c.intermediate_size) < grid || pairs(fqkv_rows) < grid || pairs(2 * c.fast_intermediate_size) < grid ||
+      G * c.head_dim > 1024 || c.vocab_size > (1 << 18)) { e->use_mega = false; return 0; }
+  int rc;
+  // every broadcast unit vector exists DA_M_REP times, `ustride` units apart
+  int umax = qkv_rows; for (int v : {c.dim, qd, c.intermediate_size, fqkv_rows, c.fast_dim, c.fast_intermediate_size, e->fv}) if (v > umax) umax = v;
+  const size_t ustride = align_up((size_t)umax, 256) + 64, ubuf = ustride * DA_M_REP;
+  // one arena for every tagged buffer, so that a request can start from "no tag is valid" with a single memset:
+  // tags are 16 bits wide, and a buffer that only the decode kernel writes would otherwise keep the previous request's
+  // units across the prefill launches in between (a tag collision there would hand a consumer stale data)
+  {
+    const size_t n_po = (size_t)c.n_local_heads * e->nsplit * G * c.head_dim, n_pml = (size_t)c.n_local_heads * e->nsplit * G * 2;
+    size_t bytes = 12 * ubuf * 4 + (n_po + n_pml + (size_t)grid + 3 * (size_t)grid + DA_CAND_CAP) * 8;
+    if ((rc = dev_alloc(e, e->u_arena, bytes))) return rc;
+    e->u_arena_bytes = bytes;
+    unsigned long long *q = (unsigned long long *)e->u_arena;      // 64-bit buffers first (alignment)
+    e->m_part_o = q; q += n_po; e->m_part_ml = q; q += n_pml; e->m_hmax = q; q += grid; e->m_hcs = q; q += 3 * grid; e->m_cand = q; q += DA_CAND_CAP;
+    uint32_t *u = (uint32_t *)q;
+    uint32_t **slots[12] = {&e->u_x, &e->u_qkv, &e->u_y, &e->u_h, &e->u_act, &e->u_fqkv, &e->u_fh, &e->u_fact, &e->u_fx0, &e->u_fx1, &e->u_fin, &e->u_flogits};
+    for (auto sl : slots) { *sl = u; u += ubuf; }
+  }
+  if ((rc = dev_alloc(e, e->m_phase, 1))) return rc;
+  e->ma_step = new MegaArgs(); e->ma_prefill = new MegaArgs();
+  for (int variant = 0; variant < 2; ++variant) {
+    MegaArgs &a = variant ? *e->ma_prefill : *e->ma_step;
+    memset(&a, 0, sizeof(a));
+    std::vector<MPhase> tab;
+    auto gemv = [&](const bf16 *W, const bf16 *bias, const bf16 *norm_w, const uint32_t *in, int in_ph, uint32_t *out, int rows, int K,
+                    int pro, int epi, int flags, int layer, int pos) {
+      MPhase p; memset(&p, 0, sizeof(p));
+      p.W = W; p.bias = bias; p.norm_w = norm_w; p.in = in; p.out = out; p.rows = rows; p.K = K; p.in_ph = (short)in_ph;
+      p.pq = (short)(((rows + 1) / 2) / grid); p.prem = (short)(((rows + 1) / 2) % grid);
+      p.kind = MK_GEMV; p.pro = (unsigned char)pro; p.epi = (unsigned char)epi; p.flags = (unsigned char)flags; p.layer = (unsigned char)layer; p.pos = (unsigned char)pos;
+      tab.push_back(p); return (int)tab.size() - 1;
+    };
+    auto other = [&](int kind, const uint32_t *in, int in_ph, uint32_t *out, int layer) {
+      MPhase p; memset(&p, 0, sizeof(p));
+      p.kind = (unsigned char)kind; p.in = in; p.in_ph = (short)in_ph; p.out = out; p.layer = (unsigned char)layer;
+      tab.push_back(p); return (int)tab.size() - 1;
+    };
+    int last = 0;
+    for (int l = 0; l < c.n_layer; ++l) {
+      LayerW &L = e->slow[l];
+      int q = gemv(L.wqkv, L.bqkv, L.attn_norm, l ? e->u_x : nullptr, last, e->u_qkv, qkv_rows, c.dim, l ? MP_RMSNORM : MP_EMBED, ME_STORE, MF_SAVE0, l, 0);
+      int at = other(MK_ATTN, e->u_qkv, q, nullptr, l);
+      int mg = other(MK_MERGE, nullptr, at, e->u_y, l);
+      int o = gemv(L.wo, L.bo, nullptr, e->u_y, mg, e->u_h, c.dim, qd, MP_PLAIN, ME_RESIDUAL, MF_RES0, l, 0);
+      int f = gemv(L.w13, nullptr, L.ffn_norm, e->u_h, o, e->u_act, 2 * c.intermediate_size, c.dim, MP_RMSNORM, ME_SWIGLU, MF_SAVE1, l, 0);
+      last = gemv(L.w2, nullptr, nullptr, e->u_act, f, e->u_x, c.dim, c.intermediate_size, MP_PLAIN, ME_RESIDUAL, MF_RES1, l, 0);
+    }
+    if (variant) other(MK_PREFILL_END, e->u_x, last, nullptr, 0);
+    else {
+      int hd_ph = gemv(c.tie_word_embeddings ? e->emb : e->out_w, nullptr, e->norm, e->u_x, last, nullptr, c.vocab_size, c.dim, MP_RMSNORM, ME_SLOWLOGITS, 0, 0, 0);
+      int hs = other(MK_HSTAT, nullptr, hd_ph, nullptr, 0);
+      int hc = other(MK_HCAND, nullptr, hs, nullptr, 0);
+      int fin_ph = hc;   // the phase that last wrote u_fin
+      const int FL = c.n_fast_layer;
+      for (int p = 0; p < c.num_codebooks; ++p) {
+        int prev = 0;
+        for (int l = 0; l < FL; ++l) {
+          LayerW &W = e->fast[l];
+          const uint32_t *lin; int lin_ph;
+          if (l == 0) { if (p == 0) { lin = e->u_x; lin_ph = last; } else { lin = e->u_fin; lin_ph = fin_ph; } }
+          else { lin = ((l - 1) & 1) ? e->u_fx1 : e->u_fx0; lin_ph = prev; }
+          int q = gemv(W.wqkv, W.bqkv, W.attn_norm, lin, lin_ph, e->u_fqkv, fqkv_rows, c.fast_dim, MP_RMSNORM, ME_STORE, MF_KEEP | MF_SAVE0, l, p);
+          int o = gemv(W.wo, W.bo, nullptr, e->u_fqkv, q, e->u_fh, c.fast_dim, fqd, MP_FASTATTN, ME_RESIDUAL, MF_KEEP | MF_RES0, l, p);
+          int f = gemv(W.w13, nullptr, W.ffn_norm, e->u_fh, o, e->u_fact, 2 * c.fast_intermediate_size, c.fast_dim, MP_RMSNORM, ME_SWIGLU, MF_KEEP | MF_SAVE1, l, p);
+          prev = gemv(W.w2, nullptr, nullptr, e->u_fact, f, (l & 1) ? e->u_fx1 : e->u_fx0, c.fast_dim, c.fast_intermediate_size, MP_PLAIN, ME_RESIDUAL, MF_KEEP | MF_RES1, l, p);
+        }
+        if (p >= 1)   // logits of pass 0 are discarded by the reference (inference.py:122)
+          fin_ph = gemv(e->fast_out, nullptr, e->fast_norm, ((FL - 1) & 1) ? e->u_fx1 : e->u_fx0, prev, e->u_flogits, e->fv, c.fast_dim, MP_RMSNORM, ME_FASTLOGITS, MF_KEEP, FL - 1, p);
+      }
+    }
+    a.n_phases = (int)tab.size();
+    memcpy(a.table, tab.data(), tab.size() * sizeof(MPhase));
+    a.rope = e->rope; a.nh = c.n_head; a.nkv = c.n_local_heads; a.hd = c.head_dim; a.S = c.max_seq_len; a.nsplit_max = e->nsplit;
+    a.eps = c.norm_eps; a.sf = (float)sqrt(1.0 / sqrt((double)c.head_dim));
+    for (int l = 0; l < c.n_layer; ++l) { a.kc[l] = e->slow[l].kc; a.vc[l] = e->slow[l].vc; a.qn[l] = e->slow[l].qn; a.kn[l] = e->slow[l].kn; }
+    a.part_o = e->m_part_o; a.part_ml = e->m_part_ml;
+    a.emb = e->emb; a.cb_emb = e->cb_emb; a.dim = c.dim; a.vocab = c.vocab_size; a.codebook_size = c.codebook_size; a.num_codebooks = c.num_codebooks;
+    a.sem_begin = c.semantic_begin_id; a.sem_end = c.semantic_end_id; a.scale_cb = c.scale_codebook_embeddings;
+    a.inv_sqrt = (float)(1.0 / sqrt((double)(c.num_codebooks + 1))); a.sqrt_c = (float)sqrt((double)(c.num_codebooks + 1));
+    a.logits = e->logits; a.logits_raw = e->logits_raw; a.hmax = e->m_hmax; a.hcs = e->m_hcs; a.cand = e->m_cand; a.delta = e->delta; a.n_rows_tok = c.num_codebooks + 1;
+    a.head_pq = ((c.vocab_size + 1) / 2) / grid; a.head_prem = ((c.vocab_size + 1) / 2) % grid;
+    a.frope = e->fast_rope;
+    for (int l = 0; l < c.n_fast_layer; ++l) { a.fqn[l] = e->fast[l].qn; a.fkn[l] = e->fast[l].kn; }
+    a.fl = c.n_fast_layer; a.fnh = c.fast_n_head; a.fnkv = c.fast_n_local_heads; a.fhd = c.fast_head_dim; a.ncb = c.num_codebooks;
+    a.fscale = (float)(1.0 / sqrt((double)c.fast_head_dim));
+    a.fast_emb = e->fast_emb; a.fdim = c.fast_dim; a.fv = e->fv; a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
+    a.noise_off0 = (long long)c.vocab_size;
+    a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.st = e->st; a.ustride = (int)ustride; a.phase_ctr = e->m_phase;
+    // shared-memory plan (from the decode-step table; the prefill table is a subset and shares it)
+    if (variant) {
+      const MegaArgs &s0 = *e->ma_step;
+      a.kmax = s0.kmax; a.lg_rows = s0.lg_rows; a.work_bytes = s0.work_bytes; a.kv_bytes = s0.kv_bytes; a.ring_bytes = s0.ring_bytes;
+      continue;
+    }
+    int kmax = 0; size_t max_entry = 0;
+    for (auto &p : tab) if (p.kind == MK_GEMV) {
+      if (p.K > kmax) kmax = p.K;
+      int nr_max = 2 * (pairs(p.rows) / grid + 1); if (nr_max > 16) nr_max = 16;      // rows of the largest tile of any CTA
+      const size_t entry = (size_t)nr_max * (2 * (size_t)p.K + 16);
+      if (entry > max_entry) max_entry = entry;
+    }
+    if ((size_t)4 * DA_TILE * c.head_dim > max_entry) max_entry = (size_t)4 * DA_TILE * c.head_dim;
+    size_t work = (size_t)(fqd + 2 * fkd + c.fast_n_head * c.num_codebooks + 4) * 4;
+    auto upd = [&](size_t v) { if (v > work) work = v; };
+    upd((size_t)(G * c.head_dim + 2 * c.head_dim + G * DA_TILE + 3 * DA_MAX_G) * 4);
+    upd((size_t)3 * (qd / grid + 2) * e->nsplit * 4);
+    upd((size_t)3 * grid * 4 + 256);
+    upd((size_t)16384 + (192 + 34) * 8 + 80 * 4 + 64);          // slow head: sort buffer + sampler scratch
+    upd((size_t)256 * 8 + 128 * DA_G_IPT * 4 + 64);              // fast heads: scratch + sort buffer
+    a.kmax = kmax; a.lg_rows = (2 * (pairs(c.vocab_size) / grid + 1) + 31) / 16 * 16; a.work_bytes = (int)work;
+    a.kv_bytes = c.n_fast_layer * c.num_codebooks * 2 * fkd * 2;
+    const int dim_max = c.dim > c.fast_dim ? c.dim : c.fast_dim;
+    const MegaSmem fixed = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, 0);
+    const long long budget = 227 * 1024 - 1024 - (long long)fixed.total;   // 1 KB for the kernel's static shared variables
+    long long ring = budget / 1024 * 1024;
+    if (ring < (long long)(2 * max_entry) || ring < 32 * 1024) { e->use_mega = false; return 0; }
+    a.ring_bytes = (int)ring;
+    e->mega_smem = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, a.ring_bytes).total;
+  }
+  CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
   return 0;
 }
 
@@ -440,57 +568,9 @@ extern "C" int dualar_finalize(dualar_engine *e) {
   CU(cudaMallocHost((void **)&e->h_st, sizeof(DAState)));
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   { const char *v = getenv("DUALAR_PDL"); if (v && v[0] == '0') g_use_pdl = false; }
-  { const char *v = getenv("DUALAR_FAST_AR"); if (v) e->use_fast_ar = v[0] == '1'; }
-  if (c.n_fast_layer > DA_MAX_FAST_LAYERS || c.fast_dim > 4096 || c.fast_intermediate_size > 4096) e->use_fast_ar = false;
-  { const int fqkv = (c.fast_n_head + 2 * c.fast_n_local_heads) * c.fast_head_dim;
-    if ((rc = dev_alloc(e, e->u_qkv, (size_t)fqkv)) || (rc = dev_alloc(e, e->u_h, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_act, (size_t)c.fast_intermediate_size)) ||
-        (rc = dev_alloc(e, e->u_x0, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_x1, (size_t)c.fast_dim)) || (rc = dev_alloc(e, e->u_fin, (size_t)c.fast_dim)) ||
-        (rc = dev_alloc(e, e->u_logits, (size_t)e->fv))) return rc; }
-  if (e->use_fast_ar) {   // the static schedule of the persistent fast-AR kernel
-    std::vector<PhaseDesc> tab;
-    const int L = c.n_fast_layer, qd = c.fast_n_head * c.fast_head_dim, kd = c.fast_n_local_heads * c.fast_head_dim;
-    int last_head_ph = -1;
-    bool fits = true;
-    for (int p = 0; p < c.num_codebooks; ++p) {
-      for (int l = 0; l < L; ++l) {
-        LayerW &W = e->fast[l];
-        const void *lin; int lin_units, lin_ph;
-        if (l == 0) {
-          if (p == 0) { lin = e->x; lin_units = 0; lin_ph = 0; }
-          else if (p == 1) { lin = e->fin; lin_units = 0; lin_ph = 0; }
-          else { lin = e->u_fin; lin_units = 1; lin_ph = last_head_ph; }
-        } else { lin = ((l - 1) & 1) ? e->u_x1 : e->u_x0; lin_units = 1; lin_ph = (int)tab.size() - 1; }
-        PhaseDesc d; memset(&d, 0, sizeof(d));
-        d.layer = (short)l; d.pos = (short)p; d.evict_last = 1;
-        PhaseDesc q = d; q.W = W.wqkv; q.bias = W.bqkv; q.norm_w = W.attn_norm; q.in = lin; q.in_units = (short)lin_units; q.in_ph = lin_ph;
-        q.out = e->u_qkv; q.rows = qd + 2 * kd; q.K = c.fast_dim; q.pro = PP_RMSNORM; q.epi = PE_STORE; tab.push_back(q);
-        PhaseDesc o = d; o.W = W.wo; o.bias = W.bo; o.in = e->u_qkv; o.in_units = 1; o.in_ph = (int)tab.size() - 1; o.res = lin; o.res_units = (short)lin_units;
-        o.out = e->u_h; o.rows = c.fast_dim; o.K = qd; o.pro = PP_FASTATTN; o.epi = PE_RESIDUAL; tab.push_back(o);
-        PhaseDesc f = d; f.W = W.w13; f.norm_w = W.ffn_norm; f.in = e->u_h; f.in_units = 1; f.in_ph = (int)tab.size() - 1;
-        f.out = e->u_act; f.rows = 2 * c.fast_intermediate_size; f.K = c.fast_dim; f.pro = PP_RMSNORM; f.epi = PE_SWIGLU; tab.push_back(f);
-        PhaseDesc g = d; g.W = W.w2; g.in = e->u_act; g.in_units = 1; g.in_ph = (int)tab.size() - 1; g.res = e->u_h; g.res_units = 1;
-        g.out = (l & 1) ? e->u_x1 : e->u_x0; g.rows = c.fast_dim; g.K = c.fast_intermediate_size; g.pro = PP_PLAIN; g.epi = PE_RESIDUAL; tab.push_back(g);
-      }
-      if (p >= 1) {
-        PhaseDesc h; memset(&h, 0, sizeof(h));
-        h.layer = (short)(L - 1); h.pos = (short)p; h.evict_last = 1;
-        h.W = e->fast_out; h.norm_w = e->fast_norm; h.in = ((L - 1) & 1) ? e->u_x1 : e->u_x0; h.in_units = 1; h.in_ph = (int)tab.size() - 1;
-        h.out = e->u_logits; h.rows = e->fv; h.K = c.fast_dim; h.pro = PP_RMSNORM; h.epi = PE_FASTLOGITS;
-        last_head_ph = (int)tab.size(); tab.push_back(h);
-      }
-    }
-    for (auto &d : tab) {
-      int nb = ((d.K >> 8) + DA_CH - 1) / DA_CH, npc = (((d.rows + 1) / 2) + e->sms - 1) / e->sms;
-      if (nb > 1 && npc * nb > DA_PART_UNITS) fits = false;
-    }
-    if (!fits || e->fv > 1024 || tab.size() + 192 > 512 * 4) e->use_fast_ar = false;
-    else {
-      e->n_phases = (int)tab.size();
-      if ((rc = dev_alloc(e, e->d_table, tab.size()))) return rc;
-      CU(cudaMemcpy(e->d_table, tab.data(), tab.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice));
-    }
-  }
-  { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 512; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc; } }
+  { const char *v = getenv("DUALAR_MEGA"); if (v) e->use_mega = v[0] != '0'; }
+  if (e->use_mega && (rc = build_mega(e)) < 0) return rc;
+  { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 1024; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc; } }
   // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
   { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);
     if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp); cudaGetLastError(); }
@@ -501,6 +581,7 @@ extern "C" int dualar_finalize(dualar_engine *e) {
   if ((rc = capture(e, false, &e->g_step, &e->launches_step))) return rc;
   if ((rc = capture(e, true, &e->g_prefill, &e->launches_prefill))) return rc;
   CU(cudaMemcpy(e->st, &init, sizeof(init), cudaMemcpyHostToDevice));
+  if (e->u_arena) CU(cudaMemset(e->u_arena, 0, e->u_arena_bytes));
   // the dry runs wrote KV position 0 / 1 of caches we own; clear them again
   for (auto &L : e->slow) if (!L.kv_external) {
     size_t n = (size_t)c.n_local_heads * c.max_seq_len * c.head_dim * sizeof(bf16);
@@ -522,6 +603,7 @@ extern "C" void dualar_destroy(dualar_engine *e) {
   if (e->h_seq) cudaFreeHost(e->h_seq);
   if (e->h_st) cudaFreeHost(e->h_st);
   if (e->arena) cudaFree(e->arena);
+  delete e->ma_step; delete e->ma_prefill;
   delete e;
 }
 
@@ -543,9 +625,9 @@ extern "C" int dualar_set_option(dualar_engine *e, const char *name, double valu
     if (e->finalized) { CU(cudaSetDevice(e->device)); CU(cudaMemcpy(&e->st->cpu_sem, &e->cpu_sem, sizeof(int), cudaMemcpyHostToDevice)); }
     return 0;
   }
-  if (!strcmp(name, "fast_ar_kernel")) {
-    if (e->finalized) return fail(DUALAR_ESTATE, "fast_ar_kernel must be set before dualar_finalize");
-    e->use_fast_ar = value != 0.0; return 0;
+  if (!strcmp(name, "mega_kernel")) {
+    if (e->finalized) return fail(DUALAR_ESTATE, "mega_kernel must be set before dualar_finalize");
+    e->use_mega = value != 0.0; return 0;
   }
   if (!strcmp(name, "candidate_delta")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "candidate_delta must be set before dualar_finalize");
@@ -655,6 +737,7 @@ extern "C" int dualar_prefill(dualar_engine *e, const int32_t *prompt, int T, in
   h->noise = e->noise; h->noise_stride = (long long)c.vocab_size + (long long)(c.num_codebooks - 1) * e->fv;
   for (int r = 0; r < R; ++r) h->tok_in[r] = prompt[(size_t)r * T];
   CU(cudaMemcpyAsync(e->st, h, sizeof(*h), cudaMemcpyHostToDevice, s));
+  if (e->u_arena) CU(cudaMemsetAsync(e->u_arena, 0, e->u_arena_bytes, s));      // no unit of an earlier request carries a valid tag
   for (int t = 0; t + 1 < T; ++t) CU(cudaGraphLaunch(e->g_prefill, s));
   CU(cudaGraphLaunch(e->g_step, s));
   e->prompt_len = T; e->max_gen = max_new; e->request_open = true;
@@ -730,9 +813,30 @@ extern "C" int dualar_read_buffer(dualar_engine *e, const char *name, void *dst,
   else if (!strcmp(name, "fast_x")) { src = e->fbuf[(c.n_fast_layer - 1) & 1]; avail = (int64_t)c.fast_dim * 2; }
   else if (!strcmp(name, "timeline")) { if (!e->tl) return fail(DUALAR_ESTATE, "run with DUALAR_TIMELINE=1"); src = e->tl; avail = (int64_t)e->tl_slots * 64; }
   else if (!strcmp(name, "fast_in")) { src = e->fin; avail = (int64_t)c.fast_dim * 2; }
+  else if (!strcmp(name, "cand")) { if (!e->m_cand) return fail(DUALAR_ESTATE, "persistent kernel not in use"); src = e->m_cand; avail = (int64_t)DA_CAND_CAP * 8; }
   else return fail(DUALAR_EINVAL, "unknown buffer '%s'", name);
   if (nbytes > avail) return fail(DUALAR_EINVAL, "buffer '%s' holds %lld bytes, %lld requested", name, (long long)avail, (long long)nbytes);
   CU(cudaSetDevice(e->device));
+  // under the persistent kernel the activation vectors live as tagged 32-bit units (bf16 value in the high half)
+  const uint32_t *units = nullptr;
+  if (e->use_mega) {
+    if (!strcmp(name, "hidden")) units = e->u_x;
+    else if (!strcmp(name, "qkv")) units = e->u_qkv;
+    else if (!strcmp(name, "y")) units = e->u_y;
+    else if (!strcmp(name, "h")) units = e->u_h;
+    else if (!strcmp(name, "act")) units = e->u_act;
+    else if (!strcmp(name, "fast_x")) units = (c.n_fast_layer - 1) & 1 ? e->u_fx1 : e->u_fx0;
+    else if (!strcmp(name, "fast_in")) units = e->u_fin;
+  }
+  if (units) {
+    const size_t n = (size_t)nbytes / 2;
+    std::vector<uint32_t> tmp(n);
+    CU(cudaMemcpyAsync(tmp.data(), units, n * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    uint16_t *o = (uint16_t *)dst;
+    for (size_t i = 0; i < n; ++i) o[i] = (uint16_t)(tmp[i] >> 16);
+    return 0;
+  }
   CU(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CU(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;

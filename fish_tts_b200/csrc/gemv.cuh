@@ -333,7 +333,7 @@ __device__ void fast_head_sample(const GemvArgs &a, float *smem) {
   }
   sp.T_bf = eff_temperature(st);
   sp.c_max = cmax_from_top_p(st->top_p);
-  uint32_t tok = sample_items<DA_FAST_IPT>(key, idx, valid, (uint32_t)V, true, sp, st, (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], scr);
+  uint32_t tok = sample_items<DA_FAST_IPT>(key, idx, valid, (uint32_t)V, true, sp, noise_src(st), (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], scr);
   if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
   for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[d] = a.fast_emb[(size_t)tok * a.fast_dim + d];
   __syncthreads();

@@ -1,0 +1,1038 @@
+// mega.cuh -- the whole dual-AR decode step (decode_one_token_ar, inference.py:83-155) as ONE persistent kernel.
+//
+// One CTA per SM (cooperative launch => co-resident), 16 compute warps + 1 producer warp.  A decode step is a static
+// table of ~340 dependent PHASES (embedding -> 28 x {wqkv, split-KV attention, merge, wo, w1/w3, w2} -> LM head ->
+// sampler -> 10 fast passes x 4 layers x {wqkv, attention+wo, w1/w3, w2} + 9 fast heads with their samplers).
+// Three mechanisms keep HBM / L2 busy while the dependency chain advances:
+//
+//   * WEIGHT RING.  What a CTA will read from global memory is known before the step starts: its contiguous slice
+//     of every weight matrix and (from st->pos) its K/V tiles.  The producer warp walks that list and streams it into a
+//     shared-memory ring with the bulk-copy engine (cp.async.bulk + mbarrier complete_tx, the 1-D TMA path), running as
+//     far ahead of the compute warps as the ring allows (entries are released by mbarrier arrivals).  The weight stream
+//     therefore never waits for a hand-over; a phase's dot products read shared memory only.
+//   * TAGGED UNITS.  Activations cross SMs as 32-bit units = bf16 value | 16-bit phase tag (64-bit units = fp32 value |
+//     32-bit tag for the attention partials and sampler statistics), written with ONE store; the consumer polls until
+//     the tag is the producing phase's.  Data and "ready" arrive together: no fence, no atomic, no grid barrier between
+//     phases (NCCL's LL protocol, on-chip through L2).
+//   * every CTA polls the COMPLETE input of every GEMV phase, so passing a phase proves that all CTAs finished the
+//     previous one; buffers are reused without further synchronisation.
+//
+// Numerics: the per-row dot product follows the canonical order of gemv.cuh and every other formula is the one of the
+// per-phase kernels (attention.cuh, sampler.cuh, misc_kernels.cuh), so this kernel and the per-phase path agree bit
+// for bit (tests/test_gpu_parity.py::test_mega_kernel_bitexact).  All spins are bounded: a lost hand-over raises the
+// device fault flag instead of hanging the GPU.
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "misc_kernels.cuh"
+#include "sampler.cuh"
+#include <type_traits>
+
+namespace da {
+
+#define DA_M_CWARPS 16
+#define DA_M_CTHREADS 512
+#define DA_M_THREADS 544            // + the producer warp
+#define DA_M_NB 32                  // ring entries in flight (mbarrier pairs)
+#define DA_M_ENTRY_BYTES 16384      // target size of one ring entry of a GEMV phase
+#define DA_M_MAX_PHASES 400
+#define DA_M_MAXL 48                // slow layers
+#define DA_M_MAXFL 8                // fast layers
+#define DA_SPIN_LIMIT (1 << 22)
+#define DA_M_REP 1                  // replicas of every broadcast unit vector (CTA b polls replica b % DA_M_REP).  Measured
+                                    // (tests/cuda/handover_bench2.cu): ONE copy is fastest -- 0.80 us per all-to-all hand-over of
+                                    // 1024 units at 148 CTAs vs 1.03 us with 4 copies; the extra stores cost more than the
+                                    // spread of the pollers saves
+
+enum { MK_GEMV = 0, MK_ATTN = 1, MK_MERGE = 2, MK_HSTAT = 3, MK_HCAND = 4, MK_PREFILL_END = 5 };
+enum { MP_PLAIN = 0, MP_RMSNORM = 1, MP_FASTATTN = 2, MP_EMBED = 3 };   // MP_EMBED: token embedding computed in place, then RMSNorm
+enum { ME_STORE = 0, ME_RESIDUAL = 1, ME_SWIGLU = 2, ME_SLOWLOGITS = 3, ME_FASTLOGITS = 4 };
+enum { MF_KEEP = 1, MF_SAVE0 = 2, MF_SAVE1 = 4, MF_RES0 = 8, MF_RES1 = 16 };
+
+struct MPhase {
+  const bf16 *W, *bias, *norm_w;
+  const uint32_t *in;    // input units
+  uint32_t *out;         // output units
+  int rows, K;
+  short in_ph;           // phase that wrote `in` (its tag)
+  unsigned char kind, pro, epi, layer, pos, flags;
+  short pq, prem;        // row pairs per CTA: floor and remainder of (rows / 2) / grid (the first `prem` CTAs take one more)
+  int pad_;
+};
+
+struct MegaArgs {
+  int n_phases;
+  // slow attention (llama.py:242-282)
+  const bf16 *rope; int nh, nkv, hd, S, nsplit_max; float eps, sf;
+  bf16 *kc[DA_M_MAXL], *vc[DA_M_MAXL]; const bf16 *qn[DA_M_MAXL], *kn[DA_M_MAXL];
+  unsigned long long *part_o, *part_ml;     // 64-bit units: [nkv][nsplit_max][G][hd], [nkv][nsplit_max][G][2]
+  // embedding (llama.py:409-429)
+  const bf16 *emb, *cb_emb; int dim, vocab, codebook_size, num_codebooks, sem_begin, sem_end, scale_cb; float inv_sqrt, sqrt_c;
+  // slow head + sampler
+  bf16 *logits, *logits_raw; unsigned long long *hmax, *hcs, *cand; float delta; int n_rows_tok, head_pq, head_prem;
+  // fast stack
+  const bf16 *frope; const bf16 *fqn[DA_M_MAXFL], *fkn[DA_M_MAXFL]; int fl, fnh, fnkv, fhd, ncb; float fscale;
+  const bf16 *fast_emb; int fdim, fv; uint32_t *u_fin; bf16 *flogits_raw, *flogits; long long noise_off0;
+  // end of step
+  int *seq; int seq_stride, im_end_id;
+  DAState *st; unsigned long long *tl; int tl_slots;
+  unsigned int *phase_ctr;   // running phase counter = source of the unit tags; NEVER reset (a request must not see the previous one's tags)
+  // shared-memory plan
+  int kmax, lg_rows, work_bytes, kv_bytes, ring_bytes;
+  int ustride;           // units between the DA_M_REP replicas of a unit buffer
+  MPhase table[DA_M_MAX_PHASES];
+};
+
+// ---- units --------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t make_unit(float v, uint32_t tag) { return ((uint32_t)f2bits(v) << 16) | tag; }
+__device__ __forceinline__ float unit_val(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint4 ld_poll4(const uint32_t *p) {
+  uint4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_poll1(const uint32_t *p) {
+  uint32_t r;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ unsigned long long ld_poll8(const unsigned long long *p) {
+  unsigned long long r;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_unit(uint32_t *p, uint32_t u) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(u) : "memory"); }
+__device__ __forceinline__ void st_unit8(void *p, unsigned long long u) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(u) : "memory"); }
+__device__ __forceinline__ unsigned long long make_unit8(uint32_t payload, uint32_t tag) { return ((unsigned long long)payload << 32) | tag; }
+__device__ __forceinline__ bool tags_ok(const uint4 &u, uint32_t tag) {
+  return ((u.x & 0xFFFFu) == tag) & ((u.y & 0xFFFFu) == tag) & ((u.z & 0xFFFFu) == tag) & ((u.w & 0xFFFFu) == tag);
+}
+// poll 8 consecutive units (one 8-element chunk) until every tag matches; false on timeout
+__device__ __noinline__ bool poll_chunk(const uint32_t *p, uint32_t tag, float *f) {
+  uint4 a, b;
+  int it = 0;
+  for (;;) {
+    a = ld_poll4(p); b = ld_poll4(p + 4);
+    if (tags_ok(a, tag) & tags_ok(b, tag)) break;
+    if (++it >= DA_SPIN_LIMIT) break;
+    __nanosleep(20);
+  }
+  f[0] = unit_val(a.x); f[1] = unit_val(a.y); f[2] = unit_val(a.z); f[3] = unit_val(a.w);
+  f[4] = unit_val(b.x); f[5] = unit_val(b.y); f[6] = unit_val(b.z); f[7] = unit_val(b.w);
+  return it < DA_SPIN_LIMIT;
+}
+// two 4-unit groups per thread, `lo` and `hi` half a vector apart: both loads of a warp are fully coalesced (16 sectors per
+// request instead of 32 half-used ones), which is worth ~0.15 us per hand-over at 148 pollers (handover_bench2.cu)
+__device__ __noinline__ bool poll_pair(const uint32_t *lo, const uint32_t *hi, uint32_t tag, float *f) {
+  uint4 a, b;
+  int it = 0;
+  for (;;) {
+    a = ld_poll4(lo); b = ld_poll4(hi);
+    if (tags_ok(a, tag) & tags_ok(b, tag)) break;
+    if (++it >= DA_SPIN_LIMIT) break;
+    __nanosleep(20);
+  }
+  f[0] = unit_val(a.x); f[1] = unit_val(a.y); f[2] = unit_val(a.z); f[3] = unit_val(a.w);
+  f[4] = unit_val(b.x); f[5] = unit_val(b.y); f[6] = unit_val(b.z); f[7] = unit_val(b.w);
+  return it < DA_SPIN_LIMIT;
+}
+// poll one 64-bit unit; payload in the high word
+__device__ __noinline__ bool poll8(const unsigned long long *p, uint32_t tag, uint32_t &payload) {
+  unsigned long long v;
+  int it = 0;
+  for (;;) {
+    v = ld_poll8(p);
+    if ((uint32_t)v == tag) break;
+    if (++it >= DA_SPIN_LIMIT) break;
+    __nanosleep(20);
+  }
+  payload = (uint32_t)(v >> 32);
+  return it < DA_SPIN_LIMIT;
+}
+// bounded mbarrier wait that does not burn issue slots: a hot try_wait loop by every waiting warp was ~25% of all
+// instructions executed by the kernel (ncu) and slowed the warps that had work on the same scheduler
+__device__ __forceinline__ bool mbar_wait_idle(uint64_t *bar, uint32_t parity, unsigned ns) {
+  uint32_t done = 0;
+  for (int it = 0; it < DA_SPIN_LIMIT; ++it) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+  return done != 0;
+}
+typedef BlockNamed<1, DA_M_CTHREADS> CBlock;           // the 512 compute threads
+__device__ __forceinline__ void cbar() { CBlock::sync(); }
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+#define DA_G_IPT 8   // fast heads: warps 0..3 of CTA 0 hold the <= 1024 logits, 8 per thread (named barrier 2)
+
+// ---- the static read list: what CTA `bid` streams through its ring in phase `ph` ------------------------------------------
+// Producer and compute warps evaluate the same functions, so they agree on the entry sequence without communicating.
+// A GEMV phase deals contiguous row ranges to the CTAs (whole w1/w3 pairs); a CTA walks its range in TILES of 16 rows, one
+// ring entry per tile.  Each row lands by its own bulk copy at a stride of 2K + 16 bytes, so that the eight row addresses
+// of an ldmatrix 8x8 block fall into eight different 16-byte bank groups (conflict-free without swizzling).
+#define DA_M_PT 4                   // partial-sum slots (tiles whose chunk partials may be outstanding at once)
+struct GemvPart { int r0, nr, nt; };   // first row, rows of this CTA, tiles
+__device__ __forceinline__ GemvPart gemv_part(int rows, int pq, int prem, int bid) {
+  GemvPart g;
+  const int p0 = bid * pq + min(bid, prem), p1 = p0 + pq + (bid < prem ? 1 : 0);
+  g.r0 = 2 * p0; g.nr = min(rows, 2 * p1) - g.r0; if (g.nr < 0) g.nr = 0;
+  g.nt = (g.nr + 15) >> 4;
+  return g;
+}
+__device__ __forceinline__ uint32_t row_stride(int K) { return 2u * (uint32_t)K + 16u; }
+
+// CANONICAL ORDER of a row's dot product in this kernel family: K is cut into chunks of 128 elements; a chunk partial is
+// the fp32 accumulator of a chain of eight m16n8k16 bf16 tensor-core MMAs (k ascending, starting from zero; the x vector
+// is replicated into all eight B columns); the row value is the sum of the chunk partials in chunk order.  Which warp
+// computes which chunk, and which other rows share the tile, does not change the result.
+__device__ __forceinline__ void mma_chunk(uint32_t tile_addr, uint32_t RS, int nrows, const uint32_t *xw, int chunk, int lane, float &v_lo, float &v_hi) {
+  int row = lane & 15; if (row >= nrows) row = 0;
+  uint32_t addr = tile_addr + (uint32_t)row * RS + (uint32_t)(((lane >> 4) << 3) + (chunk << 7)) * 2u;
+  const uint32_t *xp = xw + (chunk << 6) + (lane & 3);
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    uint32_t a0, a1, a2, a3;
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr + s * 32));
+    const uint32_t b0 = xp[s * 8], b1 = xp[s * 8 + 4];
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  v_lo = d0; v_hi = d2;     // rows lane/4 and lane/4 + 8 (every B column holds x, so every lane of a group has them)
+}
+__device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+// four consecutive activation values -> packed bf16, one 8-byte store at element offset e
+__device__ __forceinline__ void store4_xb(bf16 *xb, int e, const float *f) {
+  uint2 u;
+  u.x = (uint32_t)f2bits(f[0]) | ((uint32_t)f2bits(f[1]) << 16); u.y = (uint32_t)f2bits(f[2]) | ((uint32_t)f2bits(f[3]) << 16);
+  *reinterpret_cast<uint2 *>(xb + e) = u;
+}
+// eight consecutive activation values (bf16-exact floats) -> packed bf16, one 16-byte store
+__device__ __forceinline__ void store_chunk_xb(bf16 *xb, int c, const float *f) {
+  uint4 u;
+  u.x = (uint32_t)f2bits(f[0]) | ((uint32_t)f2bits(f[1]) << 16); u.y = (uint32_t)f2bits(f[2]) | ((uint32_t)f2bits(f[3]) << 16);
+  u.z = (uint32_t)f2bits(f[4]) | ((uint32_t)f2bits(f[5]) << 16); u.w = (uint32_t)f2bits(f[6]) | ((uint32_t)f2bits(f[7]) << 16);
+  reinterpret_cast<uint4 *>(xb)[c] = u;
+}
+struct AttnPart { int active, g, split, t0, t1, nsplit_eff, L; };
+__device__ __forceinline__ AttnPart attn_part(int pos, int nkv, int nsplit_max, int bid) {
+  AttnPart p;
+  p.L = pos + 1;
+  const int n_tiles = (p.L + DA_TILE - 1) / DA_TILE;
+  const int nsplit = min(nsplit_max, n_tiles);
+  const int tps = (n_tiles + nsplit - 1) / nsplit;
+  p.nsplit_eff = (n_tiles + tps - 1) / tps;
+  p.g = bid % nkv; p.split = bid / nkv;
+  p.active = (bid < nkv * nsplit_max) && (p.split < p.nsplit_eff);
+  p.t0 = p.split * tps; p.t1 = min(n_tiles, p.t0 + tps);
+  return p;
+}
+// rows of tile t that come from the cache (everything but the position being written now)
+__device__ __forceinline__ int tile_old_rows(int t, int pos) {
+  const int r0 = t * DA_TILE, r1 = min(pos + 1, r0 + DA_TILE);
+  return min(r1, pos) - r0;
+}
+
+struct RingCursor { uint32_t off, seq; };
+// place an entry of `size` bytes; entries never wrap (the tail of the ring is skipped and charged to the entry)
+__device__ __forceinline__ uint32_t ring_place(RingCursor &r, uint32_t size, uint32_t ring_bytes, uint32_t &charged) {
+  uint32_t pad = 0;
+  if (r.off + size > ring_bytes) { pad = ring_bytes - r.off; r.off = 0; }
+  const uint32_t at = r.off;
+  r.off += size; charged = size + pad; r.seq += 1;
+  return at;
+}
+
+// ---- shared-memory plan (host and device) -----------------------------------------------------------------------------------
+struct MegaSmem { uint32_t bars, chg, xb, raw, scratch, work, part, pcnt, lg, kvs, ring, total; };
+static inline __host__ __device__ MegaSmem mega_smem_plan(int kmax, int dim_max, int lg_rows, int work_bytes, int kv_bytes, int ring_bytes) {
+  MegaSmem m; uint32_t o = 0;
+  m.bars = o; o += 2 * DA_M_NB * 8;
+  m.chg = o; o += DA_M_NB * 4;
+  m.xb = o; o += (uint32_t)kmax * 2;
+  m.raw = o; o += 2u * (uint32_t)dim_max * 4;
+  m.scratch = o; o += 160 * 4;
+  m.work = o; o += ((uint32_t)work_bytes + 15u) & ~15u;
+  m.part = o; o += (uint32_t)DA_M_PT * (uint32_t)(kmax >> 7) * 16 * 4;    // [slot][chunk][row]
+  m.pcnt = o; o += 2 * DA_M_PT * 4;                                        // chunk counters, fold generations
+  m.lg = o; o += (((uint32_t)lg_rows * 2) + 15u) & ~15u;
+  m.kvs = o; o += ((uint32_t)kv_bytes + 15u) & ~15u;
+  o = (o + 127u) & ~127u;
+  m.ring = o; o += (uint32_t)ring_bytes;
+  m.total = o;
+  return m;
+}
+
+__device__ __forceinline__ void tl_mark(const MegaArgs &a, int slot, int k) {
+  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0 && slot < a.tl_slots) {
+    unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    a.tl[slot * 8 + k] = g;
+  }
+}
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); return g; }
+// unconditional variant for the instrumented thread of CTA 0 (producer stamps, accumulated waits)
+__device__ __forceinline__ void tl_put(const MegaArgs &a, int slot, int k, unsigned long long v) {
+  if (a.tl && blockIdx.x == 0 && slot < a.tl_slots) a.tl[slot * 8 + k] = v;
+}
+
+// two-barrier block sum over the compute threads (all get the result); scratch >= 16 floats, alternate by parity
+__device__ __forceinline__ float cblock_sum(float v, float *scratch, int lane, int w) {
+  v = warp_sum(v);
+  if (lane == 0) scratch[w] = v;
+  cbar();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < DA_M_CWARPS; ++i) t += scratch[i];   // fixed order
+  return t;
+}
+
+// =====================================================================================================================
+__global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_constant__ MegaArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  DAState *st = a.st;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int bid = blockIdx.x, grid = gridDim.x;
+  const int dim_max = a.dim > a.fdim ? a.dim : a.fdim;
+  const MegaSmem sp = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, a.ring_bytes);
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + sp.bars), *empty = full + DA_M_NB;
+  uint32_t *chg = reinterpret_cast<uint32_t *>(sm + sp.chg);
+  bf16 *xb = reinterpret_cast<bf16 *>(sm + sp.xb);
+  float *raw = reinterpret_cast<float *>(sm + sp.raw);
+  float *scratch = reinterpret_cast<float *>(sm + sp.scratch);
+  unsigned char *work = sm + sp.work;
+  float *part = reinterpret_cast<float *>(sm + sp.part);
+  volatile int *pcnt = reinterpret_cast<volatile int *>(sm + sp.pcnt), *pgen = pcnt + DA_M_PT;
+  uint16_t *lg = reinterpret_cast<uint16_t *>(sm + sp.lg);
+  bf16 *kvs = reinterpret_cast<bf16 *>(sm + sp.kvs);
+  unsigned char *ring = sm + sp.ring;
+  const uint32_t ring_bytes = (uint32_t)a.ring_bytes;
+
+  tl_mark(a, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < DA_M_NB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // request state: read once, before anything of this step can have changed it
+  const int done = *reinterpret_cast<const volatile int *>(&st->done);
+  const int pos = *reinterpret_cast<const volatile int *>(&st->pos);
+  const uint32_t tag_base = *reinterpret_cast<const volatile unsigned int *>(a.phase_ctr);
+  __syncthreads();
+  if (done) return;
+  const int nph = a.n_phases;
+  const int G = a.nh / a.nkv;
+
+  // =================================================== producer ===========================================================
+  if (w == DA_M_CWARPS) {
+    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    RingCursor rc = {0u, 0u};
+    uint32_t used = 0, tail = 0;
+    bool ok = true;
+    // lane 0 owns the ring bookkeeping; returns the smem offset of the new entry (rc.seq - 1 is its index)
+    auto reserve = [&](uint32_t size) -> uint32_t {
+      RingCursor probe = rc; uint32_t charged;
+      ring_place(probe, size, ring_bytes, charged);
+      while (used + charged > ring_bytes || rc.seq - tail >= DA_M_NB) {
+        ok = mbar_wait_idle(&empty[tail % DA_M_NB], (tail / DA_M_NB) & 1u, 100) && ok;
+        used -= chg[tail % DA_M_NB]; ++tail;
+      }
+      const uint32_t at = ring_place(rc, size, ring_bytes, charged);
+      chg[(rc.seq - 1) % DA_M_NB] = charged; used += charged;
+      return at;
+    };
+    for (int ph = 0; ph < nph; ++ph) {
+      const MPhase &d = a.table[ph];
+      if (a.tl && lane == 0) tl_put(a, 1 + ph, 4, gtime());
+      if (d.kind == MK_GEMV) {
+        const GemvPart gp = gemv_part(d.rows, d.pq, d.prem, bid);
+        const uint64_t pol = (d.flags & MF_KEEP) ? pol_keep : pol_stream;
+        const uint32_t RS = row_stride(d.K), row_bytes = 2u * (uint32_t)d.K;
+        for (int t = 0; t < gp.nt; ++t) {
+          const int n = min(16, gp.nr - 16 * t);
+          uint32_t at = 0, bi = 0;
+          if (lane == 0) {
+            at = reserve((uint32_t)n * RS); bi = (rc.seq - 1) % DA_M_NB;
+            mbar_expect_tx(&full[bi], (uint32_t)n * row_bytes);
+          }
+          at = __shfl_sync(0xffffffffu, at, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
+          if (lane < n) bulk_g2s(ring + at + (uint32_t)lane * RS, d.W + (size_t)(gp.r0 + 16 * t + lane) * d.K, row_bytes, &full[bi], pol);
+        }
+      } else if (d.kind == MK_ATTN) {
+        const AttnPart ap = attn_part(pos, a.nkv, a.nsplit_max, bid);
+        if (ap.active && lane == 0) {
+          for (int t = ap.t0; t < ap.t1; ++t) {
+            const int n_old = tile_old_rows(t, pos);
+            if (n_old <= 0) continue;
+            const uint32_t bytes = (uint32_t)n_old * a.hd * 2u;
+            const uint32_t at = reserve(2 * bytes);
+            uint64_t *fb = &full[(rc.seq - 1) % DA_M_NB];
+            mbar_expect_tx(fb, 2 * bytes);
+            const size_t src = ((size_t)ap.g * a.S + (size_t)t * DA_TILE) * a.hd;
+            bulk_g2s(ring + at, a.kc[d.layer] + src, bytes, fb, pol_stream);
+            bulk_g2s(ring + at + bytes, a.vc[d.layer] + src, bytes, fb, pol_stream);
+          }
+        }
+        __syncwarp();
+      }
+      if (a.tl && lane == 0) tl_put(a, 1 + ph, 5, gtime());
+    }
+    if (!ok) st->err = 2;
+    return;
+  }
+
+  // =================================================== compute warps =======================================================
+  auto tag_of = [&](int ph) { return (uint32_t)((tag_base + (uint32_t)ph) % 65535u) + 1u; };
+  auto tag32_of = [&](int ph) { return tag_base + (uint32_t)ph + 1u; };
+  RingCursor rc = {0u, 0u};
+  bool ok = true;
+  unsigned long long wait_ns = 0ull;
+  int sparity = 0;
+  // request parameters: read once (every access to the state is an L2 round trip on the critical path)
+  const float rp_eff = eff_rep_penalty(st);
+  const int use_pen = st->use_penalty;
+  const NoiseSrc ns = noise_src(st);
+  const float T_eff = eff_temperature(st);
+  const unsigned long long c_max_req = cmax_from_top_p(st->top_p);
+  const size_t rep_off = (size_t)(bid % DA_M_REP) * (size_t)a.ustride;
+  auto put1 = [&](uint32_t *out, uint32_t u) {
+#pragma unroll
+    for (int r = 0; r < DA_M_REP; ++r) st_unit(out + (size_t)r * a.ustride, u);
+  };
+  auto put2 = [&](uint32_t *out, uint32_t u0, uint32_t u1) {     // two adjacent units, 8-byte aligned
+    const unsigned long long v = ((unsigned long long)u1 << 32) | u0;
+#pragma unroll
+    for (int r = 0; r < DA_M_REP; ++r) st_unit8(out + (size_t)r * a.ustride, v);
+  };
+  // the next ring entry: every warp advances the cursor; only warps that read the entry wait for it to land.  An entry is
+  // released by ONE arrival -- lane 31 of the warp that folds the tile (all its units have been read by then; lane 31 never
+  // has global stores in flight, which a release-type operation would wait for), or one thread after the CTA barrier that
+  // ends an attention tile.
+  auto place = [&](uint32_t size, uint32_t &bar_idx, uint32_t &parity) -> uint32_t {
+    uint32_t charged;
+    const uint32_t at = ring_place(rc, size, ring_bytes, charged);
+    const uint32_t i = rc.seq - 1;
+    bar_idx = i % DA_M_NB; parity = (i / DA_M_NB) & 1u;
+    return at;
+  };
+  auto landed = [&](uint32_t bar_idx, uint32_t parity) {
+    if (a.tl && tid == 0) { const unsigned long long t0 = gtime(); ok = mbar_wait_idle(&full[bar_idx], parity, 20) && ok; wait_ns += gtime() - t0; }
+    else ok = mbar_wait_idle(&full[bar_idx], parity, 20) && ok;
+  };
+  // softmax statistics of the slow head carried from MK_GEMV(ME_SLOWLOGITS) to MK_HSTAT / MK_HCAND
+  float h_m = 0.f; int h_cnt = 0;
+
+  for (int ph = 0; ph < nph; ++ph) {
+    const MPhase &d = a.table[ph];
+    const uint32_t tag = tag_of(ph), in_tag = tag_of(d.in_ph);
+    const uint32_t *in = d.in ? d.in + rep_off : nullptr;
+    tl_mark(a, 1 + ph, 0);
+    if (a.tl && tid == 0 && ph > 0) tl_put(a, ph, 6, wait_ns);
+    wait_ns = 0ull;
+    float *sc = scratch + sparity * 16; sparity ^= 1;
+
+    if (d.kind == MK_GEMV) {
+      const int K = d.K, nchunk = K >> 7;
+      const GemvPart gp = gemv_part(d.rows, d.pq, d.prem, bid);
+      if (tid < 2 * DA_M_PT) pcnt[tid] = 0;      // chunk counters and fold generations of the partial-sum slots
+      // ---- (A) stage the input vector as packed bf16 (every activation is a bf16 value) ------------------------------------------
+      if (d.pro == MP_FASTATTN) {
+        // fast-layer attention for position d.pos (llama.py:246-251, 285-309), recomputed by every CTA
+        const int nh = a.fnh, nkv = a.fnkv, hd = a.fhd, qd = nh * hd, kd = nkv * hd, FG = nh / nkv;
+        const int p = d.pos, P = p + 1;
+        float *q = reinterpret_cast<float *>(work), *kcur = q + qd, *vcur = kcur + kd, *pr = vcur + kd;
+        bf16 *kv_l = kvs + (size_t)d.layer * a.ncb * 2 * kd;
+        {
+          const int c = tid, N = qd + 2 * kd;
+          if (c * 8 < N) {
+            float t[8];
+            ok = poll_pair(in + c * 4, in + N / 2 + c * 4, in_tag, t) && ok;
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              const int e = hlf * (N / 2) + c * 4;
+              float *dst = e < qd ? q + e : (e < qd + kd ? kcur + (e - qd) : vcur + (e - qd - kd));
+              *reinterpret_cast<float4 *>(dst) = make_float4(t[4 * hlf], t[4 * hlf + 1], t[4 * hlf + 2], t[4 * hlf + 3]);
+            }
+          }
+        }
+        cbar();
+        const bf16 *rope_row = a.frope + (size_t)p * hd;
+        for (int h = w; h < nh + nkv; h += DA_M_CWARPS) {
+          if (h < nh) head_norm_rope(q + h * hd, hd, a.fqn[d.layer], a.eps, rope_row, lane);
+          else head_norm_rope(kcur + (h - nh) * hd, hd, a.fkn[d.layer], a.eps, rope_row, lane);
+        }
+        cbar();
+        // this token's fast KV row -> shared-memory cache; scores for every (h, j <= pos): bf16(q @ k^T), then bf16(* scale)
+        for (int e = tid; e < kd; e += DA_M_CTHREADS) {
+          kv_l[((size_t)p * 2 + 0) * kd + e] = f2bf(kcur[e]);
+          kv_l[((size_t)p * 2 + 1) * kd + e] = f2bf(vcur[e]);
+        }
+        for (int t = tid; t < nh * P; t += DA_M_CTHREADS) {
+          const int h = t / P, j = t - h * P, g = h / FG;
+          const float *qq = q + h * hd;
+          float acc = 0.f;
+          if (j == p) {
+            const float *kk = kcur + g * hd;
+            for (int dd = 0; dd < hd; ++dd) acc = fmaf(qq[dd], kk[dd], acc);
+          } else {
+            const uint4 *kk = reinterpret_cast<const uint4 *>(kv_l + ((size_t)j * 2 + 0) * kd + g * hd);
+            for (int d8 = 0; d8 < (hd >> 3); ++d8) {
+              float kf[8]; unpack8(kk[d8], kf);
+#pragma unroll
+              for (int x = 0; x < 8; ++x) acc = fmaf(qq[d8 * 8 + x], kf[x], acc);
+            }
+          }
+          pr[h * a.ncb + j] = rbf(__fmul_rn(rbf(acc), a.fscale));
+        }
+        cbar();
+        // softmax (fp32, rounded to bf16) fused with y = bf16(p @ v): one 8-wide output chunk per thread
+        for (int c = tid; c * 8 < qd; c += DA_M_CTHREADS) {
+          const int e = c * 8, h = e / hd, dd = e - h * hd, g = h / FG;
+          float m = -INFINITY;
+          for (int jj = 0; jj < P; ++jj) m = fmaxf(m, pr[h * a.ncb + jj]);
+          float sum = 0.f;
+          for (int jj = 0; jj < P; ++jj) sum += expf(pr[h * a.ncb + jj] - m);
+          float acc[8];
+#pragma unroll
+          for (int x = 0; x < 8; ++x) acc[x] = 0.f;
+          for (int jj = 0; jj < P; ++jj) {
+            const float pj = rbf(expf(pr[h * a.ncb + jj] - m) / sum);
+            float vf[8];
+            if (jj == p) {
+#pragma unroll
+              for (int x = 0; x < 8; ++x) vf[x] = vcur[g * hd + dd + x];
+            } else unpack8(*reinterpret_cast<const uint4 *>(kv_l + ((size_t)jj * 2 + 1) * kd + g * hd + dd), vf);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) acc[x] = fmaf(pj, vf[x], acc[x]);
+          }
+#pragma unroll
+          for (int x = 0; x < 8; ++x) acc[x] = rbf(acc[x]);
+          store_chunk_xb(xb, c, acc);
+        }
+      } else {
+        // thread c < K/8 owns elements [4c, 4c+4) and [K/2 + 4c, K/2 + 4c + 4)
+        const int c = tid, e_lo = 4 * c, e_hi = (K >> 1) + 4 * c;
+        const bool mine = c * 8 < K;
+        float v[8], g[8];
+        const bool normed = d.pro == MP_RMSNORM || d.pro == MP_EMBED;
+        if (mine && normed) { unpack4(*reinterpret_cast<const uint2 *>(d.norm_w + e_lo), g); unpack4(*reinterpret_cast<const uint2 *>(d.norm_w + e_hi), g + 4); }
+        if (d.pro == MP_EMBED) {
+          // token + codebook embedding (llama.py:409-429), every CTA computes the whole vector
+          if (mine) {
+            int tok = st->tok_in[0];
+            if (tok < 0 || tok >= a.vocab) { tok = 0; st->err = 1; }
+            const bool is_sem = tok >= a.sem_begin && tok <= a.sem_end;
+            float te[8];
+            unpack4(*reinterpret_cast<const uint2 *>(a.emb + (size_t)tok * a.dim + e_lo), te); unpack4(*reinterpret_cast<const uint2 *>(a.emb + (size_t)tok * a.dim + e_hi), te + 4);
+            float vq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vq[j] = 0.f;
+            if (is_sem) {
+              for (int i = 0; i < a.num_codebooks; ++i) {       // stack(...).sum(dim=1): fp32 accumulate, one rounding
+                int cc = st->tok_in[i + 1];
+                if (cc < 0 || cc >= a.codebook_size) { cc = 0; st->err = 1; }
+                const bf16 *rowp = a.cb_emb + ((size_t)cc + (size_t)i * a.codebook_size) * a.dim;
+                float ce[8]; unpack4(*reinterpret_cast<const uint2 *>(rowp + e_lo), ce); unpack4(*reinterpret_cast<const uint2 *>(rowp + e_hi), ce + 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vq[j] += ce[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) vq[j] = rbf(vq[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = rbf(te[j] + vq[j]);
+              if (a.scale_cb && is_sem) x = st->cpu_sem ? rbf(__fdiv_rn(x, a.sqrt_c)) : rbf(__fmul_rn(x, a.inv_sqrt));
+              v[j] = x;
+            }
+          }
+        } else if (mine) ok = poll_pair(in + e_lo, in + e_hi, in_tag, v) && ok;
+        if (mine && (d.flags & (MF_SAVE0 | MF_SAVE1))) {
+          float *dst = raw + ((d.flags & MF_SAVE1) ? dim_max : 0);
+          *reinterpret_cast<float4 *>(dst + e_lo) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4 *>(dst + e_hi) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (normed) {
+          float ss = 0.f;
+          if (mine) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+          }
+          ss = cblock_sum(ss, sc, lane, w);
+          const float inv = rsqrtf(ss * (1.0f / (float)K) + a.eps);
+          if (mine) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = rbf(__fmul_rn(rbf(__fmul_rn(v[j], inv)), g[j]));
+          }
+        }
+        if (mine) { store4_xb(xb, e_lo, v); store4_xb(xb, e_hi, v + 4); }
+      }
+      cbar();
+      tl_mark(a, 1 + ph, 1);
+
+      // ---- (B) units: (tile, chunk of 128 elements) -> warp (tile * nchunk + chunk) % 16.  A unit leaves 16 partial sums in
+      //      shared memory; the warp that completes a tile's last chunk folds them in chunk order and runs the epilogue,
+      //      one row per lane -- no CTA-wide barrier between the dot products and the stores.
+      int pen_id = -1;      // penalised ids of the logits epilogues live in lanes 0..15 of every warp
+      if (d.epi == ME_FASTLOGITS && use_pen && lane < DA_WIN) pen_id = st->win[(d.pos + 1) * DA_WIN + lane];
+      if (d.epi == ME_SLOWLOGITS && use_pen && lane < a.n_rows_tok) pen_id = st->win[lane * DA_WIN];     // previous_tokens[:, 0]
+      float wmax = -INFINITY;
+      const float *resv = raw + ((d.flags & MF_RES1) ? dim_max : 0);
+      const uint32_t RS = row_stride(K);
+      const uint32_t *xw = reinterpret_cast<const uint32_t *>(xb);
+      {
+        int u = w;
+        for (int t = 0; t < gp.nt; ++t) {
+          const int n = min(16, gp.nr - 16 * t);
+          uint32_t bi, par;
+          const uint32_t at = place((uint32_t)n * RS, bi, par);
+          if (u >= (t + 1) * nchunk) continue;         // no unit of this warp in the tile
+          landed(bi, par);
+          const int slot = t & (DA_M_PT - 1);
+          float *pslot = part + (size_t)slot * (a.kmax >> 7) * 16;
+          for (; u < (t + 1) * nchunk; u += DA_M_CWARPS) {
+            const int c = u - t * nchunk;
+            float v_lo, v_hi;
+            mma_chunk(smem_u32(ring + at), RS, n, xw, c, lane, v_lo, v_hi);
+            // the slot is free once the tile DA_M_PT before this one has been folded
+            if (t >= DA_M_PT) { int it = 0; while (pgen[slot] != t / DA_M_PT) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
+            if ((lane & 3) == 0) { pslot[c * 16 + (lane >> 2)] = v_lo; pslot[c * 16 + 8 + (lane >> 2)] = v_hi; }
+            __syncwarp();
+            int last = 0;
+            if (lane == 31) {
+              __threadfence_block();
+              last = (atomicAdd((int *)&pcnt[slot], 1) == nchunk - 1);
+              if (last) __threadfence_block();
+            }
+            last = __shfl_sync(0xffffffffu, last, 31);
+            if (last) {
+              // every unit of the tile is done: fold in chunk order (lane r owns row r), free the slot and the ring entry
+              const int r = lane & 15, row = gp.r0 + 16 * t + r;
+              const bool live = lane < 16 && r < n;
+              float v = 0.f;
+#pragma unroll 4
+              for (int cc = 0; cc < nchunk; ++cc) v += pslot[cc * 16 + r];
+              __syncwarp();
+              if (lane == 31) { pcnt[slot] = 0; __threadfence_block(); pgen[slot] = t / DA_M_PT + 1; mbar_arrive(&empty[bi]); }
+              if (live && d.bias) v += bf2f(d.bias[row]);
+              if (d.epi == ME_STORE) {
+                if (live) put1(d.out + row, make_unit(v, tag));
+              } else if (d.epi == ME_RESIDUAL) {
+                if (live) put1(d.out + row, make_unit(resv[row] + rbf(v), tag));
+              } else if (d.epi == ME_SWIGLU) {
+                const float up = __shfl_down_sync(0xffffffffu, v, 1);      // row 2j = w1 (gate), row 2j+1 = w3 (up)
+                if (live && !(r & 1)) {
+                  const float gg = rbf(v), uu = rbf(up);
+                  const float sg = rbf(gg / (1.0f + expf(-gg)));
+                  put1(d.out + (row >> 1), make_unit(__fmul_rn(sg, uu), tag));
+                }
+              } else {
+                float z = rbf(v);
+                bool hit = false;
+#pragma unroll
+                for (int i = 0; i < DA_WIN; ++i) hit |= (__shfl_sync(0xffffffffu, pen_id, i) == row);
+                if (d.epi == ME_FASTLOGITS) {
+                  const size_t lo = (size_t)(d.pos - 1) * a.fv;
+                  if (live) {
+                    a.flogits_raw[lo + row] = f2bf(z);
+                    if (hit) z = penalise(z, rp_eff);
+                    a.flogits[lo + row] = f2bf(z); st_unit(d.out + row, make_unit(z, tag));
+                  }
+                } else if (live) {   // ME_SLOWLOGITS: logits stay in this CTA's shared memory for the sampler phases; global copies for read-back / fallback
+                  a.logits_raw[row] = f2bf(z);
+                  if (hit) z = penalise(z, rp_eff);
+                  a.logits[row] = f2bf(z); lg[16 * t + r] = f2bits(z); wmax = fmaxf(wmax, z);
+                }
+              }
+            }
+          }
+        }
+      }
+      tl_mark(a, 1 + ph, 2);
+
+      // ---- (C) heads ------------------------------------------------------------------------------------------------------
+      if (d.epi == ME_SLOWLOGITS) {
+        // CTA max of the penalised logits -> 64-bit unit; the fence makes this CTA's global logits visible to whoever
+        // has seen the unit (needed by the whole-vocabulary fallback sampler only)
+        wmax = warp_max(wmax);
+        if (lane == 0) sc[w] = wmax;
+        __threadfence();
+        cbar();
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < DA_M_CWARPS; ++i) m = fmaxf(m, sc[i]);
+        if (tid == 0) st_unit8(a.hmax + bid, make_unit8(__float_as_uint(m), tag32_of(ph)));
+        h_cnt = gp.nr;
+      }
+      if (d.epi == ME_FASTLOGITS && bid == 0) {
+        // warps 0-3 of CTA 0 draw the code and publish its embedding as the next pass's input
+        __shared__ uint32_t s_tok;
+        unsigned long long *scr = reinterpret_cast<unsigned long long *>(work);
+        if (w < 4) {
+          typedef BlockNamed<2, 128> G4;
+          const int V = a.fv;
+          uint32_t it8[DA_G_IPT];
+          Red r = {0ull, 0, -1};
+          {
+            float zv[8];
+            const bool mine = tid * 8 < V;     // V is a multiple of 8 (codebook sizes are)
+            if (mine) ok = poll_chunk(d.out + tid * 8, tag, zv) && ok;
+#pragma unroll
+            for (int i = 0; i < DA_G_IPT; ++i) {
+              const int e = tid * DA_G_IPT + i;
+              it8[i] = 0xFFFFFFFFu;
+              if (mine && e < V) {
+                const uint32_t key = bf16_key(f2bits(zv[i]));
+                it8[i] = ((0xFFFFu - key) << 16) | (uint32_t)e; r.m = max(r.m, (int)key);
+              }
+            }
+          }
+          SampleParams spm;
+          int par = 0;
+          if (a.tl && tid == 0) tl_put(a, 700 + ph, 0, gtime());
+          r = block_reduce<G4>(r, scr, par);
+          spm.m = bits2f(key_bf16((uint32_t)r.m));
+          Red es = {0ull, 0, -1};      // sum of exp terms as 2^-40 fixed point: order-free, identical to the per-phase path
+#pragma unroll
+          for (int i = 0; i < DA_G_IPT; ++i) if (it8[i] != 0xFFFFFFFFu) es.s += (unsigned long long)(expf(bits2f(key_bf16(0xFFFFu - (it8[i] >> 16))) - spm.m) * DA_FIX2_SCALE);
+          es = block_reduce<G4>(es, scr, par);
+          spm.S = __ull2float_rn(es.s) * (1.0f / DA_FIX2_SCALE);
+          spm.T_bf = T_eff;
+          spm.c_max = c_max_req;
+          G4::sync();
+          if (a.tl && tid == 0) tl_put(a, 700 + ph, 1, gtime());
+          uint32_t tok = sample_sorted<DA_G_IPT, 128, G4>(it8, (uint32_t)V, true, nullptr, spm, ns, (uint32_t)d.pos, a.noise_off0 + (long long)(d.pos - 1) * a.fv,
+                                                          &st->nucleus[d.pos], reinterpret_cast<uint32_t *>(scr + 256), scr);
+          if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (tid == 0) st->err = 3; }
+          if (tid == 0) { s_tok = tok; st->tok_out[d.pos + 1] = (int)tok; }
+          if (a.tl && tid == 0) tl_put(a, 700 + ph, 2, gtime());
+        }
+        cbar();
+        if (d.pos < a.ncb - 1) {
+          const uint32_t tok = s_tok;
+          for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) put1(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
+        }
+      }
+      if (a.tl && tid == 0) tl_put(a, 700 + ph, 3, gtime());
+      cbar();   // xb / part / work are reused by the next phase
+
+    } else if (d.kind == MK_ATTN) {
+      // ---- slow-layer attention for one query position: split-KV flash-decode (attention.cuh restated on ring tiles) ----------
+      const AttnPart ap = attn_part(pos, a.nkv, a.nsplit_max, bid);
+      if (ap.active) {
+        const int hd = a.hd, g = ap.g, L = ap.L;
+        const int qd = a.nh * hd, kd = a.nkv * hd;
+        float *q = reinterpret_cast<float *>(work);
+        float *knew = q + G * hd, *vnew = knew + hd, *scs = vnew + hd;     // scs: [G][DA_TILE]
+        float *s_m = scs + G * DA_TILE, *s_scale = s_m + DA_MAX_G, *s_l = s_scale + DA_MAX_G;
+        const bool owns_new = (pos / DA_TILE) >= ap.t0 && (pos / DA_TILE) < ap.t1;
+        {   // one 8-unit chunk per thread: G*hd/8 chunks of q, then hd/8 of the new k and of the new v
+          const int nq = (G * hd) >> 3, nk = owns_new ? (hd >> 3) : 0;
+          const int c = tid;
+          if (c < nq + 2 * nk) {
+            const uint32_t *src; float *dst;
+            if (c < nq) { src = in + (size_t)g * G * hd + (size_t)c * 8; dst = q + c * 8; }
+            else if (c < nq + nk) { src = in + qd + (size_t)g * hd + (size_t)(c - nq) * 8; dst = knew + (c - nq) * 8; }
+            else { src = in + qd + kd + (size_t)g * hd + (size_t)(c - nq - nk) * 8; dst = vnew + (c - nq - nk) * 8; }
+            float t[8];
+            ok = poll_chunk(src, in_tag, t) && ok;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = t[j];
+          }
+          if (tid < DA_MAX_G) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; }
+        }
+        cbar();
+        const bf16 *rope_row = a.rope + (size_t)pos * hd;
+        for (int h = w; h < G + (owns_new ? 1 : 0); h += DA_M_CWARPS) {
+          if (h < G) head_norm_rope(q + h * hd, hd, a.qn[d.layer], a.eps, rope_row, lane);
+          else head_norm_rope(knew, hd, a.kn[d.layer], a.eps, rope_row, lane);
+        }
+        cbar();
+        for (int e = tid; e < G * hd; e += DA_M_CTHREADS) q[e] = __fmul_rn(q[e], a.sf);   // q * sqrt(scale), fp32
+        if (owns_new)
+          for (int e = tid; e < hd; e += DA_M_CTHREADS) {   // KVCache.update (llama.py:142-149)
+            a.kc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(knew[e]);
+            a.vc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(vnew[e]);
+          }
+        cbar();
+        tl_mark(a, 1 + ph, 1);
+        // running softmax state: thread e owns output element (h, d) = (e / hd, e % hd), e < G*hd
+        float o_acc[2] = {0.f, 0.f};
+        float m_run = -INFINITY, l_run = 0.f;   // meaningful in warp h < G (lane-uniform)
+        const int lpr = hd / 8;            // lanes per position row (16-byte pieces)
+        const int rpw = 32 / lpr;          // rows per warp pass
+        for (int t = ap.t0; t < ap.t1; ++t) {
+          const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
+          const int n_old = min(r1, pos) - r0;
+          uint32_t bi = 0; const bf16 *kt = nullptr, *vt = nullptr;
+          if (n_old > 0) {
+            const uint32_t bytes = (uint32_t)n_old * hd * 2u;
+            uint32_t par;
+            const uint32_t at = place(2 * bytes, bi, par);
+            landed(bi, par);
+            kt = reinterpret_cast<const bf16 *>(ring + at); vt = reinterpret_cast<const bf16 *>(ring + at + bytes);
+          }
+          // scores: sc[h][j] = sum_d q_s[h][d] * (k[j][d] * sf)
+          for (int jb = w * rpw; jb < nrow; jb += DA_M_CWARPS * rpw) {
+            const int j = jb + lane / lpr, piece = lane % lpr;
+            float prt[DA_MAX_G];
+#pragma unroll
+            for (int h = 0; h < DA_MAX_G; ++h) prt[h] = 0.f;
+            if (j < nrow) {
+              float kf[8];
+              if (j < n_old) unpack8(*reinterpret_cast<const uint4 *>(kt + (size_t)j * hd + piece * 8), kf);
+              else {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) kf[x] = knew[piece * 8 + x];
+              }
+#pragma unroll
+              for (int x = 0; x < 8; ++x) kf[x] = __fmul_rn(kf[x], a.sf);
+#pragma unroll
+              for (int h = 0; h < DA_MAX_G; ++h) {
+                if (h < G) {
+                  const float *qq = q + h * hd + piece * 8;
+#pragma unroll
+                  for (int x = 0; x < 8; ++x) prt[h] = fmaf(qq[x], kf[x], prt[h]);
+                }
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < DA_MAX_G; ++h) {
+              if (h < G) {
+                float v = prt[h];
+                for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (piece == 0 && j < nrow) scs[h * DA_TILE + j] = v;
+              }
+            }
+          }
+          cbar();
+          // online softmax bookkeeping: warp h handles head h
+          if (w < G) {
+            float mx = -INFINITY;
+            for (int j = lane; j < nrow; j += 32) mx = fmaxf(mx, scs[w * DA_TILE + j]);
+            mx = warp_max(mx);
+            const float m_new = fmaxf(m_run, mx);
+            float ps = 0.f;
+            for (int j = lane; j < nrow; j += 32) { const float pp = expf(scs[w * DA_TILE + j] - m_new); scs[w * DA_TILE + j] = pp; ps += pp; }
+            ps = warp_sum(ps);
+            const float scale = expf(m_run - m_new);     // exp(-inf) = 0 on the first tile
+            l_run = l_run * scale + ps; m_run = m_new;
+            if (lane == 0) { s_scale[w] = scale; s_m[w] = m_run; s_l[w] = l_run; }
+          }
+          cbar();
+          // o = o * scale + P @ V
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int e = tid + i * DA_M_CTHREADS;
+            if (e < G * hd) {
+              const int h = e / hd, dd = e - h * hd;
+              float acc = o_acc[i] * s_scale[h];
+              const float *pp = scs + h * DA_TILE;
+              for (int j = 0; j < nrow; ++j) acc = fmaf(pp[j], j < n_old ? bf2f(vt[(size_t)j * hd + dd]) : vnew[dd], acc);
+              o_acc[i] = acc;
+            }
+          }
+          cbar();
+          if (n_old > 0 && tid == DA_M_CTHREADS - 1) mbar_arrive(&empty[bi]);      // every warp is past its last read of the tile
+        }
+        // partials out as 64-bit units
+        const uint32_t t32 = tag32_of(ph);
+        unsigned long long *po = a.part_o + (((size_t)g * a.nsplit_max + ap.split) * G) * hd;
+        unsigned long long *pml = a.part_ml + (((size_t)g * a.nsplit_max + ap.split) * G) * 2;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int e = tid + i * DA_M_CTHREADS;
+          if (e < G * hd) st_unit8(po + e, make_unit8(__float_as_uint(o_acc[i]), t32));
+        }
+        if (tid < G) { st_unit8(pml + tid * 2, make_unit8(__float_as_uint(s_m[tid]), t32)); st_unit8(pml + tid * 2 + 1, make_unit8(__float_as_uint(s_l[tid]), t32)); }
+        cbar();
+      }
+      tl_mark(a, 1 + ph, 2);
+
+    } else if (d.kind == MK_MERGE) {
+      // ---- merge the split-KV partials in split order (deterministic) and publish y as bf16 units ------------------------------
+      const AttnPart ap = attn_part(pos, a.nkv, a.nsplit_max, bid);
+      const int hd = a.hd, E = a.nh * hd, ns = ap.nsplit_eff;
+      const int e0 = (int)(((long long)E * bid) / grid), e1 = (int)(((long long)E * (bid + 1)) / grid), ne = e1 - e0;
+      float *mo = reinterpret_cast<float *>(work), *mm = mo + ne * ns, *ml = mm + ne * ns;    // [ne][ns] each
+      const uint32_t t32 = tag32_of(d.in_ph);
+      for (int t = tid; t < ne * ns; t += DA_M_CTHREADS) {
+        const int i = t / ns, s = t - i * ns, e = e0 + i;
+        const int h = e / hd, dd = e - h * hd, g = h / G, hl = h - g * G;
+        const size_t base = ((size_t)g * a.nsplit_max + s) * G + hl;
+        uint32_t vo, vm, vl;
+        ok = poll8(a.part_o + base * hd + dd, t32, vo) && ok;
+        ok = poll8(a.part_ml + base * 2, t32, vm) && ok;
+        ok = poll8(a.part_ml + base * 2 + 1, t32, vl) && ok;
+        mo[t] = __uint_as_float(vo); mm[t] = __uint_as_float(vm); ml[t] = __uint_as_float(vl);
+      }
+      cbar();
+      tl_mark(a, 1 + ph, 1);
+      if (tid < ne) {
+        const int i = tid;
+        float m = -INFINITY;
+        for (int s = 0; s < ns; ++s) m = fmaxf(m, mm[i * ns + s]);
+        float l = 0.f, o = 0.f;
+        for (int s = 0; s < ns; ++s) {
+          const float sc_s = expf(mm[i * ns + s] - m);
+          l = fmaf(ml[i * ns + s], sc_s, l);
+          o = fmaf(mo[i * ns + s], sc_s, o);
+        }
+        put1(d.out + e0 + i, make_unit(o / l, tag));
+      }
+      cbar();
+      tl_mark(a, 1 + ph, 2);
+
+    } else if (d.kind == MK_HSTAT) {
+      // ---- slow head, stage 2: global max; this CTA's share of S = sum exp(z - m) (2^-40 fixed point) and its candidate count ---
+      const uint32_t t32 = tag32_of(d.in_ph);
+      float m = -INFINITY;
+      if (tid < grid) { uint32_t v; ok = poll8(a.hmax + tid, t32, v) && ok; m = __uint_as_float(v); }
+      __threadfence();
+      m = warp_max(m);
+      if (lane == 0) sc[w] = m;
+      cbar();
+      m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < DA_M_CWARPS; ++i) m = fmaxf(m, sc[i]);
+      h_m = m;
+      const float thr = m - a.delta;
+      Red r = {0ull, 0, -1};
+      for (int i = tid; i < h_cnt; i += DA_M_CTHREADS) {
+        const float z = bits2f(lg[i]);
+        r.s += (unsigned long long)(expf(z - m) * DA_FIX2_SCALE);
+        r.c += z >= thr;
+      }
+      int par = 0;
+      r = block_reduce<CBlock>(r, reinterpret_cast<unsigned long long *>(work), par);
+      if (tid == 0) {
+        const uint32_t o32 = tag32_of(ph);
+        st_unit8(a.hcs + 3 * bid + 0, make_unit8((uint32_t)r.c, o32));
+        st_unit8(a.hcs + 3 * bid + 1, make_unit8((uint32_t)r.s, o32));
+        st_unit8(a.hcs + 3 * bid + 2, make_unit8((uint32_t)(r.s >> 32), o32));
+      }
+      cbar();
+      tl_mark(a, 1 + ph, 2);
+
+    } else if (d.kind == MK_HCAND) {
+      // ---- slow head, stage 3: candidates (z >= max - delta) of every CTA into one list; CTA 0 samples (inference.py:47-80) ------
+      const uint32_t t32 = tag32_of(d.in_ph), tag30 = tag32_of(ph) & 0x3FFFFFFFu;
+      uint32_t *hv = reinterpret_cast<uint32_t *>(work);        // [3*grid] payloads, then 4 words of results
+      __shared__ uint32_t s_base, s_n; __shared__ unsigned long long s_S;
+      for (int t = tid; t < 3 * grid; t += DA_M_CTHREADS) { uint32_t v; ok = poll8(a.hcs + t, t32, v) && ok; hv[t] = v; }
+      cbar();
+      if (w == 0) {
+        uint32_t base = 0, n = 0; unsigned long long S = 0ull;
+        for (int b = lane; b < grid; b += 32) {
+          const uint32_t c = hv[3 * b];
+          n += c; if (b < bid) base += c;
+          S += ((unsigned long long)hv[3 * b + 2] << 32) | hv[3 * b + 1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { base += __shfl_xor_sync(0xffffffffu, base, o); n += __shfl_xor_sync(0xffffffffu, n, o); S += __shfl_xor_sync(0xffffffffu, S, o); }
+        if (lane == 0) { s_base = base; s_n = n; s_S = S; }
+      }
+      cbar();
+      const float m = h_m, thr = m - a.delta;
+      const GemvPart gp = gemv_part(a.vocab, a.head_pq, a.head_prem, bid);
+      const uint32_t base = s_base, N = s_n;
+      if (N <= DA_CAND_CAP) {
+        // this CTA's candidates in vocabulary order: slot numbers increase with the index (ties of the sort need that)
+        const int per = (h_cnt + DA_M_CTHREADS - 1) / DA_M_CTHREADS;
+        const int i0 = min(h_cnt, tid * per), i1 = min(h_cnt, i0 + per);
+        uint32_t cnt = 0;
+        for (int i = i0; i < i1; ++i) cnt += bits2f(lg[i]) >= thr;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+        uint32_t *wtot = hv + 3 * grid + 8;
+        if (lane == 31) wtot[w] = inc;
+        cbar();
+        uint32_t slot = base + inc - cnt;
+        for (int i = 0; i < w; ++i) slot += wtot[i];
+        for (int i = i0; i < i1; ++i) {
+          const uint16_t b = lg[i];
+          if (bits2f(b) >= thr) {
+            const uint32_t idx = (uint32_t)(gp.r0 + i);
+            st_unit8(a.cand + slot, ((unsigned long long)(0xFFFFu - bf16_key(b)) << 48) | ((unsigned long long)idx << 30) | tag30);
+            ++slot;
+          }
+        }
+      }
+      if (bid == 0) {
+        SampleParams spm;
+        spm.m = m; spm.S = __ull2float_rn(s_S) * (1.0f / DA_FIX2_SCALE);
+        spm.T_bf = T_eff;
+        spm.c_max = c_max_req;
+        uint32_t *sm_sort = reinterpret_cast<uint32_t *>(work);
+        unsigned long long *scr = reinterpret_cast<unsigned long long *>(work + 16384);
+        cbar();   // hv is dead: work becomes the sampler's scratch
+        uint32_t idx = 0xFFFFFFFFu;
+        if (N >= 1 && N <= 4096) {      // sort-based sampler over <= 4096 candidates (8 per thread); wider nuclei take the fallback
+          constexpr int E = 8;
+          uint32_t it[E];
+#pragma unroll
+          for (int i = 0; i < E; ++i) {
+            const unsigned e = tid * E + i;
+            it[i] = 0xFFFFFFFFu;
+            if (e < N) {      // entry = inverted key (16) | vocabulary index (18) | tag (30)
+              unsigned long long k; int spin = 0;
+              for (;;) { k = ld_poll8(a.cand + e); if ((uint32_t)(k & 0x3FFFFFFFu) == tag30) break; if (++spin >= DA_SPIN_LIMIT) break; __nanosleep(20); }
+              ok = ok && spin < DA_SPIN_LIMIT;
+              it[i] = ((uint32_t)(k >> 48) << 16) | e;
+            }
+          }
+          idx = sample_sorted<E, DA_M_CTHREADS, CBlock>(it, N, (int)N == a.vocab, a.cand, spm, ns, 0u, 0ll, &st->nucleus[0], sm_sort, scr);
+        }
+        cbar();
+        if (idx == 0xFFFFFFFFu) {
+          __threadfence();
+          idx = sample_fallback<CBlock>(a.logits, a.vocab, spm, ns, 0u, 0ll, &st->nucleus[0], scr + 192, reinterpret_cast<float *>(scr + 192 + 34));
+        }
+        // inference.py:123-126: first codebook = semantic id - semantic_begin (clamped at 0); next input = its fast embedding
+        int cb0 = (int)idx - a.sem_begin; if (cb0 < 0) cb0 = 0;
+        if (cb0 >= a.codebook_size) { cb0 = a.codebook_size - 1; if (tid == 0) st->err = 3; }
+        for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) put1(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)cb0 * a.fdim + dd]), tag));
+        if (tid == 0) { st->tok_out[0] = (int)idx; st->tok_out[1] = cb0; }
+      }
+      cbar();
+      tl_mark(a, 1 + ph, 2);
+
+    } else if (d.kind == MK_PREFILL_END) {
+      // one prefill position done: wait for the last layer's output (so every CTA has finished), then load the next prompt column
+      if (bid == 0) {
+        const int c = tid;
+        float v[8];
+        if (c * 8 < a.dim) ok = poll_chunk(in + c * 8, in_tag, v) && ok;
+        cbar();
+      }
+    }
+  }
+
+  tl_mark(a, 0, 3);
+  if (!ok && lane == 0) st->err = 4;
+  if (bid == 0) {
+    cbar();
+    if (tid == 0) {
+      *a.phase_ctr = tag_base + (unsigned)nph;
+      if (a.table[nph - 1].kind == MK_PREFILL_END) {
+        const int np = pos + 1;
+        st->pos = np;
+        for (int r = 0; r < a.n_rows_tok; ++r) st->tok_in[r] = a.seq[(size_t)r * a.seq_stride + np];
+      } else {
+        GemvArgs g; g.st = st; g.seq = a.seq; g.seq_stride = a.seq_stride; g.im_end_id = a.im_end_id; g.n_rows_tok = a.n_rows_tok;
+        finish_step(g);
+      }
+    }
+  }
+}
+
+}  // namespace da

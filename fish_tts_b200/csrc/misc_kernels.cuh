@@ -72,16 +72,13 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
   unsigned long long *scr = reinterpret_cast<unsigned long long *>(smraw_sel);
   unsigned long long *scr64 = scr + 192;
   float *scrf = reinterpret_cast<float *>(scr64 + 34);
-  __shared__ float s_m, s_S;
-  // softmax statistics from the head kernel's per-CTA partials (fixed order)
-  if (threadIdx.x < 32) {   // warp 0: exact max, then per-lane strided sums + butterfly (fixed order)
+  __shared__ float s_m;
+  // the global max from the head kernel's per-CTA partials (exact, order-free)
+  if (threadIdx.x < 32) {
     float m = -INFINITY;
     for (int i = threadIdx.x; i < a.n_partials; i += 32) m = fmaxf(m, a.partials[i].x);
     m = warp_max(m);
-    float S = 0.f;
-    for (int i = threadIdx.x; i < a.n_partials; i += 32) if (a.partials[i].y > 0.f) S += a.partials[i].y * expf(a.partials[i].x - m);
-    S = warp_sum(S);
-    if (threadIdx.x == 0) { s_m = m; s_S = S; }
+    if (threadIdx.x == 0) s_m = m;
   }
   __syncthreads();
   const float m = s_m, thr = m - a.delta;
@@ -89,10 +86,13 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
   const int chunk = (a.V + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * chunk, i1 = min(a.V, i0 + chunk);
   const int lane = threadIdx.x & 31;
+  // S = sum exp(z - m) as 2^-40 fixed point: independent of summation order and of how rows were dealt to CTAs,
+  // so every kernel path computes the same S bit for bit
+  unsigned long long es = 0ull;
   for (int base = i0; base < i1; base += blockDim.x) {
     int i = base + threadIdx.x;
     uint16_t b = 0; bool c = false;
-    if (i < i1) { b = lb[i]; c = bits2f(b) >= thr; }
+    if (i < i1) { b = lb[i]; const float z = bits2f(b); c = z >= thr; es += (unsigned long long)(expf(z - m) * DA_FIX2_SCALE); }
     unsigned mask = __ballot_sync(0xffffffffu, c);
     if (mask) {
       unsigned basei = 0;
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
       }
     }
   }
+  { int par = 0; Red r = {es, 0, -1}; r = block_reduce(r, scr, par); if (threadIdx.x == 0) atomicAdd(&st->s_fix, r.s); __syncthreads(); }
   __shared__ unsigned int s_last;
   __threadfence();
   __syncthreads();
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
   __threadfence();
 
   SampleParams sp;
-  sp.m = m; sp.S = s_S;
+  sp.m = m; sp.S = __ull2float_rn(*((volatile unsigned long long *)&st->s_fix)) * (1.0f / DA_FIX2_SCALE);
   sp.T_bf = eff_temperature(st);
   sp.c_max = cmax_from_top_p(st->top_p);
   const unsigned n_cand = *((volatile unsigned *)&st->n_cand);
@@ -127,17 +128,17 @@ __global__ void __launch_bounds__(512, 1) select_sample_kernel(const SelectArgs 
       key[i] = 0; ix[i] = 0;
       if (e < n_cand) { const unsigned long long k = __ldcg(a.cand + e); key[i] = 0xFFFFu - (uint32_t)(k >> 32); ix[i] = (uint32_t)k; valid |= 1u << i; }
     }
-    idx = sample_items<DA_SEL_IPT>(key, ix, valid, (uint32_t)a.V, (int)n_cand == a.V, sp, st, 0u, 0ll, &st->nucleus[0], scr);
+    idx = sample_items<DA_SEL_IPT>(key, ix, valid, (uint32_t)a.V, (int)n_cand == a.V, sp, noise_src(st), 0u, 0ll, &st->nucleus[0], scr);
     __syncthreads();
   }
-  if (idx == 0xFFFFFFFFu) idx = sample_fallback(a.logits, a.V, sp, st, 0u, 0ll, &st->nucleus[0], scr64, scrf);
+  if (idx == 0xFFFFFFFFu) idx = sample_fallback(a.logits, a.V, sp, noise_src(st), 0u, 0ll, &st->nucleus[0], scr64, scrf);
   // inference.py:123-126: first codebook = semantic id - semantic_begin (clamped at 0); next input = its fast embedding
   int cb0 = (int)idx - a.sem_begin; if (cb0 < 0) cb0 = 0;
   if (cb0 >= a.codebook_size) { cb0 = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
   for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[d] = a.fast_emb[(size_t)cb0 * a.fast_dim + d];
   if (threadIdx.x == 0) {
     st->tok_out[0] = (int)idx; st->tok_out[1] = cb0;
-    st->n_cand = 0; st->sel_ticket = 0;
+    st->n_cand = 0; st->sel_ticket = 0; st->s_fix = 0ull;
     if (a.tl.buf) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); a.tl.buf[a.tl.slot * 8 + 3] = g; }
   }
 }
@@ -159,7 +160,7 @@ __global__ void load_step_kernel(const LoadStepArgs a) {
     st->temperature = a.temperature[0]; st->top_p = a.top_p[0]; st->rep_penalty = a.rep_penalty[0];
     st->use_penalty = a.prev ? 1 : 0;
     st->noise = a.noise; st->loop_mode = 0; st->done = 0;
-    st->n_cand = 0; st->sel_ticket = 0; st->fast_ticket = 0; st->head_ticket = 0;
+    st->n_cand = 0; st->sel_ticket = 0; st->fast_ticket = 0; st->head_ticket = 0; st->s_fix = 0ull;
     for (int g = 0; g < DA_MAX_KV_HEADS; ++g) st->attn_ticket[g] = 0;
   }
 }

@@ -52,9 +52,14 @@ __device__ __forceinline__ float eff_temperature(const DAState *st) {
   return st->cpu_sem ? t : rbf(t);
 }
 
-__device__ __forceinline__ float noise_at(const DAState *st, uint32_t head, long long head_off, uint32_t idx) {
-  if (st->noise) return bf2f(st->noise[head_off + idx]);
-  return exp1_noise(st->seed, st->step_ctr, head, idx);
+// where the Exp(1) draws come from: an explicit bf16 block (tests, "shared seeded Philox RNG") or Philox keyed by
+// (seed, step, head, element).  Loaded from the request state ONCE: the state lives in global memory and every access
+// is an L2 round trip on the decode critical path.
+struct NoiseSrc { const bf16 *noise; unsigned long long seed; unsigned int step; };
+__device__ __forceinline__ NoiseSrc noise_src(const DAState *st) { NoiseSrc n = {st->noise, st->seed, st->step_ctr}; return n; }
+__device__ __forceinline__ float noise_at(const NoiseSrc &ns, uint32_t head, long long head_off, uint32_t idx) {
+  if (ns.noise) return bf2f(ns.noise[head_off + idx]);
+  return exp1_noise(ns.seed, ns.step, head, idx);
 }
 
 __device__ __forceinline__ unsigned long long make_sortkey(uint16_t zbits, uint32_t idx) {
@@ -64,19 +69,20 @@ __device__ __forceinline__ float sortkey_logit(unsigned long long k) {
   return bits2f(key_bf16(0xFFFFu - (uint32_t)(k >> 32)));
 }
 
-// block-wide exclusive scan of one u64 per thread (blockDim <= 1024); scratch >= 33 u64
+// block-wide exclusive scan of one u64 per thread (<= 1024 threads); scratch >= 33 u64
+template <class B = BlockAll>
 __device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long *scratch,
                                                                   unsigned long long *total) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
   unsigned long long inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  __syncthreads();
+  B::sync();
   if (lane == 31) scratch[w] = inc;
-  __syncthreads();
+  B::sync();
   if (w == 0) {
     unsigned long long x = lane < nw ? scratch[lane] : 0ull, xi = x;
 #pragma unroll
@@ -87,7 +93,7 @@ __device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long 
     scratch[lane] = xi - x;            // exclusive warp offsets
     if (lane == 31) scratch[32] = xi;  // grand total
   }
-  __syncthreads();
+  B::sync();
   if (total) *total = scratch[32];
   return scratch[w] + inc - v;
 }
@@ -97,22 +103,23 @@ __device__ __forceinline__ ArgBest better(ArgBest a, ArgBest b) {   // larger r,
   if (b.r > a.r || (b.r == a.r && b.idx < a.idx)) return b;
   return a;
 }
+template <class B = BlockAll>
 __device__ __forceinline__ ArgBest block_argbest(ArgBest v, float *fs, uint32_t *is) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ArgBest t; t.r = __shfl_xor_sync(0xffffffffu, v.r, o); t.idx = __shfl_xor_sync(0xffffffffu, v.idx, o);
     v = better(v, t);
   }
-  __syncthreads();
+  B::sync();
   if (lane == 0) { fs[w] = v.r; is[w] = v.idx; }
-  __syncthreads();
+  B::sync();
   if (threadIdx.x == 0) {
     ArgBest b = {fs[0], is[0]};
     for (int i = 1; i < nw; ++i) { ArgBest t = {fs[i], is[i]}; b = better(b, t); }
     fs[32] = b.r; is[32] = b.idx;
   }
-  __syncthreads();
+  B::sync();
   ArgBest out = {fs[32], is[32]};
   return out;
 }
@@ -120,8 +127,9 @@ __device__ __forceinline__ ArgBest block_argbest(ArgBest v, float *fs, uint32_t 
 // ---- block reduction of (u64 sum, int sum, int max) with ONE barrier per call ------------------------
 // scratch: 2 x 3 x 32 u64 (ping-pong by call parity, see DESIGN.md "sampler"); all threads get the result
 struct Red { unsigned long long s; int c; int m; };
+template <class B = BlockAll>
 __device__ __forceinline__ Red block_reduce(Red v, unsigned long long *scr, int &parity) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     v.s += __shfl_xor_sync(0xffffffffu, v.s, o);
@@ -131,7 +139,7 @@ __device__ __forceinline__ Red block_reduce(Red v, unsigned long long *scr, int 
   unsigned long long *b = scr + parity * 96;
   parity ^= 1;
   if (lane == 0) { b[w] = v.s; b[32 + w] = (unsigned long long)(long long)v.c; b[64 + w] = (unsigned long long)(long long)v.m; }
-  __syncthreads();
+  B::sync();
   Red r = {0ull, 0, INT_MIN};
   for (int i = 0; i < nw; ++i) { r.s += b[i]; r.c += (int)(long long)b[32 + i]; r.m = max(r.m, (int)(long long)b[64 + i]); }
   return r;
@@ -144,9 +152,9 @@ __device__ __forceinline__ Red block_reduce(Red v, unsigned long long *scr, int 
 // (logit desc, index asc) order is found by bisection on the key (all sums exact u64 => order-free), a partially
 // kept tie group by a second bisection on the index.  Returns the sampled index, or 0xFFFFFFFF when the nucleus is
 // not proven to lie inside the item set (caller falls back); `all_present`: the items are the whole vocabulary.
-template <int IPT>
+template <int IPT, class B = BlockAll>
 __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&idx)[IPT], uint32_t valid_mask, uint32_t idx_limit,
-                                 bool all_present, const SampleParams &sp, const DAState *st, uint32_t head, long long head_off,
+                                 bool all_present, const SampleParams &sp, const NoiseSrc &st, uint32_t head, long long head_off,
                                  int *nucleus_out, unsigned long long *scr) {
   int parity = 0;
   unsigned long long w[IPT];
@@ -157,7 +165,7 @@ __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&id
     w[i] = v ? pweight(bits2f(key_bf16(key[i])), sp.m, sp.S) : 0ull;
     t.s += w[i]; t.c += v; if (v) t.m = max(t.m, (int)key[i]);
   }
-  const Red tot = block_reduce(t, scr, parity);      // total mass, item count, top key
+  const Red tot = block_reduce<B>(t, scr, parity);      // total mass, item count, top key
   const int n = tot.c, top_key = tot.m;
   // (1) lowest key kappa with G(kappa) = sum_{key >= kappa} w <= c_max
   uint32_t lo = 0, hi = 65536;
@@ -167,7 +175,7 @@ __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&id
     Red g = {0ull, 0, -1};
 #pragma unroll
     for (int i = 0; i < IPT; ++i) if (((valid_mask >> i) & 1u) && key[i] >= mid) g.s += w[i];
-    if (block_reduce(g, scr, parity).s <= sp.c_max) hi = mid; else lo = mid;
+    if (block_reduce<B>(g, scr, parity).s <= sp.c_max) hi = mid; else lo = mid;
   }
   const uint32_t kappa = hi;
   // (2) mass and count of the fully kept groups, next lower present key
@@ -176,7 +184,7 @@ __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&id
   for (int i = 0; i < IPT; ++i) if ((valid_mask >> i) & 1u) {
     if (key[i] >= kappa) { g.s += w[i]; g.c += 1; } else g.m = max(g.m, (int)key[i]);
   }
-  g = block_reduce(g, scr, parity);
+  g = block_reduce<B>(g, scr, parity);
   const int n_full = g.c, tau = g.m;
   // (3) partially kept tie group
   int c_part = 0; long long i_cut = -1;
@@ -184,7 +192,7 @@ __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&id
     Red q = {0ull, 0, -1};
 #pragma unroll
     for (int i = 0; i < IPT; ++i) if (((valid_mask >> i) & 1u) && (int)key[i] == tau) q.c += 1;
-    const int n_tau = block_reduce(q, scr, parity).c;
+    const int n_tau = block_reduce<B>(q, scr, parity).c;
     const unsigned long long wt = pweight(bits2f(key_bf16((uint32_t)tau)), sp.m, sp.S);
     const unsigned long long room = sp.c_max >= g.s ? sp.c_max - g.s : 0ull;
     const unsigned long long c = wt ? room / wt : (unsigned long long)n_tau;
@@ -198,7 +206,7 @@ __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&id
         Red z = {0ull, 0, -1};
 #pragma unroll
         for (int i = 0; i < IPT; ++i) if (((valid_mask >> i) & 1u) && (int)key[i] == tau && (long long)idx[i] <= mid) z.c += 1;
-        if (block_reduce(z, scr, parity).c >= c_part) h = mid; else l = mid;
+        if (block_reduce<B>(z, scr, parity).c >= c_part) h = mid; else l = mid;
       }
       i_cut = h;
     }
@@ -216,7 +224,7 @@ __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&id
     e2[i] = 0.f;
     if (k) { keep |= 1u << i; e2[i] = expf(rbf(bits2f(key_bf16(key[i])) / sp.T_bf) - mz); s2.s += (unsigned long long)(e2[i] * DA_FIX2_SCALE); }
   }
-  const float S2 = __ull2float_rn(block_reduce(s2, scr, parity).s) * (1.0f / DA_FIX2_SCALE);
+  const float S2 = __ull2float_rn(block_reduce<B>(s2, scr, parity).s) * (1.0f / DA_FIX2_SCALE);
   ArgBest best = {0.f, 0u};   // removed tokens have probability 0 -> r = 0; argmax ties go to index 0
 #pragma unroll
   for (int i = 0; i < IPT; ++i) if ((keep >> i) & 1u) {
@@ -224,15 +232,194 @@ __device__ uint32_t sample_items(const uint32_t (&key)[IPT], const uint32_t (&id
     ArgBest cnd = {rbf(p2 / noise_at(st, head, head_off, idx[i])), idx[i]};
     best = better(best, cnd);
   }
-  __syncthreads();
+  B::sync();
   float *fs = reinterpret_cast<float *>(scr);
-  best = block_argbest(best, fs, reinterpret_cast<uint32_t *>(fs + 40));
+  best = block_argbest<B>(best, fs, reinterpret_cast<uint32_t *>(fs + 40));
+  return best.idx;
+}
+
+
+// ---- sort-based nucleus sampler (the persistent kernel's fast path) -------------------------------------------------
+// The definition above orders the items by (logit desc, index asc), keeps the longest prefix whose exact cumulative
+// weight is <= c_max (and always the first item), renormalises and runs the Exp(1) race.  sample_items finds that prefix
+// without sorting by ~30 block-wide bisection rounds; with a handful of warps each round costs a barrier, which put the
+// nine fast heads at ~25 us each on the decode critical path.  Here the NT*E items are SORTED by a bitonic network
+// (register / shuffle / shared-memory stages), the prefix falls out of one scan, and the whole head costs ~2 us.  All sums
+// are the same exact u64 fixed-point sums, so both routines return the same token for the same logits, bit for bit.
+//
+// Items: 32-bit composites ((0xFFFF - key16) << 16) | tie, ascending = (logit desc, tie asc); `tie` is the vocabulary
+// index (fast heads) or a slot number that increases with the vocabulary index (slow-head candidate list; slot2idx maps
+// back).  Padding items are 0xFFFFFFFF.  Thread t of the NT-thread group holds items t*E .. t*E+E-1.
+// The k / j loops are RUNTIME loops on purpose: a fully unrolled network is thousands of straight-line instructions
+// that execute once per head, i.e. at instruction-fetch speed (measured: the unrolled sampler took 17-30 us per head).
+// The items stay in registers: only the in-thread strides need compile-time indices (three small blocks selected by j),
+// and for strides >= E the min/max direction is the same for all items of a thread, so a stage is E shuffles + E min/max.
+template <int E, int J>
+__device__ __forceinline__ void bitonic_inthread(uint32_t (&a)[E], bool asc) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if ((e & J) == 0 && (e | J) < E) {
+      const uint32_t lo = min(a[e], a[e | J]), hi = max(a[e], a[e | J]);
+      a[e] = asc ? lo : hi; a[e | J] = asc ? hi : lo;
+    }
+  }
+}
+// in-thread tail of a merge step k >= E: strides E/2 .. 1, one direction for the whole thread
+template <int E>
+__device__ __forceinline__ void bitonic_merge_inthread(uint32_t (&a)[E], bool asc) {
+  if (E > 8) bitonic_inthread<E, 8>(a, asc);
+  if (E > 4) bitonic_inthread<E, 4>(a, asc);
+  if (E > 2) bitonic_inthread<E, 2>(a, asc);
+  if (E > 1) bitonic_inthread<E, 1>(a, asc);
+}
+template <int E, int NT, class B>
+__device__ __forceinline__ void bitonic_sort_u32(uint32_t (&a)[E], uint32_t *sm) {
+  static_assert(E == 2 || E == 4 || E == 8 || E == 16, "items per thread");
+  const int t = threadIdx.x;
+  // (1) levels k < E: sort inside the thread (static network, directions alternate with the element index)
+#pragma unroll
+  for (int k = 2; k < E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((e & j) == 0) {
+          const bool asc = (e & k) == 0;
+          const uint32_t lo = min(a[e], a[e | j]), hi = max(a[e], a[e | j]);
+          a[e] = asc ? lo : hi; a[e | j] = asc ? hi : lo;
+        }
+      }
+    }
+  }
+  // (2) levels k >= E: the direction is a property of the thread; strides >= E cross lanes / warps, then one in-thread tail
+#pragma unroll 1
+  for (int k = E; k <= NT * E; k <<= 1) {
+    const bool asc = ((t * E) & k) == 0;
+#pragma unroll 1
+    for (int j = k >> 1; j >= E; j >>= 1) {
+      const bool takemin = (((t * E) & j) == 0) == asc;
+      if (j >= 32 * E) {            // partner lives in another warp: through shared memory
+#pragma unroll
+        for (int e = 0; e < E; ++e) sm[t * E + e] = a[e];
+        B::sync();
+        const uint32_t *pp = sm + ((t * E) ^ j);
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const uint32_t p = pp[e]; a[e] = takemin ? min(a[e], p) : max(a[e], p); }
+        B::sync();
+      } else {                      // partner is another lane of this warp
+        const int lx = j / E;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const uint32_t p = __shfl_xor_sync(0xffffffffu, a[e], lx); a[e] = takemin ? min(a[e], p) : max(a[e], p); }
+      }
+    }
+    bitonic_merge_inthread<E>(a, asc);
+  }
+}
+
+// scr: >= 2 * 3 * 32 u64 (block_reduce layout) ; sm_sort: NT*E u32.  n: number of real items.  all_present: the items are
+// the whole vocabulary.  Returns the sampled vocabulary index, or 0xFFFFFFFF when the nucleus is not proven to lie inside
+// the item set (caller falls back).
+#ifdef DA_SAMPLER_TIMING
+__device__ long long g_sampler_t[16];
+#define DA_ST(i) do { if (threadIdx.x == 0) g_sampler_t[i] = clock64(); } while (0)
+#else
+#define DA_ST(i) do { } while (0)
+#endif
+template <int E, int NT, class B>
+__device__ __noinline__ uint32_t sample_sorted(uint32_t (&a_in)[E], uint32_t n, bool all_present, const unsigned long long *slot2idx, const SampleParams &sp,
+                                  const NoiseSrc &st, uint32_t head, long long head_off, int *nucleus_out, uint32_t *sm_sort, unsigned long long *scr) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  constexpr int NW = NT / 32;
+  uint32_t a[E];                                   // registers (the argument lives in the caller's frame)
+#pragma unroll
+  for (int e = 0; e < E; ++e) a[e] = a_in[e];
+  DA_ST(0);
+  bitonic_sort_u32<E, NT, B>(a, sm_sort);
+  DA_ST(1);
+  // exact inclusive cumulative weight in sorted order (exp and division of the E items are independent: issue them together)
+  float ez[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) ez[e] = expf(bits2f(key_bf16(0xFFFFu - (a[e] >> 16))) - sp.m);
+  unsigned long long cum[E];
+  unsigned long long run = 0ull;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool v = a[e] != 0xFFFFFFFFu;
+    run += v ? (unsigned long long)(rbf(ez[e] / sp.S) * DA_FIX_SCALE) : 0ull;      // = pweight()
+    cum[e] = run;
+  }
+  DA_ST(2);
+  unsigned long long inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  unsigned long long *wsum = scr;                 // [NW] warp totals
+  int *wcnt = reinterpret_cast<int *>(scr + 40);  // [NW] kept items per warp (second round)
+  if (lane == 31) wsum[w] = inc;
+  // the sorted items go to shared memory: the kept prefix is redistributed over all threads below (after the sort it sits in
+  // the first few threads, which would otherwise run the Philox draws of the race one after the other)
+#pragma unroll
+  for (int e = 0; e < E; ++e) sm_sort[t * E + e] = a[e];
+  B::sync();
+  unsigned long long base = inc - run;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) if (i < w) base += wsum[i];
+  int kept = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) kept += (a[e] != 0xFFFFFFFFu) && (base + cum[e] <= sp.c_max || (t == 0 && e == 0));
+  kept = (int)__reduce_add_sync(0xffffffffu, (unsigned)kept);
+  if (lane == 0) wcnt[w] = kept;
+  B::sync();
+  int n_keep = 0;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) n_keep += wcnt[i];       // the kept set is a prefix of the sorted order
+  DA_ST(3);
+  if (n_keep == (int)n && !all_present) return 0xFFFFFFFFu;
+  if (t == 0 && nucleus_out) *nucleus_out = n_keep;
+  // second softmax over the kept prefix (exp terms summed as 2^-40 fixed point => order-free), items dealt round-robin
+  const uint32_t top = sm_sort[0];
+  const float mz = rbf(bits2f(key_bf16(0xFFFFu - (top >> 16))) / sp.T_bf);
+  float e2[E]; uint32_t it[E];
+  Red s2 = {0ull, 0, -1};
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = t + e * NT;
+    e2[e] = 0.f; it[e] = 0xFFFFFFFFu;
+    if (i < n_keep) {
+      it[e] = sm_sort[i];
+      e2[e] = expf(rbf(bits2f(key_bf16(0xFFFFu - (it[e] >> 16))) / sp.T_bf) - mz);
+      s2.s += (unsigned long long)(e2[e] * DA_FIX2_SCALE);
+    }
+  }
+  DA_ST(4);
+  int parity = 0;
+  B::sync();                                       // wsum / wcnt are dead: scr becomes block_reduce scratch
+  s2 = block_reduce<B>(s2, scr, parity);
+  const float S2 = __ull2float_rn(s2.s) * (1.0f / DA_FIX2_SCALE);
+  DA_ST(5);
+  ArgBest best = {0.f, 0u};   // removed tokens have probability 0 -> r = 0; argmax ties go to index 0
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (it[e] != 0xFFFFFFFFu) {
+    const uint32_t tie = it[e] & 0xFFFFu;
+    const uint32_t idx = slot2idx ? (uint32_t)((slot2idx[tie] >> 30) & 0x3FFFFu) : tie;      // candidate entry: key (16) | index (18) | tag (30)
+    const float p2 = rbf(e2[e] / S2);
+    ArgBest cnd = {rbf(p2 / noise_at(st, head, head_off, idx)), idx};
+    best = better(best, cnd);
+  }
+  DA_ST(6);
+  B::sync();
+  float *fs = reinterpret_cast<float *>(scr);
+  best = block_argbest<B>(best, fs, reinterpret_cast<uint32_t *>(fs + 40));
+  DA_ST(7);
   return best.idx;
 }
 
 // ---- fallback: nucleus wider than the candidate list (flat distributions) ------------------------
 // One CTA walks the whole logits vector from global memory; all sums are u64, so order-free.
-__device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParams &sp, const DAState *st,
+template <class B = BlockAll>
+__device__ __noinline__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParams &sp, const NoiseSrc &st,
                                     uint32_t head, long long head_off, int *nucleus_out,
                                     unsigned long long *scr64, float *scrf) {
   const uint16_t *lb = reinterpret_cast<const uint16_t *>(logits);
@@ -240,12 +427,12 @@ __device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParam
   // (1) lowest key kappa such that G(kappa) = sum_{key >= kappa} w <= c_max
   auto G_of = [&](uint32_t key) {
     unsigned long long g = 0;
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    for (int i = threadIdx.x; i < V; i += B::nthreads()) {
       uint16_t b = lb[i];
       if (bf16_key(b) >= key) g += pweight(bits2f(b), sp.m, sp.S);
     }
     unsigned long long tot;
-    block_excl_scan_u64(g, scr64, &tot);
+    block_excl_scan_u64<B>(g, scr64, &tot);
     return tot;
   };
   uint32_t lo = 0, hi = 65536;   // invariant: G(hi) <= c_max (G(65536) = 0), G(lo) > c_max
@@ -257,22 +444,22 @@ __device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParam
   uint32_t kappa = hi;
   // (2) G(kappa), count of fully kept, and the next lower present key
   unsigned long long g = 0; int cnt = 0; uint32_t below = 0; bool has_below = false;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+  for (int i = threadIdx.x; i < V; i += B::nthreads()) {
     uint16_t b = lb[i]; uint32_t k = bf16_key(b);
     if (k >= kappa) { g += pweight(bits2f(b), sp.m, sp.S); ++cnt; }
     else if (!has_below || k > below) { below = k; has_below = true; }
   }
   unsigned long long G;
-  block_excl_scan_u64(g, scr64, &G);
-  int n_full = (int)(block_sum((float)cnt, scrf) + 0.5f);
-  float bmax = block_max(has_below ? (float)below : -1.f, scrf);   // keys < 65536: exact in fp32
+  block_excl_scan_u64<B>(g, scr64, &G);
+  int n_full = (int)(block_sum<B>((float)cnt, scrf) + 0.5f);
+  float bmax = block_max<B>(has_below ? (float)below : -1.f, scrf);   // keys < 65536: exact in fp32
   int tau = (int)bmax;   // -1: nothing below
   // (3) partial group: how many members of key tau are kept, and up to which index
   int c_part = 0, i_cut = -1;
   if (tau >= 0) {
     int n_tau = 0;
-    for (int i = threadIdx.x; i < V; i += blockDim.x) n_tau += (bf16_key(lb[i]) == (uint32_t)tau);
-    n_tau = (int)(block_sum((float)n_tau, scrf) + 0.5f);
+    for (int i = threadIdx.x; i < V; i += B::nthreads()) n_tau += (bf16_key(lb[i]) == (uint32_t)tau);
+    n_tau = (int)(block_sum<B>((float)n_tau, scrf) + 0.5f);
     unsigned long long w = pweight(bits2f(key_bf16((uint32_t)tau)), sp.m, sp.S);
     unsigned long long room = sp.c_max >= G ? sp.c_max - G : 0ull;
     unsigned long long c = w ? room / w : (unsigned long long)n_tau;
@@ -281,17 +468,17 @@ __device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParam
     if (c_part > 0) {
       // index of the c_part-th member in index order: ordered block scan, chunk by chunk
       if (threadIdx.x == 0) { sh_i[0] = 0; sh_i[1] = -1; }
-      __syncthreads();
-      for (int base = 0; base < V; base += blockDim.x) {
+      B::sync();
+      for (int base = 0; base < V; base += B::nthreads()) {
         int i = base + threadIdx.x;
         unsigned long long f = (i < V && bf16_key(lb[i]) == (uint32_t)tau) ? 1ull : 0ull;
         unsigned long long tot;
-        unsigned long long ex = block_excl_scan_u64(f, scr64, &tot);
+        unsigned long long ex = block_excl_scan_u64<B>(f, scr64, &tot);
         int before = sh_i[0];
         if (f && before + (int)ex + 1 == c_part) sh_i[1] = i;
-        __syncthreads();
+        B::sync();
         if (threadIdx.x == 0) sh_i[0] = before + (int)tot;
-        __syncthreads();
+        B::sync();
         if (sh_i[1] >= 0) break;
       }
       i_cut = sh_i[1];
@@ -301,16 +488,16 @@ __device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParam
   // (4) second softmax + race over the kept set
   float mz = rbf(sp.m / sp.T_bf);   // the top logit is always kept
   unsigned long long es = 0;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+  for (int i = threadIdx.x; i < V; i += B::nthreads()) {
     uint16_t b = lb[i]; uint32_t k = bf16_key(b);
     bool keep = k >= kappa || ((int)k == tau && i <= i_cut);
     if (keep) es += (unsigned long long)(expf(rbf(bits2f(b) / sp.T_bf) - mz) * DA_FIX2_SCALE);
   }
   unsigned long long es_tot;
-  block_excl_scan_u64(es, scr64, &es_tot);
+  block_excl_scan_u64<B>(es, scr64, &es_tot);
   float S2 = __ull2float_rn(es_tot) * (1.0f / DA_FIX2_SCALE);
   ArgBest best = {0.f, 0u};
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+  for (int i = threadIdx.x; i < V; i += B::nthreads()) {
     uint16_t b = lb[i]; uint32_t k = bf16_key(b);
     bool keep = k >= kappa || ((int)k == tau && i <= i_cut);
     if (keep) {
@@ -319,7 +506,7 @@ __device__ uint32_t sample_fallback(const bf16 *logits, int V, const SampleParam
       best = better(best, c);
     }
   }
-  best = block_argbest(best, scrf, (uint32_t *)(scrf + 40));
+  best = block_argbest<B>(best, scrf, (uint32_t *)(scrf + 40));
   return best.idx;
 }
 

@@ -144,8 +144,8 @@ int dualar_set_noise(dualar_engine *e, const void *noise, int64_t n_steps);
  *     reference on CUDA (what a GPU user of the reference gets), 1 follows it on the CPU (what the
  *     golden fixtures were generated with).
  * "candidate_delta" (default 6.0, before finalize): slow-head candidates are logits >= max - delta.
- * "fast_ar_kernel" (0/1, before finalize): run the fast-AR codebook loop as one persistent cooperative
- *     kernel (fast_ar.cuh) instead of one kernel per phase; both produce bit-identical results. */
+ * "mega_kernel" (0/1, before finalize; default 1): run the whole decode step as ONE persistent cooperative
+ *     kernel (csrc/mega.cuh) instead of one kernel per phase; both produce bit-identical results. */
 int dualar_set_option(dualar_engine *e, const char *name, double value);
 
 /* ---- introspection (tests, bench) -------------------------------------------------------------

@@ -1,4 +1,8 @@
-"""DUALAR_TIMELINE=1 python tests/timeline.py : in-kernel %globaltimer stamps of one decode step (block 0 of each kernel)."""
+"""DUALAR_TIMELINE=1 python tests/timeline.py : in-kernel %globaltimer stamps of one decode step (CTA 0).
+
+Persistent kernel (default): slot 1+ph holds {phase start, input staged, compute done} of phase ph; slot 0 = kernel
+entry / exit.  DUALAR_MEGA=0: one slot per kernel of the step graph (entry, dependency wait returned, prologue done, exit)."""
+import collections
 import os
 import sys
 from pathlib import Path
@@ -19,33 +23,74 @@ prompt = synthetic_prompt(cfg, 3, 215, 5, seed=1)
 eng.prefill(prompt, 600, temperature=0.7, top_p=0.8, repetition_penalty=1.1)
 eng.decode(300)
 torch.cuda.synchronize()
+L = cfg.n_layer
+
+if n_step == 1:
+    names = []
+    for i in range(L):
+        names += [f"S.qkv", "S.attn", "S.merge", "S.wo", "S.w13", "S.w2"]
+    names += ["H.head", "H.stat", "H.cand"]
+    for p in range(cfg.num_codebooks):
+        for l in range(cfg.n_fast_layer):
+            names += ["F.qkv", "F.wo", "F.w13", "F.w2"]
+        if p:
+            names.append("F.head")
+    nph = len(names)
+    full = eng.read("timeline").numpy().astype("int64")
+    dbg = full[400:400 + nph, :4]
+    tl = full[: nph + 1]
+    t0 = tl[0, 0]
+    start = (tl[1:, 0] - t0) / 1e3
+    staged = (tl[1:, 1] - t0) / 1e3
+    done = (tl[1:, 2] - t0) / 1e3
+    end = (tl[0, 3] - t0) / 1e3
+    print(f"step total (kernel entry -> exit, CTA 0): {end:.1f} us, {nph} phases")
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    pfirst = (tl[1:, 4] - t0) / 1e3
+    plast = (tl[1:, 5] - t0) / 1e3
+    waits = tl[1:, 6] / 1e3
+    print("  ph name      start   +staged  +compute  period | ring wait (in compute) | producer: began / finished issuing this phase, relative to the phase start")
+    for i, nm in enumerate(names):
+        nxt = start[i + 1] if i + 1 < nph else end
+        period = nxt - start[i]
+        st = staged[i] - start[i] if tl[1 + i, 1] else float("nan")
+        cp = done[i] - (staged[i] if tl[1 + i, 1] else start[i])
+        a = agg[nm]; a[0] += 1; a[1] += 0.0 if st != st else st; a[2] += cp; a[3] += period
+        if i < 14 or 6 * L - 7 <= i < 6 * L + 24 or i >= nph - 12:
+            print(f"{i:4d} {nm:8s} {start[i]:8.2f} {st:8.2f} {cp:8.2f} {period:8.2f} | {waits[i]:6.2f} | {pfirst[i] - start[i]:8.2f} {plast[i] - start[i]:8.2f} | cyc take {dbg[i,0]:6d} mma {dbg[i,1]:6d} part {dbg[i,2]:6d} fold {dbg[i,3]:6d}")
+    print("kind       n   staged  compute   period      sum")
+    for k, a in agg.items():
+        n = a[0]
+        print(f"{k:8s} {n:4d} {a[1] / n:8.2f} {a[2] / n:8.2f} {a[3] / n:8.2f} {a[3]:8.1f}")
+    hs = full[700:700 + nph, :4]
+    for i, nm in enumerate(names):
+        if nm == "F.head" and i < nph - 1:
+            print(f"  F.head ph {i}: start {start[i]:.2f} staged +{staged[i]-start[i]:.2f} compute +{done[i]-staged[i]:.2f} | polled +{(hs[i,0]-t0)/1e3-done[i]:.2f} | m,S +{(hs[i,1]-hs[i,0])/1e3:.2f} | sample_sorted +{(hs[i,2]-hs[i,1])/1e3:.2f} | publish+bar +{(hs[i,3]-hs[i,2])/1e3:.2f}")
+    slow_end = start[6 * L]
+    head_end = start[6 * L + 3]
+    print(f"slow stack {slow_end:.1f} us | head+sampler {head_end - slow_end:.1f} us | fast {end - head_end:.1f} us")
+    sys.exit(0)
+
 tl = eng.read("timeline")[:n_step].numpy()
 g = tl[:, :4].astype("int64")
 t0 = g[0, 0]
-names = []
-L = cfg.n_layer
-names.append("embed")
+names = ["embed"]
 for i in range(L):
     names += [f"L{i}.qkv", f"L{i}.attn", f"L{i}.wo", f"L{i}.w13", f"L{i}.w2"]
 names += ["head", "select"]
-if n_step == len(names) + 1:
-    names.append("fast_ar")
-else:
-    for p in range(cfg.num_codebooks):
-        for l in range(cfg.n_fast_layer):
-            names += [f"F{p}.{l}.qkv", f"F{p}.{l}.wo", f"F{p}.{l}.w13", f"F{p}.{l}.w2"]
-        if p:
-            names.append(f"F{p}.head")
+for p in range(cfg.num_codebooks):
+    for l in range(cfg.n_fast_layer):
+        names += [f"F{p}.{l}.qkv", f"F{p}.{l}.wo", f"F{p}.{l}.w13", f"F{p}.{l}.w2"]
+    if p:
+        names.append(f"F{p}.head")
 assert len(names) == n_step, (len(names), n_step)
 print("slot name           entry    wait_ret  pro_done  end(b0)   | gap_from_prev_end  wait-entry  pro-wait  end-pro   (us, relative to step start)")
 prev_end = None
-import collections
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0, 0.0])
 for i, nm in enumerate(names):
     e, w, p, x = [(v - t0) / 1e3 for v in g[i]]
-    period = (g[i + 1, 0] - g[i, 0]) / 1e3 if i + 1 < n_step else float("nan")
     kind = nm.split(".")[-1] if "." in nm else nm
-    kind = ("F." if nm.startswith("F") and nm != "fast_ar" else "S.") + kind
+    kind = ("F." if nm.startswith("F") else "S.") + kind
     a = agg[kind]; a[0] += 1; a[1] += w - e; a[2] += p - w; a[3] += x - p; a[4] += (x - e)
     if i + 1 < n_step:
         a[5] += (g[i + 1, 1] - g[i, 1]) / 1e3     # wait-return to next wait-return = the serial period
@@ -57,26 +102,3 @@ print("kind        n   wait-entry  pro-wait  end-pro  total(b0)  serial period (
 for k, a in agg.items():
     n = a[0]
     print(f"{k:10s} {n:3d} {a[1] / n:9.2f} {a[2] / n:9.2f} {a[3] / n:8.2f} {a[4] / n:9.2f} {a[5] / n:9.2f}   sum {a[5]:8.1f}")
-
-if names[-1] == "fast_ar":
-    full = eng.read("timeline").numpy()
-    nph = cfg.num_codebooks * cfg.n_fast_layer * 4 + cfg.num_codebooks - 1
-    ph = full[192:192 + nph, :3].astype("int64")
-    base = ph[0, 0]
-    kinds = []
-    for p in range(cfg.num_codebooks):
-        for l in range(cfg.n_fast_layer):
-            kinds += ["qkv", "wo", "w13", "w2"]
-        if p:
-            kinds.append("head")
-    print("fast_ar phases (block 0): start -> staged -> pairs done, us")
-    import collections
-    ag = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
-    for i in range(nph):
-        st_, sg, dn = [(v - base) / 1e3 for v in ph[i]]
-        nxt = (ph[i + 1, 0] - base) / 1e3 if i + 1 < nph else dn
-        a_ = ag[kinds[i]]; a_[0] += 1; a_[1] += sg - st_; a_[2] += dn - sg; a_[3] += nxt - st_
-        if i < 20 or i > nph - 8:
-            print(f"  ph {i:3d} {kinds[i]:5s} start {st_:9.2f} staged +{sg - st_:6.2f} pairs +{dn - sg:6.2f} period {nxt - st_:6.2f}")
-    for k, a_ in ag.items():
-        print(f"  {k:5s} n={a_[0]:3d} stage {a_[1] / a_[0]:6.2f} pairs {a_[2] / a_[0]:6.2f} period {a_[3] / a_[0]:6.2f}  sum {a_[3]:8.1f}")
