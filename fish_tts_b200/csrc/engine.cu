@@ -57,12 +57,12 @@ struct dualar_engine {
   int launches_step = 0, launches_prefill = 0;
   int prompt_len = 0, max_gen = 0;
   std::vector<void *> owned;
-  unsigned long long *tl = nullptr; int tl_slots = 0;
+  unsigned long long *tl = nullptr; int tl_slots = 0; unsigned long long *tl2 = nullptr;
   // persistent whole-step kernel (mega.cuh): unit buffers, the two phase tables (decode step / one prefill position)
   uint32_t *u_x = nullptr, *u_qkv = nullptr, *u_y = nullptr, *u_h = nullptr, *u_act = nullptr;
   uint32_t *u_fqkv = nullptr, *u_fh = nullptr, *u_fact = nullptr, *u_fx0 = nullptr, *u_fx1 = nullptr, *u_fin = nullptr, *u_flogits = nullptr;
   unsigned long long *m_part_o = nullptr, *m_part_ml = nullptr, *m_hmax = nullptr, *m_hcs = nullptr, *m_cand = nullptr;
-  MegaArgs *ma_step = nullptr, *ma_prefill = nullptr; size_t mega_smem = 0; unsigned int *m_phase = nullptr; unsigned char *u_arena = nullptr; size_t u_arena_bytes = 0;
+  MegaArgs *ma_step = nullptr, *ma_prefill = nullptr; size_t mega_smem = 0; unsigned int *m_phase = nullptr; bf16 *m_fkv = nullptr; unsigned char *u_arena = nullptr; size_t u_arena_bytes = 0;
   bool use_mega = true;   // option mega_kernel / DUALAR_MEGA: 0 = one kernel per phase (the cross-check path)
 };
 
@@ -318,12 +318,15 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
   if (e->use_mega) {
     // the whole step as ONE persistent cooperative kernel (mega.cuh); the phase tables were built at finalize
     MegaArgs *a = slow_only ? e->ma_prefill : e->ma_step;
-    a->tl = e->tl; a->tl_slots = e->tl_slots;
+    a->tl = e->tl; a->tl_slots = e->tl_slots; a->tl2 = e->tl2;
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_M_THREADS); cfg.dynamicSmemBytes = e->mega_smem; cfg.stream = s;
     cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, mega_kernel, *a)); ++count;
+    const bool tl_on = e->tl != nullptr;
+    if (slow_only) { if (tl_on) CU(cudaLaunchKernelEx(&cfg, mega_kernel<true, false>, *a)); else CU(cudaLaunchKernelEx(&cfg, mega_kernel<false, false>, *a)); }
+    else { if (tl_on) CU(cudaLaunchKernelEx(&cfg, mega_kernel<true, true>, *a)); else CU(cudaLaunchKernelEx(&cfg, mega_kernel<false, true>, *a)); }
+    ++count;
     return 0;
   }
   { EmbedArgs a; memset(&a, 0, sizeof(a));
@@ -402,7 +405,7 @@ static int build_mega(dualar_engine *e) {
   auto pairs = [](int rows) { return (rows + 1) / 2; };
   if (n_step > DA_M_MAX_PHASES || c.n_layer > DA_M_MAXL || c.n_fast_layer > DA_M_MAXFL || grid > 160 || e->fv > 1024 ||
       pairs(qkv_rows) < grid || pairs(2 * c.intermediate_size) < grid || pairs(fqkv_rows) < grid || pairs(2 * c.fast_intermediate_size) < grid ||
-      G * c.head_dim > 1024 || c.vocab_size > (1 << 18)) { e->use_mega = false; return 0; }
+      G * c.head_dim > 1024 || c.vocab_size > (1 << 18) || (c.num_codebooks - 1) * 2 * fkd / 8 > 3 * DA_M_CTHREADS || c.head_dim < 32) { e->use_mega = false; return 0; }
   int rc;
   // every broadcast unit vector exists DA_M_REP times, `ustride` units apart
   int umax = qkv_rows; for (int v : {c.dim, qd, c.intermediate_size, fqkv_rows, c.fast_dim, c.fast_intermediate_size, e->fv}) if (v > umax) umax = v;
@@ -422,6 +425,7 @@ static int build_mega(dualar_engine *e) {
     for (auto sl : slots) { *sl = u; u += ubuf; }
   }
   if ((rc = dev_alloc(e, e->m_phase, 1))) return rc;
+  if ((rc = dev_alloc(e, e->m_fkv, (size_t)grid * c.n_fast_layer * c.num_codebooks * 2 * fkd))) return rc;
   e->ma_step = new MegaArgs(); e->ma_prefill = new MegaArgs();
   for (int variant = 0; variant < 2; ++variant) {
     MegaArgs &a = variant ? *e->ma_prefill : *e->ma_step;
@@ -488,7 +492,7 @@ static int build_mega(dualar_engine *e) {
     for (int l = 0; l < c.n_fast_layer; ++l) { a.fqn[l] = e->fast[l].qn; a.fkn[l] = e->fast[l].kn; }
     a.fl = c.n_fast_layer; a.fnh = c.fast_n_head; a.fnkv = c.fast_n_local_heads; a.fhd = c.fast_head_dim; a.ncb = c.num_codebooks;
     a.fscale = (float)(1.0 / sqrt((double)c.fast_head_dim));
-    a.fast_emb = e->fast_emb; a.fdim = c.fast_dim; a.fv = e->fv; a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
+    a.fkv = e->m_fkv; a.fast_emb = e->fast_emb; a.fdim = c.fast_dim; a.fv = e->fv; a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
     a.noise_off0 = (long long)c.vocab_size;
     a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.st = e->st; a.ustride = (int)ustride; a.phase_ctr = e->m_phase;
     // shared-memory plan (from the decode-step table; the prefill table is a subset and shares it)
@@ -507,13 +511,13 @@ static int build_mega(dualar_engine *e) {
     if ((size_t)4 * DA_TILE * c.head_dim > max_entry) max_entry = (size_t)4 * DA_TILE * c.head_dim;
     size_t work = (size_t)(fqd + 2 * fkd + c.fast_n_head * c.num_codebooks + 4) * 4;
     auto upd = [&](size_t v) { if (v > work) work = v; };
-    upd((size_t)(G * c.head_dim + 2 * c.head_dim + G * DA_TILE + 3 * DA_MAX_G) * 4);
+    upd((size_t)(G * c.head_dim + 2 * c.head_dim + DA_M_CWARPS * G * (2 + c.head_dim)) * 4);      // slow attention: q, new k/v, per-warp partials
     upd((size_t)3 * (qd / grid + 2) * e->nsplit * 4);
     upd((size_t)3 * grid * 4 + 256);
     upd((size_t)16384 + (192 + 34) * 8 + 80 * 4 + 64);          // slow head: sort buffer + sampler scratch
     upd((size_t)256 * 8 + 128 * DA_G_IPT * 4 + 64);              // fast heads: scratch + sort buffer
     a.kmax = kmax; a.lg_rows = (2 * (pairs(c.vocab_size) / grid + 1) + 31) / 16 * 16; a.work_bytes = (int)work;
-    a.kv_bytes = c.n_fast_layer * c.num_codebooks * 2 * fkd * 2;
+    a.kv_bytes = c.num_codebooks * 2 * fkd * 2;      // one fast layer's K/V rows; all layers live in a per-CTA global scratch
     const int dim_max = c.dim > c.fast_dim ? c.dim : c.fast_dim;
     const MegaSmem fixed = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, 0);
     const long long budget = 227 * 1024 - 1024 - (long long)fixed.total;   // 1 KB for the kernel's static shared variables
@@ -522,7 +526,11 @@ static int build_mega(dualar_engine *e) {
     a.ring_bytes = (int)ring;
     e->mega_smem = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, a.ring_bytes).total;
   }
-  CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
+  { const char *v = getenv("DUALAR_POLL_NS"); int ns = v ? atoi(v) : 0; CU(cudaMemcpyToSymbol(g_poll_ns, &ns, sizeof(int))); }
+  CU(cudaFuncSetAttribute(mega_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
+  CU(cudaFuncSetAttribute(mega_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
+  CU(cudaFuncSetAttribute(mega_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
+  CU(cudaFuncSetAttribute(mega_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
   return 0;
 }
 
@@ -570,7 +578,8 @@ extern "C" int dualar_finalize(dualar_engine *e) {
   { const char *v = getenv("DUALAR_PDL"); if (v && v[0] == '0') g_use_pdl = false; }
   { const char *v = getenv("DUALAR_MEGA"); if (v) e->use_mega = v[0] != '0'; }
   if (e->use_mega && (rc = build_mega(e)) < 0) return rc;
-  { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 1024; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc; } }
+  { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 1024; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc;
+      if ((rc = dev_alloc(e, e->tl2, (size_t)DA_M_MAX_PHASES * 160 * 4))) return rc; } }
   // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
   { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);
     if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp); cudaGetLastError(); }
@@ -813,6 +822,7 @@ extern "C" int dualar_read_buffer(dualar_engine *e, const char *name, void *dst,
   else if (!strcmp(name, "fast_x")) { src = e->fbuf[(c.n_fast_layer - 1) & 1]; avail = (int64_t)c.fast_dim * 2; }
   else if (!strcmp(name, "timeline")) { if (!e->tl) return fail(DUALAR_ESTATE, "run with DUALAR_TIMELINE=1"); src = e->tl; avail = (int64_t)e->tl_slots * 64; }
   else if (!strcmp(name, "fast_in")) { src = e->fin; avail = (int64_t)c.fast_dim * 2; }
+  else if (!strcmp(name, "timeline2")) { if (!e->tl2) return fail(DUALAR_ESTATE, "run with DUALAR_TIMELINE=1"); src = e->tl2; avail = (int64_t)DA_M_MAX_PHASES * 160 * 4 * 8; }
   else if (!strcmp(name, "cand")) { if (!e->m_cand) return fail(DUALAR_ESTATE, "persistent kernel not in use"); src = e->m_cand; avail = (int64_t)DA_CAND_CAP * 8; }
   else return fail(DUALAR_EINVAL, "unknown buffer '%s'", name);
   if (nbytes > avail) return fail(DUALAR_EINVAL, "buffer '%s' holds %lld bytes, %lld requested", name, (long long)avail, (long long)nbytes);

