@@ -130,6 +130,17 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the decode kernel, from the committed ncu capture
+    (profiles/ncu_summary.json, written from `ncu --set full`; null when no capture is committed)."""
+    try:
+        with open(ROOT / "profiles" / "ncu_summary.json") as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read_per_launch"]) + float(d["dram_bytes_write_per_launch"])
+    except Exception:
+        return None
+
+
 def workload_config(cfg, n_gpus, steps):
     return {"workload": "openaudio-s1-mini dual-AR decode, bs=1, prefilled ~10 s VoiceProfile prompt "
                         f"({sum(PROMPT.values())} positions), {steps} generated tokens, T=0.7 top_p=0.8 rp=1.1",
@@ -215,8 +226,10 @@ def main():
         mean_ctx = T + W + K / 2.0
         bytes_step = cfg.algorithmic_bytes_per_token(mean_ctx)
         achieved = bytes_step / (ms_max / 1e3 / K) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "decode-step graph (all kernels of one token)",
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                "peak_source": peak_src,
+                "kernel": ("mega_kernel: the whole decode step as one persistent cooperative kernel, one launch per token"
+                           if launches_step == 1 else "decode-step graph (all kernels of one token)"),
                 "algorithmic_bytes_per_step": bytes_step, "mean_context": mean_ctx}
         cpu_v, cores, sample = cpu_port_tokens_per_s(cfg, sd, args.cpu_steps)
         line = {

@@ -405,7 +405,9 @@ static int build_mega(dualar_engine *e) {
   auto pairs = [](int rows) { return (rows + 1) / 2; };
   if (n_step > DA_M_MAX_PHASES || c.n_layer > DA_M_MAXL || c.n_fast_layer > DA_M_MAXFL || grid > 160 || e->fv > 1024 ||
       pairs(qkv_rows) < grid || pairs(2 * c.intermediate_size) < grid || pairs(fqkv_rows) < grid || pairs(2 * c.fast_intermediate_size) < grid ||
-      G * c.head_dim > 1024 || c.vocab_size > (1 << 18) || (c.num_codebooks - 1) * 2 * fkd / 8 > 3 * DA_M_CTHREADS || c.head_dim < 32) { e->use_mega = false; return 0; }
+      G * c.head_dim > 1024 || c.vocab_size > (1 << 18) || (c.num_codebooks - 1) * 2 * fkd / 8 > 3 * DA_M_CTHREADS || c.head_dim < 32 ||
+      c.dim > 8 * DA_M_CTHREADS || c.intermediate_size > 8 * DA_M_CTHREADS || c.fast_intermediate_size > 8 * DA_M_CTHREADS || qd > 8 * DA_M_CTHREADS || fqkv_rows > 8 * DA_M_CTHREADS ||
+      3 * grid > DA_M_CTHREADS) { e->use_mega = false; return 0; }
   int rc;
   // every broadcast unit vector exists DA_M_REP times, `ustride` units apart
   int umax = qkv_rows; for (int v : {c.dim, qd, c.intermediate_size, fqkv_rows, c.fast_dim, c.fast_intermediate_size, e->fv}) if (v > umax) umax = v;
@@ -498,7 +500,7 @@ static int build_mega(dualar_engine *e) {
     // shared-memory plan (from the decode-step table; the prefill table is a subset and shares it)
     if (variant) {
       const MegaArgs &s0 = *e->ma_step;
-      a.kmax = s0.kmax; a.lg_rows = s0.lg_rows; a.work_bytes = s0.work_bytes; a.kv_bytes = s0.kv_bytes; a.ring_bytes = s0.ring_bytes;
+      a.kmax = s0.kmax; a.lg_rows = s0.lg_rows; a.work_bytes = s0.work_bytes; a.kv_bytes = s0.kv_bytes; a.ring_bytes = s0.ring_bytes; a.plan = s0.plan;
       continue;
     }
     int kmax = 0; size_t max_entry = 0;
@@ -511,7 +513,7 @@ static int build_mega(dualar_engine *e) {
     if ((size_t)4 * DA_TILE * c.head_dim > max_entry) max_entry = (size_t)4 * DA_TILE * c.head_dim;
     size_t work = (size_t)(fqd + 2 * fkd + c.fast_n_head * c.num_codebooks + 4) * 4;
     auto upd = [&](size_t v) { if (v > work) work = v; };
-    upd((size_t)(G * c.head_dim + 2 * c.head_dim + DA_M_CWARPS * G * (2 + c.head_dim)) * 4);      // slow attention: q, new k/v, per-warp partials
+    upd((size_t)(G * c.head_dim + 2 * c.head_dim + DA_M_CWARPS * G * (2 + c.head_dim)) * 4 + 4 * c.head_dim + 64);      // slow attention: q, new k/v, per-warp partials
     upd((size_t)3 * (qd / grid + 2) * e->nsplit * 4);
     upd((size_t)3 * grid * 4 + 256);
     upd((size_t)16384 + (192 + 34) * 8 + 80 * 4 + 64);          // slow head: sort buffer + sampler scratch
@@ -524,8 +526,10 @@ static int build_mega(dualar_engine *e) {
     long long ring = budget / 1024 * 1024;
     if (ring < (long long)(2 * max_entry) || ring < 32 * 1024) { e->use_mega = false; return 0; }
     a.ring_bytes = (int)ring;
-    e->mega_smem = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, a.ring_bytes).total;
+    a.plan = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, a.ring_bytes);
+    e->mega_smem = a.plan.total;
   }
+  { const char *v = getenv("DUALAR_KEEP_FRAC"); if (v) { float fr = (float)atof(v); CU(cudaMemcpyToSymbol(g_keep_frac, &fr, sizeof(float))); } }
   { const char *v = getenv("DUALAR_POLL_NS"); int ns = v ? atoi(v) : 0; CU(cudaMemcpyToSymbol(g_poll_ns, &ns, sizeof(int))); }
   CU(cudaFuncSetAttribute(mega_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
   CU(cudaFuncSetAttribute(mega_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
@@ -815,6 +819,7 @@ extern "C" int dualar_read_buffer(dualar_engine *e, const char *name, void *dst,
   else if (!strcmp(name, "fast_logits")) { src = e->flogits_raw; avail = (int64_t)(c.num_codebooks - 1) * e->fv * 2; }
   else if (!strcmp(name, "tokens")) { src = e->st->tok_out; avail = (int64_t)(c.num_codebooks + 1) * 4; }
   else if (!strcmp(name, "nucleus")) { src = e->st->nucleus; avail = (int64_t)c.num_codebooks * 4; }
+  else if (!strcmp(name, "n_cand")) { src = &e->st->n_cand; avail = 4; }
   else if (!strcmp(name, "qkv")) { src = e->qkv; avail = (int64_t)(c.n_head + 2 * c.n_local_heads) * c.head_dim * 2; }
   else if (!strcmp(name, "y")) { src = e->y; avail = (int64_t)c.n_head * c.head_dim * 2; }
   else if (!strcmp(name, "h")) { src = e->h; avail = (int64_t)c.dim * 2; }

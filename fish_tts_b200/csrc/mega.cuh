@@ -31,9 +31,10 @@
 
 namespace da {
 
-#define DA_M_CWARPS 16
-#define DA_M_CTHREADS 512
-#define DA_M_THREADS 544            // + the producer warp
+#define DA_M_CWARPS 15               // 15 compute warps + the producer warp = 512 threads: 128 registers per thread.  With 16 + 1
+#define DA_M_CTHREADS 480            // warps ptxas is capped at 96 and spills kernel-scope values into the hot loops; the step time
+#define DA_M_THREADS 512             // then moved by +-15% with unrelated code changes
+#define DA_M_PPW ((DA_TILE + DA_M_CWARPS - 1) / DA_M_CWARPS)   // positions of a 64-row K/V tile per warp
 #define DA_M_NB 32                  // ring entries in flight (mbarrier pairs)
 #define DA_M_ENTRY_BYTES 16384      // target size of one ring entry of a GEMV phase
 #define DA_M_MAX_PHASES 400
@@ -61,6 +62,7 @@ struct MPhase {
   int pad_;
 };
 
+struct MegaSmem { uint32_t bars, chg, xb, raw, scratch, work, part, pcnt, lg, kvs, ring, total; };
 struct MegaArgs {
   int n_phases;
   // slow attention (llama.py:242-282)
@@ -82,7 +84,9 @@ struct MegaArgs {
   unsigned int *phase_ctr;   // running phase counter = source of the unit tags; NEVER reset (a request must not see the previous one's tags)
   // shared-memory plan
   int kmax, lg_rows, work_bytes, kv_bytes, ring_bytes;
-  int ustride;           // units between the DA_M_REP replicas of a unit buffer
+  int ustride;           // (unused since the replica experiment; kept for the host-side buffer layout)
+  MegaSmem plan;         // shared-memory offsets: read from parameter space at every use -- thirteen 64-bit pointers held live across
+                         // the phase loop cost ~25 registers under a 96-register cap and made ptxas spill in the hot loops
   MPhase table[DA_M_MAX_PHASES];
 };
 
@@ -127,7 +131,10 @@ __device__ __noinline__ bool poll_chunk(const uint32_t *p, uint32_t tag, float *
 // two 4-unit groups per thread, `lo` and `hi` half a vector apart: both loads of a warp are fully coalesced (16 sectors per
 // request instead of 32 half-used ones), which is worth ~0.15 us per hand-over at 148 pollers (handover_bench2.cu)
 __device__ int g_poll_ns = 0;      // back-off between poll attempts (experiments: DUALAR_POLL_NS)
-__device__ __noinline__ bool poll_pair(const uint32_t *lo, const uint32_t *hi, uint32_t tag, float *f) {
+__device__ float g_keep_frac = 0.7f;  // fraction of the fast-stack lines that ask L2 for evict_last (DUALAR_KEEP_FRAC).  The stack
+                                      // (109 MB) does not fit next to the slow stream: asking for all of it thrashes (ncu: 2.2 GB
+                                      // DRAM reads per token, L2 hit 34%); 0.7 keeps a stable subset (1.69 GB, 46%)
+__device__ __forceinline__ bool poll_pair(const uint32_t *lo, const uint32_t *hi, uint32_t tag, float *f) {
   uint4 a, b;
   int it = 0;
   const int ns = g_poll_ns;
@@ -208,19 +215,22 @@ __device__ __forceinline__ void mma_chunk(uint32_t tile_addr, uint32_t RS, int n
   int row = lane & 15; if (row >= nrows) row = 0;
   const uint32_t addr = tile_addr + (uint32_t)row * RS + (uint32_t)(((lane >> 4) << 3) + (chunk << 7)) * 2u;
   const uint32_t *xp = xw + (chunk << 6) + (lane & 3);
-  uint32_t af[8][4], bfr[8][2];
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(af[s][0]), "=r"(af[s][1]), "=r"(af[s][2]), "=r"(af[s][3]) : "r"(addr + s * 32));
-    bfr[s][0] = xp[s * 8]; bfr[s][1] = xp[s * 8 + 4];
-  }
   float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
 #pragma unroll
-  for (int s = 0; s < 8; s += 2) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(e0), "+f"(e1), "+f"(e2), "+f"(e3) : "r"(af[s][0]), "r"(af[s][1]), "r"(af[s][2]), "r"(af[s][3]), "r"(bfr[s][0]), "r"(bfr[s][1]));
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(o0), "+f"(o1), "+f"(o2), "+f"(o3) : "r"(af[s + 1][0]), "r"(af[s + 1][1]), "r"(af[s + 1][2]), "r"(af[s + 1][3]), "r"(bfr[s + 1][0]), "r"(bfr[s + 1][1]));
+  for (int hb = 0; hb < 8; hb += 4) {        // fragments of four steps at a time (24 registers; all eight spilled under the 96-register cap)
+    uint32_t af[4][4], bfr[4][2];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(af[s][0]), "=r"(af[s][1]), "=r"(af[s][2]), "=r"(af[s][3]) : "r"(addr + (hb + s) * 32));
+      bfr[s][0] = xp[(hb + s) * 8]; bfr[s][1] = xp[(hb + s) * 8 + 4];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s += 2) {
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(e0), "+f"(e1), "+f"(e2), "+f"(e3) : "r"(af[s][0]), "r"(af[s][1]), "r"(af[s][2]), "r"(af[s][3]), "r"(bfr[s][0]), "r"(bfr[s][1]));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(o0), "+f"(o1), "+f"(o2), "+f"(o3) : "r"(af[s + 1][0]), "r"(af[s + 1][1]), "r"(af[s + 1][2]), "r"(af[s + 1][3]), "r"(bfr[s + 1][0]), "r"(bfr[s + 1][1]));
+    }
   }
   v_lo = e0 + o0; v_hi = e2 + o2;     // rows lane/4 and lane/4 + 8 (every B column holds x, so every lane of a group has them)
 }
@@ -233,6 +243,13 @@ __device__ __forceinline__ void store4_xb(bf16 *xb, int e, const float *f) {
   uint2 u;
   u.x = (uint32_t)f2bits(f[0]) | ((uint32_t)f2bits(f[1]) << 16); u.y = (uint32_t)f2bits(f[2]) | ((uint32_t)f2bits(f[3]) << 16);
   *reinterpret_cast<uint2 *>(xb + e) = u;
+}
+// dpl (1, 2 or 4) consecutive bf16 values as floats with ONE load; the rest of f[4] is zero
+__device__ __forceinline__ void ld_bf16_dpl(const bf16 *p, int dpl, float *f) {
+  f[0] = f[1] = f[2] = f[3] = 0.f;
+  if (dpl == 4) unpack4(*reinterpret_cast<const uint2 *>(p), f);
+  else if (dpl == 2) { const uint32_t u = *reinterpret_cast<const uint32_t *>(p); f[0] = __uint_as_float(u << 16); f[1] = __uint_as_float(u & 0xffff0000u); }
+  else f[0] = bf2f(*p);
 }
 // eight consecutive activation values (bf16-exact floats) -> packed bf16, one 16-byte store
 __device__ __forceinline__ void store_chunk_xb(bf16 *xb, int c, const float *f) {
@@ -271,7 +288,6 @@ __device__ __forceinline__ uint32_t ring_place(RingCursor &r, uint32_t size, uin
 }
 
 // ---- shared-memory plan (host and device) -----------------------------------------------------------------------------------
-struct MegaSmem { uint32_t bars, chg, xb, raw, scratch, work, part, pcnt, lg, kvs, ring, total; };
 static inline __host__ __device__ MegaSmem mega_smem_plan(int kmax, int dim_max, int lg_rows, int work_bytes, int kv_bytes, int ring_bytes) {
   MegaSmem m; uint32_t o = 0;
   m.bars = o; o += 2 * DA_M_NB * 8;
@@ -326,24 +342,25 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int bid = blockIdx.x, grid = gridDim.x;
   const int dim_max = a.dim > a.fdim ? a.dim : a.fdim;
-  const MegaSmem sp = mega_smem_plan(a.kmax, dim_max, a.lg_rows, a.work_bytes, a.kv_bytes, a.ring_bytes);
-  uint64_t *full = reinterpret_cast<uint64_t *>(sm + sp.bars), *empty = full + DA_M_NB;
-  uint32_t *chg = reinterpret_cast<uint32_t *>(sm + sp.chg);
-  bf16 *xb2 = reinterpret_cast<bf16 *>(sm + sp.xb);
-  float *raw = reinterpret_cast<float *>(sm + sp.raw);
-  float *scratch = reinterpret_cast<float *>(sm + sp.scratch);
-  unsigned char *work = sm + sp.work;
-  float *part = reinterpret_cast<float *>(sm + sp.part);
-  volatile int *pcnt = reinterpret_cast<volatile int *>(sm + sp.pcnt), *pgen = pcnt + DA_M_PT;
-  uint16_t *lg = reinterpret_cast<uint16_t *>(sm + sp.lg);
-  bf16 *kvs = reinterpret_cast<bf16 *>(sm + sp.kvs);
-  unsigned char *ring = sm + sp.ring;
+#define sm_full (reinterpret_cast<uint64_t *>(sm + a.plan.bars))
+#define sm_empty (reinterpret_cast<uint64_t *>(sm + a.plan.bars) + DA_M_NB)
+#define sm_chg (reinterpret_cast<uint32_t *>(sm + a.plan.chg))
+#define sm_xb2 (reinterpret_cast<bf16 *>(sm + a.plan.xb))
+#define sm_raw (reinterpret_cast<float *>(sm + a.plan.raw))
+#define sm_scratch (reinterpret_cast<float *>(sm + a.plan.scratch))
+#define sm_work (sm + a.plan.work)
+#define sm_part (reinterpret_cast<float *>(sm + a.plan.part))
+#define sm_pcnt (reinterpret_cast<volatile int *>(sm + a.plan.pcnt))
+#define sm_pgen (reinterpret_cast<volatile int *>(sm + a.plan.pcnt) + DA_M_PT)
+#define sm_lg (reinterpret_cast<uint16_t *>(sm + a.plan.lg))
+#define sm_kvs (reinterpret_cast<bf16 *>(sm + a.plan.kvs))
+#define sm_ring (sm + a.plan.ring)
   const uint32_t ring_bytes = (uint32_t)a.ring_bytes;
 
   if (TL) tl_mark(a, 0, 0);
-  if (tid < 2 * DA_M_PT) pcnt[tid] = 0;      // chunk counters and fold generations of the partial-sum slots
+  if (tid < 2 * DA_M_PT) sm_pcnt[tid] = 0;      // chunk counters and fold generations of the partial-sum slots
   if (tid == 0) {
-    for (int i = 0; i < DA_M_NB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < DA_M_NB; ++i) { mbar_init(&sm_full[i], 1); mbar_init(&sm_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // request state: read once, before anything of this step can have changed it
@@ -357,20 +374,22 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
 
   // =================================================== producer ===========================================================
   if (w == DA_M_CWARPS) {
-    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    // the fast stack is re-read num_codebooks times per token: ask L2 to keep (a fraction of) it, stream everything else
+    uint64_t pol_keep; { const float fr = g_keep_frac; asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(fr)); }
+    const uint64_t pol_stream = policy_evict_first();
     RingCursor rc = {0u, 0u};
     uint32_t used = 0, tail = 0;
     bool ok = true;
-    // lane 0 owns the ring bookkeeping; returns the smem offset of the new entry (rc.seq - 1 is its index)
+    // lane 0 owns the sm_ring bookkeeping; returns the smem offset of the new entry (rc.seq - 1 is its index)
     auto reserve = [&](uint32_t size) -> uint32_t {
       RingCursor probe = rc; uint32_t charged;
       ring_place(probe, size, ring_bytes, charged);
       while (used + charged > ring_bytes || rc.seq - tail >= DA_M_NB) {
-        ok = mbar_wait_idle(&empty[tail % DA_M_NB], (tail / DA_M_NB) & 1u, 100) && ok;
-        used -= chg[tail % DA_M_NB]; ++tail;
+        ok = mbar_wait_idle(&sm_empty[tail % DA_M_NB], (tail / DA_M_NB) & 1u, 100) && ok;
+        used -= sm_chg[tail % DA_M_NB]; ++tail;
       }
       const uint32_t at = ring_place(rc, size, ring_bytes, charged);
-      chg[(rc.seq - 1) % DA_M_NB] = charged; used += charged;
+      sm_chg[(rc.seq - 1) % DA_M_NB] = charged; used += charged;
       return at;
     };
     for (int ph = 0; ph < nph; ++ph) {
@@ -385,10 +404,10 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           uint32_t at = 0, bi = 0;
           if (lane == 0) {
             at = reserve((uint32_t)n * RS); bi = (rc.seq - 1) % DA_M_NB;
-            mbar_expect_tx(&full[bi], (uint32_t)n * row_bytes);
+            mbar_expect_tx(&sm_full[bi], (uint32_t)n * row_bytes);
           }
           at = __shfl_sync(0xffffffffu, at, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
-          if (lane < n) bulk_g2s(ring + at + (uint32_t)lane * RS, d.W + (size_t)(gp.r0 + 16 * t + lane) * d.K, row_bytes, &full[bi], pol);
+          if (lane < n) bulk_g2s(sm_ring + at + (uint32_t)lane * RS, d.W + (size_t)(gp.r0 + 16 * t + lane) * d.K, row_bytes, &sm_full[bi], pol);
         }
       } else if (d.kind == MK_ATTN) {
         const AttnPart ap = attn_part(pos, a.nkv, a.nsplit_max, bid);
@@ -398,11 +417,11 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             if (n_old <= 0) continue;
             const uint32_t bytes = (uint32_t)n_old * a.hd * 2u;
             const uint32_t at = reserve(2 * bytes);
-            uint64_t *fb = &full[(rc.seq - 1) % DA_M_NB];
+            uint64_t *fb = &sm_full[(rc.seq - 1) % DA_M_NB];
             mbar_expect_tx(fb, 2 * bytes);
             const size_t src = ((size_t)ap.g * a.S + (size_t)t * DA_TILE) * a.hd;
-            bulk_g2s(ring + at, a.kc[d.layer] + src, bytes, fb, pol_stream);
-            bulk_g2s(ring + at + bytes, a.vc[d.layer] + src, bytes, fb, pol_stream);
+            bulk_g2s(sm_ring + at, a.kc[d.layer] + src, bytes, fb, pol_stream);
+            bulk_g2s(sm_ring + at + bytes, a.vc[d.layer] + src, bytes, fb, pol_stream);
           }
         }
         __syncwarp();
@@ -420,23 +439,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
   bool ok = true;
   unsigned long long wait_ns = 0ull;
   int sparity = 0;
-  // request parameters: read once (every access to the state is an L2 round trip on the critical path)
-  const float rp_eff = eff_rep_penalty(st);
-  const int use_pen = st->use_penalty;
-  const NoiseSrc ns = noise_src(st);
-  const float T_eff = eff_temperature(st);
-  const unsigned long long c_max_req = cmax_from_top_p(st->top_p);
-  const size_t rep_off = (size_t)(bid % DA_M_REP) * (size_t)a.ustride;
-  auto put1 = [&](uint32_t *out, uint32_t u) {
-#pragma unroll
-    for (int r = 0; r < DA_M_REP; ++r) st_unit(out + (size_t)r * a.ustride, u);
-  };
-  auto put2 = [&](uint32_t *out, uint32_t u0, uint32_t u1) {     // two adjacent units, 8-byte aligned
-    const unsigned long long v = ((unsigned long long)u1 << 32) | u0;
-#pragma unroll
-    for (int r = 0; r < DA_M_REP; ++r) st_unit8(out + (size_t)r * a.ustride, v);
-  };
-  // the next ring entry: every warp advances the cursor; only warps that read the entry wait for it to land.  An entry is
+  // (request parameters -- repetition penalty, temperature, top-p, noise source -- are read from the state inside the logits /
+  //  sampler phases that use them: values held live across the whole phase loop are what ptxas spills first)
+  // the next sm_ring entry: every warp advances the cursor; only warps that read the entry wait for it to land.  An entry is
   // released by ONE arrival -- lane 31 of the warp that folds the tile (all its units have been read by then; lane 31 never
   // has global stores in flight, which a release-type operation would wait for), or one thread after the CTA barrier that
   // ends an attention tile.
@@ -447,10 +452,10 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     bar_idx = i % DA_M_NB; parity = (i / DA_M_NB) & 1u;
     return at;
   };
-  long long wait_cyc = 0;      // cycles this thread spent waiting for ring entries (reported per CTA when the timeline is on)
+  long long wait_cyc = 0;      // cycles this thread spent waiting for sm_ring entries (reported per CTA when the timeline is on)
   auto landed = [&](uint32_t bar_idx, uint32_t parity) {
-    if (TL && a.tl) { const long long c0 = clock64(); ok = mbar_wait_idle(&full[bar_idx], parity, 20) && ok; const long long dc = clock64() - c0; wait_cyc += dc; wait_ns += (unsigned long long)dc / 2; }
-    else ok = mbar_wait_idle(&full[bar_idx], parity, 20) && ok;
+    if (TL && a.tl) { const long long c0 = clock64(); ok = mbar_wait_idle(&sm_full[bar_idx], parity, 20) && ok; const long long dc = clock64() - c0; wait_cyc += dc; wait_ns += (unsigned long long)dc / 2; }
+    else ok = mbar_wait_idle(&sm_full[bar_idx], parity, 20) && ok;
   };
   // folds completed on each partial-sum slot in earlier phases (the generation counters in shared memory never reset)
   int gen_base[DA_M_PT];
@@ -462,27 +467,27 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
   for (int ph = 0; ph < nph; ++ph) {
     const MPhase &d = a.table[ph];
     const uint32_t tag = tag_of(ph), in_tag = tag_of(d.in_ph);
-    const uint32_t *in = d.in ? d.in + rep_off : nullptr;
+    const uint32_t *in = d.in;
     if (TL) tl_mark(a, 1 + ph, 0);
     if (TL && a.tl && tid == 0 && ph > 0) tl_put(a, ph, 6, wait_ns);
     wait_ns = 0ull;
-    float *sc = scratch + sparity * 16; sparity ^= 1;
+    float *sc = sm_scratch + sparity * 16; sparity ^= 1;
 
     if (d.kind == MK_GEMV) {
       const int K = d.K, nchunk = K >> 7;
       const GemvPart gp = gemv_part(d.rows, d.pq, d.prem, bid);
-      bf16 *xb = xb2 + (size_t)(ph & 1) * a.kmax;      // staging buffer of this phase; the other one may still be read by a slow warp of the previous phase
+      bf16 *xb = sm_xb2 + (size_t)(ph & 1) * a.kmax;      // staging buffer of this phase; the other one may still be read by a slow warp of the previous phase
       // ---- (A) stage the input vector as packed bf16 (every activation is a bf16 value) ------------------------------------------
       if (FULL && d.pro == MP_FASTATTN) {
         // fast-layer attention for position d.pos (llama.py:246-251, 285-309), recomputed by every CTA.  After the RoPE
         // barrier one WARP owns one head end to end (scores, softmax, P@V), so nothing else synchronises the CTA.
         const int nh = a.fnh, nkv = a.fnkv, hd = a.fhd, qd = nh * hd, kd = nkv * hd, FG = nh / nkv;
         const int p = d.pos, P = p + 1;
-        float *q = reinterpret_cast<float *>(work), *kcur = q + qd, *vcur = kcur + kd;
-        // The K / V rows of this token's earlier codebook positions live in a per-CTA scratch in global memory (L2): keeping
-        // all layers' rows in shared memory cost 80 KB of the weight ring.  This layer's rows are requested BEFORE the poll
+        float *q = reinterpret_cast<float *>(sm_work), *kcur = q + qd, *vcur = kcur + kd;
+        // The K / V rows of this token's earlier codebook positions live in a per-CTA sm_scratch in global memory (L2): keeping
+        // all layers' rows in shared memory cost 80 KB of the weight sm_ring.  This layer's rows are requested BEFORE the poll
         // for the new q | k | v, so the L2 round trip hides behind the hand-over wait.
-        bf16 *kv_l = kvs;                                             // [pos][k | v][kd] bf16, this layer only
+        bf16 *kv_l = sm_kvs;                                             // [pos][k | v][kd] bf16, this layer only
         bf16 *kv_g = a.fkv + ((size_t)bid * a.fl + d.layer) * a.ncb * 2 * kd;
         uint4 pre[3];
         const int n16 = p * 2 * kd / 8;                                // 16-byte pieces of the rows of positions < p
@@ -536,11 +541,11 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           // scores: 4 lanes per position, hd/4 elements each; bf16(q @ k^T), then bf16(* scale)   (llama.py:304)
           float sc_j = -INFINITY;      // lane j < P ends up with the score of position j
           for (int j0 = 0; j0 < P; j0 += 8) {
-            const int j = j0 + (lane >> 2), part = lane & 3, ne = hd >> 2;
+            const int j = j0 + (lane >> 2), prt = lane & 3, ne = hd >> 2;
             float acc = 0.f;
             if (j < P) {
-              const bf16 *kk = kv_l + ((size_t)j * 2 + 0) * kd + g * hd + part * ne;
-              const float *qp = qq + part * ne;
+              const bf16 *kk = kv_l + ((size_t)j * 2 + 0) * kd + g * hd + prt * ne;
+              const float *qp = qq + prt * ne;
               for (int x = 0; x < ne; x += 2) {
                 const float2 kf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kk + x));
                 acc = fmaf(qp[x], kf.x, acc); acc = fmaf(qp[x + 1], kf.y, acc);
@@ -558,7 +563,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           const float sum = warp_sum(ej);
           const float pj = lane < P ? rbf(ej / sum) : 0.f;
           // y = bf16(p @ v)   (llama.py:309): lane owns dims 2*lane, 2*lane+1 (+64 per extra round)
-          for (int db = 0; db < hd; db += 64) {       // uniform trip count: every lane takes part in the shuffles
+          for (int db = 0; db < hd; db += 64) {       // uniform trip count: every lane takes sm_part in the shuffles
             const int d0 = db + 2 * lane;
             const bool liv = d0 < hd;
             float y0 = 0.f, y1 = 0.f;
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           }
         } else if (mine) ok = poll_pair(in + e_lo, in + e_hi, in_tag, v) && ok;
         if (mine && (d.flags & (MF_SAVE0 | MF_SAVE1))) {
-          float *dst = raw + ((d.flags & MF_SAVE1) ? dim_max : 0);
+          float *dst = sm_raw + ((d.flags & MF_SAVE1) ? dim_max : 0);
           *reinterpret_cast<float4 *>(dst + e_lo) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4 *>(dst + e_hi) = make_float4(v[4], v[5], v[6], v[7]);
         }
@@ -640,10 +645,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       //      shared memory; the warp that completes a tile's last chunk folds them in chunk order and runs the epilogue,
       //      one row per lane -- no CTA-wide barrier between the dot products and the stores.
       int pen_id = -1;      // penalised ids of the logits epilogues live in lanes 0..15 of every warp
+      float rp_eff = 1.f; int use_pen = 0;
+      if (FULL && (d.epi == ME_FASTLOGITS || d.epi == ME_SLOWLOGITS)) { rp_eff = eff_rep_penalty(st); use_pen = st->use_penalty; }
       if (FULL && d.epi == ME_FASTLOGITS && use_pen && lane < DA_WIN) pen_id = st->win[(d.pos + 1) * DA_WIN + lane];
       if (FULL && d.epi == ME_SLOWLOGITS && use_pen && lane < a.n_rows_tok) pen_id = st->win[lane * DA_WIN];     // previous_tokens[:, 0]
       float wmax = -INFINITY;
-      const float *resv = raw + ((d.flags & MF_RES1) ? dim_max : 0);
+      const float *resv = sm_raw + ((d.flags & MF_RES1) ? dim_max : 0);
       const uint32_t RS = row_stride(K);
       const uint32_t *xw = reinterpret_cast<const uint32_t *>(xb);
       {
@@ -659,20 +666,20 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
 #pragma unroll
           for (int i = 1; i < DA_M_PT; ++i) if (slot == i) gb = gen_base[i];
           const int gen_need = gb + t / DA_M_PT;
-          float *pslot = part + (size_t)slot * (a.kmax >> 7) * 16;
+          float *pslot = sm_part + (size_t)slot * (a.kmax >> 7) * 16;
           for (; u < (t + 1) * nchunk; u += DA_M_CWARPS) {
             const int c = u - t * nchunk;
             float v_lo, v_hi;
-            mma_chunk(smem_u32(ring + at), RS, n, xw, c, lane, v_lo, v_hi);
+            mma_chunk(smem_u32(sm_ring + at), RS, n, xw, c, lane, v_lo, v_hi);
             // the slot is free once the tile DA_M_PT before this one has been folded
-            if (t >= DA_M_PT) { int it = 0; while (pgen[slot] != gen_need) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
+            if (t >= DA_M_PT) { int it = 0; while (sm_pgen[slot] != gen_need) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
             if ((lane & 3) == 0) { pslot[c * 16 + (lane >> 2)] = v_lo; pslot[c * 16 + 8 + (lane >> 2)] = v_hi; }
             __syncwarp();
             int last = 0;
-            if (lane == 31) last = (atom_add_acq_rel_cta(&pcnt[slot], 1) == nchunk - 1);      // publishes this warp's partials, observes the others' 
+            if (lane == 31) last = (atom_add_acq_rel_cta(&sm_pcnt[slot], 1) == nchunk - 1);      // publishes this warp's partials, observes the others' 
             last = __shfl_sync(0xffffffffu, last, 31);
             if (last) {
-              // every unit of the tile is done: fold in chunk order (lane r owns row r), free the slot and the ring entry
+              // every unit of the tile is done: fold in chunk order (lane r owns row r), free the slot and the sm_ring entry
               const int r = lane & 15, row = gp.r0 + 16 * t + r;
               const bool live = lane < 16 && r < n;
               float v = 0.f;
@@ -684,18 +691,18 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                 for (int cc = 0; cc < 8; ++cc) if (c8 + cc < nchunk) v += pv[cc];
               }
               __syncwarp();
-              if (lane == 31) { pcnt[slot] = 0; __threadfence_block(); pgen[slot] = gen_need + 1; mbar_arrive(&empty[bi]); }
+              if (lane == 31) { sm_pcnt[slot] = 0; __threadfence_block(); sm_pgen[slot] = gen_need + 1; mbar_arrive(&sm_empty[bi]); }
               if (live && d.bias) v += bf2f(d.bias[row]);
               if (d.epi == ME_STORE) {
-                if (live) put1(d.out + row, make_unit(v, tag));
+                if (live) st_unit(d.out + row, make_unit(v, tag));
               } else if (d.epi == ME_RESIDUAL) {
-                if (live) put1(d.out + row, make_unit(resv[row] + rbf(v), tag));
+                if (live) st_unit(d.out + row, make_unit(resv[row] + rbf(v), tag));
               } else if (d.epi == ME_SWIGLU) {
                 const float up = __shfl_down_sync(0xffffffffu, v, 1);      // row 2j = w1 (gate), row 2j+1 = w3 (up)
                 if (live && !(r & 1)) {
                   const float gg = rbf(v), uu = rbf(up);
                   const float sg = rbf(gg / (1.0f + expf(-gg)));
-                  put1(d.out + (row >> 1), make_unit(__fmul_rn(sg, uu), tag));
+                  st_unit(d.out + (row >> 1), make_unit(__fmul_rn(sg, uu), tag));
                 }
               } else if (FULL) {
                 float z = rbf(v);
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                 } else if (live) {   // ME_SLOWLOGITS: logits stay in this CTA's shared memory for the sampler phases; global copies for read-back / fallback
                   a.logits_raw[row] = f2bf(z);
                   if (hit) z = penalise(z, rp_eff);
-                  a.logits[row] = f2bf(z); lg[16 * t + r] = f2bits(z); wmax = fmaxf(wmax, z);
+                  a.logits[row] = f2bf(z); sm_lg[16 * t + r] = f2bits(z); wmax = fmaxf(wmax, z);
                 }
               }
             }
@@ -741,7 +748,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       if (FULL && d.epi == ME_FASTLOGITS && bid == 0) {
         // warps 0-3 of CTA 0 draw the code and publish its embedding as the next pass's input
         __shared__ uint32_t s_tok;
-        unsigned long long *scr = reinterpret_cast<unsigned long long *>(work);
+        unsigned long long *scr = reinterpret_cast<unsigned long long *>(sm_work);
         if (w < 4) {
           typedef BlockNamed<2, 128> G4;
           const int V = a.fv;
@@ -771,11 +778,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           for (int i = 0; i < DA_G_IPT; ++i) if (it8[i] != 0xFFFFFFFFu) es.s += (unsigned long long)(expf(bits2f(key_bf16(0xFFFFu - (it8[i] >> 16))) - spm.m) * DA_FIX2_SCALE);
           es = block_reduce<G4>(es, scr, par);
           spm.S = __ull2float_rn(es.s) * (1.0f / DA_FIX2_SCALE);
-          spm.T_bf = T_eff;
-          spm.c_max = c_max_req;
+          spm.T_bf = eff_temperature(st);
+          spm.c_max = cmax_from_top_p(st->top_p);
+          const NoiseSrc nsrc = noise_src(st);
           G4::sync();
           if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 1, gtime());
-          uint32_t tok = sample_sorted<DA_G_IPT, 128, G4>(it8, (uint32_t)V, true, nullptr, spm, ns, (uint32_t)d.pos, a.noise_off0 + (long long)(d.pos - 1) * a.fv,
+          uint32_t tok = sample_sorted<DA_G_IPT, 128, G4>(it8, (uint32_t)V, true, nullptr, spm, nsrc, (uint32_t)d.pos, a.noise_off0 + (long long)(d.pos - 1) * a.fv,
                                                           &st->nucleus[d.pos], reinterpret_cast<uint32_t *>(scr + 256), scr);
           if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (tid == 0) st->err = 3; }
           if (tid == 0) { s_tok = tok; st->tok_out[d.pos + 1] = (int)tok; }
@@ -784,18 +792,18 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         cbar();
         if (d.pos < a.ncb - 1) {
           const uint32_t tok = s_tok;
-          for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) put1(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
+          for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
         }
       }
       if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 3, gtime());
       // No CTA barrier ends a plain GEMV phase: the staging buffer alternates, the partial-sum slots are handed over by their
       // generation counters, and the first barrier of the next phase's staging cannot be passed before every fold of this
-      // phase is done.  The head phases keep one (work / lg are reused by the sampler phases that follow).
+      // phase is done.  The head phases keep one (sm_work / sm_lg are reused by the sampler phases that follow).
       if (FULL && (d.epi == ME_SLOWLOGITS || d.epi == ME_FASTLOGITS)) cbar();
 
     } else if (d.kind == MK_ATTN) {
       // ---- slow-layer attention for one query position: split-KV flash-decode (llama.py:242-282 under SDPBackend.MATH) ---------
-      // CTA (kv head g, split) walks its 64-position tiles from the ring.  Inside the CTA the positions of a tile are dealt to
+      // CTA (kv head g, split) walks its 64-position tiles from the sm_ring.  Inside the CTA the positions of a tile are dealt to
       // the 16 warps; every warp keeps its own running (max, sum, output) in registers -- lane l owns dims hd/32*l.. of all G
       // query heads -- and the warps meet once, in shared memory, after the last tile.  fp32 throughout, like torch's math
       // SDPA (q and k both scaled by sqrt(scale)); bf16 only at the very end (merge phase).
@@ -803,9 +811,10 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       if (ap.active) {
         const int hd = a.hd, g = ap.g, L = ap.L, dpl = hd >> 5;       // dims per lane (1, 2 or 4)
         const int qd = a.nh * hd, kd = a.nkv * hd;
-        float *q = reinterpret_cast<float *>(work);
+        float *q = reinterpret_cast<float *>(sm_work);
         float *knew = q + G * hd, *vnew = knew + hd;
         float *pm = vnew + hd, *pl = pm + DA_M_CWARPS * G, *po = pl + DA_M_CWARPS * G;       // per-warp partials: [16][G], [16][G], [16][G*hd]
+        bf16 *knb = reinterpret_cast<bf16 *>(po + (size_t)DA_M_CWARPS * G * hd), *vnb = knb + hd;   // the new K / V row as bf16, laid out like a tile row
         const bool owns_new = (pos / DA_TILE) >= ap.t0 && (pos / DA_TILE) < ap.t1;
         {   // one 8-unit chunk per thread: G*hd/8 chunks of q, then hd/8 of the new k and of the new v
           const int nq = (G * hd) >> 3, nk = owns_new ? (hd >> 3) : 0;
@@ -821,6 +830,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             for (int j = 0; j < 8; ++j) dst[j] = t[j];
           }
         }
+        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 0, gtime());
         cbar();
         const bf16 *rope_row = a.rope + (size_t)pos * hd;
         for (int h = w; h < G + (owns_new ? 1 : 0); h += DA_M_CWARPS) {      // one warp per head vector: qk-norm, RoPE, then its follow-up
@@ -830,13 +840,16 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           } else {
             head_norm_rope(knew, hd, a.kn[d.layer], a.eps, rope_row, lane);
             for (int e = lane; e < hd; e += 32) {   // KVCache.update (llama.py:142-149)
-              a.kc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(knew[e]);
-              a.vc[d.layer][((size_t)g * a.S + pos) * hd + e] = f2bf(vnew[e]);
+              const bf16 kb = f2bf(knew[e]), vb = f2bf(vnew[e]);
+              knb[e] = kb; vnb[e] = vb;
+              a.kc[d.layer][((size_t)g * a.S + pos) * hd + e] = kb;
+              a.vc[d.layer][((size_t)g * a.S + pos) * hd + e] = vb;
             }
           }
         }
         cbar();
         if (TL) tl_mark(a, 1 + ph, 1);
+        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 1, gtime());
         // Running (max, sum, output) of every warp live in its private slice of shared memory (pm / pl / po) and are pulled into
         // registers for two query heads at a time, so one code path serves every GQA group size and head dimension (dims per lane
         // dpl = hd / 32 <= 4) without per-shape instantiations -- unexecuted variants measurably slowed the whole kernel down.
@@ -854,8 +867,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             uint32_t par;
             const uint32_t at = place(2 * bytes, bi, par);
             landed(bi, par);
-            kt = reinterpret_cast<const bf16 *>(ring + at); vt = reinterpret_cast<const bf16 *>(ring + at + bytes);
+            kt = reinterpret_cast<const bf16 *>(sm_ring + at); vt = reinterpret_cast<const bf16 *>(sm_ring + at + bytes);
           }
+          if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 3, gtime());
           for (int h0 = 0; h0 < G; h0 += 2) {
             float qr[2][4], m_run[2], l_run[2], o_acc[2][4];
 #pragma unroll
@@ -870,29 +884,53 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                 o_acc[hh][i] = iv ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
               }
             }
-            for (int j = w; j < nrow; j += DA_M_CWARPS) {
-              float kf[4], vf[4];
+            // a warp owns at most four positions of a 64-row tile: all their scores first (independent dot products and shuffle
+            // trees overlap), then one running-max update and the P@V accumulation
+            float sj[DA_M_PPW][2];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                kf[i] = 0.f; vf[i] = 0.f;
-                if (i < dpl) {
-                  const int e = lane * dpl + i;
-                  kf[i] = __fmul_rn(j < n_old ? bf2f(kt[(size_t)j * hd + e]) : knew[e], a.sf);
-                  vf[i] = j < n_old ? bf2f(vt[(size_t)j * hd + e]) : vnew[e];
-                }
-              }
+            for (int jj = 0; jj < DA_M_PPW; ++jj) {
+              const int j = w + jj * DA_M_CWARPS;
+              float kf[4];
+              ld_bf16_dpl((j < n_old ? kt + j * hd : knb) + lane * dpl, dpl, kf);      // (rows past nrow read the new-row buffer; their scores are masked below)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) kf[i] = __fmul_rn(kf[i], a.sf);
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
-                if (h0 + hh < G) {
-                  float sdot = 0.f;
+                float sdot = 0.f;
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) sdot = fmaf(qr[hh][i], kf[i], sdot);
-                  sdot = warp_sum(sdot);
-                  const float m_new = fmaxf(m_run[hh], sdot);
-                  const float sc_old = expf(m_run[hh] - m_new), pj = expf(sdot - m_new);     // exp(-inf) = 0 on the first position
-                  l_run[hh] = l_run[hh] * sc_old + pj; m_run[hh] = m_new;
+                for (int i = 0; i < 4; ++i) sdot = fmaf(qr[hh][i], kf[i], sdot);
+                sdot = warp_sum(sdot);
+                sj[jj][hh] = (j < nrow && h0 + hh < G) ? sdot : -INFINITY;
+              }
+            }
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(pj, vf[i], o_acc[hh][i] * sc_old);
+            for (int hh = 0; hh < 2; ++hh) {
+              float m_new = m_run[hh];
+#pragma unroll
+              for (int jj = 0; jj < DA_M_PPW; ++jj) m_new = fmaxf(m_new, sj[jj][hh]);
+              if (m_new != -INFINITY) {
+                const float sc_old = expf(m_run[hh] - m_new);      // exp(-inf) = 0 before the first position
+                l_run[hh] *= sc_old; m_run[hh] = m_new;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o_acc[hh][i] *= sc_old;
+#pragma unroll
+                for (int jj = 0; jj < DA_M_PPW; ++jj) sj[jj][hh] = expf(sj[jj][hh] - m_new);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < DA_M_PPW; ++jj) sj[jj][hh] = 0.f;
+              }
+            }
+#pragma unroll
+            for (int jj = 0; jj < DA_M_PPW; ++jj) {
+              const int j = w + jj * DA_M_CWARPS;
+              if (j < nrow) {
+                float vf[4];
+                ld_bf16_dpl((j < n_old ? vt + j * hd : vnb) + lane * dpl, dpl, vf);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  l_run[hh] += sj[jj][hh];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(sj[jj][hh], vf[i], o_acc[hh][i]);
                 }
               }
             }
@@ -907,30 +945,40 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             }
             __syncwarp();
           }
-          if (n_old > 0) {      // every warp is past its last read of the tile: one arrival releases the ring entry
+          if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 4, gtime());
+          if (n_old > 0) {      // every warp is past its last read of the tile: one arrival releases the sm_ring entry
             cbar();
-            if (tid == DA_M_CTHREADS - 1) mbar_arrive(&empty[bi]);
+            if (tid == DA_M_CTHREADS - 1) mbar_arrive(&sm_empty[bi]);
           }
         }
+        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 2, gtime());
         // thread e = (h, d) folds the 16 partials in warp order
         cbar();
         const uint32_t t32 = tag32_of(ph);
         unsigned long long *pog = a.part_o + (((size_t)g * a.nsplit_max + ap.split) * G) * hd;
         unsigned long long *pmlg = a.part_ml + (((size_t)g * a.nsplit_max + ap.split) * G) * 2;
+        // scale factor of every (warp, head) once, in place of the warp's max; then thread e = (h, d) sums 16 scaled partials
+        float *pmax = pl + DA_M_CWARPS * G - DA_M_CWARPS * G;      // (pl itself keeps the sums)
+        (void)pmax;
+        if (tid < G) {
+          float m = -INFINITY;
+          for (int ww = 0; ww < DA_M_CWARPS; ++ww) m = fmaxf(m, pm[ww * G + tid]);
+          q[tid] = m;                                            // q is dead after the walk
+        }
+        cbar();
+        if (tid < DA_M_CWARPS * G) { const int h = tid % G; const float v = pm[tid]; pm[tid] = v == -INFINITY ? 0.f : expf(v - q[h]); }
+        cbar();
         for (int e = tid; e < G * hd; e += DA_M_CTHREADS) {
           const int h = e / hd, dd = e - h * hd;
-          float m = -INFINITY;
-#pragma unroll
-          for (int ww = 0; ww < DA_M_CWARPS; ++ww) m = fmaxf(m, pm[ww * G + h]);
           float l = 0.f, o = 0.f;
 #pragma unroll
           for (int ww = 0; ww < DA_M_CWARPS; ++ww) {
-            const float sc_w = pm[ww * G + h] == -INFINITY ? 0.f : expf(pm[ww * G + h] - m);      // a warp without positions
+            const float sc_w = pm[ww * G + h];
             l = fmaf(pl[ww * G + h], sc_w, l);
             o = fmaf(po[((size_t)ww * G + h) * hd + dd], sc_w, o);
           }
           st_unit8(pog + e, make_unit8(__float_as_uint(o), t32));
-          if (dd == 0) { st_unit8(pmlg + h * 2, make_unit8(__float_as_uint(m), t32)); st_unit8(pmlg + h * 2 + 1, make_unit8(__float_as_uint(l), t32)); }
+          if (dd == 0) { st_unit8(pmlg + h * 2, make_unit8(__float_as_uint(q[h]), t32)); st_unit8(pmlg + h * 2 + 1, make_unit8(__float_as_uint(l), t32)); }
         }
         cbar();
       }
@@ -941,7 +989,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       const AttnPart ap = attn_part(pos, a.nkv, a.nsplit_max, bid);
       const int hd = a.hd, E = a.nh * hd, ns = ap.nsplit_eff;
       const int e0 = (int)(((long long)E * bid) / grid), e1 = (int)(((long long)E * (bid + 1)) / grid), ne = e1 - e0;
-      float *mo = reinterpret_cast<float *>(work), *mm = mo + ne * ns, *ml = mm + ne * ns;    // [ne][ns] each
+      float *mo = reinterpret_cast<float *>(sm_work), *mm = mo + ne * ns, *ml = mm + ne * ns;    // [ne][ns] each
       const uint32_t t32 = tag32_of(d.in_ph);
       for (int t = tid; t < ne * ns; t += DA_M_CTHREADS) {
         const int i = t / ns, s = t - i * ns, e = e0 + i;
@@ -965,7 +1013,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           l = fmaf(ml[i * ns + s], sc_s, l);
           o = fmaf(mo[i * ns + s], sc_s, o);
         }
-        put1(d.out + e0 + i, make_unit(o / l, tag));
+        st_unit(d.out + e0 + i, make_unit(o / l, tag));
       }
       cbar();
       if (TL) tl_mark(a, 1 + ph, 2);
@@ -986,12 +1034,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       const float thr = m - a.delta;
       Red r = {0ull, 0, -1};
       for (int i = tid; i < h_cnt; i += DA_M_CTHREADS) {
-        const float z = bits2f(lg[i]);
+        const float z = bits2f(sm_lg[i]);
         r.s += (unsigned long long)(expf(z - m) * DA_FIX2_SCALE);
         r.c += z >= thr;
       }
       int par = 0;
-      r = block_reduce<CBlock>(r, reinterpret_cast<unsigned long long *>(work), par);
+      r = block_reduce<CBlock>(r, reinterpret_cast<unsigned long long *>(sm_work), par);
       if (tid == 0) {
         const uint32_t o32 = tag32_of(ph);
         st_unit8(a.hcs + 3 * bid + 0, make_unit8((uint32_t)r.c, o32));
@@ -1004,7 +1052,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     } else if (FULL && d.kind == MK_HCAND) {
       // ---- slow head, stage 3: candidates (z >= max - delta) of every CTA into one list; CTA 0 samples (inference.py:47-80) ------
       const uint32_t t32 = tag32_of(d.in_ph), tag30 = tag32_of(ph) & 0x3FFFFFFFu;
-      uint32_t *hv = reinterpret_cast<uint32_t *>(work);        // [3*grid] payloads, then 4 words of results
+      uint32_t *hv = reinterpret_cast<uint32_t *>(sm_work);        // [3*grid] payloads, then 4 words of results
       __shared__ uint32_t s_base, s_n; __shared__ unsigned long long s_S;
       for (int t = tid; t < 3 * grid; t += DA_M_CTHREADS) { uint32_t v; ok = poll8(a.hcs + t, t32, v) && ok; hv[t] = v; }
       cbar();
@@ -1028,7 +1076,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         const int per = (h_cnt + DA_M_CTHREADS - 1) / DA_M_CTHREADS;
         const int i0 = min(h_cnt, tid * per), i1 = min(h_cnt, i0 + per);
         uint32_t cnt = 0;
-        for (int i = i0; i < i1; ++i) cnt += bits2f(lg[i]) >= thr;
+        for (int i = i0; i < i1; ++i) cnt += bits2f(sm_lg[i]) >= thr;
         uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
@@ -1038,7 +1086,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         uint32_t slot = base + inc - cnt;
         for (int i = 0; i < w; ++i) slot += wtot[i];
         for (int i = i0; i < i1; ++i) {
-          const uint16_t b = lg[i];
+          const uint16_t b = sm_lg[i];
           if (bits2f(b) >= thr) {
             const uint32_t idx = (uint32_t)(gp.r0 + i);
             st_unit8(a.cand + slot, ((unsigned long long)(0xFFFFu - bf16_key(b)) << 48) | ((unsigned long long)idx << 30) | tag30);
@@ -1049,38 +1097,54 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       if (bid == 0) {
         SampleParams spm;
         spm.m = m; spm.S = __ull2float_rn(s_S) * (1.0f / DA_FIX2_SCALE);
-        spm.T_bf = T_eff;
-        spm.c_max = c_max_req;
-        uint32_t *sm_sort = reinterpret_cast<uint32_t *>(work);
-        unsigned long long *scr = reinterpret_cast<unsigned long long *>(work + 16384);
-        cbar();   // hv is dead: work becomes the sampler's scratch
+        spm.T_bf = eff_temperature(st);
+        spm.c_max = cmax_from_top_p(st->top_p);
+        const NoiseSrc nsrc = noise_src(st);
+        uint32_t *sm_sort = reinterpret_cast<uint32_t *>(sm_work);
+        unsigned long long *scr = reinterpret_cast<unsigned long long *>(sm_work + 16384);
+        cbar();   // hv is dead: sm_work becomes the sampler's sm_scratch
         uint32_t idx = 0xFFFFFFFFu;
-        if (N >= 1 && N <= 4096) {      // sort-based sampler over <= 4096 candidates (8 per thread); wider nuclei take the fallback
-          constexpr int E = 8;
-          uint32_t it[E];
+        // sort-based sampler over the candidate list, 8 consecutive entries per thread fetched with four 16-byte polls issued
+        // together (one L2 round trip): <= 1024 candidates by warps 0-3 (the fast heads' instantiation), <= 4096 by all 16 warps;
+        // wider nuclei take the whole-vocabulary fallback
+        typedef BlockNamed<4, 256> G8;      // warps 0-7
+        __shared__ uint32_t s_idx;
+        if (N >= 1 && N <= 4096) {
+          if (w < 8) {
+            // 16 consecutive entries per thread, fetched with 16-byte polls issued together (entry = inverted key (16) | index (18) | tag (30))
+            const unsigned e0 = tid * 16;
+            uint32_t it[16];
+            int spin = 0;
+            for (;;) {
+              bool good = true;
 #pragma unroll
-          for (int i = 0; i < E; ++i) {
-            const unsigned e = tid * E + i;
-            it[i] = 0xFFFFFFFFu;
-            if (e < N) {      // entry = inverted key (16) | vocabulary index (18) | tag (30)
-              unsigned long long k; int spin = 0;
-              for (;;) { k = ld_poll8(a.cand + e); if ((uint32_t)(k & 0x3FFFFFFFu) == tag30) break; if (++spin >= DA_SPIN_LIMIT) break; __nanosleep(20); }
-              ok = ok && spin < DA_SPIN_LIMIT;
-              it[i] = ((uint32_t)(k >> 48) << 16) | e;
+              for (int i = 0; i < 16; i += 2) {
+                unsigned long long k0 = 0, k1 = 0;
+                if (e0 + i < N) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(a.cand + e0 + i) : "memory");
+                it[i] = (e0 + i < N) ? (((uint32_t)(k0 >> 48) << 16) | (e0 + i)) : 0xFFFFFFFFu;
+                it[i + 1] = (e0 + i + 1 < N) ? (((uint32_t)(k1 >> 48) << 16) | (e0 + i + 1)) : 0xFFFFFFFFu;
+                if (e0 + i < N) good &= ((uint32_t)(k0 & 0x3FFFFFFFu) == tag30);
+                if (e0 + i + 1 < N) good &= ((uint32_t)(k1 & 0x3FFFFFFFu) == tag30);
+              }
+              if (good || ++spin >= DA_SPIN_LIMIT) break;
             }
+            ok = ok && spin < DA_SPIN_LIMIT;
+            const uint32_t r = sample_sorted<16, 256, G8>(it, N, (int)N == a.vocab, a.cand, spm, nsrc, 0u, 0ll, &st->nucleus[0], sm_sort, scr);
+            if (tid == 0) s_idx = r;
           }
-          idx = sample_sorted<E, DA_M_CTHREADS, CBlock>(it, N, (int)N == a.vocab, a.cand, spm, ns, 0u, 0ll, &st->nucleus[0], sm_sort, scr);
+          cbar();
+          idx = s_idx;
         }
         cbar();
         if (idx == 0xFFFFFFFFu) {
           __threadfence();
-          idx = sample_fallback<CBlock>(a.logits, a.vocab, spm, ns, 0u, 0ll, &st->nucleus[0], scr + 192, reinterpret_cast<float *>(scr + 192 + 34));
+          idx = sample_fallback<CBlock>(a.logits, a.vocab, spm, nsrc, 0u, 0ll, &st->nucleus[0], scr + 192, reinterpret_cast<float *>(scr + 192 + 34));
         }
         // inference.py:123-126: first codebook = semantic id - semantic_begin (clamped at 0); next input = its fast embedding
         int cb0 = (int)idx - a.sem_begin; if (cb0 < 0) cb0 = 0;
         if (cb0 >= a.codebook_size) { cb0 = a.codebook_size - 1; if (tid == 0) st->err = 3; }
-        for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) put1(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)cb0 * a.fdim + dd]), tag));
-        if (tid == 0) { st->tok_out[0] = (int)idx; st->tok_out[1] = cb0; }
+        for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)cb0 * a.fdim + dd]), tag));
+        if (tid == 0) { st->tok_out[0] = (int)idx; st->tok_out[1] = cb0; st->n_cand = N; }      // n_cand: diagnostic (candidates of this step)
       }
       cbar();
       if (TL) tl_mark(a, 1 + ph, 2);
@@ -1114,5 +1178,20 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     }
   }
 }
+
+
+#undef sm_full
+#undef sm_empty
+#undef sm_chg
+#undef sm_xb2
+#undef sm_raw
+#undef sm_scratch
+#undef sm_work
+#undef sm_part
+#undef sm_pcnt
+#undef sm_pgen
+#undef sm_lg
+#undef sm_kvs
+#undef sm_ring
 
 }  // namespace da

@@ -223,7 +223,7 @@ class DualAREngine:
             "slow_logits": ((cfg.vocab_size,), torch.bfloat16), "slow_logits_raw": ((cfg.vocab_size,), torch.bfloat16),
             "hidden": ((cfg.dim,), torch.bfloat16),
             "fast_logits": ((cfg.num_codebooks - 1, self.fast_vocab), torch.bfloat16),
-            "tokens": ((self.rows,), torch.int32), "nucleus": ((cfg.num_codebooks,), torch.int32),
+            "tokens": ((self.rows,), torch.int32), "n_cand": ((1,), torch.int32), "nucleus": ((cfg.num_codebooks,), torch.int32),
             "qkv": (((cfg.n_head + 2 * cfg.n_local_heads) * cfg.head_dim,), torch.bfloat16),
             "y": ((cfg.n_head * cfg.head_dim,), torch.bfloat16), "h": ((cfg.dim,), torch.bfloat16),
             "act": ((cfg.intermediate_size,), torch.bfloat16), "fast_x": ((cfg.fast_dim,), torch.bfloat16),

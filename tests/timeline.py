@@ -62,7 +62,7 @@ if n_step == 1:
     for k, a in agg.items():
         n = a[0]
         print(f"{k:8s} {n:4d} {a[1] / n:8.2f} {a[2] / n:8.2f} {a[3] / n:8.2f} {a[3]:8.1f}")
-    fa = full[400:400 + nph, :4]
+    fa = full[400:400 + nph, :6]
     acc = [0.0] * 5; nfa = 0
     for i, nm in enumerate(names):
         if nm == "F.wo" and fa[i, 0]:
@@ -71,6 +71,18 @@ if n_step == 1:
                 acc[k_] += (x1 - x0) / 1e3
     if nfa:
         print("  F.wo staging (mean us): poll %.2f | barrier %.2f | rope %.2f | kv+scores %.2f | softmax+PV+store+barrier %.2f" % tuple(x / nfa for x in acc))
+    acc = [0.0] * 4; nsa = 0
+    for i, nm in enumerate(names):
+        if nm == "S.attn" and fa[i, 0] and i > 6:
+            nsa += 1
+            for k_, (x0, x1) in enumerate([(tl[1 + i, 0], fa[i, 0]), (fa[i, 0], fa[i, 1]), (fa[i, 1], fa[i, 2]), (fa[i, 2], tl[1 + i, 2])]):
+                acc[k_] += (x1 - x0) / 1e3
+    if nsa:
+        print("  S.attn (CTA 0, mean us): poll q/k/v %.2f | barrier+norm+rope+barrier %.2f | tile walk %.2f | warp merge + publish %.2f" % tuple(x / nsa for x in acc))
+        w0 = [ (fa[i,3]-fa[i,1])/1e3 for i,nm in enumerate(names) if nm == 'S.attn' and fa[i,0] and i > 6]
+        w1 = [ (fa[i,4]-fa[i,3])/1e3 for i,nm in enumerate(names) if nm == 'S.attn' and fa[i,0] and i > 6]
+        w2 = [ (fa[i,2]-fa[i,4])/1e3 for i,nm in enumerate(names) if nm == 'S.attn' and fa[i,0] and i > 6]
+        print('    tile walk split: init+wait for tile %.2f | warp 0 compute %.2f | barrier after tile + state %.2f' % (sum(w0)/len(w0), sum(w1)/len(w1), sum(w2)/len(w2)))
     hs = full[700:700 + nph, :4]
     for i, nm in enumerate(names):
         if nm == "F.head" and i < nph - 1:
@@ -92,6 +104,7 @@ if n_step == 1:
     print(f"sum over GEMV phases of (max over CTAs of thread-0 ring wait): {sum(pw[i].max() for i in gem):.1f} us; of the mean: {sum(pw[i].mean() for i in gem):.1f} us; of (last done - first staged): {sum((t2[i,:,1].max() - t2[i,:,0].min()) / 1e3 for i in gem):.1f} us; of (last staged - first staged): {sum((t2[i,:,0].max() - t2[i,:,0].min()) / 1e3 for i in gem):.1f} us")
     wc = raw2[400 * 148 * 2: 400 * 148 * 2 + 148 * 16].reshape(148, 16) / 1965.0
     print(f"ring waits per warp over the whole step (us): mean {wc.mean():.1f}  min {wc.min():.1f}  max {wc.max():.1f}; per-CTA mean: min {wc.mean(1).min():.1f} (cta {int(wc.mean(1).argmin())})  max {wc.mean(1).max():.1f} (cta {int(wc.mean(1).argmax())}); CTA 0: {wc[0].mean():.1f}")
+    print('slow-head candidates of the last step:', int(eng.read('n_cand')[0]), ' nucleus sizes (slow, fast heads):', eng.read('nucleus').tolist())
     slow_end = start[6 * L]
     head_end = start[6 * L + 3]
     print(f"slow stack {slow_end:.1f} us | head+sampler {head_end - slow_end:.1f} us | fast {end - head_end:.1f} us")
