@@ -511,7 +511,7 @@ static int build_mega(dualar_engine *e) {
       if (entry > max_entry) max_entry = entry;
     }
     if ((size_t)4 * DA_TILE * c.head_dim > max_entry) max_entry = (size_t)4 * DA_TILE * c.head_dim;
-    size_t work = (size_t)(fqd + 2 * fkd + c.fast_n_head * c.num_codebooks + 4) * 4;
+    size_t work = (size_t)(fqd + 2 * fkd + c.fast_n_head * 16 + 4) * 4;
     auto upd = [&](size_t v) { if (v > work) work = v; };
     upd((size_t)(G * c.head_dim + 2 * c.head_dim + DA_M_CWARPS * G * (2 + c.head_dim)) * 4 + 4 * c.head_dim + 64);      // slow attention: q, new k/v, per-warp partials
     upd((size_t)3 * (qd / grid + 2) * e->nsplit * 4);

@@ -535,17 +535,23 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         }
         cbar();
         if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 2, gtime());
-        for (int h = w; h < nh; h += DA_M_CWARPS) {
-          const int g = h / FG;
+        // one HALF-warp per head (30 half-warps for <= 16 heads: every head in one round), both halves run the same code
+        float *prs = vcur + kd;                                     // [nh][16] scores, then probabilities
+        const int sl = lane & 15, hsel = lane & 16;
+        for (int hb = 2 * w; hb < ((nh + 1) & ~1); hb += 2 * DA_M_CWARPS) {
+          const int h_raw = hb + (lane >> 4);
+          const bool hlive = h_raw < nh;
+          const int h = hlive ? h_raw : nh - 1, g = h / FG;
           const float *qq = q + h * hd;
           // scores: 4 lanes per position, hd/4 elements each; bf16(q @ k^T), then bf16(* scale)   (llama.py:304)
-          float sc_j = -INFINITY;      // lane j < P ends up with the score of position j
-          for (int j0 = 0; j0 < P; j0 += 8) {
-            const int j = j0 + (lane >> 2), prt = lane & 3, ne = hd >> 2;
+          const int prt = sl & 3, ne = hd >> 2;
+          for (int j0 = 0; j0 < P; j0 += 4) {
+            const int j = j0 + (sl >> 2);
             float acc = 0.f;
             if (j < P) {
               const bf16 *kk = kv_l + ((size_t)j * 2 + 0) * kd + g * hd + prt * ne;
               const float *qp = qq + prt * ne;
+#pragma unroll 4
               for (int x = 0; x < ne; x += 2) {
                 const float2 kf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kk + x));
                 acc = fmaf(qp[x], kf.x, acc); acc = fmaf(qp[x + 1], kf.y, acc);
@@ -553,28 +559,30 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            const float sj = rbf(__fmul_rn(rbf(acc), a.fscale));
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) { const float v = __shfl_sync(0xffffffffu, sj, jj * 4); if (lane == j0 + jj && j0 + jj < P) sc_j = v; }
+            if (prt == 0 && j < P) prs[h * 16 + j] = rbf(__fmul_rn(rbf(acc), a.fscale));
           }
-          // softmax over j <= pos in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf) = 0)
-          const float m = warp_max(sc_j);
-          const float ej = lane < P ? expf(sc_j - m) : 0.f;
-          const float sum = warp_sum(ej);
-          const float pj = lane < P ? rbf(ej / sum) : 0.f;
-          // y = bf16(p @ v)   (llama.py:309): lane owns dims 2*lane, 2*lane+1 (+64 per extra round)
-          for (int db = 0; db < hd; db += 64) {       // uniform trip count: every lane takes sm_part in the shuffles
-            const int d0 = db + 2 * lane;
-            const bool liv = d0 < hd;
+          __syncwarp();
+          // softmax over j <= pos in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf) = 0): lane sl <-> position sl
+          const float sc_j = sl < P ? prs[h * 16 + sl] : -INFINITY;
+          float m = sc_j;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          const float ej = sl < P ? expf(sc_j - m) : 0.f;
+          float sum = ej;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float pj = sl < P ? rbf(ej / sum) : 0.f;
+          // y = bf16(p @ v)   (llama.py:309): lane sl owns dims sl*dph .. +dph of its head (dph = hd / 16: 2, 4 or 8)
+          const int dph = hd >> 4;
+          for (int d2 = 0; d2 < dph; d2 += 2) {
+            const int d0 = sl * dph + d2;
             float y0 = 0.f, y1 = 0.f;
             for (int jj = 0; jj < P; ++jj) {
-              const float pv = __shfl_sync(0xffffffffu, pj, jj);
-              if (liv) {
-                const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kv_l + ((size_t)jj * 2 + 1) * kd + g * hd + d0));
-                y0 = fmaf(pv, vf.x, y0); y1 = fmaf(pv, vf.y, y1);
-              }
+              const float pv = __shfl_sync(0xffffffffu, pj, hsel | jj);
+              const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kv_l + ((size_t)jj * 2 + 1) * kd + g * hd + d0));
+              y0 = fmaf(pv, vf.x, y0); y1 = fmaf(pv, vf.y, y1);
             }
-            if (liv) *reinterpret_cast<uint32_t *>(xb + h * hd + d0) = (uint32_t)f2bits(y0) | ((uint32_t)f2bits(y1) << 16);
+            if (hlive) *reinterpret_cast<uint32_t *>(xb + h * hd + d0) = (uint32_t)f2bits(y0) | ((uint32_t)f2bits(y1) << 16);
           }
         }
         if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 3, gtime());
