@@ -31,9 +31,10 @@
 
 namespace da {
 
-#define DA_M_CWARPS 15               // 15 compute warps + the producer warp = 512 threads: 128 registers per thread.  With 16 + 1
-#define DA_M_CTHREADS 480            // warps ptxas is capped at 96 and spills kernel-scope values into the hot loops; the step time
-#define DA_M_THREADS 512             // then moved by +-15% with unrelated code changes
+#define DA_M_CWARPS 16               // 16 compute warps + the producer warp.  The 17th warp puts five warps on one scheduler, which caps
+#define DA_M_CTHREADS 512            // ptxas at 96 registers (a few spilled kernel-scope values); 15 + 1 warps (128 registers, no spills)
+#define DA_M_THREADS 544             // measured 2.5% slower: 16 heads / 16 units per phase then take two rounds.  Everything below is
+                                     // written against these macros, so either configuration builds.
 #define DA_M_PPW ((DA_TILE + DA_M_CWARPS - 1) / DA_M_CWARPS)   // positions of a 64-row K/V tile per warp
 #define DA_M_NB 32                  // ring entries in flight (mbarrier pairs)
 #define DA_M_ENTRY_BYTES 16384      // target size of one ring entry of a GEMV phase
