@@ -33,7 +33,7 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-from fish_tts_b200.config import s1_mini_config  # noqa: E402
+from fish_tts_b200.config import fish_speech_1_5_config, s1_mini_config  # noqa: E402
 from fish_tts_b200.synthetic import make_state_dict, synthetic_prompt  # noqa: E402
 
 SAMPLING = dict(temperature=0.7, top_p=0.8, repetition_penalty=1.1)
@@ -142,10 +142,11 @@ def ncu_traffic():
 
 
 def workload_config(cfg, n_gpus, steps):
-    return {"workload": "openaudio-s1-mini dual-AR decode, bs=1, prefilled ~10 s VoiceProfile prompt "
+    name = "openaudio-s1-mini" if cfg.num_codebooks == 10 else "fish-speech-1.5 shape"
+    return {"workload": f"{name} dual-AR decode, bs=1, prefilled ~10 s VoiceProfile prompt "
                         f"({sum(PROMPT.values())} positions), {steps} generated tokens, T=0.7 top_p=0.8 rp=1.1",
             "weights": "seeded random-init (fish_tts_b200.synthetic, seed 0), bf16", "prompt_len": sum(PROMPT.values()),
-            "generated": steps, "l2": "inputs (1.31 GB of weights per step) exceed the 126 MB L2; no flush between steps",
+            "generated": steps, "l2": f"inputs ({cfg.weight_bytes()['unique_weights'] / 1e9:.2f} GB of weights per step) exceed the 126 MB L2; no flush between steps",
             "parallelism": f"{n_gpus} independent replica(s), request-level partitioning, no collective"}
 
 
@@ -158,6 +159,7 @@ def main():
     ap.add_argument("--torch-baselines", action="store_true", help="also time the oracle's torch path on this GPU (eager and torch.compile)")
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--e2e-requests", type=int, default=2)
+    ap.add_argument("--model", default="s1mini", choices=["s1mini", "v15"], help="openaudio-s1-mini (BASELINE configs[1], the headline) or the fish-speech 1.5 shape (configs[2])")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -172,7 +174,7 @@ def main():
         import torch.distributed as dist_
         dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_
-    cfg = s1_mini_config()
+    cfg = s1_mini_config() if args.model == "s1mini" else fish_speech_1_5_config()
     sd = make_state_dict(cfg, seed=0)
     eng = DualAREngine(cfg, sd, device=local, seed=1234 + rank)
     prompt = synthetic_prompt(cfg, **PROMPT, seed=1 + rank)

@@ -401,7 +401,7 @@ static int build_mega(dualar_engine *e) {
   const int qd = c.n_head * c.head_dim, kd = c.n_local_heads * c.head_dim, qkv_rows = qd + 2 * kd;
   const int fqd = c.fast_n_head * c.fast_head_dim, fkd = c.fast_n_local_heads * c.fast_head_dim, fqkv_rows = fqd + 2 * fkd;
   const int G = c.n_head / c.n_local_heads;
-  const int n_slow = 6 * c.n_layer, n_step = n_slow + 3 + c.num_codebooks * 4 * c.n_fast_layer + (c.num_codebooks - 1);
+  const int n_slow = 6 * c.n_layer, n_step = n_slow + 2 + 4 * c.n_fast_layer + c.num_codebooks * 4 * c.n_fast_layer + (c.num_codebooks - 1);
   auto pairs = [](int rows) { return (rows + 1) / 2; };
   if (n_step > DA_M_MAX_PHASES || c.n_layer > DA_M_MAXL || c.n_fast_layer > DA_M_MAXFL || grid > 160 || e->fv > 1024 ||
       pairs(qkv_rows) < grid || pairs(2 * c.intermediate_size) < grid || pairs(fqkv_rows) < grid || pairs(2 * c.fast_intermediate_size) < grid ||
@@ -458,25 +458,39 @@ static int build_mega(dualar_engine *e) {
     }
     if (variant) other(MK_PREFILL_END, e->u_x, last, nullptr, 0);
     else {
-      int hd_ph = gemv(c.tie_word_embeddings ? e->emb : e->out_w, nullptr, e->norm, e->u_x, last, nullptr, c.vocab_size, c.dim, MP_RMSNORM, ME_SLOWLOGITS, 0, 0, 0);
+      // The LM head (319 MB, HBM bound, no dependency but x) and the fast pass 0 (16 latency-bound phases that need only x) are
+      // independent: the head comes in FL*4 parts, one after each pass-0 phase, so the hand-over latency of a pass-0 phase
+      // hides behind a slice of the head's tiles instead of idling the machine.
+      const int FL = c.n_fast_layer, NPARTS = 4 * FL;
+      int hd_ph = -1, prev = 0, part = 0;
+      auto head_part = [&]() {
+        hd_ph = gemv(c.tie_word_embeddings ? e->emb : e->out_w, nullptr, e->norm, e->u_x, last, nullptr, c.vocab_size, c.dim, MP_RMSNORM, ME_SLOWLOGITS, 0, 0, 0);
+        tab.back().part = (unsigned char)part; tab.back().nparts = (unsigned char)NPARTS; ++part;
+      };
+      auto fast_layer = [&](int p, int l, const uint32_t *lin, int lin_ph, bool with_head) {
+        LayerW &W = e->fast[l];
+        if (with_head) head_part();
+        int q = gemv(W.wqkv, W.bqkv, W.attn_norm, lin, lin_ph, e->u_fqkv, fqkv_rows, c.fast_dim, MP_RMSNORM, ME_STORE, MF_KEEP | MF_SAVE0, l, p);
+        if (with_head) head_part();
+        int o = gemv(W.wo, W.bo, nullptr, e->u_fqkv, q, e->u_fh, c.fast_dim, fqd, MP_FASTATTN, ME_RESIDUAL, MF_KEEP | MF_RES0, l, p);
+        if (with_head) head_part();
+        int f = gemv(W.w13, nullptr, W.ffn_norm, e->u_fh, o, e->u_fact, 2 * c.fast_intermediate_size, c.fast_dim, MP_RMSNORM, ME_SWIGLU, MF_KEEP | MF_SAVE1, l, p);
+        if (with_head) head_part();
+        return gemv(W.w2, nullptr, nullptr, e->u_fact, f, (l & 1) ? e->u_fx1 : e->u_fx0, c.fast_dim, c.fast_intermediate_size, MP_PLAIN, ME_RESIDUAL, MF_KEEP | MF_RES1, l, p);
+      };
+      for (int l = 0; l < FL; ++l) {      // pass 0 (input: the slow hidden state), interleaved with the head
+        const uint32_t *lin = l == 0 ? e->u_x : (((l - 1) & 1) ? e->u_fx1 : e->u_fx0);
+        prev = fast_layer(0, l, lin, l == 0 ? last : prev, true);
+      }
       int hs = other(MK_HSTAT, nullptr, hd_ph, nullptr, 0);
       int hc = other(MK_HCAND, nullptr, hs, nullptr, 0);
       int fin_ph = hc;   // the phase that last wrote u_fin
-      const int FL = c.n_fast_layer;
-      for (int p = 0; p < c.num_codebooks; ++p) {
-        int prev = 0;
+      for (int p = 1; p < c.num_codebooks; ++p) {
         for (int l = 0; l < FL; ++l) {
-          LayerW &W = e->fast[l];
-          const uint32_t *lin; int lin_ph;
-          if (l == 0) { if (p == 0) { lin = e->u_x; lin_ph = last; } else { lin = e->u_fin; lin_ph = fin_ph; } }
-          else { lin = ((l - 1) & 1) ? e->u_fx1 : e->u_fx0; lin_ph = prev; }
-          int q = gemv(W.wqkv, W.bqkv, W.attn_norm, lin, lin_ph, e->u_fqkv, fqkv_rows, c.fast_dim, MP_RMSNORM, ME_STORE, MF_KEEP | MF_SAVE0, l, p);
-          int o = gemv(W.wo, W.bo, nullptr, e->u_fqkv, q, e->u_fh, c.fast_dim, fqd, MP_FASTATTN, ME_RESIDUAL, MF_KEEP | MF_RES0, l, p);
-          int f = gemv(W.w13, nullptr, W.ffn_norm, e->u_fh, o, e->u_fact, 2 * c.fast_intermediate_size, c.fast_dim, MP_RMSNORM, ME_SWIGLU, MF_KEEP | MF_SAVE1, l, p);
-          prev = gemv(W.w2, nullptr, nullptr, e->u_fact, f, (l & 1) ? e->u_fx1 : e->u_fx0, c.fast_dim, c.fast_intermediate_size, MP_PLAIN, ME_RESIDUAL, MF_KEEP | MF_RES1, l, p);
+          const uint32_t *lin = l == 0 ? e->u_fin : (((l - 1) & 1) ? e->u_fx1 : e->u_fx0);
+          prev = fast_layer(p, l, lin, l == 0 ? fin_ph : prev, false);
         }
-        if (p >= 1)   // logits of pass 0 are discarded by the reference (inference.py:122)
-          fin_ph = gemv(e->fast_out, nullptr, e->fast_norm, ((FL - 1) & 1) ? e->u_fx1 : e->u_fx0, prev, e->u_flogits, e->fv, c.fast_dim, MP_RMSNORM, ME_FASTLOGITS, MF_KEEP, FL - 1, p);
+        fin_ph = gemv(e->fast_out, nullptr, e->fast_norm, ((FL - 1) & 1) ? e->u_fx1 : e->u_fx0, prev, e->u_flogits, e->fv, c.fast_dim, MP_RMSNORM, ME_FASTLOGITS, MF_KEEP, FL - 1, p);
       }
     }
     a.n_phases = (int)tab.size();

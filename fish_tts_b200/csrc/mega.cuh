@@ -41,7 +41,7 @@ namespace da {
 #define DA_M_MAX_PHASES 400
 #define DA_M_MAXL 48                // slow layers
 #define DA_M_MAXFL 8                // fast layers
-#define DA_SPIN_LIMIT (1 << 22)
+#define DA_SPIN_LIMIT (1 << 18)      // bounded spins: a lost hand-over raises the fault flag after ~0.1 s instead of hanging the GPU
 #define DA_M_REP 1                  // replicas of every broadcast unit vector (CTA b polls replica b % DA_M_REP).  Measured
                                     // (tests/cuda/handover_bench2.cu): ONE copy is fastest -- 0.80 us per all-to-all hand-over of
                                     // 1024 units at 148 CTAs vs 1.03 us with 4 copies; the extra stores cost more than the
@@ -60,10 +60,10 @@ struct MPhase {
   short in_ph;           // phase that wrote `in` (its tag)
   unsigned char kind, pro, epi, layer, pos, flags;
   short pq, prem;        // row pairs per CTA: floor and remainder of (rows / 2) / grid (the first `prem` CTAs take one more)
-  int pad_;
+  unsigned char part, nparts, pad2_[2];   // nparts > 1: this entry handles only the part-th slice of the CTA's tiles (LM head, see build_mega)
 };
 
-struct MegaSmem { uint32_t bars, chg, xb, raw, scratch, work, part, pcnt, lg, kvs, ring, total; };
+struct MegaSmem { uint32_t bars, chg, xb, xbh, raw, scratch, work, part, pcnt, lg, kvs, ring, total; };
 struct MegaArgs {
   int n_phases;
   // slow attention (llama.py:242-282)
@@ -294,6 +294,7 @@ static inline __host__ __device__ MegaSmem mega_smem_plan(int kmax, int dim_max,
   m.bars = o; o += 2 * DA_M_NB * 8;
   m.chg = o; o += DA_M_NB * 4;
   m.xb = o; o += 2u * (uint32_t)kmax * 2;                                  // two staging buffers, by phase parity
+  m.xbh = o; o += (uint32_t)dim_max * 2;                                   // staging buffer of the LM head: survives the interleaved fast phases
   m.raw = o; o += 2u * (uint32_t)dim_max * 4;
   m.scratch = o; o += 160 * 4;
   m.work = o; o += ((uint32_t)work_bytes + 15u) & ~15u;
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
 #define sm_empty (reinterpret_cast<uint64_t *>(sm + a.plan.bars) + DA_M_NB)
 #define sm_chg (reinterpret_cast<uint32_t *>(sm + a.plan.chg))
 #define sm_xb2 (reinterpret_cast<bf16 *>(sm + a.plan.xb))
+#define sm_xbh (reinterpret_cast<bf16 *>(sm + a.plan.xbh))
 #define sm_raw (reinterpret_cast<float *>(sm + a.plan.raw))
 #define sm_scratch (reinterpret_cast<float *>(sm + a.plan.scratch))
 #define sm_work (sm + a.plan.work)
@@ -400,7 +402,8 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         const GemvPart gp = gemv_part(d.rows, d.pq, d.prem, bid);
         const uint64_t pol = (d.flags & MF_KEEP) ? pol_keep : pol_stream;
         const uint32_t RS = row_stride(d.K), row_bytes = 2u * (uint32_t)d.K;
-        for (int t = 0; t < gp.nt; ++t) {
+        const int t_lo = d.nparts > 1 ? gp.nt * d.part / d.nparts : 0, t_hi = d.nparts > 1 ? gp.nt * (d.part + 1) / d.nparts : gp.nt;
+        for (int t = t_lo; t < t_hi; ++t) {
           const int n = min(16, gp.nr - 16 * t);
           uint32_t at = 0, bi = 0;
           if (lane == 0) {
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
 #pragma unroll
   for (int i = 0; i < DA_M_PT; ++i) gen_base[i] = 0;
   // softmax statistics of the slow head carried from MK_GEMV(ME_SLOWLOGITS) to MK_HSTAT / MK_HCAND
-  float h_m = 0.f; int h_cnt = 0;
+  float h_m = 0.f, h_wmax = -INFINITY; int h_cnt = 0;
 
   for (int ph = 0; ph < nph; ++ph) {
     const MPhase &d = a.table[ph];
@@ -477,7 +480,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
     if (d.kind == MK_GEMV) {
       const int K = d.K, nchunk = K >> 7;
       const GemvPart gp = gemv_part(d.rows, d.pq, d.prem, bid);
-      bf16 *xb = sm_xb2 + (size_t)(ph & 1) * a.kmax;      // staging buffer of this phase; the other one may still be read by a slow warp of the previous phase
+      // staging buffer of this phase; the other one may still be read by a slow warp of the previous phase.  A phase that comes
+      // in parts (the LM head, interleaved with the fast pass 0) stages once, into its own buffer.
+      const bool parted = d.nparts > 1;
+      bf16 *xb = parted ? sm_xbh : sm_xb2 + (size_t)(ph & 1) * a.kmax;
+      const int t_lo = parted ? gp.nt * d.part / d.nparts : 0, t_hi = parted ? gp.nt * (d.part + 1) / d.nparts : gp.nt;
+      if (!parted || d.part == 0) {
       // ---- (A) stage the input vector as packed bf16 (every activation is a bf16 value) ------------------------------------------
       if (FULL && d.pro == MP_FASTATTN) {
         // fast-layer attention for position d.pos (llama.py:246-251, 285-309), recomputed by every CTA.  After the RoPE
@@ -647,6 +655,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         if (mine) { store4_xb(xb, e_lo, v); store4_xb(xb, e_hi, v + 4); }
       }
       cbar();
+      }      // staging
       if (TL) tl_mark(a, 1 + ph, 1);
       if (TL && a.tl2 && tid == 0) a.tl2[((size_t)ph * grid + bid) * 2] = gtime();
 
@@ -658,30 +667,32 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       if (FULL && (d.epi == ME_FASTLOGITS || d.epi == ME_SLOWLOGITS)) { rp_eff = eff_rep_penalty(st); use_pen = st->use_penalty; }
       if (FULL && d.epi == ME_FASTLOGITS && use_pen && lane < DA_WIN) pen_id = st->win[(d.pos + 1) * DA_WIN + lane];
       if (FULL && d.epi == ME_SLOWLOGITS && use_pen && lane < a.n_rows_tok) pen_id = st->win[lane * DA_WIN];     // previous_tokens[:, 0]
-      float wmax = -INFINITY;
+      if (!parted || d.part == 0) h_wmax = -INFINITY;
       const float *resv = sm_raw + ((d.flags & MF_RES1) ? dim_max : 0);
       const uint32_t RS = row_stride(K);
       const uint32_t *xw = reinterpret_cast<const uint32_t *>(xb);
       {
         int u = w;
-        for (int t = 0; t < gp.nt; ++t) {
-          const int n = min(16, gp.nr - 16 * t);
+        for (int t = t_lo; t < t_hi; ++t) {
+          const int n = min(16, gp.nr - 16 * t), tl = t - t_lo;      // tl: tile index within this phase entry (units, slots, generations)
           uint32_t bi, par;
           const uint32_t at = place((uint32_t)n * RS, bi, par);
-          if (u >= (t + 1) * nchunk) continue;         // no unit of this warp in the tile
+          if (u >= (tl + 1) * nchunk) continue;        // no unit of this warp in the tile
           landed(bi, par);
-          const int slot = t & (DA_M_PT - 1);
+          const int slot = tl & (DA_M_PT - 1);
           int gb = gen_base[0];
 #pragma unroll
           for (int i = 1; i < DA_M_PT; ++i) if (slot == i) gb = gen_base[i];
-          const int gen_need = gb + t / DA_M_PT;
+          const int gen_need = gb + tl / DA_M_PT;
           float *pslot = sm_part + (size_t)slot * (a.kmax >> 7) * 16;
-          for (; u < (t + 1) * nchunk; u += DA_M_CWARPS) {
-            const int c = u - t * nchunk;
+          for (; u < (tl + 1) * nchunk; u += DA_M_CWARPS) {
+            const int c = u - tl * nchunk;
             float v_lo, v_hi;
             mma_chunk(smem_u32(sm_ring + at), RS, n, xw, c, lane, v_lo, v_hi);
             // the slot is free once the tile DA_M_PT before this one has been folded
-            if (t >= DA_M_PT) { int it = 0; while (sm_pgen[slot] != gen_need) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
+            // (checked for every tile: a phase entry without a staging barrier -- the later LM-head parts -- can start while the
+            //  previous phase is still folding on this slot)
+            { int it = 0; while (sm_pgen[slot] != gen_need) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
             if ((lane & 3) == 0) { pslot[c * 16 + (lane >> 2)] = v_lo; pslot[c * 16 + 8 + (lane >> 2)] = v_hi; }
             __syncwarp();
             int last = 0;
@@ -728,7 +739,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                 } else if (live) {   // ME_SLOWLOGITS: logits stay in this CTA's shared memory for the sampler phases; global copies for read-back / fallback
                   a.logits_raw[row] = f2bf(z);
                   if (hit) z = penalise(z, rp_eff);
-                  a.logits[row] = f2bf(z); sm_lg[16 * t + r] = f2bits(z); wmax = fmaxf(wmax, z);
+                  a.logits[row] = f2bf(z); sm_lg[16 * t + r] = f2bits(z); h_wmax = fmaxf(h_wmax, z);
                 }
               }
             }
@@ -736,15 +747,15 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         }
       }
 #pragma unroll
-      for (int i = 0; i < DA_M_PT; ++i) gen_base[i] += (gp.nt + DA_M_PT - 1 - i) / DA_M_PT;
+      for (int i = 0; i < DA_M_PT; ++i) gen_base[i] += (t_hi - t_lo + DA_M_PT - 1 - i) / DA_M_PT;
       if (TL) tl_mark(a, 1 + ph, 2);
       if (TL && a.tl2 && tid == 0) { a.tl2[((size_t)ph * grid + bid) * 2 + 1] = gtime(); a.tl2[(size_t)DA_M_MAX_PHASES * 160 * 2 + (size_t)ph * grid + bid] = wait_ns; }
 
       // ---- (C) heads ------------------------------------------------------------------------------------------------------
-      if (FULL && d.epi == ME_SLOWLOGITS) {
+      if (FULL && d.epi == ME_SLOWLOGITS && (!parted || d.part == d.nparts - 1)) {
         // CTA max of the penalised logits -> 64-bit unit; the fence makes this CTA's global logits visible to whoever
         // has seen the unit (needed by the whole-vocabulary fallback sampler only)
-        wmax = warp_max(wmax);
+        const float wmax = warp_max(h_wmax);
         if (lane == 0) sc[w] = wmax;
         __threadfence();
         cbar();
@@ -808,7 +819,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       // No CTA barrier ends a plain GEMV phase: the staging buffer alternates, the partial-sum slots are handed over by their
       // generation counters, and the first barrier of the next phase's staging cannot be passed before every fold of this
       // phase is done.  The head phases keep one (sm_work / sm_lg are reused by the sampler phases that follow).
-      if (FULL && (d.epi == ME_SLOWLOGITS || d.epi == ME_FASTLOGITS)) cbar();
+      if (FULL && ((d.epi == ME_SLOWLOGITS && (!parted || d.part == d.nparts - 1)) || d.epi == ME_FASTLOGITS)) cbar();
 
     } else if (d.kind == MK_ATTN) {
       // ---- slow-layer attention for one query position: split-KV flash-decode (llama.py:242-282 under SDPBackend.MATH) ---------
@@ -1193,6 +1204,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
 #undef sm_empty
 #undef sm_chg
 #undef sm_xb2
+#undef sm_xbh
 #undef sm_raw
 #undef sm_scratch
 #undef sm_work

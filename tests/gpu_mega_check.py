@@ -7,14 +7,14 @@ import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
-from fish_tts_b200.config import s1_mini_config  # noqa: E402
+from fish_tts_b200.config import fish_speech_1_5_config, s1_mini_config  # noqa: E402
 from fish_tts_b200.engine import DualAREngine  # noqa: E402
 from fish_tts_b200.synthetic import make_state_dict, synthetic_prompt  # noqa: E402
 from helpers import variant_configs  # noqa: E402
 
 names = sys.argv[1:] or ["s1like", "v15like", "biased", "s1mini"]
 for name in names:
-    cfg = s1_mini_config() if name == "s1mini" else variant_configs()[name]
+    cfg = s1_mini_config() if name == "s1mini" else fish_speech_1_5_config() if name == "v15" else variant_configs()[name]
     sd = make_state_dict(cfg, seed=0)
     prompt = synthetic_prompt(cfg, 5, 12, 4, seed=1)
     outs = []
@@ -38,10 +38,14 @@ for name in names:
     print(name, "tokens equal:", bool((a[0] == b[0]).all()), "fast_logits equal:", torch.equal(a[1], b[1]),
           "slow_logits equal:", torch.equal(a[2], b[2]), "hidden equal:", torch.equal(a[3], b[3]))
     if not (a[0] == b[0]).all():
-        bad = torch.nonzero(a[0] != b[0])
+        import numpy as np
+        bad = np.argwhere(np.asarray(a[0]) != np.asarray(b[0]))
         print("  first mismatches (row, col):", bad[:8].tolist())
-        print("  mega :", a[0][:, :6].tolist())
-        print("  phase:", b[0][:, :6].tolist())
+        print("  mega :", np.asarray(a[0])[:, :6].tolist())
+        print("  phase:", np.asarray(b[0])[:, :6].tolist())
+        sl_a, sl_b = a[2].float(), b[2].float()
+        ta, tb = int(np.asarray(a[0])[0, 0]), int(np.asarray(b[0])[0, 0])
+        print(f"  slow logit of mega's token: mega {sl_a[ta]:.4f} phase {sl_b[ta]:.4f}; of phase's token: mega {sl_a[tb]:.4f} phase {sl_b[tb]:.4f}")
     if not torch.equal(a[2], b[2]):
         d = (a[2].float() - b[2].float()).abs()
         print("  slow logits max diff", d.max().item(), "n diff", int((d > 0).sum()))

@@ -409,3 +409,24 @@ def test_api_errors():
     out = eng.generate(synthetic_prompt(cfg, 2, 3, 1), 5)      # still usable after errors
     assert out.shape[1] == 5
     eng.close()
+
+
+def test_fish_speech_1_5_shape_full_size():
+    """BASELINE configs[2] shape (24 layers, GQA 8, untied 102k head, 8 x 1024 codebooks) at full size on the persistent
+    kernel: id ranges, determinism under a fixed seed, and agreement of the first decode step with the per-phase kernels"""
+    from fish_tts_b200.config import fish_speech_1_5_config
+    cfg = fish_speech_1_5_config()
+    sd = make_state_dict(cfg, seed=0)
+    prompt = synthetic_prompt(cfg, 5, 12, 4, seed=1)
+    runs = []
+    for flag in (1, 1, 0):
+        eng = DualAREngine(cfg, sd, device=0, seed=5, options={"mega_kernel": flag})
+        toks = torch.as_tensor(eng.generate(prompt, 24 if flag else 1, 0.7, 0.8, 1.1))
+        runs.append((toks, eng.read("slow_logits_raw").clone(), eng.launches_per_step()))
+        eng.close()
+    (t1, l1, n1), (t2, l2, n2), (t0, l0, n0) = runs
+    assert n1[0] == 1 and n0[0] > 1, "the 1.5 shape must run on the persistent kernel"
+    assert torch.equal(t1, t2) and torch.equal(l1, l2), "same seed, same tokens and logits"
+    assert ((t1[0] >= cfg.semantic_begin_id) & (t1[0] <= cfg.semantic_end_id)).all()
+    assert ((t1[1:] >= 0) & (t1[1:] < cfg.codebook_size)).all()
+    assert int(t1[0, 0]) == int(t0[0, 0]) or near_tie(l0, int(t1[0, 0]), int(t0[0, 0]), ulps=8.0, atol=5e-2)

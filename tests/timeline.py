@@ -29,12 +29,13 @@ if n_step == 1:
     names = []
     for i in range(L):
         names += [f"S.qkv", "S.attn", "S.merge", "S.wo", "S.w13", "S.w2"]
-    names += ["H.head", "H.stat", "H.cand"]
-    for p in range(cfg.num_codebooks):
+    for l in range(cfg.n_fast_layer):      # fast pass 0, one slice of the LM head in front of every phase
+        names += ["H.head", "F.qkv", "H.head", "F.wo", "H.head", "F.w13", "H.head", "F.w2"]
+    names += ["H.stat", "H.cand"]
+    for p in range(1, cfg.num_codebooks):
         for l in range(cfg.n_fast_layer):
             names += ["F.qkv", "F.wo", "F.w13", "F.w2"]
-        if p:
-            names.append("F.head")
+        names.append("F.head")
     nph = len(names)
     full = eng.read("timeline").numpy().astype("int64")
     dbg = full[400:400 + nph, :4]
@@ -56,7 +57,7 @@ if n_step == 1:
         st = staged[i] - start[i] if tl[1 + i, 1] else float("nan")
         cp = done[i] - (staged[i] if tl[1 + i, 1] else start[i])
         a = agg[nm]; a[0] += 1; a[1] += 0.0 if st != st else st; a[2] += cp; a[3] += period
-        if i < 14 or 6 * L - 7 <= i < 6 * L + 24 or i >= nph - 12:
+        if i < 14 or 6 * L - 7 <= i < 6 * L + 40 or i >= nph - 12:
             print(f"{i:4d} {nm:8s} {start[i]:8.2f} {st:8.2f} {cp:8.2f} {period:8.2f} | {waits[i]:6.2f} | {pfirst[i] - start[i]:8.2f} {plast[i] - start[i]:8.2f} | cyc take {dbg[i,0]:6d} mma {dbg[i,1]:6d} part {dbg[i,2]:6d} fold {dbg[i,3]:6d}")
     print("kind       n   staged  compute   period      sum")
     for k, a in agg.items():
@@ -95,7 +96,7 @@ if n_step == 1:
     print("  ph name     first_staged last_staged | first_done last_done (cta) | CTA0 done | next phase first_staged")
     for i, nm in enumerate(names):
         if t2[i, :, 0].min() == 0: continue
-        if not (12 <= i < 24 or 171 <= i < 180): continue
+        if not (12 <= i < 24 or 6 * L <= i < 6 * L + 12): continue
         s0 = t2[i, :, 0].min()
         nxt = [j for j in range(i + 1, nph) if t2[j, :, 0].min() > 0]
         nx = (t2[nxt[0], :, 0].min() - s0) / 1e3 if nxt else float('nan')
@@ -106,8 +107,8 @@ if n_step == 1:
     print(f"ring waits per warp over the whole step (us): mean {wc.mean():.1f}  min {wc.min():.1f}  max {wc.max():.1f}; per-CTA mean: min {wc.mean(1).min():.1f} (cta {int(wc.mean(1).argmin())})  max {wc.mean(1).max():.1f} (cta {int(wc.mean(1).argmax())}); CTA 0: {wc[0].mean():.1f}")
     print('slow-head candidates of the last step:', int(eng.read('n_cand')[0]), ' nucleus sizes (slow, fast heads):', eng.read('nucleus').tolist())
     slow_end = start[6 * L]
-    head_end = start[6 * L + 3]
-    print(f"slow stack {slow_end:.1f} us | head+sampler {head_end - slow_end:.1f} us | fast {end - head_end:.1f} us")
+    i_hs = names.index("H.stat")
+    print(f"slow stack {slow_end:.1f} us | LM head + fast pass 0 {start[i_hs] - slow_end:.1f} us | slow sampler {start[i_hs + 2] - start[i_hs]:.1f} us | fast passes 1.. {end - start[i_hs + 2]:.1f} us")
     sys.exit(0)
 
 tl = eng.read("timeline")[:n_step].numpy()
