@@ -596,7 +596,7 @@ extern "C" int dualar_finalize(dualar_engine *e) {
   { const char *v = getenv("DUALAR_PDL"); if (v && v[0] == '0') g_use_pdl = false; }
   { const char *v = getenv("DUALAR_MEGA"); if (v) e->use_mega = v[0] != '0'; }
   if (e->use_mega && (rc = build_mega(e)) < 0) return rc;
-  { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 1024; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc;
+  { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 2048; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc;
       if ((rc = dev_alloc(e, e->tl2, (size_t)DA_M_MAX_PHASES * 160 * 4))) return rc; } }
   // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
   { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);

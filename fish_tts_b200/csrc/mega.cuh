@@ -517,9 +517,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) { const int c = tid + i * DA_M_CTHREADS; if (c < n16) reinterpret_cast<uint4 *>(kv_l)[c] = pre[i]; }
-        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 0, gtime());
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 0, gtime());
         cbar();
-        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 1, gtime());
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 1, gtime());
         const bf16 *rope_row = a.frope + (size_t)p * hd;
         if (a.fqn[d.layer] || a.fkn[d.layer]) {      // qk-norm needs a per-head reduction first: one warp per head vector
           for (int h = w; h < nh + nkv; h += DA_M_CWARPS) {
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           kv_g[((size_t)p * 2 + 0) * kd + e] = kb; kv_g[((size_t)p * 2 + 1) * kd + e] = vb;
         }
         cbar();
-        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 2, gtime());
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 2, gtime());
         // one HALF-warp per head (30 half-warps for <= 16 heads: every head in one round), both halves run the same code
         float *prs = vcur + kd;                                     // [nh][16] scores, then probabilities
         const int sl = lane & 15, hsel = lane & 16;
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             if (hlive) *reinterpret_cast<uint32_t *>(xb + h * hd + d0) = (uint32_t)f2bits(y0) | ((uint32_t)f2bits(y1) << 16);
           }
         }
-        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 3, gtime());
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 3, gtime());
       } else {
         // thread c < K/8 owns elements [4c, 4c+4) and [K/2 + 4c, K/2 + 4c + 4)
         const int c = tid, e_lo = 4 * c, e_hi = (K >> 1) + 4 * c;
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           }
           SampleParams spm;
           int par = 0;
-          if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 0, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 0, gtime());
           r = block_reduce<G4>(r, scr, par);
           spm.m = bits2f(key_bf16((uint32_t)r.m));
           Red es = {0ull, 0, -1};      // sum of exp terms as 2^-40 fixed point: order-free, identical to the per-phase path
@@ -802,12 +802,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           spm.c_max = cmax_from_top_p(st->top_p);
           const NoiseSrc nsrc = noise_src(st);
           G4::sync();
-          if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 1, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 1, gtime());
           uint32_t tok = sample_sorted<DA_G_IPT, 128, G4>(it8, (uint32_t)V, true, nullptr, spm, nsrc, (uint32_t)d.pos, a.noise_off0 + (long long)(d.pos - 1) * a.fv,
                                                           &st->nucleus[d.pos], reinterpret_cast<uint32_t *>(scr + 256), scr);
           if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (tid == 0) st->err = 3; }
           if (tid == 0) { s_tok = tok; st->tok_out[d.pos + 1] = (int)tok; }
-          if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 2, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 2, gtime());
         }
         cbar();
         if (d.pos < a.ncb - 1) {
@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
         }
       }
-      if (TL && a.tl && tid == 0) tl_put(a, 700 + ph, 3, gtime());
+      if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 3, gtime());
       // No CTA barrier ends a plain GEMV phase: the staging buffer alternates, the partial-sum slots are handed over by their
       // generation counters, and the first barrier of the next phase's staging cannot be passed before every fold of this
       // phase is done.  The head phases keep one (sm_work / sm_lg are reused by the sampler phases that follow).
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             for (int j = 0; j < 8; ++j) dst[j] = t[j];
           }
         }
-        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 0, gtime());
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 0, gtime());
         cbar();
         const bf16 *rope_row = a.rope + (size_t)pos * hd;
         for (int h = w; h < G + (owns_new ? 1 : 0); h += DA_M_CWARPS) {      // one warp per head vector: qk-norm, RoPE, then its follow-up
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         }
         cbar();
         if (TL) tl_mark(a, 1 + ph, 1);
-        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 1, gtime());
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 1, gtime());
         // Running (max, sum, output) of every warp live in its private slice of shared memory (pm / pl / po) and are pulled into
         // registers for two query heads at a time, so one code path serves every GQA group size and head dimension (dims per lane
         // dpl = hd / 32 <= 4) without per-shape instantiations -- unexecuted variants measurably slowed the whole kernel down.
@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             landed(bi, par);
             kt = reinterpret_cast<const bf16 *>(sm_ring + at); vt = reinterpret_cast<const bf16 *>(sm_ring + at + bytes);
           }
-          if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 3, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 3, gtime());
           for (int h0 = 0; h0 < G; h0 += 2) {
             float qr[2][4], m_run[2], l_run[2], o_acc[2][4];
 #pragma unroll
@@ -965,13 +965,13 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             }
             __syncwarp();
           }
-          if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 4, gtime());
+          if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 4, gtime());
           if (n_old > 0) {      // every warp is past its last read of the tile: one arrival releases the sm_ring entry
             cbar();
             if (tid == DA_M_CTHREADS - 1) mbar_arrive(&sm_empty[bi]);
           }
         }
-        if (TL && a.tl && tid == 0) tl_put(a, 400 + ph, 2, gtime());
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 2, gtime());
         // thread e = (h, d) folds the 16 partials in warp order
         cbar();
         const uint32_t t32 = tag32_of(ph);
@@ -1091,6 +1091,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       const float m = h_m, thr = m - a.delta;
       const GemvPart gp = gemv_part(a.vocab, a.head_pq, a.head_prem, bid);
       const uint32_t base = s_base, N = s_n;
+      if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 0, gtime());
       if (N <= DA_CAND_CAP) {
         // this CTA's candidates in vocabulary order: slot numbers increase with the index (ties of the sort need that)
         const int per = (h_cnt + DA_M_CTHREADS - 1) / DA_M_CTHREADS;
@@ -1114,6 +1115,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           }
         }
       }
+      if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 1, gtime());
       if (bid == 0) {
         SampleParams spm;
         spm.m = m; spm.S = __ull2float_rn(s_S) * (1.0f / DA_FIX2_SCALE);
@@ -1149,6 +1151,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
               if (good || ++spin >= DA_SPIN_LIMIT) break;
             }
             ok = ok && spin < DA_SPIN_LIMIT;
+            if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 2, gtime());
             const uint32_t r = sample_sorted<16, 256, G8>(it, N, (int)N == a.vocab, a.cand, spm, nsrc, 0u, 0ll, &st->nucleus[0], sm_sort, scr);
             if (tid == 0) s_idx = r;
           }
@@ -1161,6 +1164,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           idx = sample_fallback<CBlock>(a.logits, a.vocab, spm, nsrc, 0u, 0ll, &st->nucleus[0], scr + 192, reinterpret_cast<float *>(scr + 192 + 34));
         }
         // inference.py:123-126: first codebook = semantic id - semantic_begin (clamped at 0); next input = its fast embedding
+        if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 3, gtime());
         int cb0 = (int)idx - a.sem_begin; if (cb0 < 0) cb0 = 0;
         if (cb0 >= a.codebook_size) { cb0 = a.codebook_size - 1; if (tid == 0) st->err = 3; }
         for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)cb0 * a.fdim + dd]), tag));

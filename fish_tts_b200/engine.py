@@ -227,7 +227,7 @@ class DualAREngine:
             "qkv": (((cfg.n_head + 2 * cfg.n_local_heads) * cfg.head_dim,), torch.bfloat16),
             "y": ((cfg.n_head * cfg.head_dim,), torch.bfloat16), "h": ((cfg.dim,), torch.bfloat16),
             "act": ((cfg.intermediate_size,), torch.bfloat16), "fast_x": ((cfg.fast_dim,), torch.bfloat16),
-            "fast_in": ((cfg.fast_dim,), torch.bfloat16), "timeline": ((1024, 8), torch.int64), "cand": ((8192,), torch.int64), "timeline2": ((400, 160, 4), torch.int64),
+            "fast_in": ((cfg.fast_dim,), torch.bfloat16), "timeline": ((2048, 8), torch.int64), "cand": ((8192,), torch.int64), "timeline2": ((400, 160, 4), torch.int64),
         }
         shape, dt = shapes[name]
         out = torch.empty(shape, dtype=dt)

@@ -38,7 +38,7 @@ if n_step == 1:
         names.append("F.head")
     nph = len(names)
     full = eng.read("timeline").numpy().astype("int64")
-    dbg = full[400:400 + nph, :4]
+    dbg = full[512:512 + nph, :4]
     tl = full[: nph + 1]
     t0 = tl[0, 0]
     start = (tl[1:, 0] - t0) / 1e3
@@ -63,7 +63,7 @@ if n_step == 1:
     for k, a in agg.items():
         n = a[0]
         print(f"{k:8s} {n:4d} {a[1] / n:8.2f} {a[2] / n:8.2f} {a[3] / n:8.2f} {a[3]:8.1f}")
-    fa = full[400:400 + nph, :6]
+    fa = full[512:512 + nph, :6]
     acc = [0.0] * 5; nfa = 0
     for i, nm in enumerate(names):
         if nm == "F.wo" and fa[i, 0]:
@@ -84,7 +84,11 @@ if n_step == 1:
         w1 = [ (fa[i,4]-fa[i,3])/1e3 for i,nm in enumerate(names) if nm == 'S.attn' and fa[i,0] and i > 6]
         w2 = [ (fa[i,2]-fa[i,4])/1e3 for i,nm in enumerate(names) if nm == 'S.attn' and fa[i,0] and i > 6]
         print('    tile walk split: init+wait for tile %.2f | warp 0 compute %.2f | barrier after tile + state %.2f' % (sum(w0)/len(w0), sum(w1)/len(w1), sum(w2)/len(w2)))
-    hs = full[700:700 + nph, :4]
+    hs = full[1024:1024 + nph, :4]
+    i_hc = names.index("H.cand")
+    if hs[i_hc, 0]:
+        x = [tl[1 + i_hc, 0]] + [hs[i_hc, k] for k in range(4)] + [tl[1 + i_hc, 2]]
+        print("  H.cand (CTA 0, us): poll stats + prefix %.2f | write candidates %.2f | fetch candidates %.2f | sample_sorted %.2f | embedding publish %.2f" % tuple((x[k + 1] - x[k]) / 1e3 for k in range(5)))
     for i, nm in enumerate(names):
         if nm == "F.head" and i < nph - 1:
             print(f"  F.head ph {i}: start {start[i]:.2f} staged +{staged[i]-start[i]:.2f} compute +{done[i]-staged[i]:.2f} | polled +{(hs[i,0]-t0)/1e3-done[i]:.2f} | m,S +{(hs[i,1]-hs[i,0])/1e3:.2f} | sample_sorted +{(hs[i,2]-hs[i,1])/1e3:.2f} | publish+bar +{(hs[i,3]-hs[i,2])/1e3:.2f}")
