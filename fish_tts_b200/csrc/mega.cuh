@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       if (FULL && (d.epi == ME_FASTLOGITS || d.epi == ME_SLOWLOGITS)) { rp_eff = eff_rep_penalty(st); use_pen = st->use_penalty; }
       if (FULL && d.epi == ME_FASTLOGITS && use_pen && lane < DA_WIN) pen_id = st->win[(d.pos + 1) * DA_WIN + lane];
       if (FULL && d.epi == ME_SLOWLOGITS && use_pen && lane < a.n_rows_tok) pen_id = st->win[lane * DA_WIN];     // previous_tokens[:, 0]
-      if (!parted || d.part == 0) h_wmax = -INFINITY;
+      if (d.epi == ME_SLOWLOGITS && (!parted || d.part == 0)) h_wmax = -INFINITY;      // the CTA maximum runs over all parts of the head
       const float *resv = sm_raw + ((d.flags & MF_RES1) ? dim_max : 0);
       const uint32_t RS = row_stride(K);
       const uint32_t *xw = reinterpret_cast<const uint32_t *>(xb);
@@ -1123,40 +1123,31 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         spm.c_max = cmax_from_top_p(st->top_p);
         const NoiseSrc nsrc = noise_src(st);
         uint32_t *sm_sort = reinterpret_cast<uint32_t *>(sm_work);
-        unsigned long long *scr = reinterpret_cast<unsigned long long *>(sm_work + 16384);
+        unsigned long long *scr = reinterpret_cast<unsigned long long *>(sm_work + 16896);
         cbar();   // hv is dead: sm_work becomes the sampler's sm_scratch
         uint32_t idx = 0xFFFFFFFFu;
-        // sort-based sampler over the candidate list, 8 consecutive entries per thread fetched with four 16-byte polls issued
-        // together (one L2 round trip): <= 1024 candidates by warps 0-3 (the fast heads' instantiation), <= 4096 by all 16 warps;
-        // wider nuclei take the whole-vocabulary fallback
-        typedef BlockNamed<4, 256> G8;      // warps 0-7
-        __shared__ uint32_t s_idx;
+        // binned sampler over the candidate list (<= 4096 candidates, all 16 warps); wider nuclei take the whole-vocabulary fallback
         if (N >= 1 && N <= 4096) {
-          if (w < 8) {
-            // 16 consecutive entries per thread, fetched with 16-byte polls issued together (entry = inverted key (16) | index (18) | tag (30))
-            const unsigned e0 = tid * 16;
-            uint32_t it[16];
-            int spin = 0;
-            for (;;) {
-              bool good = true;
+          // 8 consecutive entries per thread, fetched with 16-byte polls issued together (entry = inverted key (16) | index (18) | tag (30))
+          const unsigned e0 = tid * 8;
+          uint32_t it[8];
+          int spin = 0;
+          for (;;) {
+            bool good = true;
 #pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                unsigned long long k0 = 0, k1 = 0;
-                if (e0 + i < N) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(a.cand + e0 + i) : "memory");
-                it[i] = (e0 + i < N) ? (((uint32_t)(k0 >> 48) << 16) | (e0 + i)) : 0xFFFFFFFFu;
-                it[i + 1] = (e0 + i + 1 < N) ? (((uint32_t)(k1 >> 48) << 16) | (e0 + i + 1)) : 0xFFFFFFFFu;
-                if (e0 + i < N) good &= ((uint32_t)(k0 & 0x3FFFFFFFu) == tag30);
-                if (e0 + i + 1 < N) good &= ((uint32_t)(k1 & 0x3FFFFFFFu) == tag30);
-              }
-              if (good || ++spin >= DA_SPIN_LIMIT) break;
+            for (int i = 0; i < 8; i += 2) {
+              unsigned long long k0 = 0, k1 = 0;
+              if (e0 + i < N) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(a.cand + e0 + i) : "memory");
+              it[i] = (e0 + i < N) ? (((uint32_t)(k0 >> 48) << 16) | (e0 + i)) : 0xFFFFFFFFu;
+              it[i + 1] = (e0 + i + 1 < N) ? (((uint32_t)(k1 >> 48) << 16) | (e0 + i + 1)) : 0xFFFFFFFFu;
+              if (e0 + i < N) good &= ((uint32_t)(k0 & 0x3FFFFFFFu) == tag30);
+              if (e0 + i + 1 < N) good &= ((uint32_t)(k1 & 0x3FFFFFFFu) == tag30);
             }
-            ok = ok && spin < DA_SPIN_LIMIT;
-            if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 2, gtime());
-            const uint32_t r = sample_sorted<16, 256, G8>(it, N, (int)N == a.vocab, a.cand, spm, nsrc, 0u, 0ll, &st->nucleus[0], sm_sort, scr);
-            if (tid == 0) s_idx = r;
+            if (good || ++spin >= DA_SPIN_LIMIT) break;
           }
-          cbar();
-          idx = s_idx;
+          ok = ok && spin < DA_SPIN_LIMIT;
+          if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 2, gtime());
+          idx = sample_binned<8, DA_M_CTHREADS, CBlock>(it, N, (int)N == a.vocab, a.cand, spm, nsrc, 0u, 0ll, &st->nucleus[0], sm_sort, scr);
         }
         cbar();
         if (idx == 0xFFFFFFFFu) {

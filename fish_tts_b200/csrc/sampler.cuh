@@ -416,6 +416,139 @@ __device__ __noinline__ uint32_t sample_sorted(uint32_t (&a_in)[E], uint32_t n, 
   return best.idx;
 }
 
+// ---- binned nucleus sampler -----------------------------------------------------------------------
+// Same result as sample_sorted(), without sorting.  The nucleus is a prefix of the (logit desc, index asc) order, so only
+// the position of the cut has to be exact.  Items are binned by their distance below the maximum (NB/8 bins per unit;
+// everything further than 8 below shares the last bin) -- monotone in the logit, so bins respect the order.  Per bin the
+// kernel accumulates the exact fixed-point weight (three 15-bit limbs, 32-bit shared atomics: integer, order-free) and
+// the item count; one block scan finds the bin whose cumulative weight first exceeds c_max.  Bins ahead of it are kept
+// whole, bins after it dropped whole, and only the items of the cut bin (a few dozen) are ranked exactly against each
+// other.  The kept items stay with the threads that hold them, so the Philox draws of the race run in parallel.
+// sm: 4*NB + 2*NT + 8 words + NT u64 (and >= NT*E words for the sort fallback, taken when the cut bin has > NT items).
+template <int E, int NT, class B, int NB = 512>
+__device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, bool all_present, const unsigned long long *slot2idx, const SampleParams &sp,
+                                  const NoiseSrc &st, uint32_t head, long long head_off, int *nucleus_out, uint32_t *sm, unsigned long long *scr) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  constexpr int NW = NT / 32, BPT = (NB + NT - 1) / NT;
+  uint32_t *h0 = sm, *h1 = sm + NB, *h2 = sm + 2 * NB, *hc = sm + 3 * NB;
+  uint32_t *list = sm + 4 * NB, *flag = list + NT, *misc = flag + NT;
+  unsigned long long *wl = reinterpret_cast<unsigned long long *>(misc + 8);
+  for (int i = t; i < 4 * NB; i += NT) sm[i] = 0u;
+  if (t == 0) { misc[0] = 0u; misc[1] = (uint32_t)NB; misc[2] = 0u; misc[3] = 0u; misc[4] = 0u; }
+  B::sync();
+  uint32_t a[E]; int bin[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    a[e] = a_in[e];
+    bin[e] = NB;
+    if (a[e] != 0xFFFFFFFFu) {
+      const float z = bits2f(key_bf16(0xFFFFu - (a[e] >> 16)));
+      const unsigned long long wv = pweight(z, sp.m, sp.S);
+      const int b = (int)fminf(fmaxf((sp.m - z) * (float)(NB / 8), 0.f), (float)(NB - 1));      // clamps keep the map monotone
+      bin[e] = b;
+      const uint32_t l0 = (uint32_t)wv & 0x7FFFu, l1 = (uint32_t)(wv >> 15) & 0x7FFFu, l2 = (uint32_t)(wv >> 30);
+      if (l0) atomicAdd(h0 + b, l0);
+      if (l1) atomicAdd(h1 + b, l1);
+      if (l2) atomicAdd(h2 + b, l2);
+      atomicAdd(hc + b, 1u);
+    }
+  }
+  B::sync();
+  // block scan over the bins (thread t owns bins t*BPT ..): inclusive weight and count
+  unsigned long long hs[BPT], bw[BPT]; int cs[BPT];
+  unsigned long long run = 0ull; int crun = 0;
+#pragma unroll
+  for (int i = 0; i < BPT; ++i) {
+    const int b = t * BPT + i;
+    bw[i] = 0ull;
+    if (b < NB) { bw[i] = (unsigned long long)h0[b] + ((unsigned long long)h1[b] << 15) + ((unsigned long long)h2[b] << 30); crun += (int)hc[b]; }
+    run += bw[i]; hs[i] = run; cs[i] = crun;
+  }
+  unsigned long long inc = run; int cinc = crun;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, o);
+    const int y = __shfl_up_sync(0xffffffffu, cinc, o);
+    if (lane >= o) { inc += x; cinc += y; }
+  }
+  unsigned long long *wsum = scr;                 // [NW] warp totals
+  int *wcnt = reinterpret_cast<int *>(scr + 40);  // [NW]
+  if (lane == 31) { wsum[w] = inc; wcnt[w] = cinc; }
+  B::sync();
+  unsigned long long base = inc - run; int cbase = cinc - crun;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) if (i < w) { base += wsum[i]; cbase += wcnt[i]; }
+#pragma unroll
+  for (int i = 0; i < BPT; ++i) {
+    const unsigned long long incl = base + hs[i], excl = incl - bw[i];
+    if (excl <= sp.c_max && incl > sp.c_max) {      // the one bin where the cumulative weight crosses c_max
+      const int b = t * BPT + i;
+      misc[1] = (uint32_t)b; misc[2] = (uint32_t)excl; misc[3] = (uint32_t)(excl >> 32); misc[4] = (uint32_t)(cbase + cs[i] - (int)hc[b]);
+    }
+  }
+  B::sync();
+  const int cut = (int)misc[1];
+  const unsigned long long before = (unsigned long long)misc[2] | ((unsigned long long)misc[3] << 32);
+  const int cnt_before = (int)misc[4];
+  int mypos[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    mypos[e] = -1;
+    if (a[e] != 0xFFFFFFFFu && bin[e] == cut) {
+      const int p = (int)atomicAdd(misc, 1u);
+      mypos[e] = p;
+      if (p < NT) { list[p] = a[e]; wl[p] = pweight(bits2f(key_bf16(0xFFFFu - (a[e] >> 16))), sp.m, sp.S); }
+    }
+  }
+  B::sync();
+  const int n2 = (int)misc[0];
+  if (n2 > NT) {                                    // degenerate (a flat tail in one bin): the sorting sampler handles it
+    B::sync();
+    return sample_sorted<E, NT, B>(a_in, n, all_present, slot2idx, sp, st, head, head_off, nucleus_out, sm, scr);
+  }
+  if (t < n2) {
+    const uint32_t ci = list[t];
+    unsigned long long G = before; bool pre = false;
+    for (int j = 0; j < n2; ++j) if (list[j] < ci) { G += wl[j]; pre = true; }
+    flag[t] = ((G + wl[t] <= sp.c_max) || (!pre && cnt_before == 0)) ? 1u : 0u;      // the first item of the order is always kept
+  }
+  B::sync();
+  // second softmax over the kept items (exp terms summed as 2^-40 fixed point => order-free) and the race
+  const float mz = rbf(sp.m / sp.T_bf);             // the top item is the maximum
+  float e2[E];
+  uint32_t keep = 0u;
+  Red s2 = {0ull, 0, -1};
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    e2[e] = 0.f;
+    const bool k = a[e] != 0xFFFFFFFFu && (bin[e] < cut || (bin[e] == cut && flag[mypos[e]] != 0u));
+    if (k) {
+      keep |= 1u << e; ++s2.c;
+      e2[e] = expf(rbf(bits2f(key_bf16(0xFFFFu - (a[e] >> 16))) / sp.T_bf) - mz);
+      s2.s += (unsigned long long)(e2[e] * DA_FIX2_SCALE);
+    }
+  }
+  int parity = 0;
+  B::sync();                                       // wsum / wcnt are dead: scr becomes block_reduce scratch
+  s2 = block_reduce<B>(s2, scr, parity);
+  if (s2.c == (int)n && !all_present) return 0xFFFFFFFFu;
+  if (t == 0 && nucleus_out) *nucleus_out = s2.c;
+  const float S2 = __ull2float_rn(s2.s) * (1.0f / DA_FIX2_SCALE);
+  ArgBest best = {0.f, 0u};   // removed tokens have probability 0 -> r = 0; argmax ties go to index 0
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (keep & (1u << e)) {
+    const uint32_t tie = a[e] & 0xFFFFu;
+    const uint32_t idx = slot2idx ? (uint32_t)((slot2idx[tie] >> 30) & 0x3FFFFu) : tie;      // candidate entry: key (16) | index (18) | tag (30)
+    const float p2 = rbf(e2[e] / S2);
+    ArgBest cnd = {rbf(p2 / noise_at(st, head, head_off, idx)), idx};
+    best = better(best, cnd);
+  }
+  B::sync();
+  float *fs = reinterpret_cast<float *>(scr);
+  best = block_argbest<B>(best, fs, reinterpret_cast<uint32_t *>(fs + 40));
+  return best.idx;
+}
+
 // ---- fallback: nucleus wider than the candidate list (flat distributions) ------------------------
 // One CTA walks the whole logits vector from global memory; all sums are u64, so order-free.
 template <class B = BlockAll>
