@@ -436,6 +436,7 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
   for (int i = t; i < 4 * NB; i += NT) sm[i] = 0u;
   if (t == 0) { misc[0] = 0u; misc[1] = (uint32_t)NB; misc[2] = 0u; misc[3] = 0u; misc[4] = 0u; }
   B::sync();
+  DA_ST(0);
   uint32_t a[E]; int bin[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -454,6 +455,7 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
     }
   }
   B::sync();
+  DA_ST(1);
   // block scan over the bins (thread t owns bins t*BPT ..): inclusive weight and count
   unsigned long long hs[BPT], bw[BPT]; int cs[BPT];
   unsigned long long run = 0ull; int crun = 0;
@@ -490,6 +492,7 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
   const int cut = (int)misc[1];
   const unsigned long long before = (unsigned long long)misc[2] | ((unsigned long long)misc[3] << 32);
   const int cnt_before = (int)misc[4];
+  DA_ST(2);
   int mypos[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -502,6 +505,7 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
   }
   B::sync();
   const int n2 = (int)misc[0];
+  DA_ST(3);
   if (n2 > NT) {                                    // degenerate (a flat tail in one bin): the sorting sampler handles it
     B::sync();
     return sample_sorted<E, NT, B>(a_in, n, all_present, slot2idx, sp, st, head, head_off, nucleus_out, sm, scr);
@@ -513,6 +517,7 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
     flag[t] = ((G + wl[t] <= sp.c_max) || (!pre && cnt_before == 0)) ? 1u : 0u;      // the first item of the order is always kept
   }
   B::sync();
+  DA_ST(4);
   // second softmax over the kept items (exp terms summed as 2^-40 fixed point => order-free) and the race
   const float mz = rbf(sp.m / sp.T_bf);             // the top item is the maximum
   float e2[E];
@@ -531,6 +536,7 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
   int parity = 0;
   B::sync();                                       // wsum / wcnt are dead: scr becomes block_reduce scratch
   s2 = block_reduce<B>(s2, scr, parity);
+  DA_ST(5);
   if (s2.c == (int)n && !all_present) return 0xFFFFFFFFu;
   if (t == 0 && nucleus_out) *nucleus_out = s2.c;
   const float S2 = __ull2float_rn(s2.s) * (1.0f / DA_FIX2_SCALE);
@@ -543,9 +549,11 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
     ArgBest cnd = {rbf(p2 / noise_at(st, head, head_off, idx)), idx};
     best = better(best, cnd);
   }
+  DA_ST(6);
   B::sync();
   float *fs = reinterpret_cast<float *>(scr);
   best = block_argbest<B>(best, fs, reinterpret_cast<uint32_t *>(fs + 40));
+  DA_ST(7);
   return best.idx;
 }
 

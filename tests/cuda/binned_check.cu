@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#define DA_SAMPLER_TIMING 1
 #include "../../fish_tts_b200/csrc/sampler.cuh"
 using namespace da;
 template <int E, int NT, class G>
@@ -71,6 +72,10 @@ int main() {
         cudaError_t e = cudaMemcpy(&tk[which], t, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&nk[which], n, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&cy[which], c, 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
         cyc[big][which] += cy[which];
+      }
+      if (seed == 0 && ap == 1 && (top_p == 0.8f)) {
+        long long ts[16]; cudaMemcpyFromSymbol(ts, g_sampler_t, sizeof(ts));
+        printf("V %d dist %d binned sections (cycles): hist %lld | scan+cut %lld | list %lld | rank %lld | keep+S2 %lld | race %lld | argbest %lld | total %lld nucleus %d\n", V, dist, ts[1]-ts[0], ts[2]-ts[1], ts[3]-ts[2], ts[4]-ts[3], ts[5]-ts[4], ts[6]-ts[5], ts[7]-ts[6], cy[1], nk[1]);
       }
       ++total;
       if (tk[0] != tk[1] || nk[0] != nk[1]) { if (++bad <= 20) printf("MISMATCH V %d dist %d seed %d top_p %g all_present %d: sorted tok %u nucleus %d | binned tok %u nucleus %d\n", V, dist, seed, top_p, ap, tk[0], nk[0], tk[1], nk[1]); }
