@@ -407,7 +407,10 @@ static int build_mega(dualar_engine *e) {
       pairs(qkv_rows) < grid || pairs(2 * c.intermediate_size) < grid || pairs(fqkv_rows) < grid || pairs(2 * c.fast_intermediate_size) < grid ||
       G * c.head_dim > 1024 || c.vocab_size > (1 << 18) || (c.num_codebooks - 1) * 2 * fkd / 8 > 3 * DA_M_CTHREADS || c.head_dim < 32 ||
       c.dim > 8 * DA_M_CTHREADS || c.intermediate_size > 8 * DA_M_CTHREADS || c.fast_intermediate_size > 8 * DA_M_CTHREADS || qd > 8 * DA_M_CTHREADS || fqkv_rows > 8 * DA_M_CTHREADS ||
-      3 * grid > DA_M_CTHREADS) { e->use_mega = false; return 0; }
+      3 * grid > DA_M_CTHREADS ||
+      (c.head_dim & (c.head_dim - 1)) || c.head_dim > 256 ||                                            // a head vector = hd/8 lanes of one warp (attention staging)
+      (c.fast_head_dim & (c.fast_head_dim - 1)) || c.fast_head_dim < 32 || c.fast_head_dim > 128 ||     // ... hd/4 lanes in the fast stack
+      ((c.fast_n_head + 2 * c.fast_n_local_heads) & 1)) { e->use_mega = false; return 0; }
   int rc;
   // every broadcast unit vector exists DA_M_REP times, `ustride` units apart
   int umax = qkv_rows; for (int v : {c.dim, qd, c.intermediate_size, fqkv_rows, c.fast_dim, c.fast_intermediate_size, e->fv}) if (v > umax) umax = v;

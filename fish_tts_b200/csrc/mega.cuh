@@ -502,16 +502,55 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         const int n16 = p * 2 * kd / 8;                                // 16-byte pieces of the rows of positions < p
 #pragma unroll
         for (int i = 0; i < 3; ++i) { const int c = tid + i * DA_M_CTHREADS; if (c < n16) pre[i] = __ldcg(reinterpret_cast<const uint4 *>(kv_g) + c); }
+        // Thread c polls elements [4c, 4c+4) and [N/2 + 4c, +4) of q | k | v.  A head vector is hd/4 consecutive lanes of one warp
+        // in either half, so qk-norm and RoPE run in registers on the polled values; q goes to shared memory as fp32, the new
+        // K / V row straight into the caches as bf16 -- one CTA barrier before the scores.
         {
-          const int c = tid, N = qd + 2 * kd;
-          if (c * 8 < N) {
+          const int c = tid, N = qd + 2 * kd, LH = hd >> 2;
+          const bf16 *rope_row = a.frope + (size_t)p * hd;
+          const bool any_norm = a.fqn[d.layer] || a.fkn[d.layer];
+          if ((c & ~31) * 8 < N) {                            // warp-uniform: the shuffles below need whole warps
+            const bool act = c * 8 < N;
             float t[8];
-            ok = poll_pair(in + c * 4, in + N / 2 + c * 4, in_tag, t) && ok;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = 0.f;
+            if (act) ok = poll_pair(in + c * 4, in + N / 2 + c * 4, in_tag, t) && ok;
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
-              const int e = hlf * (N / 2) + c * 4;
-              float *dst = e < qd ? q + e : (e < qd + kd ? kcur + (e - qd) : vcur + (e - qd - kd));
-              *reinterpret_cast<float4 *>(dst) = make_float4(t[4 * hlf], t[4 * hlf + 1], t[4 * hlf + 2], t[4 * hlf + 3]);
+              float *tt = t + 4 * hlf;
+              const int e = hlf * (N / 2) + c * 4;            // global element; region and head follow from it
+              const bool is_q = e < qd, is_k = !is_q && e < qd + kd;
+              const int eh = e & (hd - 1);                    // element inside the head vector (qd, kd are multiples of hd)
+              const bf16 *nw = is_q ? a.fqn[d.layer] : (is_k ? a.fkn[d.layer] : nullptr);
+              if (any_norm) {
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ss = fmaf(tt[j], tt[j], ss);
+                for (int o = LH >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (act && nw) {
+                  const float rstd = rsqrtf(ss * (1.0f / (float)hd) + a.eps);
+                  float gw[4]; unpack4(*reinterpret_cast<const uint2 *>(nw + eh), gw);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) tt[j] = rbf(__fmul_rn(__fmul_rn(tt[j], rstd), gw[j]));
+                }
+              }
+              if (act && (is_q || is_k)) {                    // RoPE, interleaved pairs (llama.py:606-618); no fma contraction
+                float rr[4]; unpack4(*reinterpret_cast<const uint2 *>(rope_row + eh), rr);
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                  const float x0 = tt[j], x1 = tt[j + 1];
+                  tt[j] = rbf(__fsub_rn(__fmul_rn(x0, rr[j]), __fmul_rn(x1, rr[j + 1])));
+                  tt[j + 1] = rbf(__fadd_rn(__fmul_rn(x1, rr[j]), __fmul_rn(x0, rr[j + 1])));
+                }
+              }
+              if (act) {
+                if (is_q) *reinterpret_cast<float4 *>(q + e) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+                else {                                        // this position's K / V row: shared-memory cache + per-CTA scratch
+                  const size_t off = ((size_t)p * 2 + (is_k ? 0 : 1)) * kd + (size_t)(e - qd - (is_k ? 0 : kd));
+                  const uint2 pk = make_uint2((uint32_t)f2bits(tt[0]) | ((uint32_t)f2bits(tt[1]) << 16), (uint32_t)f2bits(tt[2]) | ((uint32_t)f2bits(tt[3]) << 16));
+                  *reinterpret_cast<uint2 *>(kv_l + off) = pk; *reinterpret_cast<uint2 *>(kv_g + off) = pk;
+                }
+              }
             }
           }
         }
@@ -520,29 +559,6 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 0, gtime());
         cbar();
         if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 1, gtime());
-        const bf16 *rope_row = a.frope + (size_t)p * hd;
-        if (a.fqn[d.layer] || a.fkn[d.layer]) {      // qk-norm needs a per-head reduction first: one warp per head vector
-          for (int h = w; h < nh + nkv; h += DA_M_CWARPS) {
-            if (h < nh) head_norm_rope(q + h * hd, hd, a.fqn[d.layer], a.eps, rope_row, lane);
-            else head_norm_rope(kcur + (h - nh) * hd, hd, a.fkn[d.layer], a.eps, rope_row, lane);
-          }
-        } else {                                      // plain RoPE: one interleaved pair per thread (llama.py:606-618)
-          for (int i = tid; i < (qd + kd) >> 1; i += DA_M_CTHREADS) {
-            float *vp = i < (qd >> 1) ? q + 2 * i : kcur + 2 * (i - (qd >> 1));
-            const int ip = (i < (qd >> 1) ? i : i - (qd >> 1)) % (hd >> 1);
-            const float x0 = vp[0], x1 = vp[1], cs = bf2f(rope_row[2 * ip]), sn = bf2f(rope_row[2 * ip + 1]);
-            vp[0] = rbf(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)));
-            vp[1] = rbf(__fadd_rn(__fmul_rn(x1, cs), __fmul_rn(x0, sn)));
-          }
-        }
-        cbar();
-        // this position's K / V row joins the shared-memory cache (both are bf16 values already)
-        for (int e = tid; e < kd; e += DA_M_CTHREADS) {
-          const bf16 kb = f2bf(kcur[e]), vb = f2bf(vcur[e]);
-          kv_l[((size_t)p * 2 + 0) * kd + e] = kb; kv_l[((size_t)p * 2 + 1) * kd + e] = vb;
-          kv_g[((size_t)p * 2 + 0) * kd + e] = kb; kv_g[((size_t)p * 2 + 1) * kd + e] = vb;
-        }
-        cbar();
         if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 2, gtime());
         // one HALF-warp per head (30 half-warps for <= 16 heads: every head in one round), both halves run the same code
         float *prs = vcur + kd;                                     // [nh][16] scores, then probabilities
@@ -836,37 +852,59 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         float *pm = vnew + hd, *pl = pm + DA_M_CWARPS * G, *po = pl + DA_M_CWARPS * G;       // per-warp partials: [16][G], [16][G], [16][G*hd]
         bf16 *knb = reinterpret_cast<bf16 *>(po + (size_t)DA_M_CWARPS * G * hd), *vnb = knb + hd;   // the new K / V row as bf16, laid out like a tile row
         const bool owns_new = (pos / DA_TILE) >= ap.t0 && (pos / DA_TILE) < ap.t1;
-        {   // one 8-unit chunk per thread: G*hd/8 chunks of q, then hd/8 of the new k and of the new v
-          const int nq = (G * hd) >> 3, nk = owns_new ? (hd >> 3) : 0;
+        {   // one 8-unit chunk per thread: G*hd/8 chunks of q, then hd/8 of the new k and of the new v.  A head vector is hd/8
+            // consecutive lanes of one warp, so qk-norm (llama.py:246-251) and RoPE (:606-618) run in registers on the polled
+            // values: no shared-memory round trip and a single CTA barrier before the tile walk.
+          const int LH = hd >> 3, nq = G * LH, nk = owns_new ? LH : 0;
           const int c = tid;
-          if (c < nq + 2 * nk) {
-            const uint32_t *src; float *dst;
-            if (c < nq) { src = in + (size_t)g * G * hd + (size_t)c * 8; dst = q + c * 8; }
-            else if (c < nq + nk) { src = in + qd + (size_t)g * hd + (size_t)(c - nq) * 8; dst = knew + (c - nq) * 8; }
-            else { src = in + qd + kd + (size_t)g * hd + (size_t)(c - nq - nk) * 8; dst = vnew + (c - nq - nk) * 8; }
+          if ((c & ~31) < nq + 2 * nk) {                      // warp-uniform: the shuffles below need whole warps
+            const bool act = c < nq + 2 * nk, is_q = c < nq, is_k = act && !is_q && c < nq + nk;
+            const int e0 = (c & (LH - 1)) * 8;                // first element of this chunk inside its head vector
             float t[8];
-            ok = poll_chunk(src, in_tag, t) && ok;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = t[j];
-          }
-        }
-        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 0, gtime());
-        cbar();
-        const bf16 *rope_row = a.rope + (size_t)pos * hd;
-        for (int h = w; h < G + (owns_new ? 1 : 0); h += DA_M_CWARPS) {      // one warp per head vector: qk-norm, RoPE, then its follow-up
-          if (h < G) {
-            head_norm_rope(q + h * hd, hd, a.qn[d.layer], a.eps, rope_row, lane);
-            for (int e = lane; e < hd; e += 32) q[h * hd + e] = __fmul_rn(q[h * hd + e], a.sf);   // q * sqrt(scale), fp32
-          } else {
-            head_norm_rope(knew, hd, a.kn[d.layer], a.eps, rope_row, lane);
-            for (int e = lane; e < hd; e += 32) {   // KVCache.update (llama.py:142-149)
-              const bf16 kb = f2bf(knew[e]), vb = f2bf(vnew[e]);
-              knb[e] = kb; vnb[e] = vb;
-              a.kc[d.layer][((size_t)g * a.S + pos) * hd + e] = kb;
-              a.vc[d.layer][((size_t)g * a.S + pos) * hd + e] = vb;
+            for (int j = 0; j < 8; ++j) t[j] = 0.f;
+            if (act) {
+              const uint32_t *src = is_q ? in + (size_t)g * G * hd + (size_t)c * 8
+                                  : is_k ? in + qd + (size_t)g * hd + (size_t)(c - nq) * 8 : in + qd + kd + (size_t)g * hd + (size_t)(c - nq - nk) * 8;
+              ok = poll_chunk(src, in_tag, t) && ok;
+            }
+            const bf16 *nw = is_q ? a.qn[d.layer] : (is_k ? a.kn[d.layer] : nullptr);
+            if (a.qn[d.layer] || a.kn[d.layer]) {             // nn.RMSNorm over the head vector: one rounding, after the weight multiply
+              float ss = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ss = fmaf(t[j], t[j], ss);
+              for (int o = LH >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+              if (nw) {
+                const float rstd = rsqrtf(ss * (1.0f / (float)hd) + a.eps);
+                float gw[8]; unpack4(*reinterpret_cast<const uint2 *>(nw + e0), gw); unpack4(*reinterpret_cast<const uint2 *>(nw + e0 + 4), gw + 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = rbf(__fmul_rn(__fmul_rn(t[j], rstd), gw[j]));
+              }
+            }
+            if (is_q || is_k) {                               // separate mul / mul / add kernels in the reference: no fma contraction
+              float rr[8]; const bf16 *rope_row = a.rope + (size_t)pos * hd + e0;
+              unpack4(*reinterpret_cast<const uint2 *>(rope_row), rr); unpack4(*reinterpret_cast<const uint2 *>(rope_row + 4), rr + 4);
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float x0 = t[j], x1 = t[j + 1];
+                t[j] = rbf(__fsub_rn(__fmul_rn(x0, rr[j]), __fmul_rn(x1, rr[j + 1])));
+                t[j + 1] = rbf(__fadd_rn(__fmul_rn(x1, rr[j]), __fmul_rn(x0, rr[j + 1])));
+              }
+            }
+            if (is_q) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) q[c * 8 + j] = __fmul_rn(t[j], a.sf);      // q * sqrt(scale), fp32
+            } else if (act) {                                 // KVCache.update (llama.py:142-149): both rows are bf16 values already
+              uint4 pk;
+              pk.x = (uint32_t)f2bits(t[0]) | ((uint32_t)f2bits(t[1]) << 16); pk.y = (uint32_t)f2bits(t[2]) | ((uint32_t)f2bits(t[3]) << 16);
+              pk.z = (uint32_t)f2bits(t[4]) | ((uint32_t)f2bits(t[5]) << 16); pk.w = (uint32_t)f2bits(t[6]) | ((uint32_t)f2bits(t[7]) << 16);
+              bf16 *cache = is_k ? a.kc[d.layer] : a.vc[d.layer];
+              *reinterpret_cast<uint4 *>((is_k ? knb : vnb) + e0) = pk;
+              *reinterpret_cast<uint4 *>(cache + ((size_t)g * a.S + pos) * hd + e0) = pk;
             }
           }
         }
+        if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 0, gtime());
         cbar();
         if (TL) tl_mark(a, 1 + ph, 1);
         if (TL && a.tl && tid == 0) tl_put(a, 512 + ph, 1, gtime());
