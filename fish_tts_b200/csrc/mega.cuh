@@ -162,6 +162,19 @@ __device__ __noinline__ bool poll8(const unsigned long long *p, uint32_t tag, ui
   payload = (uint32_t)(v >> 32);
   return it < DA_SPIN_LIMIT;
 }
+// three 64-bit units whose loads are issued together: one L2 round trip once all of them are there
+__device__ __noinline__ bool poll8x3(const unsigned long long *p0, const unsigned long long *p1, const unsigned long long *p2, uint32_t tag,
+                                     uint32_t &v0, uint32_t &v1, uint32_t &v2) {
+  unsigned long long a, b, c;
+  int it = 0;
+  for (;;) {
+    a = ld_poll8(p0); b = ld_poll8(p1); c = ld_poll8(p2);
+    if (((uint32_t)a == tag) & ((uint32_t)b == tag) & ((uint32_t)c == tag)) break;
+    if (++it >= DA_SPIN_LIMIT) break;
+  }
+  v0 = (uint32_t)(a >> 32); v1 = (uint32_t)(b >> 32); v2 = (uint32_t)(c >> 32);
+  return it < DA_SPIN_LIMIT;
+}
 // bounded mbarrier wait that does not burn issue slots: a hot try_wait loop by every waiting warp was ~25% of all
 // instructions executed by the kernel (ncu) and slowed the warps that had work on the same scheduler
 __device__ __forceinline__ bool mbar_wait_idle(uint64_t *bar, uint32_t parity, unsigned ns) {
@@ -911,11 +924,14 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         // Running (max, sum, output) of every warp live in its private slice of shared memory (pm / pl / po) and are pulled into
         // registers for two query heads at a time, so one code path serves every GQA group size and head dimension (dims per lane
         // dpl = hd / 32 <= 4) without per-shape instantiations -- unexecuted variants measurably slowed the whole kernel down.
-        for (int h = 0; h < G; ++h) {
-          if (lane == 0) { pm[w * G + h] = -INFINITY; pl[w * G + h] = 0.f; }
-          for (int i = 0; i < dpl; ++i) po[((size_t)w * G + h) * hd + lane * dpl + i] = 0.f;
+        // (the first tile starts from the empty state in registers; only a CTA without tiles has to write it)
+        if (ap.t1 <= ap.t0) {
+          for (int h = 0; h < G; ++h) {
+            if (lane == 0) { pm[w * G + h] = -INFINITY; pl[w * G + h] = 0.f; }
+            for (int i = 0; i < dpl; ++i) po[((size_t)w * G + h) * hd + lane * dpl + i] = 0.f;
+          }
+          __syncwarp();
         }
-        __syncwarp();
         for (int t = ap.t0; t < ap.t1; ++t) {
           const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
           const int n_old = min(r1, pos) - r0;
@@ -934,12 +950,13 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             for (int hh = 0; hh < 2; ++hh) {
               const bool hv = h0 + hh < G;
               const int h = hv ? h0 + hh : h0;
-              m_run[hh] = pm[w * G + h]; l_run[hh] = pl[w * G + h];
+              const bool first = t == ap.t0;
+              m_run[hh] = first ? -INFINITY : pm[w * G + h]; l_run[hh] = first ? 0.f : pl[w * G + h];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const bool iv = hv && i < dpl;
                 qr[hh][i] = iv ? q[h * hd + lane * dpl + i] : 0.f;
-                o_acc[hh][i] = iv ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
+                o_acc[hh][i] = (iv && !first) ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
               }
             }
             // a warp owns at most four positions of a 64-row tile: all their scores first (independent dot products and shuffle
@@ -1015,28 +1032,23 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         const uint32_t t32 = tag32_of(ph);
         unsigned long long *pog = a.part_o + (((size_t)g * a.nsplit_max + ap.split) * G) * hd;
         unsigned long long *pmlg = a.part_ml + (((size_t)g * a.nsplit_max + ap.split) * G) * 2;
-        // scale factor of every (warp, head) once, in place of the warp's max; then thread e = (h, d) sums 16 scaled partials
-        float *pmax = pl + DA_M_CWARPS * G - DA_M_CWARPS * G;      // (pl itself keeps the sums)
-        (void)pmax;
-        if (tid < G) {
-          float m = -INFINITY;
-          for (int ww = 0; ww < DA_M_CWARPS; ++ww) m = fmaxf(m, pm[ww * G + tid]);
-          q[tid] = m;                                            // q is dead after the walk
-        }
-        cbar();
-        if (tid < DA_M_CWARPS * G) { const int h = tid % G; const float v = pm[tid]; pm[tid] = v == -INFINITY ? 0.f : expf(v - q[h]); }
-        cbar();
+        // thread e = (h, d): maximum over the 16 warps, then the 16 scaled partials in warp order (every thread recomputes the
+        // scale factors of its head: 16 exps instead of two more CTA barriers)
         for (int e = tid; e < G * hd; e += DA_M_CTHREADS) {
           const int h = e / hd, dd = e - h * hd;
+          float m = -INFINITY;
+#pragma unroll
+          for (int ww = 0; ww < DA_M_CWARPS; ++ww) m = fmaxf(m, pm[ww * G + h]);
           float l = 0.f, o = 0.f;
 #pragma unroll
           for (int ww = 0; ww < DA_M_CWARPS; ++ww) {
-            const float sc_w = pm[ww * G + h];
+            const float v = pm[ww * G + h];
+            const float sc_w = v == -INFINITY ? 0.f : expf(v - m);
             l = fmaf(pl[ww * G + h], sc_w, l);
             o = fmaf(po[((size_t)ww * G + h) * hd + dd], sc_w, o);
           }
           st_unit8(pog + e, make_unit8(__float_as_uint(o), t32));
-          if (dd == 0) { st_unit8(pmlg + h * 2, make_unit8(__float_as_uint(q[h]), t32)); st_unit8(pmlg + h * 2 + 1, make_unit8(__float_as_uint(l), t32)); }
+          if (dd == 0) { st_unit8(pmlg + h * 2, make_unit8(__float_as_uint(m), t32)); st_unit8(pmlg + h * 2 + 1, make_unit8(__float_as_uint(l), t32)); }
         }
         cbar();
       }
@@ -1054,9 +1066,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         const int h = e / hd, dd = e - h * hd, g = h / G, hl = h - g * G;
         const size_t base = ((size_t)g * a.nsplit_max + s) * G + hl;
         uint32_t vo, vm, vl;
-        ok = poll8(a.part_o + base * hd + dd, t32, vo) && ok;
-        ok = poll8(a.part_ml + base * 2, t32, vm) && ok;
-        ok = poll8(a.part_ml + base * 2 + 1, t32, vl) && ok;
+        ok = poll8x3(a.part_o + base * hd + dd, a.part_ml + base * 2, a.part_ml + base * 2 + 1, t32, vo, vm, vl) && ok;
         mo[t] = __uint_as_float(vo); mm[t] = __uint_as_float(vm); ml[t] = __uint_as_float(vl);
       }
       cbar();
