@@ -534,7 +534,7 @@ static int build_mega(dualar_engine *e) {
     upd((size_t)3 * (qd / grid + 2) * e->nsplit * 4);
     upd((size_t)3 * grid * 4 + 256);
     upd((size_t)16896 + (192 + 34) * 8 + 80 * 4 + 64);          // slow head: bins / cut list (or sort buffer) + sampler scratch
-    upd((size_t)256 * 8 + (4 * 512 + 2 * 128 + 8) * 4 + 128 * 8 + 64);      // fast heads: scratch + bins / cut list
+    upd((size_t)256 * 8 + (4 * 512 + 2 * 512 + 8) * 4 + 512 * 8 + 64);      // fast heads: scratch + bins / cut list
     a.kmax = kmax; a.lg_rows = (2 * (pairs(c.vocab_size) / grid + 1) + 31) / 16 * 16; a.work_bytes = (int)work;
     a.kv_bytes = c.num_codebooks * 2 * fkd * 2;      // one fast layer's K/V rows; all layers live in a per-CTA global scratch
     const int dim_max = c.dim > c.fast_dim ? c.dim : c.fast_dim;

@@ -795,52 +795,49 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         h_cnt = gp.nr;
       }
       if (FULL && d.epi == ME_FASTLOGITS && bid == 0) {
-        // warps 0-3 of CTA 0 draw the code and publish its embedding as the next pass's input
-        __shared__ uint32_t s_tok;
+        // CTA 0 draws the code with all 16 warps (two logits per thread, binned nucleus sampler) and publishes its embedding
+        // as the next pass's input
         unsigned long long *scr = reinterpret_cast<unsigned long long *>(sm_work);
-        if (w < 4) {
-          typedef BlockNamed<2, 128> G4;
-          const int V = a.fv;
-          uint32_t it8[DA_G_IPT];
-          Red r = {0ull, 0, -1};
-          {
-            float zv[8];
-            const bool mine = tid * 8 < V;     // V is a multiple of 8 (codebook sizes are)
-            if (mine) ok = poll_chunk(d.out + tid * 8, tag, zv) && ok;
-#pragma unroll
-            for (int i = 0; i < DA_G_IPT; ++i) {
-              const int e = tid * DA_G_IPT + i;
-              it8[i] = 0xFFFFFFFFu;
-              if (mine && e < V) {
-                const uint32_t key = bf16_key(f2bits(zv[i]));
-                it8[i] = ((0xFFFFu - key) << 16) | (uint32_t)e; r.m = max(r.m, (int)key);
-              }
+        const int V = a.fv;
+        uint32_t it2[2];
+        Red r = {0ull, 0, -1};
+        {
+          const bool mine = tid * 2 < V;     // V is a multiple of 8 (codebook sizes are)
+          uint32_t u0 = 0u, u1 = 0u;
+          if (mine) {
+            int it = 0;
+            for (;;) {
+              asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(u0), "=r"(u1) : "l"(d.out + tid * 2) : "memory");
+              if (((u0 & 0xFFFFu) == tag) & ((u1 & 0xFFFFu) == tag)) break;
+              if (++it >= DA_SPIN_LIMIT) { ok = false; break; }
             }
           }
-          SampleParams spm;
-          int par = 0;
-          if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 0, gtime());
-          r = block_reduce<G4>(r, scr, par);
-          spm.m = bits2f(key_bf16((uint32_t)r.m));
-          Red es = {0ull, 0, -1};      // sum of exp terms as 2^-40 fixed point: order-free, identical to the per-phase path
-#pragma unroll
-          for (int i = 0; i < DA_G_IPT; ++i) if (it8[i] != 0xFFFFFFFFu) es.s += (unsigned long long)(expf(bits2f(key_bf16(0xFFFFu - (it8[i] >> 16))) - spm.m) * DA_FIX2_SCALE);
-          es = block_reduce<G4>(es, scr, par);
-          spm.S = __ull2float_rn(es.s) * (1.0f / DA_FIX2_SCALE);
-          spm.T_bf = eff_temperature(st);
-          spm.c_max = cmax_from_top_p(st->top_p);
-          const NoiseSrc nsrc = noise_src(st);
-          G4::sync();
-          if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 1, gtime());
-          uint32_t tok = sample_sorted<DA_G_IPT, 128, G4>(it8, (uint32_t)V, true, nullptr, spm, nsrc, (uint32_t)d.pos, a.noise_off0 + (long long)(d.pos - 1) * a.fv,
-                                                          &st->nucleus[d.pos], reinterpret_cast<uint32_t *>(scr + 256), scr);
-          if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (tid == 0) st->err = 3; }
-          if (tid == 0) { s_tok = tok; st->tok_out[d.pos + 1] = (int)tok; }
-          if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 2, gtime());
+          const uint32_t k0 = bf16_key((uint16_t)(u0 >> 16)), k1 = bf16_key((uint16_t)(u1 >> 16));
+          it2[0] = mine ? (((0xFFFFu - k0) << 16) | (uint32_t)(tid * 2)) : 0xFFFFFFFFu;
+          it2[1] = mine ? (((0xFFFFu - k1) << 16) | (uint32_t)(tid * 2 + 1)) : 0xFFFFFFFFu;
+          if (mine) r.m = (int)max(k0, k1);
         }
+        SampleParams spm;
+        int par = 0;
+        if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 0, gtime());
+        r = block_reduce<CBlock>(r, scr, par);
+        spm.m = bits2f(key_bf16((uint32_t)r.m));
+        Red es = {0ull, 0, -1};      // sum of exp terms as 2^-40 fixed point: order-free, identical to the per-phase path
+#pragma unroll
+        for (int i = 0; i < 2; ++i) if (it2[i] != 0xFFFFFFFFu) es.s += (unsigned long long)(expf(bits2f(key_bf16(0xFFFFu - (it2[i] >> 16))) - spm.m) * DA_FIX2_SCALE);
+        es = block_reduce<CBlock>(es, scr, par);
+        spm.S = __ull2float_rn(es.s) * (1.0f / DA_FIX2_SCALE);
+        spm.T_bf = eff_temperature(st);
+        spm.c_max = cmax_from_top_p(st->top_p);
+        const NoiseSrc nsrc = noise_src(st);
         cbar();
+        if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 1, gtime());
+        uint32_t tok = sample_binned<2, DA_M_CTHREADS, CBlock>(it2, (uint32_t)V, true, nullptr, spm, nsrc, (uint32_t)d.pos, a.noise_off0 + (long long)(d.pos - 1) * a.fv,
+                                                                &st->nucleus[d.pos], reinterpret_cast<uint32_t *>(scr + 256), scr);
+        if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (tid == 0) st->err = 3; }
+        if (tid == 0) st->tok_out[d.pos + 1] = (int)tok;
+        if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 2, gtime());
         if (d.pos < a.ncb - 1) {
-          const uint32_t tok = s_tok;
           for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
         }
       }

@@ -41,9 +41,9 @@ int main() {
   uint16_t *d; uint32_t *t; int *n; long long *c;
   cudaMalloc(&d, 4096 * 2); cudaMalloc(&t, 16); cudaMalloc(&n, 16); cudaMalloc(&c, 16);
   const float tops[] = {1e-9f, 0.05f, 0.3f, 0.8f, 0.95f, 1.0f};
-  int bad = 0, total = 0; long long cyc[2][2] = {{0, 0}, {0, 0}};
-  for (int big = 0; big < 2; ++big) {
-    const int V = big ? 4096 : 1024;
+  int bad = 0, total = 0; long long cyc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  for (int big = 0; big < 3; ++big) {      // 0: 1024 items, 128 threads x 8; 1: 4096 items, 512 x 8; 2: 1024 items, 512 x 2
+    const int V = big == 1 ? 4096 : 1024;
     for (int dist = 0; dist < 8; ++dist) for (int seed = 0; seed < 6; ++seed) for (float top_p : tops) for (int ap = 0; ap < 2; ++ap) {
       srand(1000 * dist + seed);
       std::vector<uint16_t> h(V);
@@ -67,7 +67,8 @@ int main() {
       for (int which = 0; which < 2; ++which) {
         cudaMemset(n, 0xFF, 4);
         const float sf = ap ? 1.0f : 3.0f;      // candidates of a larger vocabulary: S covers more than the items
-        if (big) k_check<8, 512, BlockNamed<2, 512>><<<1, 544, 32768>>>(d, V, top_p, sf, ap, which, t, n, c);
+        if (big == 1) k_check<8, 512, BlockNamed<2, 512>><<<1, 544, 32768>>>(d, V, top_p, sf, ap, which, t, n, c);
+        else if (big == 2) k_check<2, 512, BlockNamed<2, 512>><<<1, 544, 32768>>>(d, V, top_p, sf, ap, which, t, n, c);
         else k_check<8, 128, BlockNamed<2, 128>><<<1, 544, 32768>>>(d, V, top_p, sf, ap, which, t, n, c);
         cudaError_t e = cudaMemcpy(&tk[which], t, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&nk[which], n, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&cy[which], c, 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
@@ -81,7 +82,7 @@ int main() {
       if (tk[0] != tk[1] || nk[0] != nk[1]) { if (++bad <= 20) printf("MISMATCH V %d dist %d seed %d top_p %g all_present %d: sorted tok %u nucleus %d | binned tok %u nucleus %d\n", V, dist, seed, top_p, ap, tk[0], nk[0], tk[1], nk[1]); }
     }
   }
-  printf("cases %d mismatches %d | mean cycles V=1024 sorted %lld binned %lld | V=4096 sorted %lld binned %lld\n", total, bad,
-         cyc[0][0] / (total / 2), cyc[0][1] / (total / 2), cyc[1][0] / (total / 2), cyc[1][1] / (total / 2));
+  printf("cases %d mismatches %d | mean cycles 1024 items / 128 threads: sorted %lld binned %lld | 4096 / 512: sorted %lld binned %lld | 1024 / 512: sorted %lld binned %lld\n", total, bad,
+         cyc[0][0] / (total / 3), cyc[0][1] / (total / 3), cyc[1][0] / (total / 3), cyc[1][1] / (total / 3), cyc[2][0] / (total / 3), cyc[2][1] / (total / 3));
   return bad != 0;
 }

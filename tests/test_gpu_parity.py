@@ -430,3 +430,22 @@ def test_fish_speech_1_5_shape_full_size():
     assert ((t1[0] >= cfg.semantic_begin_id) & (t1[0] <= cfg.semantic_end_id)).all()
     assert ((t1[1:] >= 0) & (t1[1:] < cfg.codebook_size)).all()
     assert int(t1[0, 0]) == int(t0[0, 0]) or near_tie(l0, int(t1[0, 0]), int(t0[0, 0]), ulps=8.0, atol=5e-2)
+
+
+def test_binned_sampler_equals_sorting_sampler():
+    """The slow head's binned nucleus sampler against the sorting one, in isolation (tests/cuda/binned_check.cu): 1152 random
+    logit vectors (flat, peaked, heavy ties, all equal, long tails, a far-away half; top_p from 1e-9 to 1; items = the whole
+    vocabulary or candidates of a larger one) -- token and nucleus size must agree in every case."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "build" / "binned_check"
+    src = root / "tests" / "cuda" / "binned_check.cu"
+    deps = [src] + list((root / "fish_tts_b200" / "csrc").glob("*.cuh"))
+    if not exe.exists() or any(d.stat().st_mtime > exe.stat().st_mtime for d in deps):
+        exe.parent.mkdir(exist_ok=True)
+        subprocess.run([nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(exe), str(src)], check=True, timeout=600)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatches 0" in r.stdout, r.stdout[-2000:]
