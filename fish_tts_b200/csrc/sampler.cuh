@@ -130,18 +130,20 @@ struct Red { unsigned long long s; int c; int m; };
 template <class B = BlockAll>
 __device__ __forceinline__ Red block_reduce(Red v, unsigned long long *scr, int &parity) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    v.s += __shfl_xor_sync(0xffffffffu, v.s, o);
-    v.c += __shfl_xor_sync(0xffffffffu, v.c, o);
-    v.m = max(v.m, __shfl_xor_sync(0xffffffffu, v.m, o));
-  }
-  unsigned long long *b = scr + parity * 96;
+  // warp stage with redux.sync: the u64 sum as three 22-bit limbs (32 lanes x 2^22 < 2^32), count and max directly --
+  // five single-step reductions instead of five dependent shuffle rounds over four registers
+  const unsigned l0 = __reduce_add_sync(0xffffffffu, (unsigned)v.s & 0x3FFFFFu);
+  const unsigned l1 = __reduce_add_sync(0xffffffffu, (unsigned)(v.s >> 22) & 0x3FFFFFu);
+  const unsigned l2 = __reduce_add_sync(0xffffffffu, (unsigned)(v.s >> 44));
+  v.s = (unsigned long long)l0 + ((unsigned long long)l1 << 22) + ((unsigned long long)l2 << 44);
+  v.c = __reduce_add_sync(0xffffffffu, v.c);
+  v.m = __reduce_max_sync(0xffffffffu, v.m);
+  unsigned long long *b = scr + parity * 96;      // [nw] sums, then [nw] (count << 32 | max)
   parity ^= 1;
-  if (lane == 0) { b[w] = v.s; b[32 + w] = (unsigned long long)(long long)v.c; b[64 + w] = (unsigned long long)(long long)v.m; }
+  if (lane == 0) { b[w] = v.s; b[32 + w] = ((unsigned long long)(unsigned)v.c << 32) | (unsigned)v.m; }
   B::sync();
   Red r = {0ull, 0, INT_MIN};
-  for (int i = 0; i < nw; ++i) { r.s += b[i]; r.c += (int)(long long)b[32 + i]; r.m = max(r.m, (int)(long long)b[64 + i]); }
+  for (int i = 0; i < nw; ++i) { const unsigned long long y = b[32 + i]; r.s += b[i]; r.c += (int)(y >> 32); r.m = max(r.m, (int)(unsigned)y); }
   return r;
 }
 
