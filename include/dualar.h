@@ -145,7 +145,9 @@ int dualar_set_noise(dualar_engine *e, const void *noise, int64_t n_steps);
  *     golden fixtures were generated with).
  * "candidate_delta" (default 6.0, before finalize): slow-head candidates are logits >= max - delta.
  * "mega_kernel" (0/1, before finalize; default 1): run the whole decode step as ONE persistent cooperative
- *     kernel (csrc/mega.cuh) instead of one kernel per phase; both produce bit-identical results. */
+ *     kernel (csrc/mega.cuh) instead of one kernel per phase (kept as a cross-check).  The two sum their dot
+ *     products in different fp32 orders (tensor-core chunks vs. FMA chains), so logits agree to bf16 rounding,
+ *     not bit for bit; the samplers of both are exact on the logits they are given. */
 int dualar_set_option(dualar_engine *e, const char *name, double value);
 
 /* ---- introspection (tests, bench) -------------------------------------------------------------
