@@ -956,41 +956,45 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                 o_acc[hh][i] = (iv && !first) ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
               }
             }
-            // a warp owns at most four positions of a 64-row tile: all their scores first (independent dot products and shuffle
-            // trees overlap), then one running-max update and the P@V accumulation
-            float sj[DA_M_PPW][2];
+            // A warp owns at most four positions of a 64-row tile (rows w, w+16, w+32, w+48).  Scores: 8 lanes per position, each
+            // lane a strided set of 4-element pieces of the head vector for both query heads -- a 3-step reduction per score instead
+            // of a 32-lane one, and one exp per lane.  The probabilities are then handed to all lanes (4 shuffles per head) for the
+            // P@V accumulation, where a lane owns dpl dims of the output as before.
+            static_assert(DA_M_PPW == 4, "the score layout deals four position slots to the 32 lanes");
+            const int psl = lane >> 3, dl = lane & 7;
+            const int jme = w + psl * DA_M_CWARPS;
+            float s2[2] = {0.f, 0.f};
+            {
+              const bf16 *krow = (jme < n_old ? kt + (size_t)jme * hd : knb);      // (rows past nrow read the new-row buffer; masked below)
+              const float *q0 = q + (size_t)h0 * hd, *q1 = q + (size_t)(h0 + 1 < G ? h0 + 1 : h0) * hd;
+              for (int e = dl * 4; e < hd; e += 32) {
+                float kf[4]; unpack4(*reinterpret_cast<const uint2 *>(krow + e), kf);
+                const float4 qa = *reinterpret_cast<const float4 *>(q0 + e), qb = *reinterpret_cast<const float4 *>(q1 + e);
 #pragma unroll
-            for (int jj = 0; jj < DA_M_PPW; ++jj) {
-              const int j = w + jj * DA_M_CWARPS;
-              float kf[4];
-              ld_bf16_dpl((j < n_old ? kt + j * hd : knb) + lane * dpl, dpl, kf);      // (rows past nrow read the new-row buffer; their scores are masked below)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) kf[i] = __fmul_rn(kf[i], a.sf);
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                float sdot = 0.f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) sdot = fmaf(qr[hh][i], kf[i], sdot);
-                sdot = warp_sum(sdot);
-                sj[jj][hh] = (j < nrow && h0 + hh < G) ? sdot : -INFINITY;
+                for (int i = 0; i < 4; ++i) kf[i] = __fmul_rn(kf[i], a.sf);
+                s2[0] = fmaf(qa.x, kf[0], s2[0]); s2[0] = fmaf(qa.y, kf[1], s2[0]); s2[0] = fmaf(qa.z, kf[2], s2[0]); s2[0] = fmaf(qa.w, kf[3], s2[0]);
+                s2[1] = fmaf(qb.x, kf[0], s2[1]); s2[1] = fmaf(qb.y, kf[1], s2[1]); s2[1] = fmaf(qb.z, kf[2], s2[1]); s2[1] = fmaf(qb.w, kf[3], s2[1]);
               }
             }
+            float pj[DA_M_PPW][2];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              float m_new = m_run[hh];
-#pragma unroll
-              for (int jj = 0; jj < DA_M_PPW; ++jj) m_new = fmaxf(m_new, sj[jj][hh]);
+              float sv = s2[hh];
+              sv += __shfl_xor_sync(0xffffffffu, sv, 1); sv += __shfl_xor_sync(0xffffffffu, sv, 2); sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+              if (!(jme < nrow && h0 + hh < G)) sv = -INFINITY;
+              float mx = fmaxf(sv, __shfl_xor_sync(0xffffffffu, sv, 8));
+              mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+              const float m_new = fmaxf(m_run[hh], mx);
+              float pme = 0.f;
               if (m_new != -INFINITY) {
                 const float sc_old = expf(m_run[hh] - m_new);      // exp(-inf) = 0 before the first position
                 l_run[hh] *= sc_old; m_run[hh] = m_new;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o_acc[hh][i] *= sc_old;
-#pragma unroll
-                for (int jj = 0; jj < DA_M_PPW; ++jj) sj[jj][hh] = expf(sj[jj][hh] - m_new);
-              } else {
-#pragma unroll
-                for (int jj = 0; jj < DA_M_PPW; ++jj) sj[jj][hh] = 0.f;
+                pme = expf(sv - m_new);
               }
+#pragma unroll
+              for (int jj = 0; jj < DA_M_PPW; ++jj) pj[jj][hh] = __shfl_sync(0xffffffffu, pme, jj * 8);
             }
 #pragma unroll
             for (int jj = 0; jj < DA_M_PPW; ++jj) {
@@ -1000,9 +1004,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                 ld_bf16_dpl((j < n_old ? vt + j * hd : vnb) + lane * dpl, dpl, vf);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                  l_run[hh] += sj[jj][hh];
+                  l_run[hh] += pj[jj][hh];
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(sj[jj][hh], vf[i], o_acc[hh][i]);
+                  for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(pj[jj][hh], vf[i], o_acc[hh][i]);
                 }
               }
             }
