@@ -88,10 +88,10 @@ if n_step == 1:
     i_hc = names.index("H.cand")
     if hs[i_hc, 0]:
         x = [tl[1 + i_hc, 0]] + [hs[i_hc, k] for k in range(4)] + [tl[1 + i_hc, 2]]
-        print("  H.cand (CTA 0, us): poll stats + prefix %.2f | write candidates %.2f | fetch candidates %.2f | sample_sorted %.2f | embedding publish %.2f" % tuple((x[k + 1] - x[k]) / 1e3 for k in range(5)))
+        print("  H.cand (CTA 0, us): poll stats + prefix %.2f | write candidates %.2f | fetch candidates %.2f | sampler %.2f | embedding publish %.2f" % tuple((x[k + 1] - x[k]) / 1e3 for k in range(5)))
     for i, nm in enumerate(names):
         if nm == "F.head" and i < nph - 1:
-            print(f"  F.head ph {i}: start {start[i]:.2f} staged +{staged[i]-start[i]:.2f} compute +{done[i]-staged[i]:.2f} | polled +{(hs[i,0]-t0)/1e3-done[i]:.2f} | m,S +{(hs[i,1]-hs[i,0])/1e3:.2f} | sample_sorted +{(hs[i,2]-hs[i,1])/1e3:.2f} | publish+bar +{(hs[i,3]-hs[i,2])/1e3:.2f}")
+            print(f"  F.head ph {i}: start {start[i]:.2f} staged +{staged[i]-start[i]:.2f} compute +{done[i]-staged[i]:.2f} | polled +{(hs[i,0]-t0)/1e3-done[i]:.2f} | m,S +{(hs[i,1]-hs[i,0])/1e3:.2f} | sampler +{(hs[i,2]-hs[i,1])/1e3:.2f} | publish+bar +{(hs[i,3]-hs[i,2])/1e3:.2f}")
     raw2 = eng.read("timeline2").numpy().astype("int64").reshape(-1)
     t2 = raw2[: nph * 148 * 2].reshape(nph, 148, 2)
     pw = raw2[400 * 160 * 2: 400 * 160 * 2 + nph * 148].reshape(nph, 148) / 1e3      # ring wait of thread 0 of each CTA in each phase, us
