@@ -708,6 +708,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           const uint32_t at = place((uint32_t)n * RS, bi, par);
           if (u >= (tl + 1) * nchunk) continue;        // no unit of this warp in the tile
           landed(bi, par);
+          if (TL && a.tl && tid == 0 && tl == 0) tl_put(a, 512 + ph, 4, gtime());
           const int slot = tl & (DA_M_PT - 1);
           int gb = gen_base[0];
 #pragma unroll
@@ -718,6 +719,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             const int c = u - tl * nchunk;
             float v_lo, v_hi;
             mma_chunk(smem_u32(sm_ring + at), RS, n, xw, c, lane, v_lo, v_hi);
+            if (TL && a.tl && tid == 0 && tl == 0) tl_put(a, 512 + ph, 5, gtime() + (unsigned long long)(0.f * (v_lo + v_hi)));
             // the slot is free once the tile DA_M_PT before this one has been folded
             // (checked for every tile: a phase entry without a staging barrier -- the later LM-head parts -- can start while the
             //  previous phase is still folding on this slot)
@@ -727,6 +729,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             int last = 0;
             if (lane == 31) last = (atom_add_acq_rel_cta(&sm_pcnt[slot], 1) == nchunk - 1);      // publishes this warp's partials, observes the others' 
             last = __shfl_sync(0xffffffffu, last, 31);
+            if (TL && a.tl && tid == 0 && tl == 0) tl_put(a, 512 + ph, 6, gtime());
             if (last) {
               // every unit of the tile is done: fold in chunk order (lane r owns row r), free the slot and the sm_ring entry
               const int r = lane & 15, row = gp.r0 + 16 * t + r;

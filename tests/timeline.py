@@ -63,6 +63,17 @@ if n_step == 1:
     for k, a in agg.items():
         n = a[0]
         print(f"{k:8s} {n:4d} {a[1] / n:8.2f} {a[2] / n:8.2f} {a[3] / n:8.2f} {a[3]:8.1f}")
+    # warp 0's first unit of every GEMV phase: staged -> tile landed -> MMA chunk done -> partials handed in -> own loop done
+    un = full[512:512 + nph, 4:7]
+    uacc = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
+    for i, nm in enumerate(names):
+        if nm.split(".")[1] in ("qkv", "wo", "w13", "w2", "head") and nm != "H.head" and un[i, 0] and un[i, 1] and un[i, 2] and tl[1 + i, 1]:
+            u = uacc[nm]; u[0] += 1
+            u[1] += (un[i, 0] - tl[1 + i, 1]) / 1e3; u[2] += (un[i, 1] - un[i, 0]) / 1e3; u[3] += (un[i, 2] - un[i, 1]) / 1e3; u[4] += (tl[1 + i, 2] - un[i, 2]) / 1e3
+    print("  warp 0, first unit (mean us): kind   staged->landed | mma chunk | partials + hand-in | rest of its loop (fold if last, more units)")
+    for k, u in uacc.items():
+        n = u[0]
+        print(f"    {k:8s} {u[1] / n:8.2f} {u[2] / n:8.2f} {u[3] / n:8.2f} {u[4] / n:8.2f}")
     fa = full[512:512 + nph, :6]
     acc = [0.0] * 5; nfa = 0
     for i, nm in enumerate(names):
