@@ -475,8 +475,8 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
     const int y = __shfl_up_sync(0xffffffffu, cinc, o);
     if (lane >= o) { inc += x; cinc += y; }
   }
-  unsigned long long *wsum = scr;                 // [NW] warp totals
-  int *wcnt = reinterpret_cast<int *>(scr + 40);  // [NW]
+  unsigned long long *wsum = scr + 192;               // [NW] warp totals; clear of both block_reduce buffers (scr[0..48), scr[96..144))
+  int *wcnt = reinterpret_cast<int *>(scr + 208);     // [NW]
   if (lane == 31) { wsum[w] = inc; wcnt[w] = cinc; }
   B::sync();
   unsigned long long base = inc - run; int cbase = cinc - crun;
@@ -536,7 +536,6 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
     }
   }
   int parity = 0;
-  B::sync();                                       // wsum / wcnt are dead: scr becomes block_reduce scratch
   s2 = block_reduce<B>(s2, scr, parity);
   DA_ST(5);
   if (s2.c == (int)n && !all_present) return 0xFFFFFFFFu;
@@ -552,9 +551,20 @@ __device__ __noinline__ uint32_t sample_binned(uint32_t (&a_in)[E], uint32_t n, 
     best = better(best, cnd);
   }
   DA_ST(6);
-  B::sync();
-  float *fs = reinterpret_cast<float *>(scr);
-  best = block_argbest<B>(best, fs, reinterpret_cast<uint32_t *>(fs + 40));
+  // winner: larger r, then smaller index.  r >= +0, so its bits order like the value: one u64 key per warp from two
+  // redux steps, one barrier, every thread scans the NW keys (scr[96..): the reduction above used the other buffer)
+  {
+    const unsigned rb = __float_as_uint(best.r);
+    const unsigned mx = __reduce_max_sync(0xffffffffu, rb);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, rb == mx ? best.idx : 0xFFFFFFFFu);
+    unsigned long long *wk = scr + 96;
+    if (lane == 0) wk[w] = ((unsigned long long)mx << 32) | (0xFFFFFFFFu - mi);
+    B::sync();
+    unsigned long long k = 0ull;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) k = max(k, wk[i]);
+    best.idx = 0xFFFFFFFFu - (uint32_t)k;
+  }
   DA_ST(7);
   return best.idx;
 }
