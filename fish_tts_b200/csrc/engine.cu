@@ -61,6 +61,7 @@ struct dualar_engine {
   // persistent whole-step kernel (mega.cuh): unit buffers, the two phase tables (decode step / one prefill position)
   uint32_t *u_x = nullptr, *u_qkv = nullptr, *u_y = nullptr, *u_h = nullptr, *u_act = nullptr;
   uint32_t *u_fqkv = nullptr, *u_fh = nullptr, *u_fact = nullptr, *u_fx0 = nullptr, *u_fx1 = nullptr, *u_fin = nullptr, *u_flogits = nullptr;
+  bf16 *t0 = nullptr; bool use_t0 = true;      // first-layer q | k | v of the fast stack per code (passes >= 1)
   unsigned long long *m_part_o = nullptr, *m_part_ml = nullptr, *m_hmax = nullptr, *m_hcs = nullptr, *m_cand = nullptr;
   MegaArgs *ma_step = nullptr, *ma_prefill = nullptr; size_t mega_smem = 0; unsigned int *m_phase = nullptr; bf16 *m_fkv = nullptr; unsigned char *u_arena = nullptr; size_t u_arena_bytes = 0;
   bool use_mega = true;   // option mega_kernel / DUALAR_MEGA: 0 = one kernel per phase (the cross-check path)
@@ -431,6 +432,14 @@ static int build_mega(dualar_engine *e) {
   }
   if ((rc = dev_alloc(e, e->m_phase, 1))) return rc;
   if ((rc = dev_alloc(e, e->m_fkv, (size_t)grid * c.n_fast_layer * c.num_codebooks * 2 * fkd))) return rc;
+  { const char *v = getenv("DUALAR_T0"); if (v) e->use_t0 = v[0] != '0'; }
+  if (e->use_t0) {
+    // table of the first fast layer's q | k | v for every code (see t0_build_kernel); 16 MB for s1-mini
+    if ((rc = dev_alloc(e, e->t0, (size_t)c.codebook_size * fqkv_rows))) return rc;
+    t0_build_kernel<<<c.codebook_size, 256, (size_t)c.fast_dim * sizeof(float)>>>(e->fast_emb, e->fast[0].attn_norm, e->fast[0].wqkv, e->fast[0].bqkv, e->t0,
+                                                                                   c.fast_dim, fqkv_rows, c.norm_eps);
+    CU(cudaGetLastError());
+  }
   e->ma_step = new MegaArgs(); e->ma_prefill = new MegaArgs();
   for (int variant = 0; variant < 2; ++variant) {
     MegaArgs &a = variant ? *e->ma_prefill : *e->ma_step;
@@ -473,9 +482,12 @@ static int build_mega(dualar_engine *e) {
       auto fast_layer = [&](int p, int l, const uint32_t *lin, int lin_ph, bool with_head) {
         LayerW &W = e->fast[l];
         if (with_head) head_part();
-        int q = gemv(W.wqkv, W.bqkv, W.attn_norm, lin, lin_ph, e->u_fqkv, fqkv_rows, c.fast_dim, MP_RMSNORM, ME_STORE, MF_KEEP | MF_SAVE0, l, p);
+        // passes >= 1, first layer: the input is the embedding of a code, so wqkv's product comes from the table and the phase
+        // is dropped; the attention staging of wo reads the code (one unit in u_fin), the table row and the embedding row
+        const bool tab = e->t0 && p >= 1 && l == 0;
+        int q = tab ? lin_ph : gemv(W.wqkv, W.bqkv, W.attn_norm, lin, lin_ph, e->u_fqkv, fqkv_rows, c.fast_dim, MP_RMSNORM, ME_STORE, MF_KEEP | MF_SAVE0, l, p);
         if (with_head) head_part();
-        int o = gemv(W.wo, W.bo, nullptr, e->u_fqkv, q, e->u_fh, c.fast_dim, fqd, MP_FASTATTN, ME_RESIDUAL, MF_KEEP | MF_RES0, l, p);
+        int o = gemv(W.wo, W.bo, nullptr, tab ? lin : e->u_fqkv, q, e->u_fh, c.fast_dim, fqd, MP_FASTATTN, ME_RESIDUAL, MF_KEEP | MF_RES0 | (tab ? MF_T0 : 0), l, p);
         if (with_head) head_part();
         int f = gemv(W.w13, nullptr, W.ffn_norm, e->u_fh, o, e->u_fact, 2 * c.fast_intermediate_size, c.fast_dim, MP_RMSNORM, ME_SWIGLU, MF_KEEP | MF_SAVE1, l, p);
         if (with_head) head_part();
@@ -511,7 +523,7 @@ static int build_mega(dualar_engine *e) {
     for (int l = 0; l < c.n_fast_layer; ++l) { a.fqn[l] = e->fast[l].qn; a.fkn[l] = e->fast[l].kn; }
     a.fl = c.n_fast_layer; a.fnh = c.fast_n_head; a.fnkv = c.fast_n_local_heads; a.fhd = c.fast_head_dim; a.ncb = c.num_codebooks;
     a.fscale = (float)(1.0 / sqrt((double)c.fast_head_dim));
-    a.fkv = e->m_fkv; a.fast_emb = e->fast_emb; a.fdim = c.fast_dim; a.fv = e->fv; a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
+    a.fkv = e->m_fkv; a.t0 = e->t0; a.fast_emb = e->fast_emb; a.fdim = c.fast_dim; a.fv = e->fv; a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
     a.noise_off0 = (long long)c.vocab_size;
     a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.st = e->st; a.ustride = (int)ustride; a.phase_ctr = e->m_phase;
     // shared-memory plan (from the decode-step table; the prefill table is a subset and shares it)
@@ -658,6 +670,10 @@ extern "C" int dualar_set_option(dualar_engine *e, const char *name, double valu
   if (!strcmp(name, "mega_kernel")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "mega_kernel must be set before dualar_finalize");
     e->use_mega = value != 0.0; return 0;
+  }
+  if (!strcmp(name, "fast_qkv_table")) {
+    if (e->finalized) return fail(DUALAR_ESTATE, "fast_qkv_table must be set before dualar_finalize");
+    e->use_t0 = value != 0.0; return 0;
   }
   if (!strcmp(name, "candidate_delta")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "candidate_delta must be set before dualar_finalize");

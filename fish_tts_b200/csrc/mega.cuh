@@ -50,7 +50,7 @@ namespace da {
 enum { MK_GEMV = 0, MK_ATTN = 1, MK_MERGE = 2, MK_HSTAT = 3, MK_HCAND = 4, MK_PREFILL_END = 5 };
 enum { MP_PLAIN = 0, MP_RMSNORM = 1, MP_FASTATTN = 2, MP_EMBED = 3 };   // MP_EMBED: token embedding computed in place, then RMSNorm
 enum { ME_STORE = 0, ME_RESIDUAL = 1, ME_SWIGLU = 2, ME_SLOWLOGITS = 3, ME_FASTLOGITS = 4 };
-enum { MF_KEEP = 1, MF_SAVE0 = 2, MF_SAVE1 = 4, MF_RES0 = 8, MF_RES1 = 16 };
+enum { MF_KEEP = 1, MF_SAVE0 = 2, MF_SAVE1 = 4, MF_RES0 = 8, MF_RES1 = 16, MF_T0 = 32 };   // MF_T0: q | k | v of this attention come from the code table
 
 struct MPhase {
   const bf16 *W, *bias, *norm_w;
@@ -76,7 +76,7 @@ struct MegaArgs {
   bf16 *logits, *logits_raw; unsigned long long *hmax, *hcs, *cand; float delta; int n_rows_tok, head_pq, head_prem;
   // fast stack
   const bf16 *frope; const bf16 *fqn[DA_M_MAXFL], *fkn[DA_M_MAXFL]; int fl, fnh, fnkv, fhd, ncb; float fscale;
-  const bf16 *fast_emb; int fdim, fv; uint32_t *u_fin; bf16 *flogits_raw, *flogits; long long noise_off0;
+  const bf16 *fast_emb; const bf16 *t0; int fdim, fv; uint32_t *u_fin; bf16 *flogits_raw, *flogits; long long noise_off0;
   bf16 *fkv;             // fast K/V rows of the current token, one private copy per CTA: [cta][layer][pos][k | v][nkv * hd] (L2-resident)
   // end of step
   int *seq; int seq_stride, im_end_id;
@@ -527,7 +527,25 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             float t[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) t[j] = 0.f;
-            if (act) ok = poll_pair(in + c * 4, in + N / 2 + c * 4, in_tag, t) && ok;
+            if (d.flags & MF_T0) {
+              // first layer of a pass >= 1: the input is the embedding of the code just drawn, so q | k | v come from the table
+              // (one tagged unit carries the code; every thread polls it, then reads its 8 values and, for the residual of
+              //  this layer's wo, its share of the embedding row)
+              uint32_t u = 0u;
+              { int it = 0; for (;;) { u = ld_poll1(in); if ((u & 0xFFFFu) == in_tag) break; if (++it >= DA_SPIN_LIMIT) { ok = false; break; } } }
+              uint32_t code = u >> 16; if (code >= (uint32_t)a.codebook_size) code = 0u;
+              if (act) {
+                const bf16 *row = a.t0 + (size_t)code * N;
+                unpack4(*reinterpret_cast<const uint2 *>(row + c * 4), t); unpack4(*reinterpret_cast<const uint2 *>(row + N / 2 + c * 4), t + 4);
+              }
+              if (c * 8 < a.fdim) {
+                float xr[8];
+                const bf16 *er = a.fast_emb + (size_t)code * a.fdim + c * 8;
+                unpack4(*reinterpret_cast<const uint2 *>(er), xr); unpack4(*reinterpret_cast<const uint2 *>(er + 4), xr + 4);
+                *reinterpret_cast<float4 *>(sm_raw + c * 8) = make_float4(xr[0], xr[1], xr[2], xr[3]);
+                *reinterpret_cast<float4 *>(sm_raw + c * 8 + 4) = make_float4(xr[4], xr[5], xr[6], xr[7]);
+              }
+            } else if (act) ok = poll_pair(in + c * 4, in + N / 2 + c * 4, in_tag, t) && ok;
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
               float *tt = t + 4 * hlf;
@@ -841,7 +859,8 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         if (tid == 0) st->tok_out[d.pos + 1] = (int)tok;
         if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 2, gtime());
         if (d.pos < a.ncb - 1) {
-          for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
+          if (a.t0) { if (tid == 0) st_unit(a.u_fin, (tok << 16) | tag); }      // the code itself: the next pass looks its first q | k | v up
+          else for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)tok * a.fdim + dd]), tag));
         }
       }
       if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 3, gtime());
@@ -1210,7 +1229,8 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         if (TL && a.tl && tid == 0) tl_put(a, 1024 + ph, 3, gtime());
         int cb0 = (int)idx - a.sem_begin; if (cb0 < 0) cb0 = 0;
         if (cb0 >= a.codebook_size) { cb0 = a.codebook_size - 1; if (tid == 0) st->err = 3; }
-        for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)cb0 * a.fdim + dd]), tag));
+        if (a.t0) { if (tid == 0) st_unit(a.u_fin, ((uint32_t)cb0 << 16) | tag); }
+        else for (int dd = tid; dd < a.fdim; dd += DA_M_CTHREADS) st_unit(a.u_fin + dd, make_unit(bf2f(a.fast_emb[(size_t)cb0 * a.fdim + dd]), tag));
         if (tid == 0) { st->tok_out[0] = (int)idx; st->tok_out[1] = cb0; st->n_cand = N; }      // n_cand: diagnostic (candidates of this step)
       }
       cbar();

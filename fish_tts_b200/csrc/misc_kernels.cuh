@@ -208,4 +208,35 @@ __global__ void fill_noise_kernel(bf16 *out, long long n, unsigned long long see
     out[i] = f2bf(exp1_noise(seed, step, head, (uint32_t)i));
 }
 
+// ---- first-layer q | k | v of the fast stack for every code ------------------------------------------------------------
+// Passes >= 1 of the fast stack start from the embedding of a code (inference.py:123-149), so their first wqkv product is a
+// function of that code alone: table[code] = bf16(wqkv . rmsnorm(fast_emb[code]) + bias), with the roundings of the decode
+// kernel's staging (fp32 normalise, round, x weight, round) and an fp32 dot product per row.  Built once at finalize.
+__global__ void __launch_bounds__(256) t0_build_kernel(const bf16 *emb, const bf16 *norm_w, const bf16 *W, const bf16 *bias, bf16 *table,
+                                                       int K, int rows, float eps) {
+  extern __shared__ __align__(16) float t0_xs[];      // K floats
+  __shared__ float red[40];
+  const int code = blockIdx.x, tid = threadIdx.x;
+  float ss = 0.f;
+  for (int e = tid; e < K; e += blockDim.x) { const float v = bf2f(emb[(size_t)code * K + e]); t0_xs[e] = v; ss = fmaf(v, v, ss); }
+  ss = block_sum(ss, red);
+  const float inv = rsqrtf(ss * (1.0f / (float)K) + eps);
+  for (int e = tid; e < K; e += blockDim.x) t0_xs[e] = rbf(__fmul_rn(rbf(__fmul_rn(t0_xs[e], inv)), bf2f(norm_w[e])));
+  __syncthreads();
+  for (int r = tid; r < rows; r += blockDim.x) {
+    const uint4 *wr = reinterpret_cast<const uint4 *>(W + (size_t)r * K);
+    float acc = 0.f;
+    for (int c = 0; c < (K >> 3); ++c) {
+      const uint4 u = wr[c];
+      const float *x = t0_xs + 8 * c;
+      acc = fmaf(__uint_as_float(u.x << 16), x[0], acc); acc = fmaf(__uint_as_float(u.x & 0xffff0000u), x[1], acc);
+      acc = fmaf(__uint_as_float(u.y << 16), x[2], acc); acc = fmaf(__uint_as_float(u.y & 0xffff0000u), x[3], acc);
+      acc = fmaf(__uint_as_float(u.z << 16), x[4], acc); acc = fmaf(__uint_as_float(u.z & 0xffff0000u), x[5], acc);
+      acc = fmaf(__uint_as_float(u.w << 16), x[6], acc); acc = fmaf(__uint_as_float(u.w & 0xffff0000u), x[7], acc);
+    }
+    if (bias) acc += bf2f(bias[r]);
+    table[(size_t)code * rows + r] = f2bf(acc);
+  }
+}
+
 }  // namespace da

@@ -144,6 +144,9 @@ int dualar_set_noise(dualar_engine *e, const void *noise, int64_t n_steps);
  *     reference on CUDA (what a GPU user of the reference gets), 1 follows it on the CPU (what the
  *     golden fixtures were generated with).
  * "candidate_delta" (default 6.0, before finalize): slow-head candidates are logits >= max - delta.
+ * "fast_qkv_table" (0/1, before finalize; default 1): passes >= 1 of the fast stack start from the embedding of a
+ *     code, so the first fast layer's q|k|v is a function of that code alone; it is tabulated at finalize
+ *     (codebook_size x fast qkv rows, bf16; 16 MB for s1-mini) and that wqkv phase is dropped from the step.
  * "mega_kernel" (0/1, before finalize; default 1): run the whole decode step as ONE persistent cooperative
  *     kernel (csrc/mega.cuh) instead of one kernel per phase (kept as a cross-check).  The two sum their dot
  *     products in different fp32 orders (tensor-core chunks vs. FMA chains), so logits agree to bf16 rounding,

@@ -32,9 +32,10 @@ if n_step == 1:
     for l in range(cfg.n_fast_layer):      # fast pass 0, one slice of the LM head in front of every phase
         names += ["H.head", "F.qkv", "H.head", "F.wo", "H.head", "F.w13", "H.head", "F.w2"]
     names += ["H.stat", "H.cand"]
+    table = os.environ.get("DUALAR_T0", "1") != "0"      # first-layer wqkv of passes >= 1 comes from the code table: no phase
     for p in range(1, cfg.num_codebooks):
         for l in range(cfg.n_fast_layer):
-            names += ["F.qkv", "F.wo", "F.w13", "F.w2"]
+            names += (["F.wo", "F.w13", "F.w2"] if (table and l == 0) else ["F.qkv", "F.wo", "F.w13", "F.w2"])
         names.append("F.head")
     nph = len(names)
     full = eng.read("timeline").numpy().astype("int64")
