@@ -61,3 +61,43 @@ def sample(logits_bf16: torch.Tensor, temperature: float, top_p: float, rep_pena
         best_i = int(cand.min())
         best_r = rmax
     return best_i, n_keep
+
+
+def nucleus_sorted(z: np.ndarray, w: np.ndarray, c_max: int) -> np.ndarray:
+    """kept mask by the definition: prefix of the (logit desc, index asc) order whose inclusive fixed-point cumulative
+    weight stays <= c_max; the first item is always kept."""
+    order = np.lexsort((np.arange(z.size), -z))
+    cum = np.cumsum(w[order])
+    n_keep = max(1, int((cum <= c_max).sum()))
+    kept = np.zeros(z.size, dtype=bool)
+    kept[order[:n_keep]] = True
+    return kept
+
+
+def nucleus_binned(z: np.ndarray, w: np.ndarray, c_max: int, n_bins: int = 512, per_unit: int = 64) -> np.ndarray:
+    """kept mask the way sample_binned() (fish_tts_b200/csrc/sampler.cuh) finds it, without sorting: items binned by
+    their distance below the maximum (monotone in the logit), exact per-bin weight sums, one scan for the bin in
+    which the cumulative weight crosses c_max; bins ahead are kept whole, bins behind dropped whole, and only the
+    items of the cut bin are ranked against each other."""
+    m = np.float32(z.max())
+    b = np.minimum(np.maximum((m - z.astype(np.float32)) * np.float32(per_unit), np.float32(0)), np.float32(n_bins - 1)).astype(np.int64)
+    hist = np.zeros(n_bins, dtype=np.int64)
+    np.add.at(hist, b, w)
+    cnt = np.bincount(b, minlength=n_bins)
+    incl = np.cumsum(hist)
+    excl = incl - hist
+    cross = np.nonzero((excl <= c_max) & (incl > c_max))[0]
+    kept = np.zeros(z.size, dtype=bool)
+    if cross.size == 0:                      # the whole mass fits: everything is kept
+        kept[:] = True
+        return kept
+    cut = int(cross[0])
+    kept[b < cut] = True
+    before, cnt_before = int(excl[cut]), int(cnt[:cut].sum())
+    idx = np.nonzero(b == cut)[0]
+    for i in idx:                            # composite order inside the cut bin: logit desc, index asc
+        ahead = idx[(-z[idx] < -z[i]) | ((z[idx] == z[i]) & (idx < i))]
+        g = before + int(w[ahead].sum())
+        if g + int(w[i]) <= c_max or (ahead.size == 0 and cnt_before == 0):
+            kept[i] = True
+    return kept

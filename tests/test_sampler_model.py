@@ -44,3 +44,27 @@ def test_philox_known_answers():
     assert [int(x[0]) for x in c] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
     q = philox.exp1_noise(7, 0, 0, 200000).float()
     assert abs(q.mean().item() - 1.0) < 0.02 and q.min().item() > 0
+
+
+@pytest.mark.parametrize("dist", ["flat", "narrow", "peaks", "ties", "equal", "dominant", "tail", "split"])
+def test_binned_nucleus_equals_sorted_prefix(dist):
+    """The sort-free nucleus search of sample_binned() keeps exactly the prefix the definition keeps (numpy models of both;
+    the CUDA implementations are compared on the GPU by tests/cuda/binned_check.cu)."""
+    import numpy as np
+    rng = np.random.default_rng(hash(dist) % (2 ** 32))
+    for V in (1024, 4096):
+        for top_p in (1e-9, 0.05, 0.3, 0.8, 0.95, 1.0):
+            for s_factor in (1.0, 3.0):          # 3.0: candidates of a larger vocabulary (S covers more than the items)
+                u = rng.random(V).astype(np.float32)
+                i = np.arange(V)
+                z = {"flat": (u - 0.5) * 6, "narrow": u * 3, "peaks": np.where(i % 97 == 0, 9 + u, u * 2), "ties": np.floor(u * 8) * 0.25,
+                     "equal": np.full(V, 1.5), "dominant": np.where(i == 123, 20.0, (u - 0.5) * 4), "tail": -30 * u,
+                     "split": np.where(u < 0.5, 2 + 0.001 * u, -50.0)}[dist].astype(np.float32)
+                z = torch.from_numpy(z).bfloat16().float().numpy()
+                e = np.exp(z - z.max()).astype(np.float32)
+                S = np.float32(e.sum(dtype=np.float64)) * np.float32(s_factor)
+                p = torch.from_numpy(e / S).bfloat16().float().numpy()
+                w = (p.astype(np.float64) * sm.FIX).astype(np.int64)
+                c_max = sm.cmax_from_top_p(top_p)
+                a, b = sm.nucleus_sorted(z, w, c_max), sm.nucleus_binned(z, w, c_max)
+                assert (a == b).all(), f"{dist} V={V} top_p={top_p} S x{s_factor}: {int(a.sum())} vs {int(b.sum())} kept"
