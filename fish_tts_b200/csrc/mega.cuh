@@ -1,8 +1,9 @@
 // mega.cuh -- the whole dual-AR decode step (decode_one_token_ar, inference.py:83-155) as ONE persistent kernel.
 //
 // One CTA per SM (cooperative launch => co-resident), 16 compute warps + 1 producer warp.  A decode step is a static
-// table of ~340 dependent PHASES (embedding -> 28 x {wqkv, split-KV attention, merge, wo, w1/w3, w2} -> LM head ->
-// sampler -> 10 fast passes x 4 layers x {wqkv, attention+wo, w1/w3, w2} + 9 fast heads with their samplers).
+// table of ~346 dependent PHASES (embedding -> 28 x {wqkv, split-KV attention, merge, wo, w1/w3, w2} -> LM head in 16
+// parts interleaved with fast pass 0 -> slow sampler -> 9 fast passes x 4 layers x {wqkv, attention+wo, w1/w3, w2} + 9
+// fast heads with their samplers; the first wqkv of passes >= 1 comes from a per-code table, misc_kernels.cuh).
 // Three mechanisms keep HBM / L2 busy while the dependency chain advances:
 //
 //   * WEIGHT RING.  What a CTA will read from global memory is known before the step starts: its contiguous slice
@@ -17,10 +18,11 @@
 //   * every CTA polls the COMPLETE input of every GEMV phase, so passing a phase proves that all CTAs finished the
 //     previous one; buffers are reused without further synchronisation.
 //
-// Numerics: the per-row dot product follows the canonical order of gemv.cuh and every other formula is the one of the
-// per-phase kernels (attention.cuh, sampler.cuh, misc_kernels.cuh), so this kernel and the per-phase path agree bit
-// for bit (tests/test_gpu_parity.py::test_mega_kernel_bitexact).  All spins are bounded: a lost hand-over raises the
-// device fault flag instead of hanging the GPU.
+// Numerics: a row's dot product is summed in the CANONICAL ORDER of mma_chunk() below (128-element chunks, two chains of
+// four bf16 MMAs each, chunk partials added in chunk order); every other formula is the one of the per-phase kernels
+// (attention.cuh, sampler.cuh, misc_kernels.cuh), whose FMA chains sum in a different fp32 order: the two paths agree to
+// bf16 rounding (tests/test_gpu_parity.py::test_mega_kernel_vs_per_phase_kernels), and both samplers are exact on the
+// logits they are given.  All spins are bounded: a lost hand-over raises the device fault flag instead of hanging the GPU.
 #pragma once
 #include "attention.cuh"
 #include "common.cuh"
