@@ -127,6 +127,26 @@ def test_mega_kernel_vs_per_phase_kernels(name):
         assert near_tie(sb, int(ta[0, 0]), int(tb[0, 0]), ulps=8.0, atol=5e-2)
 
 
+@pytest.mark.parametrize("name", ["s1like", "biased", "s1mini"])
+def test_code_table_vs_wqkv_phase(name):
+    """option fast_qkv_table: passes >= 1 of the fast stack take their first q | k | v from the per-code table (an fp32 FMA
+    dot product per row at finalize) instead of running the wqkv phase (tensor-core chunks).  The slow stack is untouched, so
+    slow logits and the semantic id are identical bit for bit; the first fast head -- the first consumer of a table row --
+    agrees to accumulation-order noise."""
+    cfg = s1_mini_config() if name == "s1mini" else variant_configs()[name]
+    sd = make_state_dict(cfg, seed=0)
+    prompt = synthetic_prompt(cfg, 5, 12, 4, seed=1)
+    outs = []
+    for flag in (1, 0):
+        eng = DualAREngine(cfg, sd, device=0, seed=5, options={"fast_qkv_table": flag})
+        toks = eng.generate(prompt, 1, 0.7, 0.8, 1.1)
+        outs.append((toks, eng.read("fast_logits").clone(), eng.read("slow_logits_raw").clone()))
+        eng.close()
+    (ta, fa, sa), (tb, fb, sb) = outs
+    assert torch.equal(sa, sb) and int(ta[0, 0]) == int(tb[0, 0]) and int(ta[1, 0]) == int(tb[1, 0])
+    logits_close(fa[0], fb[0], None, f"{name}: first fast head, code table vs wqkv phase", atol=5e-2, ulps=8.0)
+
+
 @pytest.fixture(scope="module")
 def s1():
     cfg = s1_mini_config()
