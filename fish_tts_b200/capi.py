@@ -18,6 +18,8 @@ SYMBOLS = [
     "dualar_destroy", "dualar_bind_kv", "dualar_step", "dualar_prefill", "dualar_decode", "dualar_collect",
     "dualar_generate", "dualar_seed", "dualar_fill_noise", "dualar_set_noise", "dualar_read_buffer",
     "dualar_launches_per_step", "dualar_weight_bytes", "dualar_debug_sample", "dualar_set_option",
+    "dualar_batch_init", "dualar_batch_prefill", "dualar_batch_decode", "dualar_batch_collect", "dualar_batch_release",
+    "dualar_batch_read",
 ]
 
 _I32_FIELDS = [
@@ -76,6 +78,12 @@ def load() -> C.CDLL:
         "dualar_debug_sample": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
         "dualar_launches_per_step": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "dualar_weight_bytes": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "dualar_batch_init": (C.c_int, [vp, C.c_int, C.c_int]),
+        "dualar_batch_prefill": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint64, vp, vp]),
+        "dualar_batch_decode": (C.c_int, [vp, C.c_int, vp]),
+        "dualar_batch_collect": (C.c_int, [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), vp]),
+        "dualar_batch_release": (C.c_int, [vp, C.c_int]),
+        "dualar_batch_read": (C.c_int, [vp, C.c_char_p, vp, C.c_int64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

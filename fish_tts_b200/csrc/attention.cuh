@@ -48,6 +48,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_nohint(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // bounded wait: a lost transaction raises the device fault flag instead of hanging the GPU
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;

@@ -1,0 +1,570 @@
+// batch.cuh -- the kernels AROUND the tensor-core GEMMs (gemm_tc.cuh) when the decode path runs over many columns at once:
+// a column is one REQUEST (batched decode, BASELINE configs[3]) or one PROMPT POSITION (prefill, inference.py:353-362).
+//
+// Activations are [column][feature] bf16 row-major, which is directly the K-major N operand of the next GEMM.  Every formula
+// and rounding point is the one of the batch-1 kernels (attention.cuh, gemv.cuh, misc_kernels.cuh, sampler.cuh): a request's
+// result does not depend on what else is in the batch, which is what the parity tests check ("bs = B equals B independent
+// bs = 1 oracle runs"; the reference itself is batch 1 only, inference.py:73, 355).
+//
+//   b_embed_kernel       llama.py:409-429    token + codebook embedding per column
+//   b_rmsnorm_kernel     llama.py:172-177    custom RMSNorm (round before the weight multiply), one warp per column
+//   b_qkv_post_kernel    llama.py:246-251, 142-149   q/k nn.RMSNorm + RoPE in place, K/V rows into the column's cache
+//   b_attn_kernel        llama.py:258-274    split-KV flash-decode per (column, kv head), fp32 like the math SDPA backend
+//   b_fast_attn_kernel   llama.py:285-309    the fast layers' bf16 attention over <= num_codebooks positions
+//   b_head_stats_kernel / b_select_kernel / b_fast_sample_kernel    inference.py:30-80, 103-149    penalty, exact nucleus, Exp(1) race
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "sampler.cuh"
+
+namespace da {
+
+// token (column n, row r) = base[n * sn + r * sr]: decode reads DAState::tok_in of slot n, prefill a prompt column
+struct TokSrc { const int *base; long long sn, sr; };
+// position of column n = base ? base[n * sn] : pos0 + n
+struct PosSrc { const int *base; long long sn; int pos0; };
+__device__ __forceinline__ int pos_of(const PosSrc &p, int n) { return p.base ? p.base[(long long)n * p.sn] : p.pos0 + n; }
+
+// ---- embedding ---------------------------------------------------------------------------------------------------------------
+struct BEmbedArgs {
+  const bf16 *emb, *cb_emb; bf16 *x;     // x: [ncols][dim]
+  int dim, vocab, codebook_size, num_codebooks, sem_begin, sem_end, scale_cb, cpu_sem, ncols;
+  float inv_sqrt, sqrt_c;
+  TokSrc tok; int *err;
+};
+__global__ void __launch_bounds__(128) b_embed_kernel(const BEmbedArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.x;
+  int tok = a.tok.base[n * a.tok.sn];
+  if (tok < 0 || tok >= a.vocab) { tok = 0; if (threadIdx.x == 0) atomicExch(a.err, 1); }
+  const bool is_sem = tok >= a.sem_begin && tok <= a.sem_end;
+  for (int c = threadIdx.x; c * 8 < a.dim; c += blockDim.x) {
+    float te[8], vq[8];
+    unpack8(*reinterpret_cast<const uint4 *>(a.emb + (size_t)tok * a.dim + c * 8), te);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vq[j] = 0.f;
+    if (is_sem) {
+      for (int i = 0; i < a.num_codebooks; ++i) {       // stack(...).sum(dim=1): fp32 accumulate, one rounding
+        int cc = a.tok.base[n * a.tok.sn + (i + 1) * a.tok.sr];
+        if (cc < 0 || cc >= a.codebook_size) { cc = 0; atomicExch(a.err, 1); }
+        float ce[8]; unpack8(*reinterpret_cast<const uint4 *>(a.cb_emb + ((size_t)cc + (size_t)i * a.codebook_size) * a.dim + c * 8), ce);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vq[j] += ce[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vq[j] = rbf(vq[j]);
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = rbf(te[j] + vq[j]);
+      if (a.scale_cb && is_sem) x = a.cpu_sem ? rbf(__fdiv_rn(x, a.sqrt_c)) : rbf(__fmul_rn(x, a.inv_sqrt));
+      o[j] = x;
+    }
+    uint4 u;
+    u.x = (uint32_t)f2bits(o[0]) | ((uint32_t)f2bits(o[1]) << 16); u.y = (uint32_t)f2bits(o[2]) | ((uint32_t)f2bits(o[3]) << 16);
+    u.z = (uint32_t)f2bits(o[4]) | ((uint32_t)f2bits(o[5]) << 16); u.w = (uint32_t)f2bits(o[6]) | ((uint32_t)f2bits(o[7]) << 16);
+    *reinterpret_cast<uint4 *>(a.x + (size_t)n * a.dim + c * 8) = u;
+  }
+}
+
+// ---- RMSNorm: one warp per column -------------------------------------------------------------------------------------------------
+struct BNormArgs { const bf16 *x, *w; bf16 *out; int K, ncols; float eps; };
+__global__ void __launch_bounds__(128) b_rmsnorm_kernel(const BNormArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, n = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (n >= a.ncols) return;
+  const uint4 *src = reinterpret_cast<const uint4 *>(a.x + (size_t)n * a.K);
+  const int nc = a.K >> 3;
+  float ss = 0.f;
+  for (int c = lane; c < nc; c += 32) {
+    float f[8]; unpack8(src[c], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss * (1.0f / (float)a.K) + a.eps);
+  for (int c = lane; c < nc; c += 32) {
+    float f[8], g[8]; unpack8(src[c], f); unpack8(reinterpret_cast<const uint4 *>(a.w)[c], g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = rbf(__fmul_rn(rbf(__fmul_rn(f[j], inv)), g[j]));      // .type_as(x), then * weight
+    uint4 u;
+    u.x = (uint32_t)f2bits(f[0]) | ((uint32_t)f2bits(f[1]) << 16); u.y = (uint32_t)f2bits(f[2]) | ((uint32_t)f2bits(f[3]) << 16);
+    u.z = (uint32_t)f2bits(f[4]) | ((uint32_t)f2bits(f[5]) << 16); u.w = (uint32_t)f2bits(f[6]) | ((uint32_t)f2bits(f[7]) << 16);
+    reinterpret_cast<uint4 *>(a.out + (size_t)n * a.K)[c] = u;
+  }
+}
+
+// ---- q/k norm + RoPE in place, K/V rows into the cache ----------------------------------------------------------------------------
+struct BQkvPostArgs {
+  bf16 *qkv;                 // [ncols][(nh + 2 nkv) * hd]; q is rewritten in place
+  bf16 *kc, *vc;             // cache of column n at + n * slot_stride elements: [nkv][S][hd]
+  long long slot_stride;
+  const bf16 *rope, *qn, *kn;
+  int nh, nkv, hd, S, ncols; float eps;
+  PosSrc pos;
+};
+__global__ void __launch_bounds__(256) b_qkv_post_kernel(const BQkvPostArgs a) {
+  extern __shared__ __align__(16) float sm_qp[];      // 8 warps x hd floats
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int hd = a.hd, qd = a.nh * hd, kd = a.nkv * hd;
+  const int pos = pos_of(a.pos, n);
+  if (pos < 0 || pos >= a.S) return;
+  bf16 *row = a.qkv + (size_t)n * (qd + 2 * kd);
+  bf16 *kc = a.kc + (size_t)n * a.slot_stride, *vc = a.vc + (size_t)n * a.slot_stride;
+  const bf16 *rope_row = a.rope + (size_t)pos * hd;
+  float *v = sm_qp + (size_t)w * hd;
+  for (int h = w; h < a.nh + 2 * a.nkv; h += nw) {
+    bf16 *src = row + (size_t)h * hd;
+    if (h >= a.nh + a.nkv) {            // v head: KVCache.update (llama.py:142-149), no norm / rotation
+      const int g = h - a.nh - a.nkv;
+      for (int d = lane; d < hd; d += 32) vc[((size_t)g * a.S + pos) * hd + d] = src[d];
+      continue;
+    }
+    for (int d = lane; d < hd; d += 32) v[d] = bf2f(src[d]);
+    __syncwarp();
+    head_norm_rope(v, hd, h < a.nh ? a.qn : a.kn, a.eps, rope_row, lane);
+    if (h < a.nh) { for (int d = lane; d < hd; d += 32) src[d] = f2bf(v[d]); }
+    else { const int g = h - a.nh; for (int d = lane; d < hd; d += 32) kc[((size_t)g * a.S + pos) * hd + d] = f2bf(v[d]); }
+    __syncwarp();
+  }
+}
+
+// ---- slow attention: split-KV flash-decode, one query per column ----------------------------------------------------------------
+struct BAttnArgs {
+  const bf16 *qkv;           // [ncols][(nh + 2 nkv) * hd], q already normalised + rotated
+  const bf16 *kc, *vc; long long slot_stride;
+  int nh, nkv, hd, S, ncols, nsplit_max; float sf;
+  float *part_o, *part_ml;   // [ncols][nkv][nsplit_max][G][hd], [...][G][2]
+  unsigned int *tickets;     // [ncols][nkv], zero between launches
+  bf16 *y;                   // [ncols][nh * hd]
+  PosSrc pos; int *err;
+};
+// grid (nsplit_max, nkv, ncols); dynamic smem as attn_smem_bytes()
+__global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw_b[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int g = blockIdx.y, split = blockIdx.x, n = blockIdx.z;
+  const int G = a.nh / a.nkv, hd = a.hd;
+  const int pos = pos_of(a.pos, n);
+  if (pos < 0 || pos >= a.S) return;
+  const int L = pos + 1;
+  const int n_tiles = (L + DA_TILE - 1) / DA_TILE;
+  const int nsplit = min(a.nsplit_max, n_tiles);
+  const int tps = (n_tiles + nsplit - 1) / nsplit;
+  const int nsplit_eff = (n_tiles + tps - 1) / tps;
+  if (split >= nsplit_eff) return;
+  const int t0 = split * tps, t1 = min(n_tiles, t0 + tps);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = DA_ATTN_THREADS / 32;
+  float *q = reinterpret_cast<float *>(smraw_b);
+  float *sc = q + G * hd + 2 * hd;
+  float *red = sc + G * DA_TILE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(red + 80);
+  size_t off = (size_t)((unsigned char *)(bars + 2) - smraw_b);
+  off = (off + 127) & ~(size_t)127;
+  bf16 *kbuf = reinterpret_cast<bf16 *>(smraw_b + off);
+  bf16 *vbuf = kbuf + 2 * DA_TILE * hd;
+  const bf16 *kc = a.kc + (size_t)n * a.slot_stride, *vc = a.vc + (size_t)n * a.slot_stride;
+  const uint64_t pol = policy_evict_first();
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t, int buf) {
+    const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE);
+    const uint32_t bytes = (uint32_t)(r1 - r0) * hd * sizeof(bf16);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bars[buf], 2 * bytes);
+    bulk_g2s(kbuf + (size_t)buf * DA_TILE * hd, kc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
+    bulk_g2s(vbuf + (size_t)buf * DA_TILE * hd, vc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
+  };
+  if (threadIdx.x == 0) issue(t0, 0);
+  {
+    const bf16 *qsrc = a.qkv + (size_t)n * (a.nh + 2 * a.nkv) * hd + (size_t)g * G * hd;
+    for (int c = threadIdx.x; c * 8 < G * hd; c += DA_ATTN_THREADS) {
+      float t[8]; unpack8(*reinterpret_cast<const uint4 *>(qsrc + c * 8), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[c * 8 + j] = __fmul_rn(t[j], a.sf);      // q * sqrt(scale), fp32 (math SDPA)
+    }
+  }
+  __syncthreads();
+  const int n_own = (G * hd + DA_ATTN_THREADS - 1) / DA_ATTN_THREADS;
+  float o_acc[DA_MAX_G * 128 / DA_ATTN_THREADS];
+#pragma unroll
+  for (int i = 0; i < DA_MAX_G * 128 / DA_ATTN_THREADS; ++i) o_acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  __shared__ float s_m[DA_MAX_G], s_scale[DA_MAX_G], s_l[DA_MAX_G];
+  if (threadIdx.x < DA_MAX_G) { s_m[threadIdx.x] = -INFINITY; s_l[threadIdx.x] = 0.f; }
+  const int lpr = hd / 8, rpw = 32 / lpr;
+  uint32_t phase[2] = {0u, 0u};
+  bool ok = true;
+  for (int t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
+    if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);
+    ok = mbar_wait(&bars[buf], phase[buf]) && ok; phase[buf] ^= 1u;
+    const bf16 *kt = kbuf + (size_t)buf * DA_TILE * hd, *vt = vbuf + (size_t)buf * DA_TILE * hd;
+    for (int jb = w * rpw; jb < nrow; jb += nw * rpw) {
+      const int j = jb + lane / lpr, piece = lane % lpr;
+      float part[DA_MAX_G];
+#pragma unroll
+      for (int h = 0; h < DA_MAX_G; ++h) part[h] = 0.f;
+      if (j < nrow) {
+        float kf[8]; unpack8(*reinterpret_cast<const uint4 *>(kt + (size_t)j * hd + piece * 8), kf);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) kf[d] = __fmul_rn(kf[d], a.sf);
+#pragma unroll
+        for (int h = 0; h < DA_MAX_G; ++h) {
+          if (h < G) {
+            const float *qq = q + h * hd + piece * 8;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) part[h] = fmaf(qq[d], kf[d], part[h]);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < DA_MAX_G; ++h) {
+        if (h < G) {
+          float v = part[h];
+          for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (piece == 0 && j < nrow) sc[h * DA_TILE + j] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (w < G) {
+      float mx = -INFINITY;
+      for (int j = lane; j < nrow; j += 32) mx = fmaxf(mx, sc[w * DA_TILE + j]);
+      mx = warp_max(mx);
+      const float m_new = fmaxf(m_run, mx);
+      float ps = 0.f;
+      for (int j = lane; j < nrow; j += 32) { const float p = expf(sc[w * DA_TILE + j] - m_new); sc[w * DA_TILE + j] = p; ps += p; }
+      ps = warp_sum(ps);
+      const float scale = expf(m_run - m_new);
+      l_run = l_run * scale + ps; m_run = m_new;
+      if (lane == 0) { s_scale[w] = scale; s_m[w] = m_run; s_l[w] = l_run; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < DA_MAX_G * 128 / DA_ATTN_THREADS; ++i) {
+      const int e = threadIdx.x + i * DA_ATTN_THREADS;
+      if (i < n_own && e < G * hd) {
+        const int h = e / hd, d = e - h * hd;
+        float acc = o_acc[i] * s_scale[h];
+        const float *pp = sc + h * DA_TILE;
+        for (int j = 0; j < nrow; ++j) acc = fmaf(pp[j], bf2f(vt[(size_t)j * hd + d]), acc);
+        o_acc[i] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (!ok && threadIdx.x == 0) atomicExch(a.err, 2);
+  const size_t pbase = ((size_t)n * a.nkv + g) * a.nsplit_max;
+  float *po = a.part_o + ((pbase + split) * G) * hd;
+  float *pml = a.part_ml + ((pbase + split) * G) * 2;
+#pragma unroll
+  for (int i = 0; i < DA_MAX_G * 128 / DA_ATTN_THREADS; ++i) {
+    const int e = threadIdx.x + i * DA_ATTN_THREADS;
+    if (i < n_own && e < G * hd) po[e] = o_acc[i];
+  }
+  if (threadIdx.x < G) { pml[threadIdx.x * 2] = s_m[threadIdx.x]; pml[threadIdx.x * 2 + 1] = s_l[threadIdx.x]; }
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  unsigned int *ticket = a.tickets + (size_t)n * a.nkv + g;
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned)nsplit_eff - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int e = threadIdx.x; e < G * hd; e += DA_ATTN_THREADS) {      // merge in split order (deterministic)
+    const int h = e / hd;
+    float m = -INFINITY;
+    for (int s = 0; s < nsplit_eff; ++s) m = fmaxf(m, __ldcg(a.part_ml + ((pbase + s) * G + h) * 2));
+    float l = 0.f, o = 0.f;
+    for (int s = 0; s < nsplit_eff; ++s) {
+      const float *ml = a.part_ml + ((pbase + s) * G + h) * 2;
+      const float sc_s = expf(__ldcg(ml) - m);
+      l = fmaf(__ldcg(ml + 1), sc_s, l);
+      o = fmaf(__ldcg(a.part_o + ((pbase + s) * G) * hd + e), sc_s, o);
+    }
+    a.y[(size_t)n * a.nh * hd + (size_t)g * G * hd + e] = f2bf(o / l);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// ---- fast-layer attention for codebook position p, one CTA per column ---------------------------------------------------------------
+struct BFastAttnArgs {
+  const bf16 *qkv;           // [ncols][(nh + 2 nkv) * hd]
+  bf16 *kc, *vc;             // per column at + n * slot_stride: [nkv][ncb][hd]  (the reference's fast KVCache layout)
+  long long slot_stride;
+  const bf16 *rope, *qn, *kn;
+  int nh, nkv, hd, ncb, p, ncols; float eps, scale;
+  bf16 *y;                   // [ncols][nh * hd]
+};
+// dynamic smem: q[qd] | k[ncb][kd] | v[ncb][kd] | pr[nh][ncb]  floats
+__global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f) {
+  extern __shared__ __align__(16) float sm_fa[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int qd = f.nh * f.hd, kd = f.nkv * f.hd, P = f.p + 1, G = f.nh / f.nkv;
+  float *q = sm_fa, *ka = q + qd, *va = ka + f.ncb * kd, *pr = va + f.ncb * kd;
+  const bf16 *row = f.qkv + (size_t)n * (qd + 2 * kd);
+  bf16 *kc = f.kc + (size_t)n * f.slot_stride, *vc = f.vc + (size_t)n * f.slot_stride;
+  for (int c = threadIdx.x; c * 8 < qd + 2 * kd; c += blockDim.x) {
+    float t[8]; unpack8(*reinterpret_cast<const uint4 *>(row + c * 8), t);
+    const int e = c * 8;
+    float *dst = e < qd ? q + e : (e < qd + kd ? ka + f.p * kd + (e - qd) : va + f.p * kd + (e - qd - kd));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = t[j];
+  }
+  const int hd8 = f.hd >> 3, kd8 = kd >> 3;
+  for (int c = threadIdx.x; c < f.p * kd8; c += blockDim.x) {      // earlier positions from the cache
+    const int j = c / kd8, r = c - j * kd8, g = r / hd8, d8 = r - g * hd8;
+    const size_t src = ((size_t)g * f.ncb + j) * f.hd + (size_t)d8 * 8;
+    float t[8];
+    unpack8(*reinterpret_cast<const uint4 *>(kc + src), t);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) ka[c * 8 + jj] = t[jj];
+    unpack8(*reinterpret_cast<const uint4 *>(vc + src), t);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) va[c * 8 + jj] = t[jj];
+  }
+  __syncthreads();
+  const bf16 *rope_row = f.rope + (size_t)f.p * f.hd;
+  for (int h = w; h < f.nh + f.nkv; h += nw) {
+    if (h < f.nh) head_norm_rope(q + h * f.hd, f.hd, f.qn, f.eps, rope_row, lane);
+    else head_norm_rope(ka + f.p * kd + (h - f.nh) * f.hd, f.hd, f.kn, f.eps, rope_row, lane);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kd; e += blockDim.x) {               // KVCache.update (llama.py:142-149)
+    const int g = e / f.hd, d = e - g * f.hd;
+    const size_t dst = ((size_t)g * f.ncb + f.p) * f.hd + d;
+    kc[dst] = f2bf(ka[f.p * kd + e]); vc[dst] = f2bf(va[f.p * kd + e]);
+  }
+  for (int t = threadIdx.x; t < f.nh * P; t += blockDim.x) {         // bf16(q @ k^T), then bf16(* scale)   (llama.py:304)
+    const int h = t / P, j = t - h * P, g = h / G;
+    const float4 *qq = reinterpret_cast<const float4 *>(q + h * f.hd), *kk = reinterpret_cast<const float4 *>(ka + j * kd + g * f.hd);
+    float acc = 0.f;
+    for (int d = 0; d < (f.hd >> 2); ++d) {
+      const float4 x = qq[d], y = kk[d];
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    pr[h * f.ncb + j] = rbf(__fmul_rn(rbf(acc), f.scale));
+  }
+  __syncthreads();
+  // softmax in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf) = 0).  One thread per (h, j)
+  // (nh * ncb <= 256, check_config); every thread of a row walks it in the same order, so the row sum is identical
+  float pval = 0.f;
+  const int tt = threadIdx.x;
+  if (tt < f.nh * P) {
+    const int h = tt / P, j = tt - h * P;
+    float m = -INFINITY;
+    for (int jj = 0; jj < P; ++jj) m = fmaxf(m, pr[h * f.ncb + jj]);
+    float sum = 0.f;
+    for (int jj = 0; jj < P; ++jj) sum += expf(pr[h * f.ncb + jj] - m);
+    pval = rbf(expf(pr[h * f.ncb + j] - m) / sum);
+  }
+  __syncthreads();
+  if (tt < f.nh * P) { const int h = tt / P, j = tt - h * P; pr[h * f.ncb + j] = pval; }
+  __syncthreads();
+  bf16 *yo = f.y + (size_t)n * qd;
+  for (int c = threadIdx.x; c * 8 < qd; c += blockDim.x) {           // y = bf16(p @ v)   (llama.py:309)
+    const int e = c * 8, h = e / f.hd, d = e - h * f.hd, g = h / G;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int jj = 0; jj < P; ++jj) {
+      const float pj = pr[h * f.ncb + jj];
+      const float *vv = va + jj * kd + g * f.hd + d;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(pj, vv[j], acc[j]);
+    }
+    uint4 u;
+    u.x = (uint32_t)f2bits(acc[0]) | ((uint32_t)f2bits(acc[1]) << 16); u.y = (uint32_t)f2bits(acc[2]) | ((uint32_t)f2bits(acc[3]) << 16);
+    u.z = (uint32_t)f2bits(acc[4]) | ((uint32_t)f2bits(acc[5]) << 16); u.w = (uint32_t)f2bits(acc[6]) | ((uint32_t)f2bits(acc[7]) << 16);
+    *reinterpret_cast<uint4 *>(yo + e) = u;
+  }
+}
+static inline size_t b_fast_attn_smem(int nh, int nkv, int hd, int ncb) {
+  return ((size_t)nh * hd + 2 * (size_t)ncb * nkv * hd + (size_t)nh * ncb) * sizeof(float);
+}
+
+// ---- slow head, stage 1: repetition penalty + per-chunk maximum -------------------------------------------------------------------
+struct BHeadArgs {
+  bf16 *logits;              // [ncols][V] raw in, penalised out (in place)
+  bf16 *logits_raw;          // optional copy of the raw logits (tests) or null
+  float *cmax;               // [ncols][nchunk]
+  int V, nchunk, n_rows_tok;
+  DAState *st;               // [ncols]
+};
+// grid (nchunk, ncols), 512 threads
+__global__ void __launch_bounds__(512) b_head_stats_kernel(const BHeadArgs a) {
+  __shared__ float scratch[80];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.y;
+  const DAState *st = a.st + n;
+  bf16 *lg = a.logits + (size_t)n * a.V;
+  const int chunk = (a.V + a.nchunk - 1) / a.nchunk;
+  const int i0 = blockIdx.x * chunk, i1 = min(a.V, i0 + chunk);
+  const float rp_bf = eff_rep_penalty(st);
+  const int use_pen = st->use_penalty;
+  float m = -INFINITY;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    float z = bf2f(lg[i]);
+    if (a.logits_raw) a.logits_raw[(size_t)n * a.V + i] = f2bf(z);
+    if (use_pen) for (int r = 0; r < a.n_rows_tok; ++r) if (st->win[r * DA_WIN] == i) { z = penalise(z, rp_bf); lg[i] = f2bf(z); break; }   // previous_tokens[:, 0]
+    m = fmaxf(m, z);
+  }
+  m = block_max(m, scratch);
+  if (threadIdx.x == 0) a.cmax[(size_t)n * a.nchunk + blockIdx.x] = m;
+}
+
+// ---- slow head, stage 2: exact softmax statistics, candidates, sampling in the last CTA of the column ----------------------------
+struct BSelectArgs {
+  const bf16 *logits; const float *cmax; int V, nchunk; float delta;
+  unsigned long long *cand;  // [ncols][DA_CAND_CAP]
+  const bf16 *fast_emb; bf16 *fast_x;      // fast_x: [ncols][fast_dim]
+  int fast_dim, codebook_size, sem_begin;
+  DAState *st;
+};
+// grid (nchunk, ncols), 512 threads; dynamic smem: scr[192] u64 | scr64[34] | scrf[80]
+__global__ void __launch_bounds__(512, 1) b_select_kernel(const BSelectArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw_bs[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.y;
+  DAState *st = a.st + n;
+  unsigned long long *scr = reinterpret_cast<unsigned long long *>(smraw_bs);
+  unsigned long long *scr64 = scr + 192;
+  float *scrf = reinterpret_cast<float *>(scr64 + 34);
+  __shared__ float s_m;
+  if (threadIdx.x < 32) {
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < a.nchunk; i += 32) m = fmaxf(m, a.cmax[(size_t)n * a.nchunk + i]);
+    m = warp_max(m);
+    if (threadIdx.x == 0) s_m = m;
+  }
+  __syncthreads();
+  const float m = s_m, thr = m - a.delta;
+  const uint16_t *lb = reinterpret_cast<const uint16_t *>(a.logits + (size_t)n * a.V);
+  unsigned long long *cand = a.cand + (size_t)n * DA_CAND_CAP;
+  const int chunk = (a.V + a.nchunk - 1) / a.nchunk;
+  const int i0 = blockIdx.x * chunk, i1 = min(a.V, i0 + chunk);
+  const int lane = threadIdx.x & 31;
+  unsigned long long es = 0ull;
+  for (int base = i0; base < i1; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    uint16_t b = 0; bool c = false;
+    if (i < i1) { b = lb[i]; const float z = bits2f(b); c = z >= thr; es += (unsigned long long)(expf(z - m) * DA_FIX2_SCALE); }
+    const unsigned mask = __ballot_sync(0xffffffffu, c);
+    if (mask) {
+      unsigned basei = 0;
+      if (lane == 0) basei = atomicAdd(&st->n_cand, (unsigned)__popc(mask));
+      basei = __shfl_sync(0xffffffffu, basei, 0);
+      if (c) {
+        const unsigned slot = basei + __popc(mask & ((1u << lane) - 1));
+        if (slot < DA_CAND_CAP) cand[slot] = make_sortkey(b, (uint32_t)i);
+      }
+    }
+  }
+  { int par = 0; Red r = {es, 0, -1}; r = block_reduce(r, scr, par); if (threadIdx.x == 0) atomicAdd(&st->s_fix, r.s); __syncthreads(); }
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->sel_ticket, 1u) == (unsigned)a.nchunk - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  SampleParams sp;
+  sp.m = m; sp.S = __ull2float_rn(*((volatile unsigned long long *)&st->s_fix)) * (1.0f / DA_FIX2_SCALE);
+  sp.T_bf = eff_temperature(st);
+  sp.c_max = cmax_from_top_p(st->top_p);
+  const unsigned n_cand = *((volatile unsigned *)&st->n_cand);
+  uint32_t idx = 0xFFFFFFFFu;
+  if (n_cand >= 1 && n_cand <= DA_CAND_CAP) {
+    uint32_t key[16], ix[16], valid = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const unsigned e = threadIdx.x + i * blockDim.x;
+      key[i] = 0; ix[i] = 0;
+      if (e < n_cand) { const unsigned long long k = __ldcg(cand + e); key[i] = 0xFFFFu - (uint32_t)(k >> 32); ix[i] = (uint32_t)k; valid |= 1u << i; }
+    }
+    idx = sample_items<16>(key, ix, valid, (uint32_t)a.V, (int)n_cand == a.V, sp, noise_src(st), 0u, 0ll, &st->nucleus[0], scr);
+    __syncthreads();
+  }
+  if (idx == 0xFFFFFFFFu) idx = sample_fallback(a.logits + (size_t)n * a.V, a.V, sp, noise_src(st), 0u, 0ll, &st->nucleus[0], scr64, scrf);
+  int cb0 = (int)idx - a.sem_begin; if (cb0 < 0) cb0 = 0;                   // inference.py:123-126
+  if (cb0 >= a.codebook_size) { cb0 = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
+  for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[(size_t)n * a.fast_dim + d] = a.fast_emb[(size_t)cb0 * a.fast_dim + d];
+  if (threadIdx.x == 0) { st->tok_out[0] = (int)idx; st->tok_out[1] = cb0; st->n_cand = 0; st->sel_ticket = 0; st->s_fix = 0ull; }
+}
+
+// ---- fast heads: penalty + sampling of one codebook per column; the last head ends the step --------------------------------------
+struct BFastSampleArgs {
+  const bf16 *logits;        // [ncols][fv] raw
+  bf16 *logits_raw;          // optional [ncols][ncb - 1][fv] copy (tests) or null
+  int fv, head, ncb, last_head;
+  long long noise_off;
+  const bf16 *fast_emb; bf16 *fast_x; int fast_dim, codebook_size;
+  int *seq; long long seq_slot_stride; int seq_stride, im_end_id, n_rows_tok;
+  DAState *st;
+};
+// grid (ncols), 256 threads; dynamic smem: 192 u64 + 80 floats + fv bf16
+__global__ void __launch_bounds__(256) b_fast_sample_kernel(const BFastSampleArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw_fs[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.x;
+  DAState *st = a.st + n;
+  unsigned long long *scr = reinterpret_cast<unsigned long long *>(smraw_fs);
+  float *scrf = reinterpret_cast<float *>(scr + 192);
+  const bf16 *lg = a.logits + (size_t)n * a.fv;
+  const float rp_bf = eff_rep_penalty(st);
+  const int use_pen = st->use_penalty;
+  uint32_t key[DA_FAST_IPT], idx[DA_FAST_IPT], valid = 0;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < DA_FAST_IPT; ++i) {
+    const int e = threadIdx.x * DA_FAST_IPT + i;
+    idx[i] = (uint32_t)e; key[i] = 0;
+    if (e < a.fv) {
+      float z = bf2f(lg[e]);
+      if (a.logits_raw) a.logits_raw[((size_t)n * (a.ncb - 1) + (a.head - 1)) * a.fv + e] = f2bf(z);
+      if (use_pen) for (int c = 0; c < DA_WIN; ++c) if (st->win[(a.head + 1) * DA_WIN + c] == e) { z = penalise(z, rp_bf); break; }      // previous_tokens[k+1]
+      key[i] = bf16_key(f2bits(z)); valid |= 1u << i; mx = fmaxf(mx, z);
+    }
+  }
+  SampleParams sp;
+  sp.m = block_max(mx, scrf);
+  {
+    Red es = {0ull, 0, -1}; int par = 0;
+#pragma unroll
+    for (int i = 0; i < DA_FAST_IPT; ++i) if ((valid >> i) & 1u) es.s += (unsigned long long)(expf(bits2f(key_bf16(key[i])) - sp.m) * DA_FIX2_SCALE);
+    sp.S = __ull2float_rn(block_reduce(es, scr, par).s) * (1.0f / DA_FIX2_SCALE);
+    __syncthreads();
+  }
+  sp.T_bf = eff_temperature(st);
+  sp.c_max = cmax_from_top_p(st->top_p);
+  uint32_t tok = sample_items<DA_FAST_IPT>(key, idx, valid, (uint32_t)a.fv, true, sp, noise_src(st), (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], scr);
+  if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
+  if (!a.last_head) for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[(size_t)n * a.fast_dim + d] = a.fast_emb[(size_t)tok * a.fast_dim + d];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->tok_out[a.head + 1] = (int)tok;
+    if (a.last_head && !st->done) {
+      GemvArgs g; g.st = st; g.seq = a.seq + (size_t)n * a.seq_slot_stride; g.seq_stride = a.seq_stride; g.im_end_id = a.im_end_id; g.n_rows_tok = a.n_rows_tok;
+      finish_step(g);
+    }
+  }
+}
+
+}  // namespace da

@@ -1,0 +1,400 @@
+// batch_host.cuh -- host side of the many-column path: the tensor-core prefill of a prompt and batched decode.
+// Included at the end of engine.cu (it needs dualar_engine).  See include/dualar.h for the contract of the entry points.
+//
+// One schedule serves both uses: a COLUMN is a prompt position (prefill: T columns of one request, KV rows written for all of
+// them, no LM head) or a request slot (batched decode: B columns, one per slot, each with its own KV cache, position, sampling
+// state and Philox stream).  Per slow layer: RMSNorm -> wqkv GEMM -> q/k norm + RoPE + KV write -> split-KV attention -> wo GEMM
+// (+ residual) -> RMSNorm -> w1/w3 GEMM (SwiGLU epilogue) -> w2 GEMM (+ residual); all GEMMs are gemm_tc_kernel (tcgen05).
+#pragma once
+
+namespace {
+
+struct MapKey { const void *p; int rows, K, box; bool operator<(const MapKey &o) const { return std::tie(p, rows, K, box) < std::tie(o.p, o.rows, o.K, o.box); } };
+
+// activation buffers for up to `cap` columns
+struct ColBufs {
+  int cap = 0;
+  bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *y = nullptr, *h = nullptr, *act = nullptr;
+  float *part_o = nullptr, *part_ml = nullptr; unsigned int *attn_tickets = nullptr;
+  int nsplit = 1;
+  // decode only
+  bf16 *logits = nullptr, *logits_raw = nullptr, *fin = nullptr, *fx[2] = {nullptr, nullptr}, *fh = nullptr, *fqkv = nullptr, *fy = nullptr, *fact = nullptr,
+       *fxn = nullptr, *flogits = nullptr, *flogits_raw = nullptr;
+  float *cmax = nullptr; unsigned long long *cand = nullptr;
+};
+
+}  // namespace
+
+struct dualar_batch {
+  int B = 0, BN = 32, Sb = 0, nchunk = 32;
+  ColBufs c;
+  DAState *st = nullptr, *h_st = nullptr; int *seq = nullptr, *h_seq = nullptr;
+  std::vector<bf16 *> kc, vc, fkc, fvc; long long slot_stride = 0, fslot_stride = 0;
+  cudaGraphExec_t g_step = nullptr; int launches = 0;
+  std::vector<int> prompt_len, max_gen; std::vector<char> open;
+};
+
+struct dualar_tc {
+  std::map<MapKey, CUtensorMap> maps;
+  float *ws = nullptr; size_t ws_bytes = 0; unsigned int *tickets = nullptr; int *err = nullptr;
+  ColBufs pf;                 // prefill columns (cap 256)
+  bool ready = false;
+  int ksplit_override = 0, stages_override = 0;
+};
+
+static int tc_map(dualar_engine *e, const void *p, int rows, int K, int box, const CUtensorMap **out) {
+  MapKey k{p, rows, K, box};
+  auto it = e->tc->maps.find(k);
+  if (it == e->tc->maps.end()) {
+    CUtensorMap m;
+    if (!tc_make_map(&m, p, rows, K, box)) return fail(DUALAR_ECUDA, "cuTensorMapEncodeTiled failed (rows %d, K %d, box %d)", rows, K, box);
+    it = e->tc->maps.emplace(k, m).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+template <int BN> static int tc_configure() {
+  int mx = (int)((227 * 1024 - 4096) / (DA_TC_A_BYTES + BN * 128)); if (mx > DA_TC_MAX_STAGES) mx = DA_TC_MAX_STAGES;
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_tc_smem(BN, mx)));
+  return 0;
+}
+static int tc_max_stages(int BN) { int mx = (int)((227 * 1024 - 4096) / (DA_TC_A_BYTES + BN * 128)); return mx > DA_TC_MAX_STAGES ? DA_TC_MAX_STAGES : mx; }
+
+static int alloc_cols(dualar_engine *e, ColBufs &c, int cap, int nsplit, bool decode) {
+  const dualar_config &cf = e->c;
+  const int qkv_rows = (cf.n_head + 2 * cf.n_local_heads) * cf.head_dim, qd = cf.n_head * cf.head_dim, G = cf.n_head / cf.n_local_heads;
+  const int fqkv_rows = (cf.fast_n_head + 2 * cf.fast_n_local_heads) * cf.fast_head_dim, fqd = cf.fast_n_head * cf.fast_head_dim;
+  c.cap = cap; c.nsplit = nsplit;
+  int rc;
+  if ((rc = dev_alloc(e, c.x, (size_t)cap * cf.dim)) || (rc = dev_alloc(e, c.xn, (size_t)cap * cf.dim)) || (rc = dev_alloc(e, c.qkv, (size_t)cap * qkv_rows)) ||
+      (rc = dev_alloc(e, c.y, (size_t)cap * qd)) || (rc = dev_alloc(e, c.h, (size_t)cap * cf.dim)) || (rc = dev_alloc(e, c.act, (size_t)cap * cf.intermediate_size)) ||
+      (rc = dev_alloc(e, c.part_o, (size_t)cap * cf.n_local_heads * nsplit * G * cf.head_dim)) || (rc = dev_alloc(e, c.part_ml, (size_t)cap * cf.n_local_heads * nsplit * G * 2)) ||
+      (rc = dev_alloc(e, c.attn_tickets, (size_t)cap * cf.n_local_heads)))
+    return rc;
+  if (!decode) return 0;
+  if ((rc = dev_alloc(e, c.logits, (size_t)cap * cf.vocab_size)) || (rc = dev_alloc(e, c.logits_raw, (size_t)cap * cf.vocab_size)) ||
+      (rc = dev_alloc(e, c.fin, (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fx[0], (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fx[1], (size_t)cap * cf.fast_dim)) ||
+      (rc = dev_alloc(e, c.fh, (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fqkv, (size_t)cap * fqkv_rows)) || (rc = dev_alloc(e, c.fy, (size_t)cap * fqd)) ||
+      (rc = dev_alloc(e, c.fact, (size_t)cap * cf.fast_intermediate_size)) || (rc = dev_alloc(e, c.fxn, (size_t)cap * cf.fast_dim)) ||
+      (rc = dev_alloc(e, c.flogits, (size_t)cap * e->fv)) || (rc = dev_alloc(e, c.flogits_raw, (size_t)cap * (cf.num_codebooks - 1) * e->fv)) ||
+      (rc = dev_alloc(e, c.cmax, (size_t)cap * 64)) || (rc = dev_alloc(e, c.cand, (size_t)cap * DA_CAND_CAP)))
+    return rc;
+  return 0;
+}
+
+// one-time set-up of the tensor-core path (tensor-map cache, split-K workspace, the prefill column buffers)
+static int tc_init(dualar_engine *e) {
+  if (e->tc && e->tc->ready) return 0;
+  if (!e->tc) e->tc = new dualar_tc();
+  if (!tc_encode_fn()) return fail(DUALAR_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  int rc;
+  if ((rc = tc_configure<32>()) || (rc = tc_configure<64>()) || (rc = tc_configure<128>()) || (rc = tc_configure<256>())) return rc;
+  e->tc->ws_bytes = (size_t)48 << 20;
+  if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
+  if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
+  { const char *v = getenv("DUALAR_TC_KSPLIT"); if (v) e->tc->ksplit_override = atoi(v); }
+  { const char *v = getenv("DUALAR_TC_STAGES"); if (v) e->tc->stages_override = atoi(v); }
+  CU(cudaFuncSetAttribute(b_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(e->c.n_head / e->c.n_local_heads, e->c.head_dim)));
+  CU(cudaFuncSetAttribute(b_fast_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)b_fast_attn_smem(e->c.fast_n_head, e->c.fast_n_local_heads, e->c.fast_head_dim, e->c.num_codebooks)));
+  e->tc->ready = true;
+  return 0;
+}
+
+// Y[n][r] = W[r][:] . X[n][:] on the tensor cores (gemm_tc.cuh); xcap = rows of the X buffer
+static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 *X, int xcap, int ncols, int BN, int epi, const bf16 *bias,
+                   const bf16 *res, bf16 *out, int w_keep, cudaStream_t s, int &count) {
+  const CUtensorMap *mw, *mx; int rc;
+  if ((rc = tc_map(e, W, rows, K, DA_TC_BM, &mw)) || (rc = tc_map(e, X, xcap, K, BN, &mx))) return rc;
+  const int rt = (rows + DA_TC_BM - 1) / DA_TC_BM, ct = (ncols + BN - 1) / BN, tiles = rt * ct, nkb = K / DA_TC_BK;
+  int ks = 1;
+  if (tiles < 64) { ks = 128 / tiles; if (ks > nkb / 4) ks = nkb / 4; if (ks > 8) ks = 8; if (ks < 1) ks = 1; }
+  if (e->tc->ksplit_override > 0 && tiles < 64) { ks = e->tc->ksplit_override; if (ks > nkb) ks = nkb; }
+  while (ks > 1 && (size_t)tiles * ks * BN * DA_TC_BM * 4 > e->tc->ws_bytes) --ks;
+  if (tiles > 8192) return fail(DUALAR_EINVAL, "too many GEMM tiles (%d)", tiles);
+  GemmTcArgs a; memset(&a, 0, sizeof(a));
+  a.rows = rows; a.K = K; a.ncols = ncols; a.epi = epi; a.ld_out = epi == TE_SWIGLU ? rows / 2 : rows; a.w_keep = w_keep;
+  a.bias = bias; a.res = res; a.out = out; a.ws = e->tc->ws; a.tickets = e->tc->tickets; a.err = e->tc->err;
+  int st = tiles > 2 * e->sms ? 4 : 8;      // many tiles: two CTAs per SM hide each other's set-up; few tiles: deep ring per CTA
+  if (e->tc->stages_override > 0) st = e->tc->stages_override;
+  const int mxs = tc_max_stages(BN); if (st > mxs) st = mxs;
+  const int nk_per = (nkb + ks - 1) / ks; if (st > nk_per) st = nk_per < 2 ? 2 : nk_per;
+  a.stages = st;
+  const dim3 grid(rt, ct, ks), block(DA_TC_THREADS);
+  const size_t smem = gemm_tc_smem(BN, st);
+  switch (BN) {
+    case 32: CU(launch_k(gemm_tc_kernel<32>, grid, block, smem, s, *mw, *mx, a)); break;
+    case 64: CU(launch_k(gemm_tc_kernel<64>, grid, block, smem, s, *mw, *mx, a)); break;
+    case 128: CU(launch_k(gemm_tc_kernel<128>, grid, block, smem, s, *mw, *mx, a)); break;
+    case 256: CU(launch_k(gemm_tc_kernel<256>, grid, block, smem, s, *mw, *mx, a)); break;
+    default: return fail(DUALAR_EINVAL, "BN %d", BN);
+  }
+  ++count;
+  return 0;
+}
+
+static int bn_for(int ncols) { return ncols <= 32 ? 32 : ncols <= 64 ? 64 : ncols <= 128 ? 128 : 256; }
+
+struct KvTarget { bf16 *const *kc, *const *vc; long long slot_stride; int S; };   // per-layer cache bases, elements between slots, cache length
+
+// embedding + the slow stack over `ncols` columns; leaves the un-normalised last-layer output in c.x
+static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, const KvTarget &kv, const PosSrc &pos, const TokSrc &tok,
+                             cudaStream_t s, int &count) {
+  const dualar_config &cf = e->c;
+  const int qkv_rows = (cf.n_head + 2 * cf.n_local_heads) * cf.head_dim, qd = cf.n_head * cf.head_dim;
+  int rc;
+  { BEmbedArgs a; memset(&a, 0, sizeof(a));
+    a.emb = e->emb; a.cb_emb = e->cb_emb; a.x = c.x; a.dim = cf.dim; a.vocab = cf.vocab_size; a.codebook_size = cf.codebook_size; a.num_codebooks = cf.num_codebooks;
+    a.sem_begin = cf.semantic_begin_id; a.sem_end = cf.semantic_end_id; a.scale_cb = cf.scale_codebook_embeddings; a.cpu_sem = e->cpu_sem; a.ncols = ncols;
+    a.inv_sqrt = (float)(1.0 / sqrt((double)(cf.num_codebooks + 1))); a.sqrt_c = (float)sqrt((double)(cf.num_codebooks + 1)); a.tok = tok; a.err = e->tc->err;
+    CU(launch_k(b_embed_kernel, dim3(ncols), dim3(128), 0, s, a)); ++count; }
+  auto norm = [&](const bf16 *x, const bf16 *w, bf16 *out, int K) -> int {
+    BNormArgs a{x, w, out, K, ncols, cf.norm_eps};
+    CU(launch_k(b_rmsnorm_kernel, dim3((ncols + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
+  for (int l = 0; l < cf.n_layer; ++l) {
+    LayerW &L = e->slow[l];
+    if ((rc = norm(c.x, L.attn_norm, c.xn, cf.dim))) return rc;
+    if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.xn, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count))) return rc;
+    { BQkvPostArgs a; memset(&a, 0, sizeof(a));
+      a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn;
+      a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S; a.ncols = ncols; a.eps = cf.norm_eps; a.pos = pos;
+      CU(launch_k(b_qkv_post_kernel, dim3(ncols), dim3(256), (size_t)8 * cf.head_dim * sizeof(float), s, a)); ++count; }
+    { BAttnArgs a; memset(&a, 0, sizeof(a));
+      a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S;
+      a.ncols = ncols; a.nsplit_max = c.nsplit; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
+      a.tickets = c.attn_tickets; a.y = c.y; a.pos = pos; a.err = e->tc->err;
+      CU(launch_k(b_attn_kernel, dim3(c.nsplit, cf.n_local_heads, ncols), dim3(DA_ATTN_THREADS), attn_smem_bytes(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; }
+    if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count))) return rc;
+    if ((rc = norm(c.h, L.ffn_norm, c.xn, cf.dim))) return rc;
+    if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.xn, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count))) return rc;
+    if ((rc = tc_gemm(e, L.w2, cf.dim, cf.intermediate_size, c.act, c.cap, ncols, BN, TE_RESIDUAL, nullptr, c.h, c.x, 0, s, count))) return rc;
+  }
+  return 0;
+}
+
+// ---- prefill: KV rows of prompt positions [t0, t1) of the request whose token rows live in `seq` (device, row stride seq_stride) ----
+static int tc_prefill(dualar_engine *e, const KvTarget &kv, const int *seq, int seq_stride, int t0, int t1, cudaStream_t s) {
+  int rc = tc_init(e); if (rc) return rc;
+  ColBufs &c = e->tc->pf;
+  int count = 0;
+  for (int t = t0; t < t1; t += c.cap) {
+    const int ncols = t1 - t < c.cap ? t1 - t : c.cap;
+    PosSrc pos{nullptr, 0, t};
+    TokSrc tok{seq + t, 1, seq_stride};
+    if ((rc = enqueue_slow_cols(e, c, ncols, bn_for(ncols), kv, pos, tok, s, count))) return rc;
+  }
+  e->prefill_launches = count;
+  return 0;
+}
+
+// ---- batched decode ------------------------------------------------------------------------------------------------------------------
+static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
+  dualar_batch &b = *e->batch; ColBufs &c = b.c;
+  const dualar_config &cf = e->c;
+  const int B = b.B, BN = b.BN, R = cf.num_codebooks + 1;
+  const long long sst = (long long)(sizeof(DAState) / sizeof(int));
+  int rc;
+  KvTarget kv{b.kc.data(), b.vc.data(), b.slot_stride, b.Sb};
+  PosSrc pos{&b.st->pos, sst, 0};
+  TokSrc tok{b.st->tok_in, sst, 1};
+  if ((rc = enqueue_slow_cols(e, c, B, BN, kv, pos, tok, s, count))) return rc;
+  auto norm = [&](const bf16 *x, const bf16 *w, bf16 *out, int K) -> int {
+    BNormArgs a{x, w, out, K, B, cf.norm_eps};
+    CU(launch_k(b_rmsnorm_kernel, dim3((B + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
+  // LM head + slow sampler (llama.py:446-451, inference.py:103-113)
+  if ((rc = norm(c.x, e->norm, c.xn, cf.dim))) return rc;
+  if ((rc = tc_gemm(e, cf.tie_word_embeddings ? e->emb : e->out_w, cf.vocab_size, cf.dim, c.xn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.logits, 0, s, count))) return rc;
+  { BHeadArgs a{c.logits, e->batch_keep_raw ? c.logits_raw : nullptr, c.cmax, cf.vocab_size, b.nchunk, R, b.st};
+    CU(launch_k(b_head_stats_kernel, dim3(b.nchunk, B), dim3(512), 0, s, a)); ++count; }
+  { BSelectArgs a; memset(&a, 0, sizeof(a));
+    a.logits = c.logits; a.cmax = c.cmax; a.V = cf.vocab_size; a.nchunk = b.nchunk; a.delta = e->delta; a.cand = c.cand; a.fast_emb = e->fast_emb; a.fast_x = c.fin;
+    a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size; a.sem_begin = cf.semantic_begin_id; a.st = b.st;
+    CU(launch_k(b_select_kernel, dim3(b.nchunk, B), dim3(512), (size_t)(192 * 8 + 34 * 8 + 80 * 4 + 64), s, a)); ++count; }
+  // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
+  const int fqkv_rows = (cf.fast_n_head + 2 * cf.fast_n_local_heads) * cf.fast_head_dim, fqd = cf.fast_n_head * cf.fast_head_dim;
+  for (int p = 0; p < cf.num_codebooks; ++p) {
+    const bf16 *in = p == 0 ? c.x : c.fin;
+    for (int l = 0; l < cf.n_fast_layer; ++l) {
+      LayerW &L = e->fast[l];
+      bf16 *out = c.fx[l & 1];
+      if ((rc = norm(in, L.attn_norm, c.fxn, cf.fast_dim))) return rc;
+      if ((rc = tc_gemm(e, L.wqkv, fqkv_rows, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, L.bqkv, nullptr, c.fqkv, 1, s, count))) return rc;
+      { BFastAttnArgs a; memset(&a, 0, sizeof(a));
+        a.qkv = c.fqkv; a.kc = b.fkc[l]; a.vc = b.fvc[l]; a.slot_stride = b.fslot_stride; a.rope = e->fast_rope; a.qn = L.qn; a.kn = L.kn;
+        a.nh = cf.fast_n_head; a.nkv = cf.fast_n_local_heads; a.hd = cf.fast_head_dim; a.ncb = cf.num_codebooks; a.p = p; a.ncols = B;
+        a.eps = cf.norm_eps; a.scale = (float)(1.0 / sqrt((double)cf.fast_head_dim)); a.y = c.fy;
+        CU(launch_k(b_fast_attn_kernel, dim3(B), dim3(256), b_fast_attn_smem(a.nh, a.nkv, a.hd, a.ncb), s, a)); ++count; }
+      if ((rc = tc_gemm(e, L.wo, cf.fast_dim, fqd, c.fy, c.cap, B, BN, TE_RESIDUAL, L.bo, in, c.fh, 1, s, count))) return rc;
+      if ((rc = norm(c.fh, L.ffn_norm, c.fxn, cf.fast_dim))) return rc;
+      if ((rc = tc_gemm(e, L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fxn, c.cap, B, BN, TE_SWIGLU, nullptr, nullptr, c.fact, 1, s, count))) return rc;
+      if ((rc = tc_gemm(e, L.w2, cf.fast_dim, cf.fast_intermediate_size, c.fact, c.cap, B, BN, TE_RESIDUAL, nullptr, c.fh, out, 1, s, count))) return rc;
+      in = out;
+    }
+    if (p == 0) continue;      // logits of pass 0 are discarded by the reference (inference.py:122)
+    if ((rc = norm(in, e->fast_norm, c.fxn, cf.fast_dim))) return rc;
+    if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count))) return rc;
+    { BFastSampleArgs a; memset(&a, 0, sizeof(a));
+      a.logits = c.flogits; a.logits_raw = e->batch_keep_raw ? c.flogits_raw : nullptr; a.fv = e->fv; a.head = p; a.ncb = cf.num_codebooks; a.last_head = (p == cf.num_codebooks - 1);
+      a.noise_off = (long long)cf.vocab_size + (long long)(p - 1) * e->fv; a.fast_emb = e->fast_emb; a.fast_x = c.fin; a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size;
+      a.seq = b.seq; a.seq_slot_stride = (long long)R * b.Sb; a.seq_stride = b.Sb; a.im_end_id = cf.im_end_id; a.n_rows_tok = R; a.st = b.st;
+      CU(launch_k(b_fast_sample_kernel, dim3(B), dim3(256), (size_t)(192 * 8 + 80 * 4 + 64), s, a)); ++count; }
+  }
+  return 0;
+}
+
+extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_len) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  if (!e->finalized) return fail(DUALAR_ESTATE, "dualar_finalize has not been called");
+  if (e->batch) return fail(DUALAR_ESTATE, "batch slots already exist");
+  const dualar_config &cf = e->c;
+  if (max_batch < 1 || max_batch > 128) return fail(DUALAR_EINVAL, "max_batch must be in [1, 128]");
+  if (slot_seq_len <= 0 || slot_seq_len > cf.max_seq_len) slot_seq_len = cf.max_seq_len;
+  slot_seq_len = (slot_seq_len + 7) / 8 * 8;
+  if (cf.n_head / cf.n_local_heads > DA_MAX_G) return fail(DUALAR_EINVAL, "GQA group too large");
+  CU(cudaSetDevice(e->device));
+  int rc = tc_init(e); if (rc) return rc;
+  dualar_batch *b = new dualar_batch(); e->batch = b;
+  b->B = max_batch; b->BN = bn_for(max_batch); b->Sb = slot_seq_len;
+  const int R = cf.num_codebooks + 1;
+  // split-KV: enough (kv head, split) CTAs per request to fill the machine twice at small batches, one split per 256 positions at most
+  int nsplit = (2 * e->sms * 2) / (cf.n_local_heads * max_batch); if (nsplit < 1) nsplit = 1; if (nsplit > 16) nsplit = 16;
+  if ((rc = alloc_cols(e, b->c, b->BN, nsplit, true))) return rc;
+  b->slot_stride = (long long)cf.n_local_heads * b->Sb * cf.head_dim;
+  b->fslot_stride = (long long)cf.fast_n_local_heads * cf.num_codebooks * cf.fast_head_dim;
+  b->kc.resize(cf.n_layer); b->vc.resize(cf.n_layer); b->fkc.resize(cf.n_fast_layer); b->fvc.resize(cf.n_fast_layer);
+  for (int l = 0; l < cf.n_layer; ++l) if ((rc = dev_alloc(e, b->kc[l], (size_t)b->slot_stride * b->BN)) || (rc = dev_alloc(e, b->vc[l], (size_t)b->slot_stride * b->BN))) return rc;
+  for (int l = 0; l < cf.n_fast_layer; ++l) if ((rc = dev_alloc(e, b->fkc[l], (size_t)b->fslot_stride * b->BN)) || (rc = dev_alloc(e, b->fvc[l], (size_t)b->fslot_stride * b->BN))) return rc;
+  if ((rc = dev_alloc(e, b->st, (size_t)b->BN)) || (rc = dev_alloc(e, b->seq, (size_t)b->BN * R * b->Sb))) return rc;
+  CU(cudaMallocHost((void **)&b->h_st, sizeof(DAState)));
+  CU(cudaMallocHost((void **)&b->h_seq, (size_t)R * b->Sb * sizeof(int)));
+  b->prompt_len.assign(max_batch, 0); b->max_gen.assign(max_batch, 0); b->open.assign(max_batch, 0);
+  b->nchunk = 32;
+  // dry run (configures attributes, surfaces launch errors), then capture
+  int n = 0;
+  if ((rc = enqueue_batch_step(e, e->cap_stream, n)) < 0) return rc;
+  CU(cudaStreamSynchronize(e->cap_stream));
+  cudaGraph_t g;
+  CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  n = 0;
+  rc = enqueue_batch_step(e, e->cap_stream, n);
+  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
+  if (rc < 0) return rc;
+  if (ce != cudaSuccess) return fail(DUALAR_ECUDA, "batch graph capture failed: %s", cudaGetErrorString(ce));
+  CU(cudaGraphInstantiate(&b->g_step, g, 0));
+  CU(cudaGraphDestroy(g));
+  b->launches = n;
+  // the dry run advanced nothing (every slot is idle: loop_mode 0) but wrote KV row 0 and sampler scratch; start clean
+  CU(cudaMemset(b->st, 0, sizeof(DAState) * (size_t)b->BN));
+  for (int l = 0; l < cf.n_layer; ++l) { CU(cudaMemset(b->kc[l], 0, (size_t)b->slot_stride * b->BN * 2)); CU(cudaMemset(b->vc[l], 0, (size_t)b->slot_stride * b->BN * 2)); }
+  CU(cudaMemset(e->tc->err, 0, 4));
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *prompt, int T, int max_new, float temperature, float top_p, float rep,
+                                    uint64_t seed, const void *noise, void *stream) {
+  if (!e || !prompt) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
+  dualar_batch &b = *e->batch; const dualar_config &cf = e->c; const int R = cf.num_codebooks + 1;
+  if (slot < 0 || slot >= b.B) return fail(DUALAR_EINVAL, "slot %d out of range", slot);
+  if (T < 1) return fail(DUALAR_EINVAL, "empty prompt");
+  if (T >= b.Sb) return fail(DUALAR_EINVAL, "Input sequence length %d exceeds the slot length %d", T, b.Sb);
+  if (max_new <= 0 || T + max_new > b.Sb) max_new = b.Sb - T;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaStreamSynchronize(s));      // staging buffers are reused
+  int *seq = b.seq + (size_t)slot * R * b.Sb;
+  for (int r = 0; r < R; ++r) memcpy(b.h_seq + (size_t)r * T, prompt + (size_t)r * T, (size_t)T * sizeof(int));
+  CU(cudaMemcpy2DAsync(seq, (size_t)b.Sb * sizeof(int), b.h_seq, (size_t)T * sizeof(int), (size_t)T * sizeof(int), R, cudaMemcpyHostToDevice, s));
+  std::vector<bf16 *> kc(cf.n_layer), vc(cf.n_layer);
+  for (int l = 0; l < cf.n_layer; ++l) { kc[l] = b.kc[l] + (size_t)slot * b.slot_stride; vc[l] = b.vc[l] + (size_t)slot * b.slot_stride; }
+  KvTarget kv{kc.data(), vc.data(), 0, b.Sb};
+  int rc = tc_prefill(e, kv, seq, b.Sb, 0, T - 1, s); if (rc) return rc;
+  // the slot joins the batch at the LAST prompt position: the next batched step produces its first token (no penalty, inference.py:353-362)
+  DAState *h = b.h_st; memset(h, 0, sizeof(*h));
+  h->pos = T - 1; h->max_gen = max_new; h->prompt_len = T; h->loop_mode = 1; h->temperature = temperature; h->top_p = top_p; h->rep_penalty = rep;
+  h->seed = seed; h->cpu_sem = e->cpu_sem; h->noise = (const bf16 *)noise; h->noise_stride = (long long)cf.vocab_size + (long long)(cf.num_codebooks - 1) * e->fv;
+  for (int r = 0; r < R; ++r) h->tok_in[r] = prompt[(size_t)r * T + (T - 1)];
+  CU(cudaMemcpyAsync(b.st + slot, h, sizeof(*h), cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));      // `kc` / `vc` / the staging state live on this stack frame / in pinned memory
+  b.prompt_len[slot] = T; b.max_gen[slot] = max_new; b.open[slot] = 1;
+  return 0;
+}
+
+extern "C" int dualar_batch_decode(dualar_engine *e, int n_steps, void *stream) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
+  CU(cudaSetDevice(e->device));
+  for (int i = 0; i < n_steps; ++i) CU(cudaGraphLaunch(e->batch->g_step, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dualar_batch_collect(dualar_engine *e, int slot, int32_t *out, int cap, int *n_tokens, int *finished, void *stream) {
+  if (!e || !n_tokens) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
+  dualar_batch &b = *e->batch; const int R = e->c.num_codebooks + 1;
+  if (slot < 0 || slot >= b.B || !b.open[slot]) return fail(DUALAR_ESTATE, "slot %d holds no request", slot);
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(b.h_st, b.st + slot, sizeof(DAState), cudaMemcpyDeviceToHost, s));
+  int gerr = 0; CU(cudaMemcpyAsync(&gerr, e->tc->err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (b.h_st->err || gerr) return fail(DUALAR_EDEVICE, "device fault flag: slot %d, kernels %d (1: token id out of range, 2: bulk-copy wait timed out, 3: code >= codebook_size, 5-7: tensor-core pipeline wait timed out)", b.h_st->err, gerr);
+  const int n = b.h_st->n_gen;
+  *n_tokens = n;
+  if (finished) *finished = b.h_st->done;
+  if (out && n > 0) {
+    if (cap < n) return fail(DUALAR_EINVAL, "output capacity %d < %d generated columns", cap, n);
+    const int *seq = b.seq + (size_t)slot * R * b.Sb;
+    CU(cudaMemcpy2DAsync(b.h_seq, (size_t)n * sizeof(int), seq + b.prompt_len[slot], (size_t)b.Sb * sizeof(int), (size_t)n * sizeof(int), R, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int r = 0; r < R; ++r) memcpy(out + (size_t)r * cap, b.h_seq + (size_t)r * n, (size_t)n * sizeof(int));
+  }
+  return 0;
+}
+
+extern "C" int dualar_batch_release(dualar_engine *e, int slot) {
+  if (!e || !e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
+  dualar_batch &b = *e->batch;
+  if (slot < 0 || slot >= b.B) return fail(DUALAR_EINVAL, "slot %d out of range", slot);
+  CU(cudaSetDevice(e->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemset(b.st + slot, 0, sizeof(DAState)));      // idle: loop_mode 0, position 0
+  b.open[slot] = 0;
+  return 0;
+}
+
+extern "C" int dualar_batch_read(dualar_engine *e, const char *name, void *dst, int64_t nbytes, void *stream) {
+  if (!e || !name || !dst) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
+  dualar_batch &b = *e->batch; const dualar_config &cf = e->c;
+  const void *src = nullptr; int64_t avail = 0; size_t pitch = 0, width = 0; int rows = 0;
+  if (!strcmp(name, "slow_logits")) { src = b.c.logits; avail = (int64_t)b.B * cf.vocab_size * 2; }
+  else if (!strcmp(name, "slow_logits_raw")) { src = b.c.logits_raw; avail = (int64_t)b.B * cf.vocab_size * 2; }
+  else if (!strcmp(name, "hidden")) { src = b.c.x; avail = (int64_t)b.B * cf.dim * 2; }
+  else if (!strcmp(name, "fast_logits")) { src = b.c.flogits_raw; avail = (int64_t)b.B * (cf.num_codebooks - 1) * e->fv * 2; }
+  else if (!strcmp(name, "launches")) { *(int *)dst = b.launches; return nbytes >= 4 ? 0 : fail(DUALAR_EINVAL, "4 bytes needed"); }
+  else if (!strcmp(name, "state")) { src = b.st; avail = (int64_t)b.B * sizeof(DAState); }
+  else if (!strcmp(name, "tokens")) { src = b.st->tok_out; pitch = sizeof(DAState); width = (size_t)(cf.num_codebooks + 1) * 4; rows = b.B; avail = (int64_t)rows * width; }
+  else if (!strcmp(name, "positions")) { src = &b.st->pos; pitch = sizeof(DAState); width = 4; rows = b.B; avail = (int64_t)rows * width; }
+  else if (!strcmp(name, "done")) { src = &b.st->done; pitch = sizeof(DAState); width = 4; rows = b.B; avail = (int64_t)rows * width; }
+  else if (!strcmp(name, "n_gen")) { src = &b.st->n_gen; pitch = sizeof(DAState); width = 4; rows = b.B; avail = (int64_t)rows * width; }
+  else return fail(DUALAR_EINVAL, "unknown batch buffer '%s'", name);
+  if (nbytes > avail) return fail(DUALAR_EINVAL, "batch buffer '%s' holds %lld bytes, %lld requested", name, (long long)avail, (long long)nbytes);
+  CU(cudaSetDevice(e->device));
+  if (pitch) CU(cudaMemcpy2DAsync(dst, width, src, pitch, width, (size_t)(nbytes / (int64_t)width), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  else CU(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+static void batch_destroy(dualar_engine *e) {
+  if (e->batch) {
+    if (e->batch->g_step) cudaGraphExecDestroy(e->batch->g_step);
+    if (e->batch->h_st) cudaFreeHost(e->batch->h_st);
+    if (e->batch->h_seq) cudaFreeHost(e->batch->h_seq);
+    delete e->batch; e->batch = nullptr;
+  }
+  delete e->tc; e->tc = nullptr;
+}

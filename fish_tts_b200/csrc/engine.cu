@@ -9,6 +9,7 @@
 
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/dualar.h"
@@ -17,8 +18,13 @@
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
 #include "mega.cuh"
+#include "gemm_tc.cuh"
+#include "batch.cuh"
 
 using namespace da;
+
+struct dualar_tc;      // tensor-core path: tensor maps, split-K workspace, prefill columns (batch_host.cuh)
+struct dualar_batch;   // batched decode: request slots (batch_host.cuh)
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, ...) {
@@ -48,6 +54,7 @@ struct dualar_engine {
   bf16 *fin = nullptr, *fbuf[2] = {nullptr, nullptr}, *fh = nullptr, *fqkv = nullptr, *fact = nullptr, *flogits = nullptr, *flogits_raw = nullptr;
   float *part_o = nullptr, *part_ml = nullptr; float2 *partials = nullptr; unsigned long long *cand = nullptr;
   DAState *st = nullptr; int *seq = nullptr; int *h_seq = nullptr; DAState *h_st = nullptr;
+  int *h_err_sticky = nullptr, *d_err_sticky = nullptr;   // step mode: fault flag of finished steps, in mapped pinned memory
   void *kv_arena = nullptr;
   int nsplit = 1, fv = 0, gemv_grid = 0;
   float delta = 6.0f; int cpu_sem = 0;
@@ -64,6 +71,11 @@ struct dualar_engine {
   bf16 *t0 = nullptr; bool use_t0 = true;      // first-layer q | k | v of the fast stack per code (passes >= 1)
   unsigned long long *m_part_o = nullptr, *m_part_ml = nullptr, *m_hmax = nullptr, *m_hcs = nullptr, *m_cand = nullptr;
   MegaArgs *ma_step = nullptr, *ma_prefill = nullptr; size_t mega_smem = 0; unsigned int *m_phase = nullptr; bf16 *m_fkv = nullptr; unsigned char *u_arena = nullptr; size_t u_arena_bytes = 0;
+  dualar_tc *tc = nullptr; dualar_batch *batch = nullptr;
+  int prefill_mode = 0;          // option prefill_mode: 0 = whole prompt through the tensor-core GEMMs, 1 = one position per launch (round-1 path, cross-check)
+  int prefill_launches = 0;      // kernels the last tensor-core prefill launched
+  bool batch_keep_raw = true;    // batched decode keeps a copy of the raw logits for dualar_batch_read
+  bool l2_window = false; float l2_hit_ratio = 0.0f; size_t l2_persist_bytes = 0;   // DUALAR_L2_WINDOW / DUALAR_L2_HIT: access-policy window over the fast stack
   bool use_mega = true;   // option mega_kernel / DUALAR_MEGA: 0 = one kernel per phase (the cross-check path)
 };
 
@@ -248,11 +260,12 @@ template <int PRO, int EPI> static size_t gemv_smem(const dualar_engine *e, cons
   return f + work + 16;
 }
 template <int PRO, int EPI> static int launch_gemv(dualar_engine *e, GemvArgs a, cudaStream_t s, int &count) {
-  static size_t configured = 0;
+  static size_t configured[64] = {0};      // function attributes are per device: one high-water mark per device ordinal
   size_t smem = gemv_smem<PRO, EPI>(e, a);
-  if (smem > configured) {
+  size_t &conf = configured[e->device & 63];
+  if (smem > conf) {
     CU(cudaFuncSetAttribute(gemv_kernel<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 200 * 1024 ? smem : 200 * 1024)));
-    configured = 200 * 1024 > smem ? 200 * 1024 : smem;
+    conf = 200 * 1024 > smem ? 200 * 1024 : smem;
   }
   int npairs = (a.rows + 1) / 2;
   int grid = npairs < 2 * e->sms ? npairs : 2 * e->sms;
@@ -281,8 +294,8 @@ static int enqueue_slow_layer(dualar_engine *e, int li, cudaStream_t s, int &cou
     t.sf = (float)sqrt(1.0 / sqrt((double)c.head_dim));
     t.part_o = e->part_o; t.part_ml = e->part_ml; t.y = e->y; t.nsplit_max = e->nsplit; t.st = e->st; t.tl.buf = e->tl; t.tl.slot = count;
     size_t smem = attn_smem_bytes(c.n_head / c.n_local_heads, c.head_dim);
-    static size_t configured = 0;   // per process: grow the opt-in limit when a bigger shape comes along
-    if (smem > configured) { CU(cudaFuncSetAttribute(attn_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+    static size_t configured[64] = {0};   // per device: grow the opt-in limit when a bigger shape comes along
+    if (smem > configured[e->device & 63]) { CU(cudaFuncSetAttribute(attn_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[e->device & 63] = smem; }
     CU(launch_k(attn_slow_kernel, dim3(e->nsplit, c.n_local_heads), dim3(DA_ATTN_THREADS), smem, s, t)); ++count; }
   { GemvArgs a = base_args(L.wo, L.bo, c.dim, qd, 0); a.x = e->y; a.res = e->x; a.out = e->h;
     if ((rc = launch_gemv<PRO_PLAIN, EPI_RESIDUAL>(e, a, s, count)) < 0) return rc; }
@@ -351,8 +364,8 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
     a.logits = e->logits; a.partials = e->partials; a.n_partials = head_grid; a.V = c.vocab_size; a.delta = e->delta; a.cand = e->cand;
     a.fast_emb = e->fast_emb; a.fast_x = e->fin; a.fast_dim = c.fast_dim; a.codebook_size = c.codebook_size; a.sem_begin = c.semantic_begin_id; a.st = e->st; a.tl.buf = e->tl; a.tl.slot = count;
     size_t smem = 192 * 8 + 34 * 8 + 80 * 4 + 64;
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    static bool configured[64] = {false};   // per device
+    if (!configured[e->device & 63]) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[e->device & 63] = true; }
     CU(launch_k(select_sample_kernel, dim3(e->sms), dim3(512), smem, s, a)); ++count; }
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
   for (int p = 0; p < c.num_codebooks; ++p) {
@@ -388,6 +401,25 @@ static int capture(dualar_engine *e, bool slow_only, cudaGraphExec_t *out, int *
   cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
   if (rc < 0) return rc;
   if (ce != cudaSuccess) return fail(DUALAR_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+  if (e->l2_window && !slow_only) {
+    // the fast stack is re-read num_codebooks times per token: cover it with an access-policy window on every kernel node of the
+    // decode graph (hitRatio = the share of the window the persisting carve-out can hold), everything else streams
+    size_t nn = 0; CU(cudaGraphGetNodes(g, nullptr, &nn));
+    std::vector<cudaGraphNode_t> nodes(nn); CU(cudaGraphGetNodes(g, nodes.data(), &nn));
+    int max_win = 0; cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+    // the hot set: the fast layers and the rows of fast_output that are used (fast_embeddings ahead of them is a row gather)
+    char *w0 = (char *)e->fast[0].wqkv, *w1 = (char *)(e->fast_out + (size_t)e->fv * e->c.fast_dim);
+    size_t bytes = (size_t)(w1 - w0); if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
+    for (auto nd : nodes) {
+      cudaGraphNodeType ty; CU(cudaGraphNodeGetType(nd, &ty));
+      if (ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeAttrValue v; memset(&v, 0, sizeof(v));
+      v.accessPolicyWindow.base_ptr = w0; v.accessPolicyWindow.num_bytes = bytes;
+      v.accessPolicyWindow.hitRatio = e->l2_hit_ratio > 0.f ? e->l2_hit_ratio : (float)((double)e->l2_persist_bytes / (double)bytes > 1.0 ? 1.0 : (double)e->l2_persist_bytes / (double)bytes); v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      CU(cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v));
+    }
+  }
   CU(cudaGraphInstantiate(out, g, 0));
   CU(cudaGraphDestroy(g));
   *count = n;
@@ -525,7 +557,7 @@ static int build_mega(dualar_engine *e) {
     a.fscale = (float)(1.0 / sqrt((double)c.fast_head_dim));
     a.fkv = e->m_fkv; a.t0 = e->t0; a.fast_emb = e->fast_emb; a.fdim = c.fast_dim; a.fv = e->fv; a.u_fin = e->u_fin; a.flogits_raw = e->flogits_raw; a.flogits = e->flogits;
     a.noise_off0 = (long long)c.vocab_size;
-    a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.st = e->st; a.ustride = (int)ustride; a.phase_ctr = e->m_phase;
+    a.seq = e->seq; a.seq_stride = c.max_seq_len; a.im_end_id = c.im_end_id; a.st = e->st; a.phase_ctr = e->m_phase;
     // shared-memory plan (from the decode-step table; the prefill table is a subset and shares it)
     if (variant) {
       const MegaArgs &s0 = *e->ma_step;
@@ -559,6 +591,7 @@ static int build_mega(dualar_engine *e) {
     e->mega_smem = a.plan.total;
   }
   { const char *v = getenv("DUALAR_KEEP_FRAC"); if (v) { float fr = (float)atof(v); CU(cudaMemcpyToSymbol(g_keep_frac, &fr, sizeof(float))); } }
+  { const char *v = getenv("DUALAR_KEEP_MODE"); if (v) { int md = atoi(v); CU(cudaMemcpyToSymbol(g_keep_mode, &md, sizeof(int))); } }
   { const char *v = getenv("DUALAR_POLL_NS"); int ns = v ? atoi(v) : 0; CU(cudaMemcpyToSymbol(g_poll_ns, &ns, sizeof(int))); }
   CU(cudaFuncSetAttribute(mega_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
   CU(cudaFuncSetAttribute(mega_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem));
@@ -607,15 +640,29 @@ extern "C" int dualar_finalize(dualar_engine *e) {
     return rc;
   CU(cudaMallocHost((void **)&e->h_seq, (size_t)(c.num_codebooks + 1) * c.max_seq_len * sizeof(int)));
   CU(cudaMallocHost((void **)&e->h_st, sizeof(DAState)));
+  CU(cudaHostAlloc((void **)&e->h_err_sticky, sizeof(int), cudaHostAllocMapped)); *e->h_err_sticky = 0;
+  CU(cudaHostGetDevicePointer((void **)&e->d_err_sticky, e->h_err_sticky, 0));
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   { const char *v = getenv("DUALAR_PDL"); if (v && v[0] == '0') g_use_pdl = false; }
   { const char *v = getenv("DUALAR_MEGA"); if (v) e->use_mega = v[0] != '0'; }
   if (e->use_mega && (rc = build_mega(e)) < 0) return rc;
   { const char *v = getenv("DUALAR_TIMELINE"); if (v && v[0] == '1') { e->tl_slots = 2048; if ((rc = dev_alloc(e, e->tl, (size_t)e->tl_slots * 8))) return rc;
       if ((rc = dev_alloc(e, e->tl2, (size_t)DA_M_MAX_PHASES * 160 * 4))) return rc; } }
-  // the fast stack is re-read num_codebooks times per token: let it persist in L2 as far as the device allows
-  { int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);
-    if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp); cudaGetLastError(); }
+  // the fast stack is re-read num_codebooks times per token.  Experiment switch: a persisting-L2 carve-out + access-policy window over
+  // it (DUALAR_L2_WINDOW=1, hit ratio DUALAR_L2_HIT) instead of the per-copy fractional evict_last hints
+  { const char *v = getenv("DUALAR_L2_WINDOW"); e->l2_window = v && v[0] == '1';
+    if (e->l2_window) {
+      int maxp = 0, l2 = 0, maxw = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+      cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, e->device); cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+      if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp); cudaGetLastError();
+      const char *h = getenv("DUALAR_L2_HIT");
+      e->l2_hit_ratio = h ? (float)atof(h) : 0.0f;      // 0: carve-out / window size
+      if (e->l2_hit_ratio > 1.0f) e->l2_hit_ratio = 1.0f;
+      e->l2_persist_bytes = maxp > 0 ? (size_t)maxp : 0;
+      fprintf(stderr, "[dualar] L2 %d MB, max persisting %d MB, max window %d MB, fast stack %.1f MB, hit ratio %s\n", l2 >> 20, maxp >> 20, maxw >> 20,
+              e->fast_bytes / 1048576.0, h ? h : "carve-out / window");
+      int one = 1; CU(cudaMemcpyToSymbol(g_l2_window, &one, sizeof(int)));
+    } }
   // a benign state for the dry runs inside capture()
   DAState init; memset(&init, 0, sizeof(init)); init.temperature = 0.7f; init.top_p = 0.8f; init.rep_penalty = 1.1f;
   init.tok_in[0] = c.semantic_begin_id; init.seed = e->seed; init.cpu_sem = e->cpu_sem;
@@ -634,16 +681,21 @@ extern "C" int dualar_finalize(dualar_engine *e) {
   return 0;
 }
 
+static void batch_destroy(dualar_engine *e);
+static int tc_prefill_own(dualar_engine *e, int t0, int t1, cudaStream_t s);
+
 extern "C" void dualar_destroy(dualar_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
+  batch_destroy(e);
   if (e->g_step) cudaGraphExecDestroy(e->g_step);
   if (e->g_prefill) cudaGraphExecDestroy(e->g_prefill);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (void *p : e->owned) cudaFree(p);
   if (e->h_seq) cudaFreeHost(e->h_seq);
   if (e->h_st) cudaFreeHost(e->h_st);
+  if (e->h_err_sticky) cudaFreeHost(e->h_err_sticky);
   if (e->arena) cudaFree(e->arena);
   delete e->ma_step; delete e->ma_prefill;
   delete e;
@@ -667,6 +719,7 @@ extern "C" int dualar_set_option(dualar_engine *e, const char *name, double valu
     if (e->finalized) { CU(cudaSetDevice(e->device)); CU(cudaMemcpy(&e->st->cpu_sem, &e->cpu_sem, sizeof(int), cudaMemcpyHostToDevice)); }
     return 0;
   }
+  if (!strcmp(name, "prefill_mode")) { e->prefill_mode = value != 0.0; return 0; }
   if (!strcmp(name, "mega_kernel")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "mega_kernel must be set before dualar_finalize");
     e->use_mega = value != 0.0; return 0;
@@ -709,8 +762,14 @@ extern "C" int dualar_step(dualar_engine *e, const int32_t *x, const int32_t *in
   LoadStepArgs a{x, input_pos, prev, prev_stride, temperature, top_p, rep, (const bf16 *)noise, e->c.num_codebooks + 1, e->st};
   load_step_kernel<<<1, 256, 0, s>>>(a); CU(cudaGetLastError());
   CU(cudaGraphLaunch(e->g_step, s));
-  store_step_kernel<<<1, 32, 0, s>>>(e->st, out, e->c.num_codebooks + 1); CU(cudaGetLastError());
+  store_step_kernel<<<1, 32, 0, s>>>(e->st, out, e->c.num_codebooks + 1, e->d_err_sticky); CU(cudaGetLastError());
   e->request_open = false;
+  // the step is asynchronous, like the reference's compiled step: a device fault raised by an EARLIER step (the kernels record it
+  // in a sticky word that store_step_kernel copies to mapped host memory) is reported by the next call
+  if (e->h_err_sticky && *e->h_err_sticky) {
+    const int code = *e->h_err_sticky; *e->h_err_sticky = 0;
+    return fail(DUALAR_EDEVICE, "device fault flag %d in an earlier step (1: token id out of range, 2: bulk-copy wait timed out, 3: code >= codebook_size, 4: hand-over poll timed out)", code);
+  }
   return 0;
 }
 
@@ -777,14 +836,19 @@ extern "C" int dualar_prefill(dualar_engine *e, const int32_t *prompt, int T, in
   for (int r = 0; r < R; ++r) memcpy(e->h_seq + (size_t)r * T, prompt + (size_t)r * T, (size_t)T * sizeof(int));
   CU(cudaMemcpy2DAsync(e->seq, (size_t)c.max_seq_len * sizeof(int), e->h_seq, (size_t)T * sizeof(int), (size_t)T * sizeof(int), R, cudaMemcpyHostToDevice, s));
   DAState *h = e->h_st; memset(h, 0, sizeof(*h));
-  h->pos = 0; h->n_gen = 0; h->max_gen = max_new; h->prompt_len = T; h->loop_mode = 1; h->use_penalty = 0;
+  const bool tc_pf = e->prefill_mode == 0 && T > 1;
+  h->pos = tc_pf ? T - 1 : 0; h->n_gen = 0; h->max_gen = max_new; h->prompt_len = T; h->loop_mode = 1; h->use_penalty = 0;
   h->temperature = temperature; h->top_p = top_p; h->rep_penalty = rep; h->seed = e->seed; h->step_ctr = 0;
   h->cpu_sem = e->cpu_sem;
   h->noise = e->noise; h->noise_stride = (long long)c.vocab_size + (long long)(c.num_codebooks - 1) * e->fv;
-  for (int r = 0; r < R; ++r) h->tok_in[r] = prompt[(size_t)r * T];
+  for (int r = 0; r < R; ++r) h->tok_in[r] = prompt[(size_t)r * T + (tc_pf ? T - 1 : 0)];
   CU(cudaMemcpyAsync(e->st, h, sizeof(*h), cudaMemcpyHostToDevice, s));
   if (e->u_arena) CU(cudaMemsetAsync(e->u_arena, 0, e->u_arena_bytes, s));      // no unit of an earlier request carries a valid tag
-  for (int t = 0; t + 1 < T; ++t) CU(cudaGraphLaunch(e->g_prefill, s));
+  if (tc_pf) {
+    // the reference prefills the whole prompt in ONE forward (inference.py:353-362); here positions [0, T-1) go through the
+    // tensor-core GEMMs (KV rows only, no head), the last position through the decode step below, which samples the first token
+    int rc = tc_prefill_own(e, 0, T - 1, s); if (rc) return rc;
+  } else for (int t = 0; t + 1 < T; ++t) CU(cudaGraphLaunch(e->g_prefill, s));
   CU(cudaGraphLaunch(e->g_step, s));
   e->prompt_len = T; e->max_gen = max_new; e->request_open = true;
   return 0;
@@ -806,7 +870,7 @@ extern "C" int dualar_collect(dualar_engine *e, int32_t *out, int cap, int *n_to
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaMemcpyAsync(e->h_st, e->st, sizeof(DAState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  if (e->h_st->err) return fail(DUALAR_EDEVICE, "device fault flag %d (1: token id out of range, 2: bulk-copy wait timed out, 3: code >= codebook_size)", e->h_st->err);
+  if (e->h_st->err) return fail(DUALAR_EDEVICE, "device fault flag %d (1: token id out of range, 2: bulk-copy wait timed out, 3: code >= codebook_size, 4: hand-over poll timed out)", e->h_st->err);
   int n = e->h_st->n_gen;
   *n_tokens = n;
   if (finished) *finished = e->h_st->done;
@@ -902,4 +966,14 @@ extern "C" int dualar_weight_bytes(const dualar_engine *e, int64_t *total, int64
   if (total) *total = (int64_t)e->arena_bytes;
   if (fast) *fast = (int64_t)e->fast_bytes;
   return 0;
+}
+
+#include "batch_host.cuh"
+
+static int tc_prefill_own(dualar_engine *e, int t0, int t1, cudaStream_t s) {
+  const dualar_config &c = e->c;
+  std::vector<bf16 *> kc(c.n_layer), vc(c.n_layer);
+  for (int l = 0; l < c.n_layer; ++l) { kc[l] = e->slow[l].kc; vc[l] = e->slow[l].vc; }
+  KvTarget kv{kc.data(), vc.data(), 0, c.max_seq_len};
+  return tc_prefill(e, kv, e->seq, c.max_seq_len, t0, t1, s);      // (kernel arguments are copied at launch: the vectors may go out of scope)
 }

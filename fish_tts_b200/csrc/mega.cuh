@@ -87,7 +87,6 @@ struct MegaArgs {
   unsigned int *phase_ctr;   // running phase counter = source of the unit tags; NEVER reset (a request must not see the previous one's tags)
   // shared-memory plan
   int kmax, lg_rows, work_bytes, kv_bytes, ring_bytes;
-  int ustride;           // (unused since the replica experiment; kept for the host-side buffer layout)
   MegaSmem plan;         // shared-memory offsets: read from parameter space at every use -- thirteen 64-bit pointers held live across
                          // the phase loop cost ~25 registers under a 96-register cap and made ptxas spill in the hot loops
   MPhase table[DA_M_MAX_PHASES];
@@ -134,6 +133,9 @@ __device__ __noinline__ bool poll_chunk(const uint32_t *p, uint32_t tag, float *
 // two 4-unit groups per thread, `lo` and `hi` half a vector apart: both loads of a warp are fully coalesced (16 sectors per
 // request instead of 32 half-used ones), which is worth ~0.15 us per hand-over at 148 pollers (handover_bench2.cu)
 __device__ int g_poll_ns = 0;      // back-off between poll attempts (experiments: DUALAR_POLL_NS)
+__device__ int g_l2_window = 0;      // 1: the fast stack is covered by a cudaAccessPolicyWindow on the kernel node (engine.cu capture());
+                                     // its bulk copies then carry no per-copy cache hint so that the window's property applies
+__device__ int g_keep_mode = 0;      // what the other (1 - keep_frac) lines of the fast stack ask for: 0 evict_first, 1 evict_unchanged (DUALAR_KEEP_MODE)
 __device__ float g_keep_frac = 0.7f;  // fraction of the fast-stack lines that ask L2 for evict_last (DUALAR_KEEP_FRAC).  The stack
                                       // (109 MB) does not fit next to the slow stream: asking for all of it thrashes (ncu: 2.2 GB
                                       // DRAM reads per token, L2 hit 34%); 0.7 keeps a stable subset (1.69 GB, 46%)
@@ -393,8 +395,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
   // =================================================== producer ===========================================================
   if (w == DA_M_CWARPS) {
     // the fast stack is re-read num_codebooks times per token: ask L2 to keep (a fraction of) it, stream everything else
-    uint64_t pol_keep; { const float fr = g_keep_frac; asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(fr)); }
+    uint64_t pol_keep;
+    { const float fr = g_keep_frac;
+      if (g_keep_mode == 1) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, %1;" : "=l"(pol_keep) : "f"(fr));
+      else asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(fr)); }
     const uint64_t pol_stream = policy_evict_first();
+    const bool use_window = g_l2_window != 0;
     RingCursor rc = {0u, 0u};
     uint32_t used = 0, tail = 0;
     bool ok = true;
@@ -426,7 +432,10 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
             mbar_expect_tx(&sm_full[bi], (uint32_t)n * row_bytes);
           }
           at = __shfl_sync(0xffffffffu, at, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
-          if (lane < n) bulk_g2s(sm_ring + at + (uint32_t)lane * RS, d.W + (size_t)(gp.r0 + 16 * t + lane) * d.K, row_bytes, &sm_full[bi], pol);
+          if (lane < n) {
+            if (use_window && (d.flags & MF_KEEP)) bulk_g2s_nohint(sm_ring + at + (uint32_t)lane * RS, d.W + (size_t)(gp.r0 + 16 * t + lane) * d.K, row_bytes, &sm_full[bi]);
+            else bulk_g2s(sm_ring + at + (uint32_t)lane * RS, d.W + (size_t)(gp.r0 + 16 * t + lane) * d.K, row_bytes, &sm_full[bi], pol);
+          }
         }
       } else if (d.kind == MK_ATTN) {
         const AttnPart ap = attn_part(pos, a.nkv, a.nsplit_max, bid);

@@ -159,14 +159,17 @@ __global__ void load_step_kernel(const LoadStepArgs a) {
     st->pos = a.input_pos[0];
     st->temperature = a.temperature[0]; st->top_p = a.top_p[0]; st->rep_penalty = a.rep_penalty[0];
     st->use_penalty = a.prev ? 1 : 0;
-    st->noise = a.noise; st->loop_mode = 0; st->done = 0;
+    st->noise = a.noise; st->loop_mode = 0; st->done = 0; st->err = 0;
     st->n_cand = 0; st->sel_ticket = 0; st->fast_ticket = 0; st->head_ticket = 0; st->s_fix = 0ull;
     for (int g = 0; g < DA_MAX_KV_HEADS; ++g) st->attn_ticket[g] = 0;
   }
 }
-__global__ void store_step_kernel(const DAState *st, int *out, int n_rows) {
+__global__ void store_step_kernel(const DAState *st, int *out, int n_rows, int *err_sticky) {
   if (threadIdx.x < n_rows) out[threadIdx.x] = st->tok_out[threadIdx.x];
-  if (threadIdx.x == 0) const_cast<DAState *>(st)->step_ctr += 1;
+  if (threadIdx.x == 0) {
+    const_cast<DAState *>(st)->step_ctr += 1;
+    if (st->err && err_sticky) *err_sticky = st->err;      // mapped host word: the next dualar_step call reports it
+  }
 }
 
 // ---- loop-mode prefill bookkeeping -----------------------------------------------------------------

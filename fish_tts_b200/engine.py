@@ -170,6 +170,52 @@ class DualAREngine:
                                             self._stream()))
         return out[:, : n.value].copy()
 
+    # ---- batched decode: B requests share every weight byte (include/dualar.h "batched decode") -------------------
+    def batch_init(self, max_batch: int, slot_seq_len: int = 0):
+        """Allocate ``max_batch`` request slots (own KV cache of ``slot_seq_len`` positions each) and capture the batched step."""
+        capi.check(self.lib.dualar_batch_init(self._h, int(max_batch), int(slot_seq_len)))
+        self.max_batch = int(max_batch)
+        self._batch_noise = {}
+
+    def batch_prefill(self, slot: int, prompt, max_new_tokens: int, temperature: float = 0.7, top_p: float = 0.7,
+                      repetition_penalty: float = 1.5, seed: int = 0, noise: Optional[torch.Tensor] = None):
+        """Tensor-core prefill of one request into ``slot``; its first token comes out of the next ``batch_decode`` step."""
+        p = np.ascontiguousarray(np.asarray(prompt.cpu() if isinstance(prompt, torch.Tensor) else prompt, dtype=np.int32))
+        assert p.ndim == 2 and p.shape[0] == self.rows, f"prompt must be ({self.rows}, T)"
+        if noise is not None:
+            assert noise.dtype == torch.bfloat16 and noise.is_cuda and noise.is_contiguous()
+        self._batch_noise[slot] = noise
+        capi.check(self.lib.dualar_batch_prefill(self._h, int(slot), p.ctypes.data, p.shape[1], int(max_new_tokens),
+                                                 float(temperature), float(top_p), float(repetition_penalty), int(seed),
+                                                 _ptr(noise), self._stream()))
+
+    def batch_decode(self, n_steps: int):
+        capi.check(self.lib.dualar_batch_decode(self._h, int(n_steps), self._stream()))
+
+    def batch_collect(self, slot: int, capacity: Optional[int] = None):
+        """-> (tokens (C+1, n) int32 ndarray, finished) of one slot."""
+        cap = capacity or self.cfg.max_seq_len
+        out = np.zeros((self.rows, cap), dtype=np.int32)
+        n, fin = C.c_int(0), C.c_int(0)
+        capi.check(self.lib.dualar_batch_collect(self._h, int(slot), out.ctypes.data, cap, C.byref(n), C.byref(fin), self._stream()))
+        return out[:, : n.value].copy(), bool(fin.value)
+
+    def batch_release(self, slot: int):
+        capi.check(self.lib.dualar_batch_release(self._h, int(slot)))
+
+    def batch_read(self, name: str) -> torch.Tensor:
+        cfg, B = self.cfg, self.max_batch
+        shapes = {
+            "slow_logits": ((B, cfg.vocab_size), torch.bfloat16), "slow_logits_raw": ((B, cfg.vocab_size), torch.bfloat16),
+            "hidden": ((B, cfg.dim), torch.bfloat16), "fast_logits": ((B, cfg.num_codebooks - 1, self.fast_vocab), torch.bfloat16),
+            "tokens": ((B, self.rows), torch.int32), "positions": ((B,), torch.int32), "done": ((B,), torch.int32),
+            "n_gen": ((B,), torch.int32), "launches": ((1,), torch.int32),
+        }
+        shape, dt = shapes[name]
+        out = torch.empty(shape, dtype=dt)
+        capi.check(self.lib.dualar_batch_read(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(), self._stream()))
+        return out
+
     def set_option(self, name: str, value: float):
         capi.check(self.lib.dualar_set_option(self._h, name.encode(), float(value)))
 

@@ -123,6 +123,32 @@ int dualar_generate(dualar_engine *e, const int32_t *prompt, int prompt_len, int
                     float temperature, float top_p, float repetition_penalty, int32_t *out,
                     int out_capacity, int *n_tokens, void *stream);
 
+/* ---- batched decode: B requests advance together (BASELINE configs[3], "batched decode bs=32") -----------------
+ * The reference is batch 1 only (inference.py:73 reads `logits[0, -1]`, :355 views the prompt as (1, C+1, T)), so there is
+ * no reference entry point to mirror: these calls are the loop API above with a `slot` argument.  A slot is one request:
+ * its own KV cache (`slot_seq_len` positions), position, repetition window, sampling parameters and Philox stream, so its
+ * tokens are those of the same request run alone.  One decode step streams every weight byte ONCE for all slots: the
+ * linears are tcgen05 GEMMs (csrc/gemm_tc.cuh) with the requests as the N dimension.
+ *   dualar_batch_init     after dualar_finalize: allocates `max_batch` slots and captures the batched step as a CUDA graph
+ *   dualar_batch_prefill  HOST prompt (num_codebooks+1, prompt_len) int32 -> KV rows of the slot through the tensor-core
+ *                         prefill; the slot then joins the batch and the NEXT dualar_batch_decode step produces its first
+ *                         token.  `noise`: optional explicit Exp(1) draws (device, layout of dualar_set_noise), NULL = Philox(seed)
+ *   dualar_batch_decode   n_steps batched steps, no host round trip; finished or empty slots ride along as no-ops
+ *   dualar_batch_collect  like dualar_collect, for one slot
+ *   dualar_batch_release  frees the slot for the next request (continuous batching)
+ *   dualar_batch_read     introspection (tests, bench): "slow_logits_raw" / "slow_logits" (B x vocab bf16), "hidden" (B x dim),
+ *                         "fast_logits" (B x (num_codebooks-1) x fast_vocab), "tokens" (B x (num_codebooks+1) int32),
+ *                         "positions" / "done" / "n_gen" (B int32), "launches" (1 int32: kernels per batched step) */
+int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_len);
+int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *prompt, int prompt_len, int max_new_tokens,
+                         float temperature, float top_p, float repetition_penalty, uint64_t seed, const void *noise,
+                         void *stream);
+int dualar_batch_decode(dualar_engine *e, int n_steps, void *stream);
+int dualar_batch_collect(dualar_engine *e, int slot, int32_t *out, int out_capacity, int *n_tokens, int *finished,
+                         void *stream);
+int dualar_batch_release(dualar_engine *e, int slot);
+int dualar_batch_read(dualar_engine *e, const char *name, void *host_dst, int64_t n_bytes, void *stream);
+
 /* ---- sampling noise ---------------------------------------------------------------------------
  * The reference draws `q ~ Exp(1)` with torch's generator (inference.py:26).  Here the draws come
  * from a counter-based Philox4x32-10 stream keyed by (seed, step, head, element), so any process
@@ -147,6 +173,9 @@ int dualar_set_noise(dualar_engine *e, const void *noise, int64_t n_steps);
  * "fast_qkv_table" (0/1, before finalize; default 1): passes >= 1 of the fast stack start from the embedding of a
  *     code, so the first fast layer's q|k|v is a function of that code alone; it is tabulated at finalize
  *     (codebook_size x fast qkv rows, bf16; 16 MB for s1-mini) and that wqkv phase is dropped from the step.
+ * "prefill_mode" (0/1, default 0): 0 = dualar_prefill pushes prompt positions [0, T-1) through the tensor-core GEMMs in chunks of
+ *     256 positions (the reference prefills in one forward, inference.py:353-362); 1 = one position per launch through the decode
+ *     kernel (the round-1 path, kept as a cross-check).
  * "mega_kernel" (0/1, before finalize; default 1): run the whole decode step as ONE persistent cooperative
  *     kernel (csrc/mega.cuh) instead of one kernel per phase (kept as a cross-check).  The two sum their dot
  *     products in different fp32 orders (tensor-core chunks vs. FMA chains), so logits agree to bf16 rounding,
