@@ -40,6 +40,7 @@ struct dualar_tc {
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
   int ksplit_override = 0, stages_override = 0;
+  bool fuse_norm = true;      // DUALAR_TC_FUSE_NORM=0: separate RMSNorm kernels in front of the decode GEMMs (cross-check)
 };
 
 static int tc_map(dualar_engine *e, const void *p, int rows, int K, int box, const CUtensorMap **out) {
@@ -90,6 +91,8 @@ static int tc_init(dualar_engine *e) {
   if (!tc_encode_fn()) return fail(DUALAR_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   int rc;
   if ((rc = tc_configure<32>()) || (rc = tc_configure<64>()) || (rc = tc_configure<128>()) || (rc = tc_configure<256>())) return rc;
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  { const char *v = getenv("DUALAR_TC_FUSE_NORM"); e->tc->fuse_norm = !(v && v[0] == '0'); }
   e->tc->ws_bytes = (size_t)48 << 20;
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
@@ -103,8 +106,10 @@ static int tc_init(dualar_engine *e) {
 }
 
 // Y[n][r] = W[r][:] . X[n][:] on the tensor cores (gemm_tc.cuh); xcap = rows of the X buffer
+// norm_w != nullptr: X is the UN-normalised activation and the kernel applies RMSNorm(norm_w) itself (BN = 32 only, see tc_can_fuse_norm)
+static bool tc_can_fuse_norm(const dualar_engine *e, int BN, int K) { return e->tc->fuse_norm && BN == 32 && K % 256 == 0 && K <= 4096; }
 static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 *X, int xcap, int ncols, int BN, int epi, const bf16 *bias,
-                   const bf16 *res, bf16 *out, int w_keep, cudaStream_t s, int &count) {
+                   const bf16 *res, bf16 *out, int w_keep, cudaStream_t s, int &count, const bf16 *norm_w = nullptr) {
   const CUtensorMap *mw, *mx; int rc;
   if ((rc = tc_map(e, W, rows, K, DA_TC_BM, &mw)) || (rc = tc_map(e, X, xcap, K, BN, &mx))) return rc;
   const int rt = (rows + DA_TC_BM - 1) / DA_TC_BM, ct = (ncols + BN - 1) / BN, tiles = rt * ct, nkb = K / DA_TC_BK;
@@ -122,6 +127,16 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
   const int nk_per = (nkb + ks - 1) / ks; if (st > nk_per) st = nk_per < 2 ? 2 : nk_per;
   a.stages = st;
   const dim3 grid(rt, ct, ks), block(DA_TC_THREADS);
+  if (norm_w) {
+    if (!tc_can_fuse_norm(e, BN, K) || ct != 1) return fail(DUALAR_EINVAL, "fused norm needs BN 32 and one column tile");
+    a.xraw = X; a.norm_w = norm_w; a.eps = e->c.norm_eps;
+    size_t smx = gemm_tc_smem_xn(BN, st, nk_per);
+    while (smx > 200 * 1024 && st > 2) { --st; smx = gemm_tc_smem_xn(BN, st, nk_per); }
+    if (smx > 200 * 1024) return fail(DUALAR_EINVAL, "fused-norm operand does not fit shared memory (K %d, splits %d)", K, ks);
+    a.stages = st;
+    CU(launch_k(gemm_tc_kernel<32, true>, grid, block, smx, s, *mw, *mx, a)); ++count;
+    return 0;
+  }
   const size_t smem = gemm_tc_smem(BN, st);
   switch (BN) {
     case 32: CU(launch_k(gemm_tc_kernel<32>, grid, block, smem, s, *mw, *mx, a)); break;
@@ -154,20 +169,27 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
     CU(launch_k(b_rmsnorm_kernel, dim3((ncols + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
   for (int l = 0; l < cf.n_layer; ++l) {
     LayerW &L = e->slow[l];
-    if ((rc = norm(c.x, L.attn_norm, c.xn, cf.dim))) return rc;
-    if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.xn, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count))) return rc;
+    const bool fuse = tc_can_fuse_norm(e, BN, cf.dim);      // decode: the GEMM normalises its own operand, one kernel fewer per norm
+    if (fuse) { if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.x, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count, L.attn_norm))) return rc; }
+    else {
+      if ((rc = norm(c.x, L.attn_norm, c.xn, cf.dim))) return rc;
+      if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.xn, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count))) return rc;
+    }
     { BQkvPostArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn;
       a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S; a.ncols = ncols; a.eps = cf.norm_eps; a.pos = pos;
-      CU(launch_k(b_qkv_post_kernel, dim3(ncols), dim3(256), (size_t)8 * cf.head_dim * sizeof(float), s, a)); ++count; }
+      CU(launch_k(b_qkv_post_kernel, dim3(ncols, (cf.n_head + 2 * cf.n_local_heads + 7) / 8), dim3(256), (size_t)8 * cf.head_dim * sizeof(float), s, a)); ++count; }
     { BAttnArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S;
       a.ncols = ncols; a.nsplit_max = c.nsplit; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
       a.tickets = c.attn_tickets; a.y = c.y; a.pos = pos; a.err = e->tc->err;
       CU(launch_k(b_attn_kernel, dim3(c.nsplit, cf.n_local_heads, ncols), dim3(DA_ATTN_THREADS), attn_smem_bytes(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; }
     if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count))) return rc;
-    if ((rc = norm(c.h, L.ffn_norm, c.xn, cf.dim))) return rc;
-    if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.xn, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count))) return rc;
+    if (fuse) { if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.h, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count, L.ffn_norm))) return rc; }
+    else {
+      if ((rc = norm(c.h, L.ffn_norm, c.xn, cf.dim))) return rc;
+      if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.xn, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count))) return rc;
+    }
     if ((rc = tc_gemm(e, L.w2, cf.dim, cf.intermediate_size, c.act, c.cap, ncols, BN, TE_RESIDUAL, nullptr, c.h, c.x, 0, s, count))) return rc;
   }
   return 0;
@@ -218,27 +240,37 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
     for (int l = 0; l < cf.n_fast_layer; ++l) {
       LayerW &L = e->fast[l];
       bf16 *out = c.fx[l & 1];
-      if ((rc = norm(in, L.attn_norm, c.fxn, cf.fast_dim))) return rc;
-      if ((rc = tc_gemm(e, L.wqkv, fqkv_rows, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, L.bqkv, nullptr, c.fqkv, 1, s, count))) return rc;
+      const bool fuse = tc_can_fuse_norm(e, BN, cf.fast_dim);
+      if (fuse) { if ((rc = tc_gemm(e, L.wqkv, fqkv_rows, cf.fast_dim, in, c.cap, B, BN, TE_STORE, L.bqkv, nullptr, c.fqkv, 1, s, count, L.attn_norm))) return rc; }
+      else {
+        if ((rc = norm(in, L.attn_norm, c.fxn, cf.fast_dim))) return rc;
+        if ((rc = tc_gemm(e, L.wqkv, fqkv_rows, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, L.bqkv, nullptr, c.fqkv, 1, s, count))) return rc;
+      }
       { BFastAttnArgs a; memset(&a, 0, sizeof(a));
         a.qkv = c.fqkv; a.kc = b.fkc[l]; a.vc = b.fvc[l]; a.slot_stride = b.fslot_stride; a.rope = e->fast_rope; a.qn = L.qn; a.kn = L.kn;
         a.nh = cf.fast_n_head; a.nkv = cf.fast_n_local_heads; a.hd = cf.fast_head_dim; a.ncb = cf.num_codebooks; a.p = p; a.ncols = B;
         a.eps = cf.norm_eps; a.scale = (float)(1.0 / sqrt((double)cf.fast_head_dim)); a.y = c.fy;
         CU(launch_k(b_fast_attn_kernel, dim3(B), dim3(256), b_fast_attn_smem(a.nh, a.nkv, a.hd, a.ncb), s, a)); ++count; }
       if ((rc = tc_gemm(e, L.wo, cf.fast_dim, fqd, c.fy, c.cap, B, BN, TE_RESIDUAL, L.bo, in, c.fh, 1, s, count))) return rc;
-      if ((rc = norm(c.fh, L.ffn_norm, c.fxn, cf.fast_dim))) return rc;
-      if ((rc = tc_gemm(e, L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fxn, c.cap, B, BN, TE_SWIGLU, nullptr, nullptr, c.fact, 1, s, count))) return rc;
+      if (fuse) { if ((rc = tc_gemm(e, L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fh, c.cap, B, BN, TE_SWIGLU, nullptr, nullptr, c.fact, 1, s, count, L.ffn_norm))) return rc; }
+      else {
+        if ((rc = norm(c.fh, L.ffn_norm, c.fxn, cf.fast_dim))) return rc;
+        if ((rc = tc_gemm(e, L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fxn, c.cap, B, BN, TE_SWIGLU, nullptr, nullptr, c.fact, 1, s, count))) return rc;
+      }
       if ((rc = tc_gemm(e, L.w2, cf.fast_dim, cf.fast_intermediate_size, c.fact, c.cap, B, BN, TE_RESIDUAL, nullptr, c.fh, out, 1, s, count))) return rc;
       in = out;
     }
     if (p == 0) continue;      // logits of pass 0 are discarded by the reference (inference.py:122)
-    if ((rc = norm(in, e->fast_norm, c.fxn, cf.fast_dim))) return rc;
-    if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count))) return rc;
+    if (tc_can_fuse_norm(e, BN, cf.fast_dim)) { if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, in, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count, e->fast_norm))) return rc; }
+    else {
+      if ((rc = norm(in, e->fast_norm, c.fxn, cf.fast_dim))) return rc;
+      if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count))) return rc;
+    }
     { BFastSampleArgs a; memset(&a, 0, sizeof(a));
       a.logits = c.flogits; a.logits_raw = e->batch_keep_raw ? c.flogits_raw : nullptr; a.fv = e->fv; a.head = p; a.ncb = cf.num_codebooks; a.last_head = (p == cf.num_codebooks - 1);
       a.noise_off = (long long)cf.vocab_size + (long long)(p - 1) * e->fv; a.fast_emb = e->fast_emb; a.fast_x = c.fin; a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size;
       a.seq = b.seq; a.seq_slot_stride = (long long)R * b.Sb; a.seq_stride = b.Sb; a.im_end_id = cf.im_end_id; a.n_rows_tok = R; a.st = b.st;
-      CU(launch_k(b_fast_sample_kernel, dim3(B), dim3(256), (size_t)(192 * 8 + 80 * 4 + 64), s, a)); ++count; }
+      CU(launch_k(b_fast_sample_kernel, dim3(B), dim3(256), b_fast_sample_smem(), s, a)); ++count; }
   }
   return 0;
 }
@@ -258,7 +290,8 @@ extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_l
   b->B = max_batch; b->BN = bn_for(max_batch); b->Sb = slot_seq_len;
   const int R = cf.num_codebooks + 1;
   // split-KV: enough (kv head, split) CTAs per request to fill the machine twice at small batches, one split per 256 positions at most
-  int nsplit = (2 * e->sms * 2) / (cf.n_local_heads * max_batch); if (nsplit < 1) nsplit = 1; if (nsplit > 16) nsplit = 16;
+  int nsplit = (8 * e->sms) / (cf.n_local_heads * max_batch); if (nsplit < 2) nsplit = 2; if (nsplit > 16) nsplit = 16;
+  { const char *v = getenv("DUALAR_BATCH_NSPLIT"); if (v) nsplit = atoi(v); }
   if ((rc = alloc_cols(e, b->c, b->BN, nsplit, true))) return rc;
   b->slot_stride = (long long)cf.n_local_heads * b->Sb * cf.head_dim;
   b->fslot_stride = (long long)cf.fast_n_local_heads * cf.num_codebooks * cf.fast_head_dim;
@@ -269,7 +302,9 @@ extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_l
   CU(cudaMallocHost((void **)&b->h_st, sizeof(DAState)));
   CU(cudaMallocHost((void **)&b->h_seq, (size_t)R * b->Sb * sizeof(int)));
   b->prompt_len.assign(max_batch, 0); b->max_gen.assign(max_batch, 0); b->open.assign(max_batch, 0);
-  b->nchunk = 32;
+  // slow sampler: (chunks x requests) CTAs of 512 threads scan the logits; the register-heavy sampler code runs one CTA per SM, so
+  // more CTAs than SMs only adds waves
+  b->nchunk = e->sms / max_batch; if (b->nchunk < 1) b->nchunk = 1; if (b->nchunk > 32) b->nchunk = 32;
   // dry run (configures attributes, surfaces launch errors), then capture
   int n = 0;
   if ((rc = enqueue_batch_step(e, e->cap_stream, n)) < 0) return rc;

@@ -68,6 +68,7 @@ struct dualar_engine {
   // persistent whole-step kernel (mega.cuh): unit buffers, the two phase tables (decode step / one prefill position)
   uint32_t *u_x = nullptr, *u_qkv = nullptr, *u_y = nullptr, *u_h = nullptr, *u_act = nullptr;
   uint32_t *u_fqkv = nullptr, *u_fh = nullptr, *u_fact = nullptr, *u_fx0 = nullptr, *u_fx1 = nullptr, *u_fin = nullptr, *u_flogits = nullptr;
+  bf16 *dbg_fast = nullptr;                    // dualar_debug_sample: forced fast-head logits
   bf16 *t0 = nullptr; bool use_t0 = true;      // first-layer q | k | v of the fast stack per code (passes >= 1)
   unsigned long long *m_part_o = nullptr, *m_part_ml = nullptr, *m_hmax = nullptr, *m_hcs = nullptr, *m_cand = nullptr;
   MegaArgs *ma_step = nullptr, *ma_prefill = nullptr; size_t mega_smem = 0; unsigned int *m_phase = nullptr; bf16 *m_fkv = nullptr; unsigned char *u_arena = nullptr; size_t u_arena_bytes = 0;
@@ -801,6 +802,31 @@ extern "C" int dualar_debug_sample(dualar_engine *e, int head, const void *logit
   cudaStream_t s = (cudaStream_t)stream;
   LoadStepArgs la{e->st->tok_in, &e->st->pos, prev, prev_stride, temperature, top_p, rep, (const bf16 *)noise, c.num_codebooks + 1, e->st};
   load_step_kernel<<<1, 256, 0, s>>>(la); CU(cudaGetLastError());
+  if (e->use_mega) {
+    // the PRODUCT path's sampler: one whole decode step of the persistent kernel whose logits epilogues are fed the caller's logits
+    // (MegaArgs::force_slow / force_fast), so the repetition penalty, the per-CTA statistics, the ordered candidate list, the binned /
+    // sorting / whole-vocabulary samplers and the fast-head samplers that run in production are the ones under test
+    MegaArgs a = *e->ma_step;
+    a.tl = nullptr; a.tl_slots = 0; a.tl2 = nullptr;
+    bf16 *ff = nullptr;
+    if (head == 0) a.force_slow = (const bf16 *)logits;
+    else {
+      // only head `head`'s slice is the caller's; the other fast heads sample from zeros (their ids are not read)
+      if (!e->dbg_fast) { int rc = dev_alloc(e, e->dbg_fast, (size_t)(c.num_codebooks - 1) * e->fv); if (rc) return rc; }
+      ff = e->dbg_fast;
+      CU(cudaMemsetAsync(ff, 0, (size_t)(c.num_codebooks - 1) * e->fv * sizeof(bf16), s));
+      CU(cudaMemcpyAsync(ff + (size_t)(head - 1) * e->fv, logits, (size_t)e->fv * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+      a.force_fast = ff;
+    }
+    if (e->u_arena) CU(cudaMemsetAsync(e->u_arena, 0, e->u_arena_bytes, s));
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_M_THREADS); cfg.dynamicSmemBytes = e->mega_smem; cfg.stream = s;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, mega_kernel<false, true>, a));
+    CU(cudaMemcpyAsync(out_token, &e->st->tok_out[head == 0 ? 0 : head + 1], sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
   if (head == 0) {
     debug_stats_kernel<<<e->sms, 512, 0, s>>>((const bf16 *)logits, e->logits, e->partials, c.vocab_size, c.num_codebooks + 1, e->st); CU(cudaGetLastError());
     SelectArgs a; memset(&a, 0, sizeof(a));

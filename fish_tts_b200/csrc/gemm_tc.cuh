@@ -52,6 +52,9 @@ struct GemmTcArgs {
   const bf16 *bias;          // [rows] or null
   const bf16 *res;           // TE_RESIDUAL: [ncols][ld_out]
   bf16 *out;                 // [ncols][ld_out]
+  const bf16 *xraw;          // XN kernels: un-normalised activations [ncols][K]; the kernel applies the custom RMSNorm itself
+  const bf16 *norm_w;        //             norm weight [K]
+  float eps;
   float *ws;                 // split-K partials [tile][split][BN][128]
   unsigned int *tickets;     // split-K arrival counters, one per tile, zero between launches
   int *err;                  // device fault flag (DAState::err or a stand-alone word)
@@ -117,15 +120,26 @@ static inline size_t gemm_tc_smem(int BN, int stages) {
   const size_t ring = (size_t)stages * (DA_TC_A_BYTES + (size_t)BN * 128), stg = (size_t)BN * DA_TC_BM * 4;
   return (ring > stg ? ring : stg) + 1024;
 }
+// XN kernels: a ring of weight tiles only, then the resident activation operand of the CTA's nk k-blocks
+static inline size_t gemm_tc_smem_xn(int BN, int stages, int nk) {
+  const size_t ring = (size_t)stages * DA_TC_A_BYTES, stg = (size_t)BN * DA_TC_BM * 4;
+  return (ring > stg ? ring : stg) + (size_t)nk * BN * 128 + 1024;
+}
 
 // grid (row tiles, column tiles, K splits)
-template <int BN>
+// XN = true (BN = 32, batched decode): the activation operand is NOT loaded by TMA; the epilogue warps, idle during the main loop,
+// read the un-normalised rows, apply the reference's RMSNorm (llama.py:172-177: fp32 normalise, round, x weight, round -- every CTA
+// recomputes the row statistics, 64 KB of L2 reads) and write the CTA's k-range into shared memory in the same 128-byte-swizzle
+// K-major layout TMA would have produced.  That removes one kernel (and one kernel boundary, ~5 us in a dependent chain) per norm.
+template <int BN, bool XN = false>
 __global__ void __launch_bounds__(DA_TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmTcArgs a) {
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "TMEM allocations are powers of two >= 32 columns");
+  static_assert(!XN || BN == 32, "the fused-norm operand staging deals 8 rows to each of the four epilogue warps");
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[DA_TC_MAX_STAGES], empty_bar[DA_TC_MAX_STAGES], accum_bar;
+  __shared__ __align__(8) uint64_t full_bar[DA_TC_MAX_STAGES], empty_bar[DA_TC_MAX_STAGES], accum_bar, xready_bar;
   __shared__ uint32_t s_tmem, s_last;
+  __shared__ float s_inv[XN ? BN : 1];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z, nz = gridDim.z;
   const int stages = a.stages;
@@ -133,7 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   unsigned char *sA = sbase, *sB = sbase + (size_t)stages * DA_TC_A_BYTES;
   const int nkb_all = a.K / DA_TC_BK;
   const int kb0 = (nkb_all * z) / nz, kb1 = (nkb_all * (z + 1)) / nz, nk = kb1 - kb0;
-  constexpr uint32_t STAGE_BYTES = DA_TC_A_BYTES + BN * 128;
+  constexpr uint32_t STAGE_BYTES = DA_TC_A_BYTES + (XN ? 0 : BN * 128);      // XN: sB holds all k-blocks of this CTA, written by the epilogue warps
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   long long *dbg = a.dbg ? a.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
@@ -141,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   if (tid == 0) {
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&accum_bar, 1);
+    if (XN) mbar_init(&xready_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmX);
   }
@@ -166,13 +181,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");
       if (dbg) dbg[2] = clock64();
-      for (int i = 0; i < npre; ++i) tma_load_2d(sB + (size_t)i * BN * 128, &tmX, (kb0 + i) * DA_TC_BK, tile_n * BN, &full_bar[i], pol_x);
+      if (!XN) for (int i = 0; i < npre; ++i) tma_load_2d(sB + (size_t)i * BN * 128, &tmX, (kb0 + i) * DA_TC_BK, tile_n * BN, &full_bar[i], pol_x);
       for (int i = npre; i < nk && ok; ++i) {
         const int s = i % stages; const uint32_t ph = (uint32_t)(i / stages) & 1u;
         ok = mbar_wait_bounded(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_2d(sA + (size_t)s * DA_TC_A_BYTES, &tmW, (kb0 + i) * DA_TC_BK, tile_m * DA_TC_BM, &full_bar[s], pol_w);
-        tma_load_2d(sB + (size_t)s * BN * 128, &tmX, (kb0 + i) * DA_TC_BK, tile_n * BN, &full_bar[s], pol_x);
+        if (!XN) tma_load_2d(sB + (size_t)s * BN * 128, &tmX, (kb0 + i) * DA_TC_BK, tile_n * BN, &full_bar[s], pol_x);
       }
       if (!ok) atomicExch(a.err, 5);
     }
@@ -180,13 +195,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BN);
+      if (XN) { ok = mbar_wait_bounded(&xready_bar, 0u); tc_fence_after(); }
       for (int i = 0; i < nk && ok; ++i) {
         const int s = i % stages; const uint32_t ph = (uint32_t)(i / stages) & 1u;
         ok = mbar_wait_bounded(&full_bar[s], ph);
         tc_fence_after();
         if (dbg && i == 0) dbg[3] = clock64();
         const uint64_t da0 = umma_desc_sw128(smem_u32(sA + (size_t)s * DA_TC_A_BYTES));
-        const uint64_t db0 = umma_desc_sw128(smem_u32(sB + (size_t)s * BN * 128));
+        const uint64_t db0 = umma_desc_sw128(smem_u32(sB + (size_t)(XN ? i : s) * BN * 128));
 #pragma unroll
         for (int k = 0; k < DA_TC_BK / 16; ++k) umma_bf16(tmem, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, (uint32_t)((i | k) != 0));
         umma_commit(&empty_bar[s]);
@@ -206,6 +222,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int te = tid - 64, wq = warp & 3, r_in = wq * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
+    if (XN) {
+      // ---- (X) the normalised activation operand of this CTA's k-range, built in shared memory ---------------------------------------
+      // row statistics: warp wq owns rows wq, wq + 4, ...; per lane the chunks lane, lane + 32, ... in ascending order, then a butterfly
+      // (the summation order of b_rmsnorm_kernel, so fused and unfused paths agree bit for bit)
+      const int K = a.K, cpl = K >> 8;      // 16-byte chunks per lane
+      float ss[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) ss[r] = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < cpl; c0 += 4) {
+        uint4 v[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int n = wq + 4 * r;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n < a.ncols && c0 + j < cpl) v[r][j] = *reinterpret_cast<const uint4 *>(a.xraw + (size_t)n * K + ((size_t)(c0 + j) * 32 + lane) * 8);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int n = wq + 4 * r;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n < a.ncols && c0 + j < cpl) {
+              float f[8]; unpack8(v[r][j], f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) ss[r] = fmaf(f[q], f[q], ss[r]);
+            }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float tot = warp_sum(ss[r]);
+        if (lane == 0) s_inv[wq + 4 * r] = rsqrtf(tot * (1.0f / (float)K) + a.eps);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // transform + swizzled store: 16-byte chunk c16 of row n of k-block kb goes to  sB + kb * BN * 128 + n * 128 + ((c16 ^ (n & 7)) << 4)
+      const int per_row = nk * 8, total = BN * per_row;
+#pragma unroll 2
+      for (int c = te; c < total; c += 128) {
+        const int n = c / per_row, kc = c - n * per_row, kb = kc >> 3, c16 = kc & 7;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (n < a.ncols) {
+          const size_t k0 = (size_t)(kb0 + kb) * DA_TC_BK + (size_t)c16 * 8;
+          float f[8], g[8];
+          unpack8(*reinterpret_cast<const uint4 *>(a.xraw + (size_t)n * K + k0), f);
+          unpack8(*reinterpret_cast<const uint4 *>(a.norm_w + k0), g);
+          const float inv = s_inv[n];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) f[q] = rbf(__fmul_rn(rbf(__fmul_rn(f[q], inv)), g[q]));      // .type_as(x), then * weight
+          u.x = (uint32_t)f2bits(f[0]) | ((uint32_t)f2bits(f[1]) << 16); u.y = (uint32_t)f2bits(f[2]) | ((uint32_t)f2bits(f[3]) << 16);
+          u.z = (uint32_t)f2bits(f[4]) | ((uint32_t)f2bits(f[5]) << 16); u.w = (uint32_t)f2bits(f[6]) | ((uint32_t)f2bits(f[7]) << 16);
+        }
+        *reinterpret_cast<uint4 *>(sB + (size_t)kb * BN * 128 + (size_t)n * 128 + (size_t)((c16 ^ (n & 7)) << 4)) = u;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(&xready_bar);
+    }
     ok = mbar_wait_bounded(&accum_bar, 0u);
     tc_fence_after();
     if (dbg && tid == 64) dbg[5] = clock64();
@@ -240,25 +314,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (is_final && ok) {
       const float *wsp = a.ws + (size_t)ntile_lin * nz * BN * DA_TC_BM;
       const int n_items = ncols_here * (DA_TC_BM / 8);
-#pragma unroll 1
-      for (int item = te; item < n_items; item += 128) {
-        const int n_l = item >> 4, g8 = (item & 15) * 8, row0 = tile_m * DA_TC_BM + g8;
-        if (row0 >= a.rows) continue;                                // rows is a multiple of 8
-        float acc[8];
-        if (nz > 1) {
-#pragma unroll
-          for (int i2 = 0; i2 < 8; ++i2) acc[i2] = 0.f;
-#pragma unroll 4
-          for (int zz = 0; zz < nz; ++zz) {                          // partials in split order
-            const float4 *pz = reinterpret_cast<const float4 *>(wsp + ((size_t)zz * BN + n_l) * DA_TC_BM + g8);
-            const float4 p0 = __ldcg(pz), p1 = __ldcg(pz + 1);
-            acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w; acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
-          }
-        } else {
-          const float4 *pz = reinterpret_cast<const float4 *>(stg + n_l * DA_TC_BM + g8);
-          const float4 p0 = pz[0], p1 = pz[1];
-          acc[0] = p0.x; acc[1] = p0.y; acc[2] = p0.z; acc[3] = p0.w; acc[4] = p1.x; acc[5] = p1.y; acc[6] = p1.z; acc[7] = p1.w;
-        }
+      // bias / residual / SwiGLU on the 8 rows [row0, row0 + 8) of column n_l, 16 contiguous bytes out
+      auto finish = [&](const float *acc, int n_l, int g8) {
+        const int row0 = tile_m * DA_TC_BM + g8;
+        if (row0 >= a.rows) return;                                  // rows is a multiple of 8
         float y[8];
         if (a.bias) {
           float bb[8]; unpack8(*reinterpret_cast<const uint4 *>(a.bias + row0), bb);
@@ -286,6 +345,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           u.x = (uint32_t)f2bits(y[0]) | ((uint32_t)f2bits(y[1]) << 16); u.y = (uint32_t)f2bits(y[2]) | ((uint32_t)f2bits(y[3]) << 16);
           u.z = (uint32_t)f2bits(y[4]) | ((uint32_t)f2bits(y[5]) << 16); u.w = (uint32_t)f2bits(y[6]) | ((uint32_t)f2bits(y[7]) << 16);
           *reinterpret_cast<uint4 *>(a.out + n * a.ld_out + row0) = u;
+        }
+      };
+      if (nz > 1) {
+        // split-K: the partials of TWO items (2 x nz x 32 bytes, nz <= 8) are requested before the first add, so the reduction costs one
+        // L2 round trip per pair of items instead of one per partial; they are added in split order (deterministic)
+#pragma unroll 1
+        for (int item = te; item < n_items; item += 256) {
+          const int item1 = item + 128; const bool two = item1 < n_items;
+          const int nl0 = item >> 4, g0 = (item & 15) * 8, nl1 = two ? item1 >> 4 : nl0, g1 = two ? (item1 & 15) * 8 : g0;
+          float4 p[2][8][2];
+#pragma unroll
+          for (int zz = 0; zz < 8; ++zz) {
+            if (zz < nz) {
+              const float4 *q0 = reinterpret_cast<const float4 *>(wsp + ((size_t)zz * BN + nl0) * DA_TC_BM + g0);
+              const float4 *q1 = reinterpret_cast<const float4 *>(wsp + ((size_t)zz * BN + nl1) * DA_TC_BM + g1);
+              p[0][zz][0] = __ldcg(q0); p[0][zz][1] = __ldcg(q0 + 1); p[1][zz][0] = __ldcg(q1); p[1][zz][1] = __ldcg(q1 + 1);
+            }
+          }
+#pragma unroll
+          for (int w2 = 0; w2 < 2; ++w2) {
+            if (w2 == 1 && !two) break;
+            float acc[8];
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) acc[i2] = 0.f;
+#pragma unroll
+            for (int zz = 0; zz < 8; ++zz) {
+              if (zz < nz) {
+                acc[0] += p[w2][zz][0].x; acc[1] += p[w2][zz][0].y; acc[2] += p[w2][zz][0].z; acc[3] += p[w2][zz][0].w;
+                acc[4] += p[w2][zz][1].x; acc[5] += p[w2][zz][1].y; acc[6] += p[w2][zz][1].z; acc[7] += p[w2][zz][1].w;
+              }
+            }
+            finish(acc, w2 ? nl1 : nl0, w2 ? g1 : g0);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int item = te; item < n_items; item += 128) {
+          const int n_l = item >> 4, g8 = (item & 15) * 8;
+          const float4 *pz = reinterpret_cast<const float4 *>(stg + n_l * DA_TC_BM + g8);
+          const float4 p0 = pz[0], p1 = pz[1];
+          const float acc[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          finish(acc, n_l, g8);
         }
       }
     }

@@ -84,6 +84,9 @@ struct MegaArgs {
   int *seq; int seq_stride, im_end_id;
   DAState *st; unsigned long long *tl; int tl_slots;
   unsigned long long *tl2;   // optional per-CTA stamps [phase][cta][staged, done] (DUALAR_TIMELINE=1): who is the slowest CTA of a phase?
+  // test hook (dualar_debug_sample): when set, the logits epilogues take the linear's output from these buffers instead of the dot
+  // product, so that penalty, statistics, candidate list and samplers of THIS kernel run on caller-supplied logits
+  const bf16 *force_slow, *force_fast;      // [vocab] / [(num_codebooks - 1) * fv], or null
   unsigned int *phase_ctr;   // running phase counter = source of the unit tags; NEVER reset (a request must not see the previous one's tags)
   // shared-memory plan
   int kmax, lg_rows, work_bytes, kv_bytes, ring_bytes;
@@ -201,9 +204,6 @@ __device__ __forceinline__ int atom_add_acq_rel_cta(volatile int *p, int v) {
 typedef BlockNamed<1, DA_M_CTHREADS> CBlock;           // the 512 compute threads
 __device__ __forceinline__ void cbar() { CBlock::sync(); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 #define DA_G_IPT 8   // fast heads: warps 0..3 of CTA 0 hold the <= 1024 logits, 8 per thread (named barrier 2)
 
@@ -787,6 +787,9 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
                 }
               } else if (FULL) {
                 float z = rbf(v);
+                if (d.epi == ME_SLOWLOGITS ? a.force_slow != nullptr : a.force_fast != nullptr) {
+                  if (live) z = d.epi == ME_SLOWLOGITS ? bf2f(a.force_slow[row]) : bf2f(a.force_fast[(size_t)(d.pos - 1) * a.fv + row]);
+                }
                 bool hit = false;
 #pragma unroll
                 for (int i = 0; i < DA_WIN; ++i) hit |= (__shfl_sync(0xffffffffu, pen_id, i) == row);

@@ -190,9 +190,13 @@ int dualar_set_option(dualar_engine *e, const char *name, double value);
  * scratch of the LAST slow layer executed: "qkv", "y", "h", "act" (bf16), plus "fast_x" / "fast_in". */
 int dualar_read_buffer(dualar_engine *e, const char *name, void *host_dst, int64_t n_bytes,
                        void *stream);
-/* test hook: run ONLY the sampler (inference.py:30-80) of head `head` on caller-supplied bf16 logits
+/* test hook: run the sampler (inference.py:30-80) of head `head` on caller-supplied bf16 logits
  * (vocab_size of them for head 0, min(1024, codebook_size) for a fast head).  Device pointers as in
- * dualar_step; writes the sampled index to out_token (1 int32, device). */
+ * dualar_step; writes the sampled index to out_token (1 int32, device).
+ * With option mega_kernel = 1 (the default) this runs ONE WHOLE STEP of the persistent decode kernel whose logits epilogues
+ * are fed the caller's logits, so the product path's penalty, statistics, candidate list and samplers are what is tested
+ * (the engine's KV row at the current position is overwritten: prefill again before decoding); with mega_kernel = 0 it runs
+ * the per-phase kernels' sampler. */
 int dualar_debug_sample(dualar_engine *e, int head, const void *logits, const int32_t *previous_tokens,
                         int64_t prev_row_stride, const float *temperature, const float *top_p,
                         const float *repetition_penalty, const void *noise, int32_t *out_token,

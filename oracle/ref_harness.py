@@ -1,8 +1,10 @@
 """ORACLE SUPPORT (test infrastructure) -- run the UNMODIFIED reference from /root/reference.
 
-Used only here in the build container (the GPU box has no /root/reference) to
-  * validate ``oracle/dualar_oracle.py`` bit-for-bit against the real thing, and
-  * generate the golden fixtures under ``tests/golden/`` (``tests/golden/make_golden.py``).
+Used to
+  * validate ``oracle/dualar_oracle.py`` bit-for-bit against the real thing (build container),
+  * generate the golden fixtures under ``tests/golden/`` (``tests/golden/make_golden.py``, build container), and
+  * time the reference's own CPU and ``torch.compile`` paths beside ours in ``bench.py`` (GPU box: from the copy
+    ``oracle/make_ref.py`` places under ``oracle/_ref/``, git-ignored, shipped with the snapshot).
 
 What has to be faked so the reference imports and loads without network or vocoder deps
 (SURVEY.md section 8c):
@@ -26,7 +28,17 @@ from pathlib import Path
 
 import torch
 
-REFERENCE_ROOT = Path(os.environ.get("FISH_TTS_REFERENCE", "/root/reference"))
+def _find_root() -> Path:
+    """/root/reference in the build container; oracle/_ref/ (the copy oracle/make_ref.py ships) on the GPU box"""
+    cands = [Path(os.environ["FISH_TTS_REFERENCE"])] if os.environ.get("FISH_TTS_REFERENCE") else []
+    cands += [Path("/root/reference"), Path(__file__).resolve().parent / "_ref"]
+    for c in cands:
+        if (c / "fish_tts" / "models" / "inference.py").exists():
+            return c
+    return cands[-1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -1,3 +1,4 @@
-timeout 300 ./build/gemm_tc_check > gpurun_out/r2_gemm_check.log 2>&1; echo "gemm rc $?" >> gpurun_out/r2_gemm_check.log; grep -v "^PASS" gpurun_out/r2_gemm_check.log | grep -v "prefill-like\|stamps" | tail -n 12
-timeout 900 python -m pytest tests/test_gpu_batch.py -q -s -m gpu > gpurun_out/r2_pytest_batch.log 2>&1; echo "batch rc $?" >> gpurun_out/r2_pytest_batch.log; tail -n 25 gpurun_out/r2_pytest_batch.log | cut -c1-300
-timeout 900 python tests/batch_time.py 32 8 > gpurun_out/r2_batch_time.log 2>&1; echo "time rc $?" >> gpurun_out/r2_batch_time.log; cat gpurun_out/r2_batch_time.log | cut -c1-400
+for cfgs in "X=1" "DUALAR_PDL=0" "DUALAR_TC_KSPLIT=1" "DUALAR_TC_KSPLIT=2" "DUALAR_TC_KSPLIT=4" "DUALAR_TC_STAGES=2" "DUALAR_TC_STAGES=4" "DUALAR_TC_FUSE_NORM=0" "DUALAR_BATCH_NSPLIT=1" "DUALAR_BATCH_NSPLIT=8"; do
+  echo "== $cfgs"; env BT_SKIP_PREFILL=1 $cfgs timeout 300 python tests/batch_time.py 32 2>&1 | grep "batched decode" | cut -c1-120
+done > gpurun_out/r2_batch_sweep.log 2>&1
+cat gpurun_out/r2_batch_sweep.log

@@ -123,6 +123,28 @@ def test_batch_invariance_and_slot_independence():
         assert torch.equal(slows_a[2][s], slows_b[4][s]) and torch.equal(fasts_a[2][s], fasts_b[4][s]), f"step {s}: logits depend on the batch"
 
 
+def test_fused_norm_gemm_equals_separate_norm_kernel(monkeypatch):
+    """the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>: RMSNorm applied while staging the activation tile in
+    shared memory); with DUALAR_TC_FUSE_NORM=0 a separate RMSNorm kernel runs in front of a TMA-fed GEMM.  Same formulas, same
+    summation order: tokens and logits must agree bit for bit."""
+    cfg = variant_configs()["s1like"]
+    sd = make_state_dict(cfg, seed=0)
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("DUALAR_TC_FUSE_NORM", fuse)
+        eng = DualAREngine(cfg, sd, device=0)
+        eng.batch_init(5, cfg.max_seq_len)
+        _, cols, slows, fasts = run_batch(eng, cfg, REQS, 8)
+        outs.append((cols, slows, fasts, int(eng.batch_read("launches")[0])))
+        eng.close()
+    (ca, sa, fa, la), (cb, sb, fb, lb) = outs
+    assert la < lb, f"fusing the norms must remove launches ({la} vs {lb})"
+    for sl in range(5):
+        assert (ca[sl] == cb[sl]).all()
+        for s in range(8):
+            assert torch.equal(sa[sl][s], sb[sl][s]) and torch.equal(fa[sl][s], fb[sl][s]), f"slot {sl} step {s}"
+
+
 def test_continuous_batching_refill_does_not_disturb_neighbours():
     cfg = variant_configs()["s1like"]
     sd = make_state_dict(cfg, seed=0)

@@ -210,34 +210,67 @@ def test_s1_mini_greedy_256_steps(s1):
 
 
 # ---- 1. the sampler alone -------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dist", ["peaky", "conditioned", "flat", "ties", "one_hot"])
-def test_sampler_exact_on_identical_logits(s1, dist):
-    cfg, m, eng, sd = s1
-    g = torch.Generator().manual_seed({"peaky": 1, "conditioned": 2, "flat": 3, "ties": 4, "one_hot": 5}[dist])
+@pytest.fixture(scope="module")
+def s1_per_phase():
+    cfg = s1_mini_config()
+    sd = make_state_dict(cfg, seed=0)
+    eng = DualAREngine(cfg, sd, device=0, options={"mega_kernel": 0})
+    yield cfg, eng
+    eng.close()
+
+
+def adversarial_logits(dist, n, cfg, head, g):
+    if dist == "peaky":
+        lg = torch.randn(n, generator=g) * 4.0
+    elif dist == "conditioned":
+        lg = torch.randn(n, generator=g) * 0.64
+        if head == 0:
+            lg[: cfg.semantic_begin_id] -= 8.0
+            lg[cfg.semantic_end_id + 1:] -= 8.0
+    elif dist == "flat":
+        lg = torch.randn(n, generator=g) * 0.3          # every logit is a candidate (> DA_CAND_CAP): whole-vocabulary fallback walk
+    elif dist == "ties":
+        lg = torch.randint(-3, 4, (n,), generator=g).float() * 0.5
+    elif dist == "mid6000":
+        # 4096 < candidates <= DA_CAND_CAP (8192): the persistent kernel's binned sampler declines (fallback), the per-phase
+        # kernels' bisection sampler still takes the list
+        lg = torch.full((n,), -9.0)
+        k = min(6000, n // 2)
+        lg[torch.randperm(n, generator=g)[:k]] = torch.randn(k, generator=g) * 0.5
+    elif dist == "plateau":
+        # few candidates, but the nucleus wants more than the list holds (mass just below the candidate threshold): the list
+        # samplers must notice and hand over to the whole-vocabulary walk
+        lg = torch.full((n,), -6.5) + torch.randn(n, generator=g) * 0.05
+        k = min(300, n // 4)
+        lg[torch.randperm(n, generator=g)[:k]] = torch.randn(k, generator=g) * 0.1
+    else:
+        lg = torch.full((n,), -5.0); lg[int(torch.randint(0, n, (1,), generator=g))] = 9.0
+    return lg.bfloat16()
+
+
+@pytest.mark.parametrize("path", ["persistent_kernel", "per_phase_kernels"])
+@pytest.mark.parametrize("dist", ["peaky", "conditioned", "flat", "ties", "one_hot", "mid6000", "plateau"])
+def test_sampler_exact_on_identical_logits(s1, s1_per_phase, path, dist):
+    """the samplers of BOTH kernel paths against the reference sampler on identical adversarial logits, bit-exact.
+    persistent_kernel: dualar_debug_sample runs one whole step of mega_kernel with its logits epilogues fed these logits, i.e. the
+    product path's penalty + per-CTA statistics + ordered candidate list + sample_binned / sample_sorted / sample_fallback<CBlock>
+    (slow head) and the 16-warp binned sampler (fast heads)."""
+    cfg = s1[0]
+    eng = s1[2] if path == "persistent_kernel" else s1_per_phase[1]
+    g = torch.Generator().manual_seed({"peaky": 1, "conditioned": 2, "flat": 3, "ties": 4, "one_hot": 5, "mid6000": 6, "plateau": 7}[dist])
     V, fv = cfg.vocab_size, 1024
     for trial, (T, p, rp) in enumerate([(0.7, 0.8, 1.1), (0.7, 0.7, 1.5), (1.0, 1.0, 1.0), (0.7, 1e-9, 1.0), (0.3, 0.5, 1.2), (1.5, 0.95, 0.8)]):
         for head in (0, 3):
             n = V if head == 0 else fv
-            if dist == "peaky":
-                lg = torch.randn(n, generator=g) * 4.0
-            elif dist == "conditioned":
-                lg = torch.randn(n, generator=g) * 0.64
-                if head == 0:
-                    lg[: cfg.semantic_begin_id] -= 8.0
-                    lg[cfg.semantic_end_id + 1:] -= 8.0
-            elif dist == "flat":
-                lg = torch.randn(n, generator=g) * 0.3          # nucleus far wider than the candidate list -> fallback walk
-            elif dist == "ties":
-                lg = torch.randint(-3, 4, (n,), generator=g).float() * 0.5
-            else:
-                lg = torch.full((n,), -5.0); lg[int(torch.randint(0, n, (1,), generator=g))] = 9.0
-            lg = lg.bfloat16()
+            lg = adversarial_logits(dist, n, cfg, head, g)
             window = torch.randint(0, fv, (cfg.num_codebooks + 1, 16), generator=g, dtype=torch.int32).cuda()
+            if head == 0 and dist in ("conditioned", "mid6000"):      # put the penalised ids where the mass is
+                window[:, 0] = torch.topk(lg.float(), cfg.num_codebooks + 1).indices.to(torch.int32).cuda()
             blk = eng.step_noise(5, trial)
             t = [torch.tensor(v, device="cuda", dtype=torch.float) for v in (T, p, rp)]
             mine = eng.debug_sample(head, lg, window, *t, blk)
             ref = oracle_sample(cfg, lg, head, window, T, p, rp, blk)
-            assert mine == ref, f"{dist} head {head} T={T} p={p} rp={rp}: {mine} != {ref}"
+            assert mine == ref, f"{path} {dist} head {head} T={T} p={p} rp={rp}: {mine} != {ref}"
 
 
 # ---- 3. the engine-owned loop ----------------------------------------------------------------------------------
