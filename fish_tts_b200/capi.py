@@ -19,7 +19,7 @@ SYMBOLS = [
     "dualar_generate", "dualar_seed", "dualar_fill_noise", "dualar_set_noise", "dualar_read_buffer",
     "dualar_launches_per_step", "dualar_weight_bytes", "dualar_debug_sample", "dualar_set_option",
     "dualar_batch_init", "dualar_batch_prefill", "dualar_batch_decode", "dualar_batch_collect", "dualar_batch_release",
-    "dualar_batch_read",
+    "dualar_batch_read", "dualar_decode_async", "dualar_wait",
 ]
 
 _I32_FIELDS = [
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
         "dualar_batch_collect": (C.c_int, [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), vp]),
         "dualar_batch_release": (C.c_int, [vp, C.c_int]),
         "dualar_batch_read": (C.c_int, [vp, C.c_char_p, vp, C.c_int64, vp]),
+        "dualar_decode_async": (C.c_int, [vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]),
+        "dualar_wait": (C.c_int, [vp, C.c_int, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

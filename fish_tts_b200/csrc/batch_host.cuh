@@ -40,7 +40,10 @@ struct dualar_tc {
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
   int ksplit_override = 0, stages_override = 0;
-  bool fuse_norm = true;      // DUALAR_TC_FUSE_NORM=0: separate RMSNorm kernels in front of the decode GEMMs (cross-check)
+  bool fuse_norm = false;     // DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>) instead of a separate
+                              // RMSNorm kernel in front of them.  Bit-identical (tests/test_gpu_batch.py), 145 kernels fewer per step -- and measured
+                              // SLOWER on B200 (5.45 vs 4.83 ms per bs-32 step): every CTA re-reads the full rows for the statistics and stages the
+                              // operand behind the dependency wait, which costs more than the ~3 us a separate 8-CTA kernel adds to the chain
 };
 
 static int tc_map(dualar_engine *e, const void *p, int rows, int K, int box, const CUtensorMap **out) {
@@ -92,7 +95,7 @@ static int tc_init(dualar_engine *e) {
   int rc;
   if ((rc = tc_configure<32>()) || (rc = tc_configure<64>()) || (rc = tc_configure<128>()) || (rc = tc_configure<256>())) return rc;
   CU(cudaFuncSetAttribute(gemm_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  { const char *v = getenv("DUALAR_TC_FUSE_NORM"); e->tc->fuse_norm = !(v && v[0] == '0'); }
+  { const char *v = getenv("DUALAR_TC_FUSE_NORM"); e->tc->fuse_norm = v && v[0] == '1'; }
   e->tc->ws_bytes = (size_t)48 << 20;
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <tuple>
@@ -75,6 +76,8 @@ struct dualar_engine {
   dualar_tc *tc = nullptr; dualar_batch *batch = nullptr;
   int prefill_mode = 0;          // option prefill_mode: 0 = whole prompt through the tensor-core GEMMs, 1 = one position per launch (round-1 path, cross-check)
   int prefill_launches = 0;      // kernels the last tensor-core prefill launched
+  bool prefix_reuse = true, kv_dirty = true; std::vector<int32_t> prev_prompt; int prev_T = 0, last_reuse = 0;   // KV reuse across requests (dualar_prefill)
+  cudaEvent_t ev_ring[8] = {nullptr}; int ev_next = 0; int stream_cols = 0, steps_enqueued = 0;      // dualar_decode_async
   bool batch_keep_raw = true;    // batched decode keeps a copy of the raw logits for dualar_batch_read
   bool l2_window = false; float l2_hit_ratio = 0.0f; size_t l2_persist_bytes = 0;   // DUALAR_L2_WINDOW / DUALAR_L2_HIT: access-policy window over the fast stack
   bool use_mega = true;   // option mega_kernel / DUALAR_MEGA: 0 = one kernel per phase (the cross-check path)
@@ -697,6 +700,7 @@ extern "C" void dualar_destroy(dualar_engine *e) {
   if (e->h_seq) cudaFreeHost(e->h_seq);
   if (e->h_st) cudaFreeHost(e->h_st);
   if (e->h_err_sticky) cudaFreeHost(e->h_err_sticky);
+  for (auto &ev : e->ev_ring) if (ev) cudaEventDestroy(ev);
   if (e->arena) cudaFree(e->arena);
   delete e->ma_step; delete e->ma_prefill;
   delete e;
@@ -720,7 +724,8 @@ extern "C" int dualar_set_option(dualar_engine *e, const char *name, double valu
     if (e->finalized) { CU(cudaSetDevice(e->device)); CU(cudaMemcpy(&e->st->cpu_sem, &e->cpu_sem, sizeof(int), cudaMemcpyHostToDevice)); }
     return 0;
   }
-  if (!strcmp(name, "prefill_mode")) { e->prefill_mode = value != 0.0; return 0; }
+  if (!strcmp(name, "prefill_mode")) { e->prefill_mode = value != 0.0; e->kv_dirty = true; return 0; }
+  if (!strcmp(name, "prefix_reuse")) { e->prefix_reuse = value != 0.0; return 0; }
   if (!strcmp(name, "mega_kernel")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "mega_kernel must be set before dualar_finalize");
     e->use_mega = value != 0.0; return 0;
@@ -764,7 +769,7 @@ extern "C" int dualar_step(dualar_engine *e, const int32_t *x, const int32_t *in
   load_step_kernel<<<1, 256, 0, s>>>(a); CU(cudaGetLastError());
   CU(cudaGraphLaunch(e->g_step, s));
   store_step_kernel<<<1, 32, 0, s>>>(e->st, out, e->c.num_codebooks + 1, e->d_err_sticky); CU(cudaGetLastError());
-  e->request_open = false;
+  e->request_open = false; e->kv_dirty = true;
   // the step is asynchronous, like the reference's compiled step: a device fault raised by an EARLIER step (the kernels record it
   // in a sticky word that store_step_kernel copies to mapped host memory) is reported by the next call
   if (e->h_err_sticky && *e->h_err_sticky) {
@@ -802,6 +807,7 @@ extern "C" int dualar_debug_sample(dualar_engine *e, int head, const void *logit
   cudaStream_t s = (cudaStream_t)stream;
   LoadStepArgs la{e->st->tok_in, &e->st->pos, prev, prev_stride, temperature, top_p, rep, (const bf16 *)noise, c.num_codebooks + 1, e->st};
   load_step_kernel<<<1, 256, 0, s>>>(la); CU(cudaGetLastError());
+  e->kv_dirty = true;
   if (e->use_mega) {
     // the PRODUCT path's sampler: one whole decode step of the persistent kernel whose logits epilogues are fed the caller's logits
     // (MegaArgs::force_slow / force_fast), so the repetition penalty, the per-CTA statistics, the ordered candidate list, the binned /
@@ -863,6 +869,21 @@ extern "C" int dualar_prefill(dualar_engine *e, const int32_t *prompt, int T, in
   CU(cudaMemcpy2DAsync(e->seq, (size_t)c.max_seq_len * sizeof(int), e->h_seq, (size_t)T * sizeof(int), (size_t)T * sizeof(int), R, cudaMemcpyHostToDevice, s));
   DAState *h = e->h_st; memset(h, 0, sizeof(*h));
   const bool tc_pf = e->prefill_mode == 0 && T > 1;
+  // KV reuse: the reference re-runs the whole prompt for every utterance although the VoiceProfile part of it
+  // never changes (synthesizer.py:363-377, 415-429).  The KV rows of the positions this prompt SHARES with the previous
+  // request's prompt are still in the cache -- decode only ever writes rows >= the prompt length -- so the tensor-core prefill
+  // starts at the first differing position.
+  int reuse = 0;
+  if (tc_pf && e->prefix_reuse && !e->kv_dirty) {
+    const int lim = std::min(T - 1, e->prev_T);      // the last prompt position always goes through the decode step
+    while (reuse < lim) {
+      bool same = true;
+      for (int r = 0; r < R && same; ++r) same = prompt[(size_t)r * T + reuse] == e->prev_prompt[(size_t)r * e->prev_T + reuse];
+      if (!same) break;
+      ++reuse;
+    }
+  }
+  e->prev_prompt.assign(prompt, prompt + (size_t)R * T); e->prev_T = T; e->kv_dirty = !tc_pf; e->last_reuse = reuse;
   h->pos = tc_pf ? T - 1 : 0; h->n_gen = 0; h->max_gen = max_new; h->prompt_len = T; h->loop_mode = 1; h->use_penalty = 0;
   h->temperature = temperature; h->top_p = top_p; h->rep_penalty = rep; h->seed = e->seed; h->step_ctr = 0;
   h->cpu_sem = e->cpu_sem;
@@ -873,10 +894,10 @@ extern "C" int dualar_prefill(dualar_engine *e, const int32_t *prompt, int T, in
   if (tc_pf) {
     // the reference prefills the whole prompt in ONE forward (inference.py:353-362); here positions [0, T-1) go through the
     // tensor-core GEMMs (KV rows only, no head), the last position through the decode step below, which samples the first token
-    int rc = tc_prefill_own(e, 0, T - 1, s); if (rc) return rc;
+    int rc = tc_prefill_own(e, reuse, T - 1, s); if (rc) return rc;
   } else for (int t = 0; t + 1 < T; ++t) CU(cudaGraphLaunch(e->g_prefill, s));
   CU(cudaGraphLaunch(e->g_step, s));
-  e->prompt_len = T; e->max_gen = max_new; e->request_open = true;
+  e->prompt_len = T; e->max_gen = max_new; e->request_open = true; e->stream_cols = 0; e->steps_enqueued = 0;
   return 0;
 }
 
@@ -885,7 +906,50 @@ extern "C" int dualar_decode(dualar_engine *e, int n_steps, void *stream) {
   if (!e->request_open) return fail(DUALAR_ESTATE, "dualar_decode without a prefilled request");
   CU(cudaSetDevice(e->device));
   for (int i = 0; i < n_steps; ++i) CU(cudaGraphLaunch(e->g_step, (cudaStream_t)stream));
+  e->steps_enqueued += n_steps;
   return 0;
+}
+
+// ---- streaming hand-off (generate_streaming, inference.py:643-738; synthesize_stream, synthesizer.py:483-584) ---------------------
+// n_steps decode steps, then -- on the same stream, so without any host wait in between -- an asynchronous copy of the columns
+// they produced into a caller-owned (pinned) HOST buffer and of (n_gen, done) into host_state, then an event.  The host can enqueue
+// the NEXT chunk before it waits for this one, so the decode stream never idles while the codec consumes a chunk.
+extern "C" int dualar_decode_async(dualar_engine *e, int n_steps, int32_t *host_out, int32_t *host_state, void *stream, int *ticket) {
+  if (!e || !host_out || !host_state || !ticket) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->request_open) return fail(DUALAR_ESTATE, "dualar_decode_async without a prefilled request");
+  if (n_steps < 0) return fail(DUALAR_EINVAL, "n_steps < 0");
+  const dualar_config &c = e->c; const int R = c.num_codebooks + 1;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // column j of the request lives at seq[:, prompt_len + j]; the prefill call itself produced column 0.  Columns handed out so
+  // far: stream_cols; columns that exist once these steps have run: at most 1 + steps enqueued (fewer after <|im_end|>: the host
+  // reads n_gen from host_state to know how many of the copied columns are real)
+  const int first = e->stream_cols;
+  int avail = 1 + e->steps_enqueued + n_steps; if (avail > e->max_gen) avail = e->max_gen;
+  int n = avail - first; if (n < 0) n = 0; if (n > n_steps + 1) n = n_steps + 1;
+  for (int i = 0; i < n_steps; ++i) CU(cudaGraphLaunch(e->g_step, s));
+  e->steps_enqueued += n_steps;
+  if (n > 0) CU(cudaMemcpy2DAsync(host_out, (size_t)(n_steps + 1) * sizeof(int), e->seq + e->prompt_len + first, (size_t)c.max_seq_len * sizeof(int),
+                                  (size_t)n * sizeof(int), R, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(host_state, &e->st->n_gen, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(host_state + 1, &e->st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(host_state + 2, &e->st->err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  host_state[3] = first; host_state[4] = n;
+  e->stream_cols = first + n;
+  const int t = e->ev_next; e->ev_next = (e->ev_next + 1) % 8;
+  if (!e->ev_ring[t]) CU(cudaEventCreateWithFlags(&e->ev_ring[t], cudaEventDisableTiming));
+  CU(cudaEventRecord(e->ev_ring[t], s));
+  *ticket = t;
+  return 0;
+}
+// block = 0: returns 0 when the chunk has landed, 1 when it has not; block = 1: waits for it
+extern "C" int dualar_wait(dualar_engine *e, int ticket, int block) {
+  if (!e || ticket < 0 || ticket >= 8 || !e->ev_ring[ticket]) return fail(DUALAR_EINVAL, "bad ticket");
+  if (block) { CU(cudaEventSynchronize(e->ev_ring[ticket])); return 0; }
+  cudaError_t q = cudaEventQuery(e->ev_ring[ticket]);
+  if (q == cudaSuccess) return 0;
+  if (q == cudaErrorNotReady) return 1;
+  return fail(DUALAR_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
 }
 
 extern "C" int dualar_collect(dualar_engine *e, int32_t *out, int cap, int *n_tokens, int *finished, void *stream) {
@@ -943,6 +1007,10 @@ extern "C" int dualar_read_buffer(dualar_engine *e, const char *name, void *dst,
   else if (!strcmp(name, "tokens")) { src = e->st->tok_out; avail = (int64_t)(c.num_codebooks + 1) * 4; }
   else if (!strcmp(name, "nucleus")) { src = e->st->nucleus; avail = (int64_t)c.num_codebooks * 4; }
   else if (!strcmp(name, "n_cand")) { src = &e->st->n_cand; avail = 4; }
+  else if (!strcmp(name, "prefix_reused") || !strcmp(name, "prefill_launches")) {      // host-side counters of the last dualar_prefill
+    if (nbytes < 4) return fail(DUALAR_EINVAL, "4 bytes needed");
+    *(int *)dst = !strcmp(name, "prefix_reused") ? e->last_reuse : e->prefill_launches; return 0;
+  }
   else if (!strcmp(name, "qkv")) { src = e->qkv; avail = (int64_t)(c.n_head + 2 * c.n_local_heads) * c.head_dim * 2; }
   else if (!strcmp(name, "y")) { src = e->y; avail = (int64_t)c.n_head * c.head_dim * 2; }
   else if (!strcmp(name, "h")) { src = e->h; avail = (int64_t)c.dim * 2; }

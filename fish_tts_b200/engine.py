@@ -148,6 +148,48 @@ class DualAREngine:
     def decode(self, n_steps: int):
         capi.check(self.lib.dualar_decode(self._h, int(n_steps), self._stream()))
 
+    def stream(self, prompt, max_new_tokens: int, temperature: float = 0.7, top_p: float = 0.7, repetition_penalty: float = 1.5,
+               first_chunk: int = 10, chunk: int = 20):
+        """Generator over host arrays (C+1, n) of freshly generated columns -- the hand-off ``synthesize_stream`` needs
+        (synthesizer.py:548-559: first ``min_first_chunk`` columns, then ``chunk_tokens`` at a time).
+
+        Each chunk is ``dualar_decode_async``: decode steps, then an asynchronous copy of the new columns into a pinned host buffer
+        and an event, all on the decode stream; chunk k + 1 is enqueued BEFORE the host waits for chunk k, so the GPU keeps decoding
+        while the caller (the vocoder thread) consumes a chunk.  No blocking ``collect()`` on the decode stream."""
+        self.prefill(prompt, max_new_tokens, temperature, top_p, repetition_penalty)
+        limit = int(max_new_tokens) if max_new_tokens and max_new_tokens > 0 else self.cfg.max_seq_len
+        size = max(first_chunk, chunk) + 1
+        bufs = [torch.zeros((self.rows, size), dtype=torch.int32).pin_memory() for _ in range(3)]
+        states = [torch.zeros(5, dtype=torch.int32).pin_memory() for _ in range(3)]
+        pending = []      # (ticket, buffer index, pitch)
+
+        def enqueue(n_steps, k):
+            t = C.c_int(0)
+            capi.check(self.lib.dualar_decode_async(self._h, int(n_steps), bufs[k].data_ptr(), states[k].data_ptr(), self._stream(), C.byref(t)))
+            pending.append((t.value, k, n_steps + 1))
+
+        enqueue(first_chunk - 1, 0)          # the prefill call already produced column 0
+        k, sent, enq = 1, 0, first_chunk
+        if enq < limit:
+            enqueue(min(chunk, limit - enq), k); enq += min(chunk, limit - enq); k = (k + 1) % 3
+        while pending:
+            ticket, bi, pitch = pending.pop(0)
+            capi.check(self.lib.dualar_wait(self._h, ticket, 1))
+            n_gen, done, err, first, ncopied = (int(v) for v in states[bi])
+            if err:
+                raise capi.DualarError(-5, f"device fault flag {err} during streaming decode")
+            n_valid = max(0, min(n_gen, first + ncopied) - first)
+            if n_valid:
+                flat = bufs[bi].view(-1)[: self.rows * pitch].view(self.rows, pitch)
+                yield flat[:, :n_valid].numpy().copy()
+                sent += n_valid
+            if done:
+                for tk, _, _ in pending:      # chunks enqueued past the end are no-ops on the device; drain their events
+                    capi.check(self.lib.dualar_wait(self._h, tk, 1))
+                return
+            if enq < limit and len(pending) < 2:
+                enqueue(min(chunk, limit - enq), k); enq += min(chunk, limit - enq); k = (k + 1) % 3
+
     def collect(self, capacity: Optional[int] = None):
         """-> (tokens (C+1, n) int32 ndarray, finished)."""
         cap = capacity or self.cfg.max_seq_len
@@ -269,7 +311,7 @@ class DualAREngine:
             "slow_logits": ((cfg.vocab_size,), torch.bfloat16), "slow_logits_raw": ((cfg.vocab_size,), torch.bfloat16),
             "hidden": ((cfg.dim,), torch.bfloat16),
             "fast_logits": ((cfg.num_codebooks - 1, self.fast_vocab), torch.bfloat16),
-            "tokens": ((self.rows,), torch.int32), "n_cand": ((1,), torch.int32), "nucleus": ((cfg.num_codebooks,), torch.int32),
+            "tokens": ((self.rows,), torch.int32), "n_cand": ((1,), torch.int32), "prefix_reused": ((1,), torch.int32), "prefill_launches": ((1,), torch.int32), "nucleus": ((cfg.num_codebooks,), torch.int32),
             "qkv": (((cfg.n_head + 2 * cfg.n_local_heads) * cfg.head_dim,), torch.bfloat16),
             "y": ((cfg.n_head * cfg.head_dim,), torch.bfloat16), "h": ((cfg.dim,), torch.bfloat16),
             "act": ((cfg.intermediate_size,), torch.bfloat16), "fast_x": ((cfg.fast_dim,), torch.bfloat16),

@@ -175,9 +175,12 @@ def generate(*, model, prompt: torch.Tensor, max_new_tokens: int, audio_masks=No
 
 @torch.inference_mode()
 def generate_streaming(*, model, prompt: torch.Tensor, max_new_tokens: int, audio_masks=None, audio_parts=None,
-                       decode_one_token: Callable = decode_one_token_ar, chunk: int = 4, **sampling_kwargs) -> Iterator[torch.Tensor]:
+                       decode_one_token: Callable = decode_one_token_ar, first_chunk: int = 10, chunk: int = 20,
+                       **sampling_kwargs) -> Iterator[torch.Tensor]:
     """inference.py:643-738: yields (C, 1) code columns as they are produced (the semantic row is dropped, :721, 271).
-    ``chunk`` decode steps are enqueued per host round trip; the first column is delivered right after the prefill."""
+    Columns leave the device in chunks (``first_chunk`` then ``chunk`` columns, the sizes ``synthesize_stream`` batches for the
+    vocoder, synthesizer.py:548-559) through pinned host buffers with an event per chunk; the next chunk's decode steps are
+    already enqueued while this one is consumed (``DualAREngine.stream``)."""
     eng = _engine_of(model)
     cfg = model.config
     T = prompt.size(1)
@@ -186,15 +189,10 @@ def generate_streaming(*, model, prompt: torch.Tensor, max_new_tokens: int, audi
     if not max_new_tokens or T + max_new_tokens > cfg.max_seq_len:
         max_new_tokens = cfg.max_seq_len - T
     t, p, rp = _sampling(sampling_kwargs)
-    eng.prefill(prompt.to(torch.int32).cpu().numpy(), max_new_tokens, t, p, rp)
-    sent, finished = 0, False
-    while not finished:
-        cols, finished = eng.collect()
-        for j in range(sent, cols.shape[1]):
-            yield torch.from_numpy(cols[1:, j: j + 1].copy()).to(prompt.device)
-        sent = cols.shape[1]
-        if not finished:
-            eng.decode(min(chunk, max_new_tokens - sent))
+    for cols in eng.stream(prompt.to(torch.int32).cpu().numpy(), max_new_tokens, t, p, rp, first_chunk=first_chunk, chunk=chunk):
+        block = torch.from_numpy(cols[1:]).to(prompt.device)
+        for j in range(block.size(1)):
+            yield block[:, j: j + 1]
 
 
 # ---- drop-in beneath the unmodified reference -------------------------------------------------------------------------
@@ -223,6 +221,18 @@ def install(inference_module=None):
         dev = next(model.parameters()).device
         model._dualar_engine = DualAREngine(cfg, sd, device=dev, freqs_cis=model.freqs_cis, fast_freqs_cis=model.fast_freqs_cis)
         model._dualar_config = cfg
+        # the engine holds its own repacked copy of every weight: release the reference module's (1.4 GB for s1-mini, plus the
+        # max_seq_len^2 causal mask) instead of keeping both on the GPU.  The module stays in charge of config / tokenizer / prompt
+        # building only; its forward is never called again (generate / generate_streaming / decode_one_token_ar are replaced).
+        del sd
+        for prm in model.parameters():
+            prm.data = torch.empty(0, device=dev, dtype=prm.dtype)
+        for name, buf in list(model.named_buffers()):
+            if buf.numel() > 1024:
+                mod, _, leaf = name.rpartition(".")
+                setattr(model.get_submodule(mod) if mod else model, leaf, torch.empty(0, device=dev, dtype=buf.dtype))
+        if dev.type == "cuda":
+            torch.cuda.empty_cache()
         return model, decode_one_token_ar
 
     def _cfg_model(model):

@@ -77,6 +77,44 @@ def run_rank(generate_fn: Callable[[Utterance], np.ndarray], utterances: Sequenc
     return res
 
 
+def run_rank_batched(engine, utterances: Sequence[Utterance], rank: int, world: int, max_batch: int, poll_steps: int = 16,
+                     sync: Optional[Callable[[], None]] = None, seed_base: int = 0) -> RankResult:
+    """This rank's share through the engine's request slots with CONTINUOUS BATCHING: every free slot is refilled from the queue
+    (tensor-core prefill), ``poll_steps`` batched decode steps run without a host round trip, finished slots are collected and
+    released.  ``engine`` is a DualAREngine on which ``batch_init(max_batch, ...)`` has been called.  Longest-first within the
+    rank keeps the tail short.  One device -> host read of the ``done`` flags per ``poll_steps`` steps."""
+    mine = partition_longest_first([u.cost for u in utterances], world)[rank]
+    queue = sorted(mine, key=lambda i: (-utterances[i].cost, i))
+    res = RankResult(rank=rank)
+    slots: dict[int, int] = {}          # slot -> utterance index
+    free = list(range(max_batch))
+    if sync:
+        sync()
+    t0 = time.perf_counter()
+    while queue or slots:
+        while free and queue:
+            i = queue.pop(0)
+            u = utterances[i]
+            sl = free.pop()
+            engine.batch_prefill(sl, u.prompt, u.max_new_tokens, u.temperature, u.top_p, u.repetition_penalty, seed=seed_base + u.uid)
+            slots[sl] = i
+        engine.batch_decode(poll_steps)
+        done = engine.batch_read("done").numpy()
+        for sl in [s for s in slots if done[s]]:
+            u = utterances[slots.pop(sl)]
+            out, fin = engine.batch_collect(sl)
+            assert fin
+            engine.batch_release(sl)
+            free.append(sl)
+            res.uids.append(u.uid)
+            res.codes[u.uid] = out
+            res.tokens += int(out.shape[1])
+    if sync:
+        sync()
+    res.seconds = time.perf_counter() - t0
+    return res
+
+
 def aggregate(res: RankResult, dist=None, device=None) -> dict:
     """Whole-job numbers: total tokens over the MAX rank time (never a sum of per-rank rates)."""
     import torch

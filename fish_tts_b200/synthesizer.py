@@ -156,7 +156,8 @@ class FishTTS:
             buf, first = [], True
             for col in inference.generate_streaming(model=self._model, prompt=prompt, max_new_tokens=kwargs.get("max_tokens", 2048),
                                                     temperature=kwargs.get("temperature", 0.7), top_p=kwargs.get("top_p", 0.8),
-                                                    repetition_penalty=kwargs.get("repetition_penalty", 1.1)):
+                                                    repetition_penalty=kwargs.get("repetition_penalty", 1.1),
+                                                    first_chunk=min_first_chunk, chunk=chunk_tokens):
                 col = col.clone()
                 col[col < 0] = 0                                  # inference.py:817-818
                 buf.append(col)

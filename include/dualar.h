@@ -118,6 +118,16 @@ int dualar_prefill(dualar_engine *e, const int32_t *prompt, int prompt_len, int 
 int dualar_decode(dualar_engine *e, int n_steps, void *stream);
 int dualar_collect(dualar_engine *e, int32_t *out, int out_capacity, int *n_tokens, int *finished,
                    void *stream);
+/* Streaming hand-off (generate_streaming, inference.py:643-738 / synthesize_stream, synthesizer.py:483-584): `n_steps` more
+ * decode steps, then -- on the same stream, with no host wait in between -- an asynchronous copy of every column produced
+ * and not yet handed out into the caller's (pinned) HOST buffer host_out, laid out (num_codebooks+1, n_steps+1) int32
+ * row-major, and an event.  host_state is 5 int32 in (pinned) host memory: [0] columns generated so far, [1] request
+ * finished, [2] device fault flag -- valid once dualar_wait reports the ticket -- and, set before the call returns, [3]
+ * index of the first column of this chunk, [4] columns copied (some may lie beyond [0] after <|im_end|>).  The host can
+ * enqueue the next chunk before waiting for this one, so the decode stream never idles while the codec consumes a chunk.
+ * dualar_wait: block = 1 waits for the chunk, block = 0 polls (returns 1 while it has not landed). */
+int dualar_decode_async(dualar_engine *e, int n_steps, int32_t *host_out, int32_t *host_state, void *stream, int *ticket);
+int dualar_wait(dualar_engine *e, int ticket, int block);
 /* prefill + decode to the end + collect in one call (what `generate` does). */
 int dualar_generate(dualar_engine *e, const int32_t *prompt, int prompt_len, int max_new_tokens,
                     float temperature, float top_p, float repetition_penalty, int32_t *out,
@@ -176,6 +186,8 @@ int dualar_set_noise(dualar_engine *e, const void *noise, int64_t n_steps);
  * "prefill_mode" (0/1, default 0): 0 = dualar_prefill pushes prompt positions [0, T-1) through the tensor-core GEMMs in chunks of
  *     256 positions (the reference prefills in one forward, inference.py:353-362); 1 = one position per launch through the decode
  *     kernel (the round-1 path, kept as a cross-check).
+ * "prefix_reuse" (0/1, default 1): dualar_prefill keeps the KV rows of the prompt positions shared with the previous request's
+ *     prompt (the prefilled VoiceProfile references, synthesizer.py:363-377) and prefills only from the first differing position.
  * "mega_kernel" (0/1, before finalize; default 1): run the whole decode step as ONE persistent cooperative
  *     kernel (csrc/mega.cuh) instead of one kernel per phase (kept as a cross-check).  The two sum their dot
  *     products in different fp32 orders (tensor-core chunks vs. FMA chains), so logits agree to bf16 rounding,
@@ -187,7 +199,9 @@ int dualar_set_option(dualar_engine *e, const char *name, double value);
  * (before it), "hidden" (dim bf16, the un-normalised last-layer output), "fast_logits"
  * ((num_codebooks-1) x fast_vocab bf16, before the penalty), "tokens" (num_codebooks+1 int32),
  * "nucleus" (num_codebooks int32: how many candidates survived top-p per head); and the per-layer
- * scratch of the LAST slow layer executed: "qkv", "y", "h", "act" (bf16), plus "fast_x" / "fast_in". */
+ * scratch of the LAST slow layer executed: "qkv", "y", "h", "act" (bf16), plus "fast_x" / "fast_in"; and two host-side
+ * counters of the last dualar_prefill (1 int32 each): "prefix_reused" (prompt positions whose KV rows were kept),
+ * "prefill_launches" (kernels the tensor-core prefill launched). */
 int dualar_read_buffer(dualar_engine *e, const char *name, void *host_dst, int64_t n_bytes,
                        void *stream);
 /* test hook: run the sampler (inference.py:30-80) of head `head` on caller-supplied bf16 logits

@@ -68,6 +68,9 @@ class OracleModel:
     dtype: torch.dtype
     freqs_cis: Tensor = None
     fast_freqs_cis: Tensor = None
+    accum: Optional[torch.dtype] = None           # None: the reference's own F.linear (cuBLAS / MKL accumulation order).  torch.float64:
+                                                  # "ground truth" -- every linear accumulated in fp64 and rounded to the model dtype at the
+                                                  # same point, i.e. the reference's rounding points WITHOUT any fp32 summation-order noise
     kv: list = field(default_factory=list)        # per slow layer [k_cache, v_cache]
     fast_kv: list = field(default_factory=list)   # per fast layer [k_cache, v_cache]
     max_seq_len: int = -1
@@ -107,6 +110,15 @@ class OracleModel:
 # layers
 # --------------------------------------------------------------------------------------
 
+def linear(m: "OracleModel", x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+    """nn.Linear as the reference calls it (m.accum is None), or the same contraction accumulated in m.accum (tests only: the
+    yardstick against which both our kernels and torch's own bf16 GEMMs are measured, tests/test_gpu_parity.py)."""
+    if m.accum is None:
+        return F.linear(x, w, b)
+    y = F.linear(x.to(m.accum), w.to(m.accum), None if b is None else b.to(m.accum))
+    return y.to(x.dtype)
+
+
 def rms_norm(x: Tensor, weight: Tensor, eps: float) -> Tensor:
     """llama.py:172-177 -- fp32 normalise, round to x.dtype, THEN multiply by weight."""
     xf = x.float()
@@ -143,7 +155,7 @@ def attention(m: OracleModel, prefix: str, kv, x, freqs_cis, mask, input_pos,
     w = m.w
     bsz, seqlen, _ = x.shape
     q_size, kv_size = n_head * head_dim, n_local_heads * head_dim
-    qkv = F.linear(x, w[f"{prefix}.wqkv.weight"], w.get(f"{prefix}.wqkv.bias"))
+    qkv = linear(m, x, w[f"{prefix}.wqkv.weight"], w.get(f"{prefix}.wqkv.bias"))
     q, k, v = qkv.split([q_size, kv_size, kv_size], dim=-1)
     q = q.view(bsz, seqlen, n_head, head_dim)
     k = k.view(bsz, seqlen, n_local_heads, head_dim)
@@ -165,7 +177,7 @@ def attention(m: OracleModel, prefix: str, kv, x, freqs_cis, mask, input_pos,
     else:
         y = eq_scaled_dot_product_attention(q, k, v, mask)
     y = y.transpose(1, 2).contiguous().view(bsz, seqlen, q_size)
-    return F.linear(y, w[f"{prefix}.wo.weight"], w.get(f"{prefix}.wo.bias"))
+    return linear(m, y, w[f"{prefix}.wo.weight"], w.get(f"{prefix}.wo.bias"))
 
 
 def block(m: OracleModel, prefix: str, kv, x, freqs_cis, mask, input_pos, fast: bool) -> Tensor:
@@ -178,9 +190,9 @@ def block(m: OracleModel, prefix: str, kv, x, freqs_cis, mask, input_pos, fast: 
     h = x + attention(m, f"{prefix}.attention", kv, rms_norm(x, w[f"{prefix}.attention_norm.weight"], cfg.norm_eps),
                       freqs_cis, mask, input_pos, *dims)
     hn = rms_norm(h, w[f"{prefix}.ffn_norm.weight"], cfg.norm_eps)
-    ff = F.linear(F.silu(F.linear(hn, w[f"{prefix}.feed_forward.w1.weight"])) *
-                  F.linear(hn, w[f"{prefix}.feed_forward.w3.weight"]),
-                  w[f"{prefix}.feed_forward.w2.weight"])
+    ff = linear(m, F.silu(linear(m, hn, w[f"{prefix}.feed_forward.w1.weight"])) *
+                linear(m, hn, w[f"{prefix}.feed_forward.w3.weight"]),
+                w[f"{prefix}.feed_forward.w2.weight"])
     return h + ff
 
 
@@ -206,7 +218,7 @@ def forward_generate(m: OracleModel, inp: Tensor, input_pos: Tensor):
         x = x[:, -1:]
     slow_out = rms_norm(x, w["norm.weight"], cfg.norm_eps)
     head = w["embeddings.weight"] if cfg.tie_word_embeddings else w["output.weight"]
-    return F.linear(slow_out, head), x
+    return linear(m, slow_out, head), x
 
 
 def forward_generate_fast(m: OracleModel, x: Tensor, input_pos: Tensor) -> Tensor:
@@ -218,7 +230,7 @@ def forward_generate_fast(m: OracleModel, x: Tensor, input_pos: Tensor) -> Tenso
     for i in range(cfg.n_fast_layer):
         x = block(m, f"fast_layers.{i}", m.fast_kv[i], x, fast_freqs_cis, fast_mask, input_pos, fast=True)
     fast_out = rms_norm(x, w["fast_norm.weight"], cfg.norm_eps)
-    return F.linear(fast_out, w["fast_output.weight"])
+    return linear(m, fast_out, w["fast_output.weight"])
 
 
 # --------------------------------------------------------------------------------------

@@ -80,7 +80,7 @@ def main():
 
     t0 = time.perf_counter()
     try:
-        inference.generate(model=model, prompt=prompt.to(args.device), max_new_tokens=W + K + 2, audio_masks=None, audio_parts=None,
+        inference.generate(model=model, prompt=prompt.to(args.device), max_new_tokens=W + K + 1, audio_masks=None, audio_parts=None,
                            decode_one_token=timed_step, temperature=0.7, top_p=0.8, repetition_penalty=1.1)
     except _BudgetSpent:
         pass

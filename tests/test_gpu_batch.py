@@ -124,8 +124,8 @@ def test_batch_invariance_and_slot_independence():
 
 
 def test_fused_norm_gemm_equals_separate_norm_kernel(monkeypatch):
-    """the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>: RMSNorm applied while staging the activation tile in
-    shared memory); with DUALAR_TC_FUSE_NORM=0 a separate RMSNorm kernel runs in front of a TMA-fed GEMM.  Same formulas, same
+    """DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>: RMSNorm applied while staging
+    the activation tile in shared memory); default: a separate RMSNorm kernel runs in front of a TMA-fed GEMM.  Same formulas, same
     summation order: tokens and logits must agree bit for bit."""
     cfg = variant_configs()["s1like"]
     sd = make_state_dict(cfg, seed=0)
