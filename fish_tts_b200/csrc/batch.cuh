@@ -146,13 +146,23 @@ struct BAttnArgs {
   bf16 *y;                   // [ncols][nh * hd]
   PosSrc pos; int *err;
 };
-// grid (nsplit_max, nkv, ncols); dynamic smem as attn_smem_bytes()
+// grid (nsplit_max, nkv, ncols); dynamic smem b_attn_smem().  CTA (kv head, split) walks its 64-position tiles (bulk copies, double
+// buffered).  Inside the CTA the positions of a tile are dealt to the 8 warps (rows w, w + 8, ...): every warp keeps its own running
+// (max, sum, output) for two query heads at a time -- scores with 8 lanes per position (a 3-step reduction and one exp per lane),
+// probabilities handed to all lanes for P@V where a lane owns hd/32 output dims -- and the warps meet ONCE, after the last tile
+// (the decode kernel's tile walk, mega.cuh).  One CTA barrier per tile instead of three, no idle warps during the softmax.
+#define DA_B_AWARPS (DA_ATTN_THREADS / 32)
+static inline size_t b_attn_smem(int G, int hd) {
+  size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t);
+  f = (f + 127) & ~(size_t)127;
+  return f + 128 + 4 * (size_t)DA_TILE * hd * sizeof(bf16);
+}
 __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnArgs a) {
   extern __shared__ __align__(128) unsigned char smraw_b[];
   pdl_launch_dependents();
   pdl_wait();
   const int g = blockIdx.y, split = blockIdx.x, n = blockIdx.z;
-  const int G = a.nh / a.nkv, hd = a.hd;
+  const int G = a.nh / a.nkv, hd = a.hd, dpl = hd >> 5;      // output dims per lane (1, 2 or 4)
   const int pos = pos_of(a.pos, n);
   if (pos < 0 || pos >= a.S) return;
   const int L = pos + 1;
@@ -162,11 +172,10 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
   const int nsplit_eff = (n_tiles + tps - 1) / tps;
   if (split >= nsplit_eff) return;
   const int t0 = split * tps, t1 = min(n_tiles, t0 + tps);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = DA_ATTN_THREADS / 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float *q = reinterpret_cast<float *>(smraw_b);
-  float *sc = q + G * hd + 2 * hd;
-  float *red = sc + G * DA_TILE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(red + 80);
+  float *pm = q + G * hd, *pl = pm + DA_B_AWARPS * G, *po = pl + DA_B_AWARPS * G;      // per-warp partials: [8][G], [8][G], [8][G][hd]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(po + (size_t)DA_B_AWARPS * G * hd);
   size_t off = (size_t)((unsigned char *)(bars + 2) - smraw_b);
   off = (off + 127) & ~(size_t)127;
   bf16 *kbuf = reinterpret_cast<bf16 *>(smraw_b + off);
@@ -196,86 +205,117 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
     }
   }
   __syncthreads();
-  const int n_own = (G * hd + DA_ATTN_THREADS - 1) / DA_ATTN_THREADS;
-  float o_acc[DA_MAX_G * 128 / DA_ATTN_THREADS];
-#pragma unroll
-  for (int i = 0; i < DA_MAX_G * 128 / DA_ATTN_THREADS; ++i) o_acc[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-  __shared__ float s_m[DA_MAX_G], s_scale[DA_MAX_G], s_l[DA_MAX_G];
-  if (threadIdx.x < DA_MAX_G) { s_m[threadIdx.x] = -INFINITY; s_l[threadIdx.x] = 0.f; }
-  const int lpr = hd / 8, rpw = 32 / lpr;
   uint32_t phase[2] = {0u, 0u};
   bool ok = true;
+  const int psl = lane >> 3, dl = lane & 7;
   for (int t = t0; t < t1; ++t) {
     const int buf = (t - t0) & 1;
     const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
     if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);
     ok = mbar_wait(&bars[buf], phase[buf]) && ok; phase[buf] ^= 1u;
     const bf16 *kt = kbuf + (size_t)buf * DA_TILE * hd, *vt = vbuf + (size_t)buf * DA_TILE * hd;
-    for (int jb = w * rpw; jb < nrow; jb += nw * rpw) {
-      const int j = jb + lane / lpr, piece = lane % lpr;
-      float part[DA_MAX_G];
+    for (int h0 = 0; h0 < G; h0 += 2) {
+      float m_run[2], l_run[2], o_acc[2][4];
+      const bool first = t == t0;
 #pragma unroll
-      for (int h = 0; h < DA_MAX_G; ++h) part[h] = 0.f;
-      if (j < nrow) {
-        float kf[8]; unpack8(*reinterpret_cast<const uint4 *>(kt + (size_t)j * hd + piece * 8), kf);
+      for (int hh = 0; hh < 2; ++hh) {
+        const bool hv = h0 + hh < G;
+        const int h = hv ? h0 + hh : h0;
+        m_run[hh] = first ? -INFINITY : pm[w * G + h]; l_run[hh] = first ? 0.f : pl[w * G + h];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) kf[d] = __fmul_rn(kf[d], a.sf);
+        for (int i = 0; i < 4; ++i) o_acc[hh][i] = (hv && i < dpl && !first) ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
+      }
+      const float *q0 = q + (size_t)h0 * hd, *q1 = q + (size_t)(h0 + 1 < G ? h0 + 1 : h0) * hd;
+#pragma unroll 1
+      for (int half = 0; half < DA_TILE / (4 * DA_B_AWARPS); ++half) {      // 4 position slots per warp per round: rows w + 8 * (4 half + slot)
+        const int jme = w + DA_B_AWARPS * (4 * half + psl);
+        float s2[2] = {0.f, 0.f};
+        if (jme < nrow) {
+          const bf16 *krow = kt + (size_t)jme * hd;
+          for (int e = dl * 4; e < hd; e += 32) {
+            float kf[4];
+            { const uint2 u = *reinterpret_cast<const uint2 *>(krow + e);
+              kf[0] = __uint_as_float(u.x << 16); kf[1] = __uint_as_float(u.x & 0xffff0000u); kf[2] = __uint_as_float(u.y << 16); kf[3] = __uint_as_float(u.y & 0xffff0000u); }
+            const float4 qa = *reinterpret_cast<const float4 *>(q0 + e), qb = *reinterpret_cast<const float4 *>(q1 + e);
 #pragma unroll
-        for (int h = 0; h < DA_MAX_G; ++h) {
-          if (h < G) {
-            const float *qq = q + h * hd + piece * 8;
+            for (int i = 0; i < 4; ++i) kf[i] = __fmul_rn(kf[i], a.sf);
+            s2[0] = fmaf(qa.x, kf[0], s2[0]); s2[0] = fmaf(qa.y, kf[1], s2[0]); s2[0] = fmaf(qa.z, kf[2], s2[0]); s2[0] = fmaf(qa.w, kf[3], s2[0]);
+            s2[1] = fmaf(qb.x, kf[0], s2[1]); s2[1] = fmaf(qb.y, kf[1], s2[1]); s2[1] = fmaf(qb.z, kf[2], s2[1]); s2[1] = fmaf(qb.w, kf[3], s2[1]);
+          }
+        }
+        float pj[4][2];
 #pragma unroll
-            for (int d = 0; d < 8; ++d) part[h] = fmaf(qq[d], kf[d], part[h]);
+        for (int hh = 0; hh < 2; ++hh) {
+          float sv = s2[hh];
+          sv += __shfl_xor_sync(0xffffffffu, sv, 1); sv += __shfl_xor_sync(0xffffffffu, sv, 2); sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+          if (!(jme < nrow && h0 + hh < G)) sv = -INFINITY;
+          float mx = fmaxf(sv, __shfl_xor_sync(0xffffffffu, sv, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+          const float m_new = fmaxf(m_run[hh], mx);
+          float pme = 0.f;
+          if (m_new != -INFINITY) {
+            const float sc_old = expf(m_run[hh] - m_new);      // exp(-inf) = 0 before the first position
+            l_run[hh] *= sc_old; m_run[hh] = m_new;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o_acc[hh][i] *= sc_old;
+            pme = expf(sv - m_new);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) pj[jj][hh] = __shfl_sync(0xffffffffu, pme, jj * 8);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = w + DA_B_AWARPS * (4 * half + jj);
+          if (j < nrow) {
+            float vf[4] = {0.f, 0.f, 0.f, 0.f};
+            const bf16 *vp = vt + (size_t)j * hd + lane * dpl;
+            if (dpl == 4) { const uint2 u = *reinterpret_cast<const uint2 *>(vp); vf[0] = __uint_as_float(u.x << 16); vf[1] = __uint_as_float(u.x & 0xffff0000u); vf[2] = __uint_as_float(u.y << 16); vf[3] = __uint_as_float(u.y & 0xffff0000u); }
+            else if (dpl == 2) { const uint32_t u = *reinterpret_cast<const uint32_t *>(vp); vf[0] = __uint_as_float(u << 16); vf[1] = __uint_as_float(u & 0xffff0000u); }
+            else vf[0] = bf2f(*vp);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              l_run[hh] += pj[jj][hh];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(pj[jj][hh], vf[i], o_acc[hh][i]);
+            }
           }
         }
       }
 #pragma unroll
-      for (int h = 0; h < DA_MAX_G; ++h) {
-        if (h < G) {
-          float v = part[h];
-          for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (piece == 0 && j < nrow) sc[h * DA_TILE + j] = v;
+      for (int hh = 0; hh < 2; ++hh) {
+        if (h0 + hh < G) {
+          const int h = h0 + hh;
+          if (lane == 0) { pm[w * G + h] = m_run[hh]; pl[w * G + h] = l_run[hh]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (i < dpl) po[((size_t)w * G + h) * hd + lane * dpl + i] = o_acc[hh][i];
         }
       }
+      __syncwarp();
     }
-    __syncthreads();
-    if (w < G) {
-      float mx = -INFINITY;
-      for (int j = lane; j < nrow; j += 32) mx = fmaxf(mx, sc[w * DA_TILE + j]);
-      mx = warp_max(mx);
-      const float m_new = fmaxf(m_run, mx);
-      float ps = 0.f;
-      for (int j = lane; j < nrow; j += 32) { const float p = expf(sc[w * DA_TILE + j] - m_new); sc[w * DA_TILE + j] = p; ps += p; }
-      ps = warp_sum(ps);
-      const float scale = expf(m_run - m_new);
-      l_run = l_run * scale + ps; m_run = m_new;
-      if (lane == 0) { s_scale[w] = scale; s_m[w] = m_run; s_l[w] = l_run; }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < DA_MAX_G * 128 / DA_ATTN_THREADS; ++i) {
-      const int e = threadIdx.x + i * DA_ATTN_THREADS;
-      if (i < n_own && e < G * hd) {
-        const int h = e / hd, d = e - h * hd;
-        float acc = o_acc[i] * s_scale[h];
-        const float *pp = sc + h * DA_TILE;
-        for (int j = 0; j < nrow; ++j) acc = fmaf(pp[j], bf2f(vt[(size_t)j * hd + d]), acc);
-        o_acc[i] = acc;
-      }
-    }
-    __syncthreads();
+    __syncthreads();      // every warp is past its last read of the tile: its buffer may be refilled
   }
   if (!ok && threadIdx.x == 0) atomicExch(a.err, 2);
+  // fold the 8 warps' partials in warp order: thread e = (h, d)
   const size_t pbase = ((size_t)n * a.nkv + g) * a.nsplit_max;
-  float *po = a.part_o + ((pbase + split) * G) * hd;
+  float *pog = a.part_o + ((pbase + split) * G) * hd;
   float *pml = a.part_ml + ((pbase + split) * G) * 2;
+  for (int e = threadIdx.x; e < G * hd; e += DA_ATTN_THREADS) {
+    const int h = e / hd, dd = e - h * hd;
+    float m = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < DA_MAX_G * 128 / DA_ATTN_THREADS; ++i) {
-    const int e = threadIdx.x + i * DA_ATTN_THREADS;
-    if (i < n_own && e < G * hd) po[e] = o_acc[i];
+    for (int ww = 0; ww < DA_B_AWARPS; ++ww) m = fmaxf(m, pm[ww * G + h]);
+    float l = 0.f, o = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < DA_B_AWARPS; ++ww) {
+      const float v = pm[ww * G + h];
+      const float sc_w = v == -INFINITY ? 0.f : expf(v - m);
+      l = fmaf(pl[ww * G + h], sc_w, l);
+      o = fmaf(po[((size_t)ww * G + h) * hd + dd], sc_w, o);
+    }
+    if (nsplit_eff == 1) a.y[(size_t)n * a.nh * hd + (size_t)g * G * hd + e] = f2bf(o / l);      // single split: no partials, no ticket
+    else { pog[e] = o; if (dd == 0) { pml[h * 2] = m; pml[h * 2 + 1] = l; } }
   }
-  if (threadIdx.x < G) { pml[threadIdx.x * 2] = s_m[threadIdx.x]; pml[threadIdx.x * 2 + 1] = s_l[threadIdx.x]; }
+  if (nsplit_eff == 1) return;
   __shared__ unsigned int s_last;
   __threadfence();
   __syncthreads();

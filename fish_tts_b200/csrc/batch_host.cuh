@@ -39,7 +39,7 @@ struct dualar_tc {
   float *ws = nullptr; size_t ws_bytes = 0; unsigned int *tickets = nullptr; int *err = nullptr;
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
-  int ksplit_override = 0, stages_override = 0;
+  int ksplit_override = 0, stages_override = 0, bn_override = 0;
   bool fuse_norm = false;     // DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>) instead of a separate
                               // RMSNorm kernel in front of them.  Bit-identical (tests/test_gpu_batch.py), 145 kernels fewer per step -- and measured
                               // SLOWER on B200 (5.45 vs 4.83 ms per bs-32 step): every CTA re-reads the full rows for the statistics and stages the
@@ -101,7 +101,9 @@ static int tc_init(dualar_engine *e) {
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
   { const char *v = getenv("DUALAR_TC_KSPLIT"); if (v) e->tc->ksplit_override = atoi(v); }
   { const char *v = getenv("DUALAR_TC_STAGES"); if (v) e->tc->stages_override = atoi(v); }
-  CU(cudaFuncSetAttribute(b_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(e->c.n_head / e->c.n_local_heads, e->c.head_dim)));
+  { const char *v = getenv("DUALAR_TC_PREFILL_BN"); if (v) e->tc->bn_override = atoi(v); }
+  if (e->c.head_dim < 32) return fail(DUALAR_EINVAL, "the tensor-core path needs head_dim >= 32 (a lane owns head_dim / 32 output dims in the attention kernel)");
+  CU(cudaFuncSetAttribute(b_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_attn_smem(e->c.n_head / e->c.n_local_heads, e->c.head_dim)));
   CU(cudaFuncSetAttribute(b_fast_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)b_fast_attn_smem(e->c.fast_n_head, e->c.fast_n_local_heads, e->c.fast_head_dim, e->c.num_codebooks)));
   e->tc->ready = true;
@@ -112,13 +114,22 @@ static int tc_init(dualar_engine *e) {
 // norm_w != nullptr: X is the UN-normalised activation and the kernel applies RMSNorm(norm_w) itself (BN = 32 only, see tc_can_fuse_norm)
 static bool tc_can_fuse_norm(const dualar_engine *e, int BN, int K) { return e->tc->fuse_norm && BN == 32 && K % 256 == 0 && K <= 4096; }
 static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 *X, int xcap, int ncols, int BN, int epi, const bf16 *bias,
-                   const bf16 *res, bf16 *out, int w_keep, cudaStream_t s, int &count, const bf16 *norm_w = nullptr) {
+                   const bf16 *res, bf16 *out, int w_keep, cudaStream_t s, int &count, const bf16 *norm_w = nullptr, bool prefill = false) {
   const CUtensorMap *mw, *mx; int rc;
+  if (prefill) {
+    // prefill: parallelism comes from COLUMN tiles, never from split-K -- a K split of a 256-column tile writes and re-reads
+    // 128 x 256 fp32 partials per CTA, more bytes than the weights themselves; and with the K range whole, a position's result does
+    // not depend on how the prompt was cut into chunks (prefix reuse prefills a short tail and must reproduce the full prefill).
+    // Take the widest tile that still yields ~100 CTAs.
+    const int rt0 = (rows + DA_TC_BM - 1) / DA_TC_BM;
+    for (BN = 256; BN > 32; BN >>= 1) if (ncols > BN / 2 && rt0 * ((ncols + BN - 1) / BN) >= 96) break;
+    if (e->tc->bn_override > 0) BN = e->tc->bn_override;
+  }
   if ((rc = tc_map(e, W, rows, K, DA_TC_BM, &mw)) || (rc = tc_map(e, X, xcap, K, BN, &mx))) return rc;
   const int rt = (rows + DA_TC_BM - 1) / DA_TC_BM, ct = (ncols + BN - 1) / BN, tiles = rt * ct, nkb = K / DA_TC_BK;
   int ks = 1;
-  if (tiles < 64) { ks = 128 / tiles; if (ks > nkb / 4) ks = nkb / 4; if (ks > 8) ks = 8; if (ks < 1) ks = 1; }
-  if (e->tc->ksplit_override > 0 && tiles < 64) { ks = e->tc->ksplit_override; if (ks > nkb) ks = nkb; }
+  if (!prefill && tiles < 64) { ks = 128 / tiles; if (ks > nkb / 4) ks = nkb / 4; if (ks > 8) ks = 8; if (ks < 1) ks = 1; }
+  if (!prefill && e->tc->ksplit_override > 0 && tiles < 64) { ks = e->tc->ksplit_override; if (ks > nkb) ks = nkb; }
   while (ks > 1 && (size_t)tiles * ks * BN * DA_TC_BM * 4 > e->tc->ws_bytes) --ks;
   if (tiles > 8192) return fail(DUALAR_EINVAL, "too many GEMM tiles (%d)", tiles);
   GemmTcArgs a; memset(&a, 0, sizeof(a));
@@ -158,7 +169,7 @@ struct KvTarget { bf16 *const *kc, *const *vc; long long slot_stride; int S; }; 
 
 // embedding + the slow stack over `ncols` columns; leaves the un-normalised last-layer output in c.x
 static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, const KvTarget &kv, const PosSrc &pos, const TokSrc &tok,
-                             cudaStream_t s, int &count) {
+                             cudaStream_t s, int &count, bool prefill = false) {
   const dualar_config &cf = e->c;
   const int qkv_rows = (cf.n_head + 2 * cf.n_local_heads) * cf.head_dim, qd = cf.n_head * cf.head_dim;
   int rc;
@@ -172,11 +183,11 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
     CU(launch_k(b_rmsnorm_kernel, dim3((ncols + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
   for (int l = 0; l < cf.n_layer; ++l) {
     LayerW &L = e->slow[l];
-    const bool fuse = tc_can_fuse_norm(e, BN, cf.dim);      // decode: the GEMM normalises its own operand, one kernel fewer per norm
+    const bool fuse = !prefill && tc_can_fuse_norm(e, BN, cf.dim);      // decode (optional): the GEMM normalises its own operand
     if (fuse) { if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.x, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count, L.attn_norm))) return rc; }
     else {
       if ((rc = norm(c.x, L.attn_norm, c.xn, cf.dim))) return rc;
-      if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.xn, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count))) return rc;
+      if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.xn, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count, nullptr, prefill))) return rc;
     }
     { BQkvPostArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn;
@@ -186,14 +197,14 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S;
       a.ncols = ncols; a.nsplit_max = c.nsplit; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
       a.tickets = c.attn_tickets; a.y = c.y; a.pos = pos; a.err = e->tc->err;
-      CU(launch_k(b_attn_kernel, dim3(c.nsplit, cf.n_local_heads, ncols), dim3(DA_ATTN_THREADS), attn_smem_bytes(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; }
-    if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count))) return rc;
+      CU(launch_k(b_attn_kernel, dim3(c.nsplit, cf.n_local_heads, ncols), dim3(DA_ATTN_THREADS), b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; }
+    if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count, nullptr, prefill))) return rc;
     if (fuse) { if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.h, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count, L.ffn_norm))) return rc; }
     else {
       if ((rc = norm(c.h, L.ffn_norm, c.xn, cf.dim))) return rc;
-      if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.xn, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count))) return rc;
+      if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.xn, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count, nullptr, prefill))) return rc;
     }
-    if ((rc = tc_gemm(e, L.w2, cf.dim, cf.intermediate_size, c.act, c.cap, ncols, BN, TE_RESIDUAL, nullptr, c.h, c.x, 0, s, count))) return rc;
+    if ((rc = tc_gemm(e, L.w2, cf.dim, cf.intermediate_size, c.act, c.cap, ncols, BN, TE_RESIDUAL, nullptr, c.h, c.x, 0, s, count, nullptr, prefill))) return rc;
   }
   return 0;
 }
@@ -207,7 +218,7 @@ static int tc_prefill(dualar_engine *e, const KvTarget &kv, const int *seq, int 
     const int ncols = t1 - t < c.cap ? t1 - t : c.cap;
     PosSrc pos{nullptr, 0, t};
     TokSrc tok{seq + t, 1, seq_stride};
-    if ((rc = enqueue_slow_cols(e, c, ncols, bn_for(ncols), kv, pos, tok, s, count))) return rc;
+    if ((rc = enqueue_slow_cols(e, c, ncols, bn_for(ncols), kv, pos, tok, s, count, true))) return rc;
   }
   e->prefill_launches = count;
   return 0;

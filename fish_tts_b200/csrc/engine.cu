@@ -80,6 +80,7 @@ struct dualar_engine {
   cudaEvent_t ev_ring[8] = {nullptr}; int ev_next = 0; int stream_cols = 0, steps_enqueued = 0;      // dualar_decode_async
   bool batch_keep_raw = true;    // batched decode keeps a copy of the raw logits for dualar_batch_read
   bool l2_window = false; float l2_hit_ratio = 0.0f; size_t l2_persist_bytes = 0;   // DUALAR_L2_WINDOW / DUALAR_L2_HIT: access-policy window over the fast stack
+  bool chunk_group = true;   // DUALAR_CHUNK_GROUP=0: one 128-element chunk per unit everywhere (round 1 behaviour)
   bool use_mega = true;   // option mega_kernel / DUALAR_MEGA: 0 = one kernel per phase (the cross-check path)
 };
 
@@ -469,6 +470,7 @@ static int build_mega(dualar_engine *e) {
   if ((rc = dev_alloc(e, e->m_phase, 1))) return rc;
   if ((rc = dev_alloc(e, e->m_fkv, (size_t)grid * c.n_fast_layer * c.num_codebooks * 2 * fkd))) return rc;
   { const char *v = getenv("DUALAR_T0"); if (v) e->use_t0 = v[0] != '0'; }
+  { const char *v = getenv("DUALAR_CHUNK_GROUP"); if (v) e->chunk_group = v[0] != '0'; }
   if (e->use_t0) {
     // table of the first fast layer's q | k | v for every code (see t0_build_kernel); 16 MB for s1-mini
     if ((rc = dev_alloc(e, e->t0, (size_t)c.codebook_size * fqkv_rows))) return rc;
@@ -487,6 +489,12 @@ static int build_mega(dualar_engine *e) {
       p.W = W; p.bias = bias; p.norm_w = norm_w; p.in = in; p.out = out; p.rows = rows; p.K = K; p.in_ph = (short)in_ph;
       p.pq = (short)(((rows + 1) / 2) / grid); p.prem = (short)(((rows + 1) / 2) % grid);
       p.kind = MK_GEMV; p.pro = (unsigned char)pro; p.epi = (unsigned char)epi; p.flags = (unsigned char)flags; p.layer = (unsigned char)layer; p.pos = (unsigned char)pos;
+      // chunks per unit: with more than 16 (tile, chunk) units on the busiest CTA half the warps would take a second round; a warp then
+      // computes `cgroup` consecutive chunks per unit instead (the per-chunk partials and their summation order stay what they were)
+      { const int nchunk = K >> 7, tiles = (2 * (((rows + 1) / 2) / grid + 1) + 15) / 16;
+        int cg = 1;
+        if (e->chunk_group) while (tiles * nchunk / cg > DA_M_CWARPS && cg < nchunk && cg < 4) { ++cg; while (nchunk % cg) ++cg; }
+        p.cgroup = (unsigned char)cg; }
       tab.push_back(p); return (int)tab.size() - 1;
     };
     auto other = [&](int kind, const uint32_t *in, int in_ph, uint32_t *out, int layer) {
@@ -514,6 +522,10 @@ static int build_mega(dualar_engine *e) {
       auto head_part = [&]() {
         hd_ph = gemv(c.tie_word_embeddings ? e->emb : e->out_w, nullptr, e->norm, e->u_x, last, nullptr, c.vocab_size, c.dim, MP_RMSNORM, ME_SLOWLOGITS, 0, 0, 0);
         tab.back().part = (unsigned char)part; tab.back().nparts = (unsigned char)NPARTS; ++part;
+        { const int nchunk = c.dim >> 7, tiles_all = (2 * (((c.vocab_size + 1) / 2) / grid + 1) + 15) / 16, tiles = (tiles_all + NPARTS - 1) / NPARTS;
+          int cg = 1;
+          if (e->chunk_group) while (tiles * nchunk / cg > DA_M_CWARPS && cg < nchunk && cg < 4) { ++cg; while (nchunk % cg) ++cg; }
+          tab.back().cgroup = (unsigned char)cg; }
       };
       auto fast_layer = [&](int p, int l, const uint32_t *lin, int lin_ph, bool with_head) {
         LayerW &W = e->fast[l];

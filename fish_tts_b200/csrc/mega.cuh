@@ -62,7 +62,9 @@ struct MPhase {
   short in_ph;           // phase that wrote `in` (its tag)
   unsigned char kind, pro, epi, layer, pos, flags;
   short pq, prem;        // row pairs per CTA: floor and remainder of (rows / 2) / grid (the first `prem` CTAs take one more)
-  unsigned char part, nparts, pad2_[2];   // nparts > 1: this entry handles only the part-th slice of the CTA's tiles (LM head, see build_mega)
+  unsigned char part, nparts, cgroup, pad2_;   // nparts > 1: this entry handles only the part-th slice of the CTA's tiles (LM head, see build_mega)
+                                               // cgroup: consecutive 128-element chunks one warp computes per unit (1, or more when a CTA
+                                               // would otherwise hold more than 16 units and half the warps would go round twice)
 };
 
 struct MegaSmem { uint32_t bars, chg, xb, xbh, raw, scratch, work, part, pcnt, lg, kvs, ring, total; };
@@ -731,11 +733,12 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
       const uint32_t *xw = reinterpret_cast<const uint32_t *>(xb);
       {
         int u = w;
+        const int cg = d.cgroup ? d.cgroup : 1, upt = nchunk / cg;      // units per tile
         for (int t = t_lo; t < t_hi; ++t) {
           const int n = min(16, gp.nr - 16 * t), tl = t - t_lo;      // tl: tile index within this phase entry (units, slots, generations)
           uint32_t bi, par;
           const uint32_t at = place((uint32_t)n * RS, bi, par);
-          if (u >= (tl + 1) * nchunk) continue;        // no unit of this warp in the tile
+          if (u >= (tl + 1) * upt) continue;           // no unit of this warp in the tile
           landed(bi, par);
           if (TL && a.tl && tid == 0 && tl == 0) tl_put(a, 512 + ph, 4, gtime());
           const int slot = tl & (DA_M_PT - 1);
@@ -744,19 +747,21 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
           for (int i = 1; i < DA_M_PT; ++i) if (slot == i) gb = gen_base[i];
           const int gen_need = gb + tl / DA_M_PT;
           float *pslot = sm_part + (size_t)slot * (a.kmax >> 7) * 16;
-          for (; u < (tl + 1) * nchunk; u += DA_M_CWARPS) {
-            const int c = u - tl * nchunk;
-            float v_lo, v_hi;
-            mma_chunk(smem_u32(sm_ring + at), RS, n, xw, c, lane, v_lo, v_hi);
-            if (TL && a.tl && tid == 0 && tl == 0) tl_put(a, 512 + ph, 5, gtime() + (unsigned long long)(0.f * (v_lo + v_hi)));
+          for (; u < (tl + 1) * upt; u += DA_M_CWARPS) {
+            const int c0 = (u - tl * upt) * cg;
             // the slot is free once the tile DA_M_PT before this one has been folded
             // (checked for every tile: a phase entry without a staging barrier -- the later LM-head parts -- can start while the
             //  previous phase is still folding on this slot)
             { int it = 0; while (sm_pgen[slot] != gen_need) { if (++it >= DA_SPIN_LIMIT) { ok = false; break; } __nanosleep(20); } }
-            if ((lane & 3) == 0) { pslot[c * 16 + (lane >> 2)] = v_lo; pslot[c * 16 + 8 + (lane >> 2)] = v_hi; }
+            for (int c = c0; c < c0 + cg; ++c) {      // every chunk keeps its own partial: the fold adds them in chunk order (canonical)
+              float v_lo, v_hi;
+              mma_chunk(smem_u32(sm_ring + at), RS, n, xw, c, lane, v_lo, v_hi);
+              if (TL && a.tl && tid == 0 && tl == 0) tl_put(a, 512 + ph, 5, gtime() + (unsigned long long)(0.f * (v_lo + v_hi)));
+              if ((lane & 3) == 0) { pslot[c * 16 + (lane >> 2)] = v_lo; pslot[c * 16 + 8 + (lane >> 2)] = v_hi; }
+            }
             __syncwarp();
             int last = 0;
-            if (lane == 31) last = (atom_add_acq_rel_cta(&sm_pcnt[slot], 1) == nchunk - 1);      // publishes this warp's partials, observes the others' 
+            if (lane == 31) last = (atom_add_acq_rel_cta(&sm_pcnt[slot], cg) == nchunk - cg);      // publishes this warp's partials, observes the others'
             last = __shfl_sync(0xffffffffu, last, 31);
             if (TL && a.tl && tid == 0 && tl == 0) tl_put(a, 512 + ph, 6, gtime());
             if (last) {

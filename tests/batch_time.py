@@ -24,6 +24,7 @@ def ev():
 
 
 eng = DualAREngine(cfg, sd, device=0, seed=1234)
+eng.set_option("prefix_reuse", 0)      # every prefill below pays for the whole prompt
 for T in ((223, 512, 1024) if not os.environ.get("BT_SKIP_PREFILL") else ()):
     prompt = synthetic_prompt(cfg, 3, T - 8, 5, seed=1)
     for mode in (0, 1) if T == 223 else (0,):
