@@ -119,6 +119,8 @@ class DualARConfig:
         fast = self.n_fast_layer * layer(self.fast_dim, self.fast_n_head, self.fast_n_local_heads,
                                          self.fast_head_dim, self.fast_intermediate_size, self.fast_attention_qk_norm)
         fast_head = 2 * self.codebook_size * self.fast_dim
+        if self.fast_dim != self.dim:      # fast_project_in (llama.py:510-513)
+            fast += 2 * (self.fast_dim * self.dim + self.fast_dim)
         kv_per_pos = self.n_layer * 2 * self.n_local_heads * self.head_dim * 2
         return {"slow_layers": slow, "lm_head": head, "fast_layers": fast,
                 "fast_head": fast_head, "kv_per_pos": kv_per_pos,

@@ -19,7 +19,7 @@ struct ColBufs {
   int nsplit = 1;
   // decode only
   bf16 *logits = nullptr, *logits_raw = nullptr, *fin = nullptr, *fx[2] = {nullptr, nullptr}, *fh = nullptr, *fqkv = nullptr, *fy = nullptr, *fact = nullptr,
-       *fxn = nullptr, *flogits = nullptr, *flogits_raw = nullptr;
+       *fxn = nullptr, *flogits = nullptr, *flogits_raw = nullptr, *fpi = nullptr;
   float *cmax = nullptr; unsigned long long *cand = nullptr;
 };
 
@@ -31,6 +31,7 @@ struct dualar_batch {
   DAState *st = nullptr, *h_st = nullptr; int *seq = nullptr, *h_seq = nullptr;
   std::vector<bf16 *> kc, vc, fkc, fvc; long long slot_stride = 0, fslot_stride = 0;
   cudaGraphExec_t g_step = nullptr; int launches = 0;
+  cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;      // LM head + slow sampler run beside fast pass 0
   std::vector<int> prompt_len, max_gen; std::vector<char> open;
 };
 
@@ -81,6 +82,7 @@ static int alloc_cols(dualar_engine *e, ColBufs &c, int cap, int nsplit, bool de
       (rc = dev_alloc(e, c.fin, (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fx[0], (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fx[1], (size_t)cap * cf.fast_dim)) ||
       (rc = dev_alloc(e, c.fh, (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fqkv, (size_t)cap * fqkv_rows)) || (rc = dev_alloc(e, c.fy, (size_t)cap * fqd)) ||
       (rc = dev_alloc(e, c.fact, (size_t)cap * cf.fast_intermediate_size)) || (rc = dev_alloc(e, c.fxn, (size_t)cap * cf.fast_dim)) ||
+      (rc = dev_alloc(e, c.fpi, (size_t)cap * cf.fast_dim)) ||
       (rc = dev_alloc(e, c.flogits, (size_t)cap * e->fv)) || (rc = dev_alloc(e, c.flogits_raw, (size_t)cap * (cf.num_codebooks - 1) * e->fv)) ||
       (rc = dev_alloc(e, c.cmax, (size_t)cap * 64)) || (rc = dev_alloc(e, c.cand, (size_t)cap * DA_CAND_CAP)))
     return rc;
@@ -122,13 +124,17 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
     // not depend on how the prompt was cut into chunks (prefix reuse prefills a short tail and must reproduce the full prefill).
     // Take the widest tile that still yields ~100 CTAs.
     const int rt0 = (rows + DA_TC_BM - 1) / DA_TC_BM;
-    for (BN = 256; BN > 32; BN >>= 1) if (ncols > BN / 2 && rt0 * ((ncols + BN - 1) / BN) >= 96) break;
+    const int ks0 = (rt0 < 16 && K / DA_TC_BK >= 16) ? 4 : 1;
+    for (BN = 256; BN > 32; BN >>= 1) if (ncols > BN / 2 && rt0 * ks0 * ((ncols + BN - 1) / BN) >= 96) break;
     if (e->tc->bn_override > 0) BN = e->tc->bn_override;
   }
   if ((rc = tc_map(e, W, rows, K, DA_TC_BM, &mw)) || (rc = tc_map(e, X, xcap, K, BN, &mx))) return rc;
   const int rt = (rows + DA_TC_BM - 1) / DA_TC_BM, ct = (ncols + BN - 1) / BN, tiles = rt * ct, nkb = K / DA_TC_BK;
   int ks = 1;
   if (!prefill && tiles < 64) { ks = 128 / tiles; if (ks > nkb / 4) ks = nkb / 4; if (ks > 8) ks = 8; if (ks < 1) ks = 1; }
+  // prefill: a K split only for the matrices with very few row tiles (wo, w2: 8), chosen from the MATRIX alone so that a position's
+  // summation order does not depend on how the prompt was chunked
+  if (prefill && rt < 16 && nkb >= 16) ks = 4;
   if (!prefill && e->tc->ksplit_override > 0 && tiles < 64) { ks = e->tc->ksplit_override; if (ks > nkb) ks = nkb; }
   while (ks > 1 && (size_t)tiles * ks * BN * DA_TC_BM * 4 > e->tc->ws_bytes) --ks;
   if (tiles > 8192) return fail(DUALAR_EINVAL, "too many GEMM tiles (%d)", tiles);
@@ -238,19 +244,28 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
   auto norm = [&](const bf16 *x, const bf16 *w, bf16 *out, int K) -> int {
     BNormArgs a{x, w, out, K, B, cf.norm_eps};
     CU(launch_k(b_rmsnorm_kernel, dim3((B + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
-  // LM head + slow sampler (llama.py:446-451, inference.py:103-113)
-  if ((rc = norm(c.x, e->norm, c.xn, cf.dim))) return rc;
-  if ((rc = tc_gemm(e, cf.tie_word_embeddings ? e->emb : e->out_w, cf.vocab_size, cf.dim, c.xn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.logits, 0, s, count))) return rc;
+  // LM head + slow sampler (llama.py:446-451, inference.py:103-113) on a SECOND stream: they need only the slow hidden state, and so
+  // does pass 0 of the fast stack (whose logits the reference discards, inference.py:121-122) -- the two branches are independent
+  // until pass 1 consumes the sampled semantic id.  Fork / join with events (captured as graph edges).
+  cudaStream_t s2 = e->batch_fork ? b.side_stream : s;
+  if (e->batch_fork) { CU(cudaEventRecord(b.ev_fork, s)); CU(cudaStreamWaitEvent(s2, b.ev_fork, 0)); }
+  { BNormArgs a{c.x, e->norm, c.xn, cf.dim, B, cf.norm_eps};
+    CU(launch_k(b_rmsnorm_kernel, dim3((B + 3) / 4), dim3(128), 0, s2, a)); ++count; }
+  if ((rc = tc_gemm(e, cf.tie_word_embeddings ? e->emb : e->out_w, cf.vocab_size, cf.dim, c.xn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.logits, 0, s2, count))) return rc;
   { BHeadArgs a{c.logits, e->batch_keep_raw ? c.logits_raw : nullptr, c.cmax, cf.vocab_size, b.nchunk, R, b.st};
-    CU(launch_k(b_head_stats_kernel, dim3(b.nchunk, B), dim3(512), 0, s, a)); ++count; }
+    CU(launch_k(b_head_stats_kernel, dim3(b.nchunk, B), dim3(512), 0, s2, a)); ++count; }
   { BSelectArgs a; memset(&a, 0, sizeof(a));
     a.logits = c.logits; a.cmax = c.cmax; a.V = cf.vocab_size; a.nchunk = b.nchunk; a.delta = e->delta; a.cand = c.cand; a.fast_emb = e->fast_emb; a.fast_x = c.fin;
     a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size; a.sem_begin = cf.semantic_begin_id; a.st = b.st;
-    CU(launch_k(b_select_kernel, dim3(b.nchunk, B), dim3(512), (size_t)(192 * 8 + 34 * 8 + 80 * 4 + 64), s, a)); ++count; }
+    CU(launch_k(b_select_kernel, dim3(b.nchunk, B), dim3(512), (size_t)(192 * 8 + 34 * 8 + 80 * 4 + 64), s2, a)); ++count; }
+  if (e->batch_fork) CU(cudaEventRecord(b.ev_join, s2));
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
   const int fqkv_rows = (cf.fast_n_head + 2 * cf.fast_n_local_heads) * cf.fast_head_dim, fqd = cf.fast_n_head * cf.fast_head_dim;
+  if (e->fpi_w) {      // hidden_states = fast_project_in(x)   (llama.py:590)
+    if ((rc = tc_gemm(e, e->fpi_w, cf.fast_dim, cf.dim, c.x, c.cap, B, BN, TE_STORE, e->fpi_b, nullptr, c.fpi, 1, s, count))) return rc;
+  }
   for (int p = 0; p < cf.num_codebooks; ++p) {
-    const bf16 *in = p == 0 ? c.x : c.fin;
+    const bf16 *in = p == 0 ? (e->fpi_w ? c.fpi : c.x) : c.fin;
     for (int l = 0; l < cf.n_fast_layer; ++l) {
       LayerW &L = e->fast[l];
       bf16 *out = c.fx[l & 1];
@@ -274,7 +289,10 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
       if ((rc = tc_gemm(e, L.w2, cf.fast_dim, cf.fast_intermediate_size, c.fact, c.cap, B, BN, TE_RESIDUAL, nullptr, c.fh, out, 1, s, count))) return rc;
       in = out;
     }
-    if (p == 0) continue;      // logits of pass 0 are discarded by the reference (inference.py:122)
+    if (p == 0) {              // logits of pass 0 are discarded by the reference (inference.py:122)
+      if (e->batch_fork) CU(cudaStreamWaitEvent(s, b.ev_join, 0));      // join: pass 1 starts from the embedding of the sampled id
+      continue;
+    }
     if (tc_can_fuse_norm(e, BN, cf.fast_dim)) { if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, in, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count, e->fast_norm))) return rc; }
     else {
       if ((rc = norm(in, e->fast_norm, c.fxn, cf.fast_dim))) return rc;
@@ -316,6 +334,9 @@ extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_l
   CU(cudaMallocHost((void **)&b->h_st, sizeof(DAState)));
   CU(cudaMallocHost((void **)&b->h_seq, (size_t)R * b->Sb * sizeof(int)));
   b->prompt_len.assign(max_batch, 0); b->max_gen.assign(max_batch, 0); b->open.assign(max_batch, 0);
+  CU(cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  { const char *v = getenv("DUALAR_BATCH_FORK"); e->batch_fork = !(v && v[0] == '0'); }
   // slow sampler: (chunks x requests) CTAs of 512 threads scan the logits; the register-heavy sampler code runs one CTA per SM, so
   // more CTAs than SMs only adds waves
   b->nchunk = e->sms / max_batch; if (b->nchunk < 1) b->nchunk = 1; if (b->nchunk > 32) b->nchunk = 32;
@@ -441,6 +462,9 @@ extern "C" int dualar_batch_read(dualar_engine *e, const char *name, void *dst, 
 static void batch_destroy(dualar_engine *e) {
   if (e->batch) {
     if (e->batch->g_step) cudaGraphExecDestroy(e->batch->g_step);
+    if (e->batch->side_stream) cudaStreamDestroy(e->batch->side_stream);
+    if (e->batch->ev_fork) cudaEventDestroy(e->batch->ev_fork);
+    if (e->batch->ev_join) cudaEventDestroy(e->batch->ev_join);
     if (e->batch->h_st) cudaFreeHost(e->batch->h_st);
     if (e->batch->h_seq) cudaFreeHost(e->batch->h_seq);
     delete e->batch; e->batch = nullptr;

@@ -49,6 +49,7 @@ struct dualar_engine {
   std::map<std::string, Slot> slots;
   std::vector<LayerW> slow, fast;
   bf16 *emb = nullptr, *cb_emb = nullptr, *norm = nullptr, *out_w = nullptr, *fast_emb = nullptr, *fast_norm = nullptr, *fast_out = nullptr;
+  bf16 *fpi_w = nullptr, *fpi_b = nullptr, *fpi = nullptr; uint32_t *u_fpi = nullptr;      // fast_project_in (fast_dim != dim): weights, projected hidden state
   bf16 *rope = nullptr, *fast_rope = nullptr; bool rope_loaded = false, fast_rope_loaded = false;
   // activations
   bf16 *x = nullptr, *h = nullptr, *qkv = nullptr, *y = nullptr, *act = nullptr, *logits = nullptr, *logits_raw = nullptr;
@@ -79,6 +80,7 @@ struct dualar_engine {
   bool prefix_reuse = true, kv_dirty = true; std::vector<int32_t> prev_prompt; int prev_T = 0, last_reuse = 0;   // KV reuse across requests (dualar_prefill)
   cudaEvent_t ev_ring[8] = {nullptr}; int ev_next = 0; int stream_cols = 0, steps_enqueued = 0;      // dualar_decode_async
   bool batch_keep_raw = true;    // batched decode keeps a copy of the raw logits for dualar_batch_read
+  bool batch_fork = true;        // batched decode: LM head + slow sampler on a side stream beside fast pass 0 (DUALAR_BATCH_FORK=0: one stream)
   bool l2_window = false; float l2_hit_ratio = 0.0f; size_t l2_persist_bytes = 0;   // DUALAR_L2_WINDOW / DUALAR_L2_HIT: access-policy window over the fast stack
   bool chunk_group = true;   // DUALAR_CHUNK_GROUP=0: one 128-element chunk per unit everywhere (round 1 behaviour)
   bool use_mega = true;   // option mega_kernel / DUALAR_MEGA: 0 = one kernel per phase (the cross-check path)
@@ -129,6 +131,10 @@ static size_t plan(dualar_engine *e, bool assign) {
   take(e->rope, "freqs_cis", c.max_seq_len, c.head_dim);
   off = align_up(off, 2u << 20);
   if (assign) e->fast_off = off;
+  if (c.fast_dim != c.dim) {      // fast_project_in = nn.Linear(dim, fast_dim) (llama.py:510-513, 590)
+    take(e->fpi_w, "fast_project_in.weight", c.fast_dim, c.dim);
+    take(e->fpi_b, "fast_project_in.bias", 1, c.fast_dim);
+  }
   take(e->fast_emb, "fast_embeddings.weight", c.codebook_size, c.fast_dim);
   if (assign) e->fast.resize(c.n_fast_layer);
   for (int i = 0; i < c.n_fast_layer; ++i) {
@@ -145,7 +151,7 @@ static size_t plan(dualar_engine *e, bool assign) {
 
 static int check_config(const dualar_config &c) {
   if (c.abi_version != DUALAR_ABI_VERSION) return fail(DUALAR_EINVAL, "abi_version %d != %d", c.abi_version, DUALAR_ABI_VERSION);
-  if (c.fast_dim != c.dim) return fail(DUALAR_EINVAL, "fast_dim != dim (fast_project_in) is not supported");
+  if (c.fast_dim % 256) return fail(DUALAR_EINVAL, "fast_dim must be a multiple of 256");
   if (c.dim % 256 || c.intermediate_size % 256 || (c.n_head * c.head_dim) % 256 || c.fast_intermediate_size % 256 ||
       (c.fast_n_head * c.fast_head_dim) % 256)
     return fail(DUALAR_EINVAL, "dim, intermediate_size and n_head*head_dim must be multiples of 256");
@@ -373,8 +379,12 @@ static int enqueue_step(dualar_engine *e, cudaStream_t s, bool slow_only, int &c
     if (!configured[e->device & 63]) { CU(cudaFuncSetAttribute(select_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[e->device & 63] = true; }
     CU(launch_k(select_sample_kernel, dim3(e->sms), dim3(512), smem, s, a)); ++count; }
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
+  if (e->fpi_w) {      // hidden_states = fast_project_in(x)   (llama.py:590)
+    GemvArgs a = base_args(e->fpi_w, e->fpi_b, c.fast_dim, c.dim, 1); a.x = e->x; a.out = e->fpi;
+    if ((rc = launch_gemv<PRO_PLAIN, EPI_STORE>(e, a, s, count)) < 0) return rc;
+  }
   for (int p = 0; p < c.num_codebooks; ++p) {
-    const bf16 *in = p == 0 ? e->x : e->fin;
+    const bf16 *in = p == 0 ? (e->fpi_w ? e->fpi : e->x) : e->fin;
     for (int l = 0; l < c.n_fast_layer; ++l) {
       bf16 *out = e->fbuf[l & 1];
       if ((rc = enqueue_fast_layer(e, l, p, in, out, s, count)) < 0) return rc;
@@ -439,10 +449,11 @@ static int build_mega(dualar_engine *e) {
   const int qd = c.n_head * c.head_dim, kd = c.n_local_heads * c.head_dim, qkv_rows = qd + 2 * kd;
   const int fqd = c.fast_n_head * c.fast_head_dim, fkd = c.fast_n_local_heads * c.fast_head_dim, fqkv_rows = fqd + 2 * fkd;
   const int G = c.n_head / c.n_local_heads;
-  const int n_slow = 6 * c.n_layer, n_step = n_slow + 2 + 4 * c.n_fast_layer + c.num_codebooks * 4 * c.n_fast_layer + (c.num_codebooks - 1);
+  const int n_slow = 6 * c.n_layer, n_step = n_slow + 3 + 4 * c.n_fast_layer + c.num_codebooks * 4 * c.n_fast_layer + (c.num_codebooks - 1);
   auto pairs = [](int rows) { return (rows + 1) / 2; };
   if (n_step > DA_M_MAX_PHASES || c.n_layer > DA_M_MAXL || c.n_fast_layer > DA_M_MAXFL || grid > 160 || e->fv > 1024 ||
       pairs(qkv_rows) < grid || pairs(2 * c.intermediate_size) < grid || pairs(fqkv_rows) < grid || pairs(2 * c.fast_intermediate_size) < grid ||
+      c.fast_dim > 8 * DA_M_CTHREADS ||
       G * c.head_dim > 1024 || c.vocab_size > (1 << 18) || (c.num_codebooks - 1) * 2 * fkd / 8 > 3 * DA_M_CTHREADS || c.head_dim < 32 ||
       c.dim > 8 * DA_M_CTHREADS || c.intermediate_size > 8 * DA_M_CTHREADS || c.fast_intermediate_size > 8 * DA_M_CTHREADS || qd > 8 * DA_M_CTHREADS || fqkv_rows > 8 * DA_M_CTHREADS ||
       3 * grid > DA_M_CTHREADS ||
@@ -458,13 +469,13 @@ static int build_mega(dualar_engine *e) {
   // units across the prefill launches in between (a tag collision there would hand a consumer stale data)
   {
     const size_t n_po = (size_t)c.n_local_heads * e->nsplit * G * c.head_dim, n_pml = (size_t)c.n_local_heads * e->nsplit * G * 2;
-    size_t bytes = 12 * ubuf * 4 + (n_po + n_pml + (size_t)grid + 3 * (size_t)grid + DA_CAND_CAP) * 8;
+    size_t bytes = 13 * ubuf * 4 + (n_po + n_pml + (size_t)grid + 3 * (size_t)grid + DA_CAND_CAP) * 8;
     if ((rc = dev_alloc(e, e->u_arena, bytes))) return rc;
     e->u_arena_bytes = bytes;
     unsigned long long *q = (unsigned long long *)e->u_arena;      // 64-bit buffers first (alignment)
     e->m_part_o = q; q += n_po; e->m_part_ml = q; q += n_pml; e->m_hmax = q; q += grid; e->m_hcs = q; q += 3 * grid; e->m_cand = q; q += DA_CAND_CAP;
     uint32_t *u = (uint32_t *)q;
-    uint32_t **slots[12] = {&e->u_x, &e->u_qkv, &e->u_y, &e->u_h, &e->u_act, &e->u_fqkv, &e->u_fh, &e->u_fact, &e->u_fx0, &e->u_fx1, &e->u_fin, &e->u_flogits};
+    uint32_t **slots[13] = {&e->u_x, &e->u_qkv, &e->u_y, &e->u_h, &e->u_act, &e->u_fqkv, &e->u_fh, &e->u_fact, &e->u_fx0, &e->u_fx1, &e->u_fin, &e->u_flogits, &e->u_fpi};
     for (auto sl : slots) { *sl = u; u += ubuf; }
   }
   if ((rc = dev_alloc(e, e->m_phase, 1))) return rc;
@@ -541,9 +552,12 @@ static int build_mega(dualar_engine *e) {
         if (with_head) head_part();
         return gemv(W.w2, nullptr, nullptr, e->u_fact, f, (l & 1) ? e->u_fx1 : e->u_fx0, c.fast_dim, c.fast_intermediate_size, MP_PLAIN, ME_RESIDUAL, MF_KEEP | MF_RES1, l, p);
       };
+      // fast_dim != dim: pass 0 starts from fast_project_in(x) (llama.py:590), one more GEMV phase (bias in the epilogue)
+      int p0_ph = last; const uint32_t *p0_in = e->u_x;
+      if (e->fpi_w) { p0_ph = gemv(e->fpi_w, e->fpi_b, nullptr, e->u_x, last, e->u_fpi, c.fast_dim, c.dim, MP_PLAIN, ME_STORE, MF_KEEP, 0, 0); p0_in = e->u_fpi; }
       for (int l = 0; l < FL; ++l) {      // pass 0 (input: the slow hidden state), interleaved with the head
-        const uint32_t *lin = l == 0 ? e->u_x : (((l - 1) & 1) ? e->u_fx1 : e->u_fx0);
-        prev = fast_layer(0, l, lin, l == 0 ? last : prev, true);
+        const uint32_t *lin = l == 0 ? p0_in : (((l - 1) & 1) ? e->u_fx1 : e->u_fx0);
+        prev = fast_layer(0, l, lin, l == 0 ? p0_ph : prev, true);
       }
       int hs = other(MK_HSTAT, nullptr, hd_ph, nullptr, 0);
       int hc = other(MK_HCAND, nullptr, hs, nullptr, 0);
@@ -646,7 +660,7 @@ extern "C" int dualar_finalize(dualar_engine *e) {
   if ((rc = dev_alloc(e, e->x, c.dim)) || (rc = dev_alloc(e, e->h, c.dim)) || (rc = dev_alloc(e, e->qkv, qkv_rows)) ||
       (rc = dev_alloc(e, e->y, c.n_head * c.head_dim)) || (rc = dev_alloc(e, e->act, c.intermediate_size)) ||
       (rc = dev_alloc(e, e->logits, c.vocab_size)) || (rc = dev_alloc(e, e->logits_raw, c.vocab_size)) ||
-      (rc = dev_alloc(e, e->fin, c.fast_dim)) || (rc = dev_alloc(e, e->fbuf[0], c.fast_dim)) || (rc = dev_alloc(e, e->fbuf[1], c.fast_dim)) ||
+      (rc = dev_alloc(e, e->fin, c.fast_dim)) || (rc = dev_alloc(e, e->fpi, c.fast_dim)) || (rc = dev_alloc(e, e->fbuf[0], c.fast_dim)) || (rc = dev_alloc(e, e->fbuf[1], c.fast_dim)) ||
       (rc = dev_alloc(e, e->fh, c.fast_dim)) || (rc = dev_alloc(e, e->fqkv, fqkv_rows)) || (rc = dev_alloc(e, e->fact, c.fast_intermediate_size)) ||
       (rc = dev_alloc(e, e->flogits, (size_t)c.num_codebooks * e->fv)) || (rc = dev_alloc(e, e->flogits_raw, (size_t)c.num_codebooks * e->fv)) ||
       (rc = dev_alloc(e, e->part_o, (size_t)c.n_local_heads * e->nsplit * G * c.head_dim)) ||

@@ -57,8 +57,6 @@ def _layer_shapes(prefix: str, dim: int, n_head: int, n_kv: int, hd: int, inter:
 
 def weight_manifest(cfg: DualARConfig):
     """Every persistent tensor of the reference model: list of (key, shape, kind)."""
-    if cfg.fast_dim != cfg.dim:
-        raise NotImplementedError("fast_project_in (fast_dim != dim) is not on the supported path")
     m = [("embeddings.weight", (cfg.vocab_size, cfg.dim), "w"),
          ("codebook_embeddings.weight", (cfg.codebook_size * cfg.num_codebooks, cfg.dim), "w")]
     for i in range(cfg.n_layer):
@@ -68,6 +66,9 @@ def weight_manifest(cfg: DualARConfig):
     m.append(("norm.weight", (cfg.dim,), "n"))
     if not cfg.tie_word_embeddings:
         m.append(("output.weight", (cfg.vocab_size, cfg.dim), "w"))
+    if cfg.fast_dim != cfg.dim:      # fast_project_in = nn.Linear(dim, fast_dim), registered before fast_embeddings (llama.py:510-516)
+        m.append(("fast_project_in.weight", (cfg.fast_dim, cfg.dim), "w"))
+        m.append(("fast_project_in.bias", (cfg.fast_dim,), "b"))
     m.append(("fast_embeddings.weight", (cfg.codebook_size, cfg.fast_dim), "w"))
     for i in range(cfg.n_fast_layer):
         m += _layer_shapes(f"fast_layers.{i}", cfg.fast_dim, cfg.fast_n_head, cfg.fast_n_local_heads,

@@ -197,7 +197,8 @@ def block(m: OracleModel, prefix: str, kv, x, freqs_cis, mask, input_pos, fast: 
 
 
 def forward_generate(m: OracleModel, inp: Tensor, input_pos: Tensor):
-    """llama.py:400-453 (+ override 582-591; fast_project_in is Identity when fast_dim == dim).
+    """llama.py:400-453 (+ override 582-591: hidden_states = fast_project_in(x), an nn.Linear(dim, fast_dim) when fast_dim != dim,
+    llama.py:510-513, Identity otherwise).
     inp: (1, C+1, T) int.  Returns (logits (1,1,V), hidden_states (1,1,dim) -- the UN-normalised x)."""
     cfg, w = m.cfg, m.w
     embeds = []
@@ -218,7 +219,10 @@ def forward_generate(m: OracleModel, inp: Tensor, input_pos: Tensor):
         x = x[:, -1:]
     slow_out = rms_norm(x, w["norm.weight"], cfg.norm_eps)
     head = w["embeddings.weight"] if cfg.tie_word_embeddings else w["output.weight"]
-    return linear(m, slow_out, head), x
+    logits = linear(m, slow_out, head)
+    if "fast_project_in.weight" in w:      # DualARTransformer.forward_generate, llama.py:590
+        x = linear(m, x, w["fast_project_in.weight"], w.get("fast_project_in.bias"))
+    return logits, x
 
 
 def forward_generate_fast(m: OracleModel, x: Tensor, input_pos: Tensor) -> Tensor:

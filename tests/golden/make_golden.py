@@ -58,7 +58,10 @@ def run_case(cfg, sd, prompt, n_new, mode, seed, full_logits=True):
 def main():
     t0 = time.time()
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])      # e.g. `make_golden.py projected`: (re)generate the fixtures of the named variants only
     for name, cfg in variant_configs().items():
+        if only and name not in only:
+            continue
         sd = make_state_dict(cfg, seed=0)
         prompt = synthetic_prompt(cfg, 5, 12, 4, seed=1)
         for mode in ("sampled", "greedy", "hot"):
@@ -70,6 +73,8 @@ def main():
         g = run_case(cfg, sd2, prompt, 40, "sampled", seed=11)
         torch.save(g, OUT / f"tiny_{name}_eos.pt")
         print(name, "eos", g["seq"].shape, "ended with", int(g["seq"][0, -1]), "im_end", cfg.im_end_id)
+    if only and "s1mini" not in only:
+        return
     cfg = s1_mini_config()
     sd = make_state_dict(cfg, seed=0)
     prompt = synthetic_prompt(cfg, 6, 20, 4, seed=1)

@@ -1,5 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_batch.py tests/test_gpu_api.py -x -q -s -m gpu > gpurun_out/r2_pytest_batch.log 2>&1; echo "batch rc $?" >> gpurun_out/r2_pytest_batch.log; grep -E "^\[|passed|failed|Error|error|assert" gpurun_out/r2_pytest_batch.log | cut -c1-300 | tail -n 12
-timeout 600 python tests/batch_time.py 32 8 > gpurun_out/r2_batch_time.log 2>&1; cat gpurun_out/r2_batch_time.log | cut -c1-230
-for ns in 1 2 8; do echo "== NSPLIT $ns"; BT_SKIP_PREFILL=1 DUALAR_BATCH_NSPLIT=$ns timeout 300 python tests/batch_time.py 32 2>&1 | grep "batched decode" | cut -c1-100; done
-python tests/batch_profile.py --batch 32 --steps 1 > gpurun_out/r2_bprof_plain.log 2>&1 && ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_ncu_launches_batch32.csv python tests/batch_profile.py --batch 32 --steps 1 > gpurun_out/r2_bprof_ncu.log 2>&1
-python tests/prefill_profile.py --positions 223 > gpurun_out/r2_pf_plain.log 2>&1 && ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_ncu_launches_prefill223.csv python tests/prefill_profile.py --positions 223 > gpurun_out/r2_pf_ncu.log 2>&1; tail -n 1 gpurun_out/r2_pf_plain.log
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r2_pytest_gpu.log 2>&1; echo "gpu rc $?" >> gpurun_out/r2_pytest_gpu.log; tail -n 8 gpurun_out/r2_pytest_gpu.log | cut -c1-400
+timeout 600 python tests/batch_time.py 32 > gpurun_out/r2_batch_time.log 2>&1; cat gpurun_out/r2_batch_time.log | cut -c1-230
+echo "== no fork"; BT_SKIP_PREFILL=1 DUALAR_BATCH_FORK=0 timeout 300 python tests/batch_time.py 32 2>&1 | grep "batched decode" | cut -c1-100

@@ -46,4 +46,6 @@ def variant_configs():
                                fast_head_dim=32, num_codebooks=8),
         "biased": tiny_config(attention_qkv_bias=True, attention_o_bias=True, fast_attention_qk_norm=True,
                               n_layer=2, head_dim=64, n_head=4, n_local_heads=4),
+        "projected": tiny_config(fast_dim=512, fast_n_head=8, fast_n_local_heads=4, fast_head_dim=64,             # fast_dim != dim:
+                                 fast_intermediate_size=768, n_layer=2),                                          # fast_project_in (llama.py:510-513)
     }

@@ -68,3 +68,42 @@ def test_binned_nucleus_equals_sorted_prefix(dist):
                 c_max = sm.cmax_from_top_p(top_p)
                 a, b = sm.nucleus_sorted(z, w, c_max), sm.nucleus_binned(z, w, c_max)
                 assert (a == b).all(), f"{dist} V={V} top_p={top_p} S x{s_factor}: {int(a.sum())} vs {int(b.sum())} kept"
+
+
+def test_where_the_three_nucleus_definitions_can_differ():
+    """DESIGN.md section 5.  The nucleus is {j : bf16(cum_j) <= bf16(top_p)} over the sorted bf16 probabilities; three
+    definitions of cum_j are in play:
+      (R) the reference: torch.cumsum on the bf16 tensor (CPU: an fp32 running sum; CUDA: a parallel scan in unspecified order),
+      (O) the oracle with stable_ties: an fp32 running sum in sorted order, rounded to bf16 per element (= R on the CPU),
+      (K) the kernels: the EXACT sum (2^-44 fixed point), compared against the bf16 rounding boundary of top_p.
+    bf16(cum_j) only changes at a bf16 rounding boundary, and the cut is decided at ONE boundary: M = the midpoint between
+    bf16(top_p) and its successor.  K and O/R can therefore only disagree when the exact cumulative sum at the cut passes M
+    within the rounding error of an fp32 running sum of n terms <= 1 (n * 2^-24).  Checked here on random vectors: whenever
+    the nucleus sizes differ, the exact sum at the boundary index lies within that error of M; otherwise they are identical --
+    and they are identical in the overwhelming majority of cases."""
+    import numpy as np
+    rng = np.random.default_rng(123)
+    differ, total = 0, 0
+    for V in (1024, 4096):
+        for scale in (0.3, 0.64, 2.5):
+            for top_p in (0.3, 0.7, 0.8, 0.95):
+                for _ in range(12):
+                    z = torch.from_numpy((rng.standard_normal(V) * scale).astype(np.float32)).bfloat16()
+                    zs, _ = torch.sort(z, descending=True, stable=True)
+                    p = torch.softmax(zs, dim=-1)                                         # bf16 probabilities, the reference's own op
+                    tp = torch.tensor(top_p).bfloat16()
+                    n_ref = int((torch.cumsum(p, dim=-1) <= tp).sum())                    # (R) on the CPU
+                    n_orc = int((torch.cumsum(p.float(), dim=-1).to(torch.bfloat16) <= tp).sum())      # (O)
+                    w = (p.float().double().numpy() * sm.FIX).astype(np.int64)
+                    cum = np.cumsum(w)
+                    c_max = sm.cmax_from_top_p(top_p)
+                    n_k = int((cum <= c_max).sum())                                       # (K)
+                    total += 1
+                    assert n_ref == n_orc, "stable_ties keeps the reference's CPU nucleus (cumsum order is the sorted order on both)"
+                    if n_k != n_orc:
+                        differ += 1
+                        j = min(n_k, n_orc)                                               # first index on which they disagree
+                        gap = abs(int(cum[min(j, V - 1)]) - c_max) / sm.FIX
+                        assert abs(n_k - n_orc) <= 2 and gap <= V * 2.0 ** -23 + float(p[min(j, V - 1)]), \
+                            f"nucleus sizes {n_k} vs {n_orc} differ away from the rounding boundary (gap {gap:.3e})"
+    assert differ <= 0.05 * total, f"{differ}/{total} vectors with a boundary disagreement"
