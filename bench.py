@@ -18,7 +18,7 @@ semantic id + num_codebooks codes.
   roofline   algorithmic bytes per step (unique weights once + KV over the mean context) / mean step time, against the
              measured HBM copy peak of MEASURED_PEAKS.json.
   Extras on the same line at N = 1 (skipped with --no-extras): `batch32` (configs[3]: 32 request slots, mixed prompts, tcgen05
-  GEMMs), `prefill` (223 positions through the tensor-core prefill), `streaming` (first-chunk latency / RTF through the chunked
+  GEMMs), `batch128` (128 slots as 4 concurrently running groups of 32), `prefill` (223 positions through the tensor-core prefill), `streaming` (first-chunk latency / RTF through the chunked
   hand-off), `cpu_baseline` and `torch_baselines`: the UNMODIFIED reference's own init_model + generate (oracle/ref_bench.py on the
   copy oracle/make_ref.py ships) on this box's host cores and, under torch.compile(mode="reduce-overhead"), on this GPU.
 --workload batch: the batched decode step alone (configs[3]); --workload utterances: configs[4], N utterances with mixed lengths
@@ -210,10 +210,11 @@ def run_reference(args, rank: int):
 
 
 # ---- measurements on our engine -----------------------------------------------------------------------------------------------------
-def measure_batch(eng, cfg, B, steps, warmup, slot_len=1152, seed=2):
+def measure_batch(eng, cfg, B, steps, warmup, slot_len=1152, seed=2, group_slots=None):
     """configs[3]: B request slots, prompt lengths uniform in [64, 512], one batched step = one token for every slot"""
     import numpy as np
-    eng.batch_init(B, slot_len)
+    eng.batch_init(B, slot_len, group_slots)
+    groups = int(eng.batch_read("groups")[0])
     rng = np.random.default_rng(seed)
     lens = rng.integers(64, 513, size=B)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -235,12 +236,14 @@ def measure_batch(eng, cfg, B, steps, warmup, slot_len=1152, seed=2):
     by = wb["unique_weights"] + wb["kv_per_pos"] * (ctx + 1) * B
     peak, peak_src = measured_peak()
     launches = int(eng.batch_read("launches")[0])
-    return {"value": B / ms * 1e3, "unit": "tokens/s", "batch": B, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+    return {"value": B / ms * 1e3, "unit": "tokens/s", "batch": B, "groups": groups, "ms_per_step": ms, "steps": steps, "warmup": warmup,
             "launches_per_step": launches, "prefill_ms_total": t_pf, "mean_prompt": float(lens.mean()),
-            "workload": f"batched decode bs={B}, prompt lengths uniform in [64, 512] (seed {seed}), one KV cache per slot, T=0.7 top_p=0.8 rp=1.1",
+            "workload": f"batched decode bs={B}" + (f" as {groups} concurrent groups of {-(-B // groups)} slots" if groups > 1 else "") +
+                        f", prompt lengths uniform in [64, 512] (seed {seed}), one KV cache per slot, T=0.7 top_p=0.8 rp=1.1",
             "roofline": {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": by / ms / 1e6 / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": by, "mean_context": ctx,
-                         "kernel": "one batched step: tcgen05 GEMMs (weights streamed once for all slots) + per-slot attention / samplers"}}
+                         "kernel": "one batched step: tcgen05 GEMMs (weights streamed once per group of slots) + per-slot attention / samplers; "
+                                   "algorithmic bytes count the weights ONCE per step however many groups stream them"}}
 
 
 def measure_stream(eng, cfg, prompt, n_tokens, first_chunk=10, chunk=20):
@@ -294,8 +297,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="decode", choices=["decode", "batch", "utterances", "stream"])
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--group-slots", type=int, default=None, help="request slots per concurrently running group (default 32)")
     ap.add_argument("--utterances", type=int, default=4096)
-    ap.add_argument("--no-extras", action="store_true", help="decode workload: skip batch32 / prefill / streaming / reference baselines")
+    ap.add_argument("--no-extras", action="store_true", help="decode workload: skip batch32 / batch128 / prefill / streaming / reference baselines")
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--e2e-requests", type=int, default=2)
     ap.add_argument("--model", default="s1mini", choices=["s1mini", "v15"], help="openaudio-s1-mini (BASELINE configs[1], the headline) or the fish-speech 1.5 shape (configs[2])")
@@ -445,6 +449,10 @@ def main():
             line["streaming"]["codec_stand_in"] = codec_stand_in(torch.device("cuda", local))
             line["batch32"] = measure_batch(eng, cfg, 32, 128, 16)
             eng.close()
+            # 128 request slots as 4 concurrently running groups of 32 (a fresh engine: slots are allocated once per engine)
+            eng = DualAREngine(cfg, sd, device=local, seed=1234 + rank)
+            line["batch128"] = measure_batch(eng, cfg, 128, 64, 8)
+            eng.close()
             torch.cuda.empty_cache()
             line["cpu_baseline"] = cpu_baseline(args, cfg, args.cpu_steps)
             tb = run_ref_bench("cuda", True, args.model, T, 4, 128, budget=60, timeout=420)
@@ -462,7 +470,7 @@ def main():
 
 def run_batch_workload(args, cfg, eng, dist, rank, world, local):
     with ClockSampler(local) as clocks:
-        m = measure_batch(eng, cfg, args.batch, args.steps if args.steps != 1024 else 256, max(args.warmup, 3), seed=2 + rank)
+        m = measure_batch(eng, cfg, args.batch, args.steps if args.steps != 1024 else 256, max(args.warmup, 3), seed=2 + rank, group_slots=args.group_slots)
     t = torch.tensor([m["ms_per_step"]], device="cuda")
     if dist:
         dist.barrier(); dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -489,7 +497,7 @@ def run_utterances(args, cfg, eng, dist, rank, world, local):
         dist.barrier()
     with ClockSampler(local) as clocks:
         if B > 1:
-            eng.batch_init(B, 512 + 1024 + 64)
+            eng.batch_init(B, 512 + 1024 + 64, args.group_slots)
             res = replicas.run_rank_batched(eng, utts, rank, world, B, sync=sync)
         else:
             res = replicas.run_rank(lambda u: eng.generate(u.prompt, u.max_new_tokens, u.temperature, u.top_p, u.repetition_penalty), utts, rank, world, sync=sync)

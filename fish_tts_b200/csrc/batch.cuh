@@ -33,14 +33,13 @@ struct BEmbedArgs {
   float inv_sqrt, sqrt_c;
   TokSrc tok; int *err;
 };
-__global__ void __launch_bounds__(128) b_embed_kernel(const BEmbedArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int n = blockIdx.x;
+template <class B> __device__ __forceinline__ void b_embed_body(const BEmbedArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm) {
+  (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
+  const int n = bx;
   int tok = a.tok.base[n * a.tok.sn];
   if (tok < 0 || tok >= a.vocab) { tok = 0; if (threadIdx.x == 0) atomicExch(a.err, 1); }
   const bool is_sem = tok >= a.sem_begin && tok <= a.sem_end;
-  for (int c = threadIdx.x; c * 8 < a.dim; c += blockDim.x) {
+  for (int c = threadIdx.x; c * 8 < a.dim; c += B::nthreads()) {
     float te[8], vq[8];
     unpack8(*reinterpret_cast<const uint4 *>(a.emb + (size_t)tok * a.dim + c * 8), te);
 #pragma unroll
@@ -69,13 +68,18 @@ __global__ void __launch_bounds__(128) b_embed_kernel(const BEmbedArgs a) {
     *reinterpret_cast<uint4 *>(a.x + (size_t)n * a.dim + c * 8) = u;
   }
 }
+__global__ void __launch_bounds__(128) b_embed_kernel(const BEmbedArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm_b_embed_body[];
+  pdl_launch_dependents();
+  pdl_wait();
+  b_embed_body<BlockAll>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_embed_body);
+}
 
 // ---- RMSNorm: one warp per column -------------------------------------------------------------------------------------------------
 struct BNormArgs { const bf16 *x, *w; bf16 *out; int K, ncols; float eps; };
-__global__ void __launch_bounds__(128) b_rmsnorm_kernel(const BNormArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = threadIdx.x & 31, n = blockIdx.x * 4 + (threadIdx.x >> 5);
+template <class B> __device__ __forceinline__ void b_rmsnorm_body(const BNormArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm) {
+  (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
+  const int lane = threadIdx.x & 31, n = bx * (B::nthreads() >> 5) + (threadIdx.x >> 5);
   if (n >= a.ncols) return;
   const uint4 *src = reinterpret_cast<const uint4 *>(a.x + (size_t)n * a.K);
   const int nc = a.K >> 3;
@@ -97,6 +101,12 @@ __global__ void __launch_bounds__(128) b_rmsnorm_kernel(const BNormArgs a) {
     reinterpret_cast<uint4 *>(a.out + (size_t)n * a.K)[c] = u;
   }
 }
+__global__ void __launch_bounds__(128) b_rmsnorm_kernel(const BNormArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm_b_rmsnorm_body[];
+  pdl_launch_dependents();
+  pdl_wait();
+  b_rmsnorm_body<BlockAll>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_rmsnorm_body);
+}
 
 // ---- q/k norm + RoPE in place, K/V rows into the cache ----------------------------------------------------------------------------
 struct BQkvPostArgs {
@@ -107,11 +117,10 @@ struct BQkvPostArgs {
   int nh, nkv, hd, S, ncols; float eps;
   PosSrc pos;
 };
-__global__ void __launch_bounds__(256) b_qkv_post_kernel(const BQkvPostArgs a) {
-  extern __shared__ __align__(16) float sm_qp[];      // 8 warps x hd floats
-  pdl_launch_dependents();
-  pdl_wait();
-  const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+template <class B> __device__ __forceinline__ void b_qkv_post_body(const BQkvPostArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm) {
+  (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
+  float *sm_qp = reinterpret_cast<float *>(dsm);      // one head vector (hd floats) per warp
+  const int n = bx, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
   const int hd = a.hd, qd = a.nh * hd, kd = a.nkv * hd;
   const int pos = pos_of(a.pos, n);
   if (pos < 0 || pos >= a.S) return;
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(256) b_qkv_post_kernel(const BQkvPostArgs a) {
   const bf16 *rope_row = a.rope + (size_t)pos * hd;
   float *v = sm_qp + (size_t)w * hd;
   // grid (ncols, head groups): one head vector per warp, so the dependent round trips of a head run in parallel across heads
-  for (int h = blockIdx.y * nw + w; h < a.nh + 2 * a.nkv; h += nw * gridDim.y) {
+  for (int h = by * nw + w; h < a.nh + 2 * a.nkv; h += nw * gy) {
     bf16 *src = row + (size_t)h * hd;
     if (h >= a.nh + a.nkv) {            // v head: KVCache.update (llama.py:142-149), no norm / rotation
       const int g = h - a.nh - a.nkv;
@@ -134,6 +143,12 @@ __global__ void __launch_bounds__(256) b_qkv_post_kernel(const BQkvPostArgs a) {
     else { const int g = h - a.nh; for (int d = lane; d < hd; d += 32) kc[((size_t)g * a.S + pos) * hd + d] = f2bf(v[d]); }
     __syncwarp();
   }
+}
+__global__ void __launch_bounds__(256) b_qkv_post_kernel(const BQkvPostArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm_b_qkv_post_body[];
+  pdl_launch_dependents();
+  pdl_wait();
+  b_qkv_post_body<BlockAll>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_qkv_post_body);
 }
 
 // ---- slow attention: split-KV flash-decode, one query per column ----------------------------------------------------------------
@@ -157,11 +172,15 @@ static inline size_t b_attn_smem(int G, int hd) {
   f = (f + 127) & ~(size_t)127;
   return f + 128 + 4 * (size_t)DA_TILE * hd * sizeof(bf16);
 }
-__global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnArgs a) {
-  extern __shared__ __align__(128) unsigned char smraw_b[];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int g = blockIdx.y, split = blockIdx.x, n = blockIdx.z;
+// `bars`: two mbarriers in STATIC shared memory; `phase`: their parities as this thread has seen them.  The stand-alone kernel
+// initialises them per launch (init = true); the persistent kernel initialises them once and carries the parities from unit to unit --
+// re-initialising an mbarrier in the middle of a kernel (through a per-thread address: a plain 64-bit store + a sync-unit cache
+// invalidate in SASS) lost the transaction that followed on B200.
+template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm,
+                                                               uint64_t *bars, uint32_t (&phase)[2], bool init) {
+  (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
+  unsigned char *smraw_b = dsm;
+  const int g = by, split = bx, n = bz;
   const int G = a.nh / a.nkv, hd = a.hd, dpl = hd >> 5;      // output dims per lane (1, 2 or 4)
   const int pos = pos_of(a.pos, n);
   if (pos < 0 || pos >= a.S) return;
@@ -177,18 +196,17 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float *q = reinterpret_cast<float *>(smraw_b);
   float *pm = q + G * hd, *pl = pm + DA_B_AWARPS * G, *po = pl + DA_B_AWARPS * G;      // per-warp partials: [8][G], [8][G], [8][G][hd]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(po + (size_t)DA_B_AWARPS * G * hd);
-  size_t off = (size_t)((unsigned char *)(bars + 2) - smraw_b);
+  size_t off = (size_t)((unsigned char *)(po + (size_t)DA_B_AWARPS * G * hd) - smraw_b) + 16;
   off = (off + 127) & ~(size_t)127;
   bf16 *kbuf = reinterpret_cast<bf16 *>(smraw_b + off);
   bf16 *vbuf = kbuf + 2 * DA_TILE * hd;
   const bf16 *kc = a.kc + (size_t)n * a.slot_stride, *vc = a.vc + (size_t)n * a.slot_stride;
   const uint64_t pol = policy_evict_first();
-  if (threadIdx.x == 0) {
+  if (init && threadIdx.x == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  B::sync();
   auto issue = [&](int t, int buf) {
     const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE);
     const uint32_t bytes = (uint32_t)(r1 - r0) * hd * sizeof(bf16);
@@ -206,8 +224,7 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
       for (int j = 0; j < 8; ++j) q[c * 8 + j] = __fmul_rn(t[j], a.sf);      // q * sqrt(scale), fp32 (math SDPA)
     }
   }
-  __syncthreads();
-  uint32_t phase[2] = {0u, 0u};
+  B::sync();
   bool ok = true;
   const int psl = lane >> 3, dl = lane & 7;
   for (int t = t0; t < t1; ++t) {
@@ -294,7 +311,7 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
       }
       __syncwarp();
     }
-    __syncthreads();      // every warp is past its last read of the tile: its buffer may be refilled
+    B::sync();      // every warp is past its last read of the tile: its buffer may be refilled
   }
   if (!ok && threadIdx.x == 0) atomicExch(a.err, 2);
   // fold the 8 warps' partials in warp order: thread e = (h, d)
@@ -320,10 +337,10 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
   if (nsplit_eff == 1) return;
   __shared__ unsigned int s_last;
   __threadfence();
-  __syncthreads();
+  B::sync();
   unsigned int *ticket = a.tickets + (size_t)n * a.nkv + g;
   if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned)nsplit_eff - 1);
-  __syncthreads();
+  B::sync();
   if (!s_last) return;
   __threadfence();
   for (int e = threadIdx.x; e < G * hd; e += DA_ATTN_THREADS) {      // merge in split order (deterministic)
@@ -341,6 +358,14 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
+__global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm_b_attn_body[];
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __align__(8) uint64_t s_bars[2];
+  uint32_t phase[2] = {0u, 0u};
+  b_attn_body<BlockAll>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_attn_body, s_bars, phase, true);
+}
 
 // ---- fast-layer attention for codebook position p, one CTA per column ---------------------------------------------------------------
 struct BFastAttnArgs {
@@ -352,16 +377,15 @@ struct BFastAttnArgs {
   bf16 *y;                   // [ncols][nh * hd]
 };
 // dynamic smem: q[qd] | k[ncb][kd] | v[ncb][kd] | pr[nh][ncb]  floats
-__global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f) {
-  extern __shared__ __align__(16) float sm_fa[];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+template <class B> __device__ __forceinline__ void b_fast_attn_body(const BFastAttnArgs &f, int bx, int by, int bz, int gy, unsigned char *dsm) {
+  (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
+  float *sm_fa = reinterpret_cast<float *>(dsm);
+  const int n = bx, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = B::nthreads() >> 5;
   const int qd = f.nh * f.hd, kd = f.nkv * f.hd, P = f.p + 1, G = f.nh / f.nkv;
   float *q = sm_fa, *ka = q + qd, *va = ka + f.ncb * kd, *pr = va + f.ncb * kd;
   const bf16 *row = f.qkv + (size_t)n * (qd + 2 * kd);
   bf16 *kc = f.kc + (size_t)n * f.slot_stride, *vc = f.vc + (size_t)n * f.slot_stride;
-  for (int c = threadIdx.x; c * 8 < qd + 2 * kd; c += blockDim.x) {
+  for (int c = threadIdx.x; c * 8 < qd + 2 * kd; c += B::nthreads()) {
     float t[8]; unpack8(*reinterpret_cast<const uint4 *>(row + c * 8), t);
     const int e = c * 8;
     float *dst = e < qd ? q + e : (e < qd + kd ? ka + f.p * kd + (e - qd) : va + f.p * kd + (e - qd - kd));
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f)
     for (int j = 0; j < 8; ++j) dst[j] = t[j];
   }
   const int hd8 = f.hd >> 3, kd8 = kd >> 3;
-  for (int c = threadIdx.x; c < f.p * kd8; c += blockDim.x) {      // earlier positions from the cache
+  for (int c = threadIdx.x; c < f.p * kd8; c += B::nthreads()) {      // earlier positions from the cache
     const int j = c / kd8, r = c - j * kd8, g = r / hd8, d8 = r - g * hd8;
     const size_t src = ((size_t)g * f.ncb + j) * f.hd + (size_t)d8 * 8;
     float t[8];
@@ -380,19 +404,19 @@ __global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f)
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) va[c * 8 + jj] = t[jj];
   }
-  __syncthreads();
+  B::sync();
   const bf16 *rope_row = f.rope + (size_t)f.p * f.hd;
   for (int h = w; h < f.nh + f.nkv; h += nw) {
     if (h < f.nh) head_norm_rope(q + h * f.hd, f.hd, f.qn, f.eps, rope_row, lane);
     else head_norm_rope(ka + f.p * kd + (h - f.nh) * f.hd, f.hd, f.kn, f.eps, rope_row, lane);
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < kd; e += blockDim.x) {               // KVCache.update (llama.py:142-149)
+  B::sync();
+  for (int e = threadIdx.x; e < kd; e += B::nthreads()) {               // KVCache.update (llama.py:142-149)
     const int g = e / f.hd, d = e - g * f.hd;
     const size_t dst = ((size_t)g * f.ncb + f.p) * f.hd + d;
     kc[dst] = f2bf(ka[f.p * kd + e]); vc[dst] = f2bf(va[f.p * kd + e]);
   }
-  for (int t = threadIdx.x; t < f.nh * P; t += blockDim.x) {         // bf16(q @ k^T), then bf16(* scale)   (llama.py:304)
+  for (int t = threadIdx.x; t < f.nh * P; t += B::nthreads()) {         // bf16(q @ k^T), then bf16(* scale)   (llama.py:304)
     const int h = t / P, j = t - h * P, g = h / G;
     const float4 *qq = reinterpret_cast<const float4 *>(q + h * f.hd), *kk = reinterpret_cast<const float4 *>(ka + j * kd + g * f.hd);
     float acc = 0.f;
@@ -402,7 +426,7 @@ __global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f)
     }
     pr[h * f.ncb + j] = rbf(__fmul_rn(rbf(acc), f.scale));
   }
-  __syncthreads();
+  B::sync();
   // softmax in fp32, rounded to bf16 (llama.py:305-306; masked columns are exp(-inf) = 0).  One thread per (h, j)
   // (nh * ncb <= 256, check_config); every thread of a row walks it in the same order, so the row sum is identical
   float pval = 0.f;
@@ -415,11 +439,11 @@ __global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f)
     for (int jj = 0; jj < P; ++jj) sum += expf(pr[h * f.ncb + jj] - m);
     pval = rbf(expf(pr[h * f.ncb + j] - m) / sum);
   }
-  __syncthreads();
+  B::sync();
   if (tt < f.nh * P) { const int h = tt / P, j = tt - h * P; pr[h * f.ncb + j] = pval; }
-  __syncthreads();
+  B::sync();
   bf16 *yo = f.y + (size_t)n * qd;
-  for (int c = threadIdx.x; c * 8 < qd; c += blockDim.x) {           // y = bf16(p @ v)   (llama.py:309)
+  for (int c = threadIdx.x; c * 8 < qd; c += B::nthreads()) {           // y = bf16(p @ v)   (llama.py:309)
     const int e = c * 8, h = e / f.hd, d = e - h * f.hd, g = h / G;
     float acc[8];
 #pragma unroll
@@ -435,6 +459,12 @@ __global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f)
     u.z = (uint32_t)f2bits(acc[4]) | ((uint32_t)f2bits(acc[5]) << 16); u.w = (uint32_t)f2bits(acc[6]) | ((uint32_t)f2bits(acc[7]) << 16);
     *reinterpret_cast<uint4 *>(yo + e) = u;
   }
+}
+__global__ void __launch_bounds__(256) b_fast_attn_kernel(const BFastAttnArgs f) {
+  extern __shared__ __align__(128) unsigned char dsm_b_fast_attn_body[];
+  pdl_launch_dependents();
+  pdl_wait();
+  b_fast_attn_body<BlockAll>(f, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_fast_attn_body);
 }
 static inline size_t b_fast_attn_smem(int nh, int nkv, int hd, int ncb) {
   return ((size_t)nh * hd + 2 * (size_t)ncb * nkv * hd + (size_t)nh * ncb) * sizeof(float);
@@ -569,11 +599,10 @@ struct BFastSampleArgs {
   DAState *st;
 };
 // grid (ncols), 256 threads; dynamic smem: b_fast_sample_smem()
-__global__ void __launch_bounds__(256) b_fast_sample_kernel(const BFastSampleArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw_fs[];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int n = blockIdx.x;
+template <class B> __device__ __forceinline__ void b_fast_sample_body(const BFastSampleArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm) {
+  (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
+  unsigned char *smraw_fs = dsm;
+  const int n = bx;
   DAState *st = a.st + n;
   unsigned long long *scr = reinterpret_cast<unsigned long long *>(smraw_fs);      // 256 u64: block_reduce buffers + the binned sampler's warp totals
   float *scrf = reinterpret_cast<float *>(scr + 256);                               // 80 floats
@@ -583,7 +612,7 @@ __global__ void __launch_bounds__(256) b_fast_sample_kernel(const BFastSampleArg
   const float rp_bf = eff_rep_penalty(st);
   const int use_pen = st->use_penalty;
   if (threadIdx.x < DA_WIN) s_pen[threadIdx.x] = use_pen ? st->win[(a.head + 1) * DA_WIN + threadIdx.x] : -1;      // previous_tokens[k+1]
-  __syncthreads();
+  B::sync();
   uint32_t it4[DA_FAST_IPT];
   float mx = -INFINITY;
 #pragma unroll
@@ -602,22 +631,22 @@ __global__ void __launch_bounds__(256) b_fast_sample_kernel(const BFastSampleArg
     }
   }
   SampleParams sp;
-  sp.m = block_max(mx, scrf);
+  sp.m = block_max<B>(mx, scrf);
   {
     Red es = {0ull, 0, -1}; int par = 0;
 #pragma unroll
     for (int i = 0; i < DA_FAST_IPT; ++i) if (it4[i] != 0xFFFFFFFFu) es.s += (unsigned long long)(expf(bits2f(key_bf16(0xFFFFu - (it4[i] >> 16))) - sp.m) * DA_FIX2_SCALE);
-    sp.S = __ull2float_rn(block_reduce(es, scr, par).s) * (1.0f / DA_FIX2_SCALE);
-    __syncthreads();
+    sp.S = __ull2float_rn(block_reduce<B>(es, scr, par).s) * (1.0f / DA_FIX2_SCALE);
+    B::sync();
   }
   sp.T_bf = eff_temperature(st);
   sp.c_max = cmax_from_top_p(st->top_p);
   // the binned exact nucleus search (sampler.cuh: same sums, same token as the bisection / sorting samplers) -- 5 block-wide steps
   // instead of ~35 bisection rounds
-  uint32_t tok = sample_binned<DA_FAST_IPT, 256, BlockAll>(it4, (uint32_t)a.fv, true, nullptr, sp, noise_src(st), (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], smb, scr);
+  uint32_t tok = sample_binned<DA_FAST_IPT, 256, B>(it4, (uint32_t)a.fv, true, nullptr, sp, noise_src(st), (uint32_t)a.head, a.noise_off, &st->nucleus[a.head], smb, scr);
   if (tok >= (uint32_t)a.codebook_size) { tok = a.codebook_size - 1; if (threadIdx.x == 0) st->err = 3; }
-  if (!a.last_head) for (int d = threadIdx.x; d < a.fast_dim; d += blockDim.x) a.fast_x[(size_t)n * a.fast_dim + d] = a.fast_emb[(size_t)tok * a.fast_dim + d];
-  __syncthreads();
+  if (!a.last_head) for (int d = threadIdx.x; d < a.fast_dim; d += B::nthreads()) a.fast_x[(size_t)n * a.fast_dim + d] = a.fast_emb[(size_t)tok * a.fast_dim + d];
+  B::sync();
   if (threadIdx.x == 0) {
     st->tok_out[a.head + 1] = (int)tok;
     if (a.last_head && !st->done) {
@@ -625,6 +654,12 @@ __global__ void __launch_bounds__(256) b_fast_sample_kernel(const BFastSampleArg
       finish_step(g);
     }
   }
+}
+__global__ void __launch_bounds__(256) b_fast_sample_kernel(const BFastSampleArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm_b_fast_sample_body[];
+  pdl_launch_dependents();
+  pdl_wait();
+  b_fast_sample_body<BlockAll>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_fast_sample_body);
 }
 
 }  // namespace da

@@ -23,6 +23,14 @@ struct ColBufs {
   float *cmax = nullptr; unsigned long long *cand = nullptr;
 };
 
+// the step's kernel sequence recorded as phases of the persistent kernel (bstep.cuh) instead of being launched
+struct BRec {
+  std::vector<BPhase> ph; std::vector<CUtensorMap> maps; std::map<const CUtensorMap *, int> idx;
+  int split = -1;      // phases [0, split) run before the slow sampler's kernels, [split, n) after them
+  BPhase &add(int kind, dim3 g) { BPhase p; memset(&p, 0, sizeof(p)); p.kind = kind; p.gx = (int)g.x; p.gy = (int)g.y; p.gz = (int)g.z; ph.push_back(p); return ph.back(); }
+  int map_index(const CUtensorMap *m) { auto it = idx.find(m); if (it != idx.end()) return it->second; const int i = (int)maps.size(); maps.push_back(*m); idx[m] = i; return i; }
+};
+
 }  // namespace
 
 struct dualar_batch {
@@ -30,16 +38,23 @@ struct dualar_batch {
   ColBufs c;
   DAState *st = nullptr, *h_st = nullptr; int *seq = nullptr, *h_seq = nullptr;
   std::vector<bf16 *> kc, vc, fkc, fvc; long long slot_stride = 0, fslot_stride = 0;
-  cudaGraphExec_t g_step = nullptr; int launches = 0;
+  cudaGraphExec_t g_step = nullptr, g_step_p = nullptr; int launches = 0, launches_p = 0;      // per-kernel graph / persistent graph
   cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;      // LM head + slow sampler run beside fast pass 0
   std::vector<int> prompt_len, max_gen; std::vector<char> open;
+  float *ws = nullptr; unsigned int *tickets = nullptr;      // split-K workspace of THIS group's GEMMs (groups run concurrently)
+  cudaStream_t stream = nullptr; cudaEvent_t ev_done = nullptr;      // the group's own stream when there are several groups
+  // persistent step (bstep.cuh): two cooperative launches around the slow sampler's kernels
+  bool persistent = false; BPhase *d_phases = nullptr; CUtensorMap *d_maps = nullptr; unsigned int *gbar = nullptr;
+  int n_phases = 0, split = 0, bs_stages = 0; size_t bs_smem = 0; long long *d_tl = nullptr; std::vector<int> kinds;
 };
 
 struct dualar_tc {
   std::map<MapKey, CUtensorMap> maps;
-  float *ws = nullptr; size_t ws_bytes = 0; unsigned int *tickets = nullptr; int *err = nullptr;
+  float *ws = nullptr; size_t ws_bytes = 0; unsigned int *tickets = nullptr; int *err = nullptr;      // ws / tickets: the workspace GEMMs are enqueued with (a group's while its step is captured)
+  float *ws_own = nullptr; unsigned int *tickets_own = nullptr;
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
+  BRec *rec = nullptr;        // non-null while the step is being recorded for the persistent kernel
   int ksplit_override = 0, stages_override = 0, bn_override = 0;
   bool fuse_norm = false;     // DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>) instead of a separate
                               // RMSNorm kernel in front of them.  Bit-identical (tests/test_gpu_batch.py), 145 kernels fewer per step -- and measured
@@ -100,6 +115,7 @@ static int tc_init(dualar_engine *e) {
   { const char *v = getenv("DUALAR_TC_FUSE_NORM"); e->tc->fuse_norm = v && v[0] == '1'; }
   e->tc->ws_bytes = (size_t)48 << 20;
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
+  e->tc->ws_own = e->tc->ws; e->tc->tickets_own = e->tc->tickets;
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
   { const char *v = getenv("DUALAR_TC_KSPLIT"); if (v) e->tc->ksplit_override = atoi(v); }
   { const char *v = getenv("DUALAR_TC_STAGES"); if (v) e->tc->stages_override = atoi(v); }
@@ -147,6 +163,12 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
   const int nk_per = (nkb + ks - 1) / ks; if (st > nk_per) st = nk_per < 2 ? 2 : nk_per;
   a.stages = st;
   const dim3 grid(rt, ct, ks), block(DA_TC_THREADS);
+  if (BRec *r = e->tc->rec) {
+    if (norm_w || prefill) return fail(DUALAR_EINVAL, "the persistent step records plain decode GEMMs only");
+    BPhase &p = r->add(BP_GEMM, grid);
+    p.map_w = r->map_index(mw); p.map_x = r->map_index(mx); p.u.gemm = a;
+    return 0;
+  }
   if (norm_w) {
     if (!tc_can_fuse_norm(e, BN, K) || ct != 1) return fail(DUALAR_EINVAL, "fused norm needs BN 32 and one column tile");
     a.xraw = X; a.norm_w = norm_w; a.eps = e->c.norm_eps;
@@ -183,9 +205,11 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
     a.emb = e->emb; a.cb_emb = e->cb_emb; a.x = c.x; a.dim = cf.dim; a.vocab = cf.vocab_size; a.codebook_size = cf.codebook_size; a.num_codebooks = cf.num_codebooks;
     a.sem_begin = cf.semantic_begin_id; a.sem_end = cf.semantic_end_id; a.scale_cb = cf.scale_codebook_embeddings; a.cpu_sem = e->cpu_sem; a.ncols = ncols;
     a.inv_sqrt = (float)(1.0 / sqrt((double)(cf.num_codebooks + 1))); a.sqrt_c = (float)sqrt((double)(cf.num_codebooks + 1)); a.tok = tok; a.err = e->tc->err;
-    CU(launch_k(b_embed_kernel, dim3(ncols), dim3(128), 0, s, a)); ++count; }
+    if (BRec *r = e->tc->rec) r->add(BP_EMBED, dim3(ncols)).u.embed = a;
+    else { CU(launch_k(b_embed_kernel, dim3(ncols), dim3(128), 0, s, a)); ++count; } }
   auto norm = [&](const bf16 *x, const bf16 *w, bf16 *out, int K) -> int {
     BNormArgs a{x, w, out, K, ncols, cf.norm_eps};
+    if (BRec *r = e->tc->rec) { r->add(BP_NORM, dim3((ncols + 7) / 8)).u.norm = a; return 0; }      // one warp per column, 8 compute warps
     CU(launch_k(b_rmsnorm_kernel, dim3((ncols + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
   for (int l = 0; l < cf.n_layer; ++l) {
     LayerW &L = e->slow[l];
@@ -198,12 +222,16 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
     { BQkvPostArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn;
       a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S; a.ncols = ncols; a.eps = cf.norm_eps; a.pos = pos;
-      CU(launch_k(b_qkv_post_kernel, dim3(ncols, (cf.n_head + 2 * cf.n_local_heads + 7) / 8), dim3(256), (size_t)8 * cf.head_dim * sizeof(float), s, a)); ++count; }
+      const dim3 g(ncols, (cf.n_head + 2 * cf.n_local_heads + 7) / 8);
+      if (BRec *r = e->tc->rec) r->add(BP_QKV_POST, g).u.post = a;
+      else { CU(launch_k(b_qkv_post_kernel, g, dim3(256), (size_t)8 * cf.head_dim * sizeof(float), s, a)); ++count; } }
     { BAttnArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S;
       a.ncols = ncols; a.nsplit_max = c.nsplit; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
       a.tickets = c.attn_tickets; a.y = c.y; a.pos = pos; a.err = e->tc->err;
-      CU(launch_k(b_attn_kernel, dim3(c.nsplit, cf.n_local_heads, ncols), dim3(DA_ATTN_THREADS), b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; }
+      const dim3 g(c.nsplit, cf.n_local_heads, ncols);
+      if (BRec *r = e->tc->rec) r->add(BP_ATTN, g).u.attn = a;
+      else { CU(launch_k(b_attn_kernel, g, dim3(DA_ATTN_THREADS), b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; } }
     if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count, nullptr, prefill))) return rc;
     if (fuse) { if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.h, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count, L.ffn_norm))) return rc; }
     else {
@@ -231,6 +259,18 @@ static int tc_prefill(dualar_engine *e, const KvTarget &kv, const int *seq, int 
 }
 
 // ---- batched decode ------------------------------------------------------------------------------------------------------------------
+// slow sampler (inference.py:103-113): repetition penalty + chunk maxima, then exact nucleus statistics and the draw in the last CTA per request
+static int enqueue_slow_sampler(dualar_engine *e, cudaStream_t s2, int &count) {
+  dualar_batch &b = *e->batch; ColBufs &c = b.c; const dualar_config &cf = e->c; const int B = b.B, R = cf.num_codebooks + 1;
+  { BHeadArgs a{c.logits, e->batch_keep_raw ? c.logits_raw : nullptr, c.cmax, cf.vocab_size, b.nchunk, R, b.st};
+    CU(launch_k(b_head_stats_kernel, dim3(b.nchunk, B), dim3(512), 0, s2, a)); ++count; }
+  { BSelectArgs a; memset(&a, 0, sizeof(a));
+    a.logits = c.logits; a.cmax = c.cmax; a.V = cf.vocab_size; a.nchunk = b.nchunk; a.delta = e->delta; a.cand = c.cand; a.fast_emb = e->fast_emb; a.fast_x = c.fin;
+    a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size; a.sem_begin = cf.semantic_begin_id; a.st = b.st;
+    CU(launch_k(b_select_kernel, dim3(b.nchunk, B), dim3(512), (size_t)(192 * 8 + 34 * 8 + 80 * 4 + 64), s2, a)); ++count; }
+  return 0;
+}
+
 static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
   dualar_batch &b = *e->batch; ColBufs &c = b.c;
   const dualar_config &cf = e->c;
@@ -243,22 +283,22 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
   if ((rc = enqueue_slow_cols(e, c, B, BN, kv, pos, tok, s, count))) return rc;
   auto norm = [&](const bf16 *x, const bf16 *w, bf16 *out, int K) -> int {
     BNormArgs a{x, w, out, K, B, cf.norm_eps};
+    if (BRec *r = e->tc->rec) { r->add(BP_NORM, dim3((B + 7) / 8)).u.norm = a; return 0; }
     CU(launch_k(b_rmsnorm_kernel, dim3((B + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
   // LM head + slow sampler (llama.py:446-451, inference.py:103-113) on a SECOND stream: they need only the slow hidden state, and so
   // does pass 0 of the fast stack (whose logits the reference discards, inference.py:121-122) -- the two branches are independent
   // until pass 1 consumes the sampled semantic id.  Fork / join with events (captured as graph edges).
-  cudaStream_t s2 = e->batch_fork ? b.side_stream : s;
-  if (e->batch_fork) { CU(cudaEventRecord(b.ev_fork, s)); CU(cudaStreamWaitEvent(s2, b.ev_fork, 0)); }
+  BRec *rec = e->tc->rec;
+  const bool fork = e->batch_fork && !rec;
+  cudaStream_t s2 = fork ? b.side_stream : s;
+  if (fork) { CU(cudaEventRecord(b.ev_fork, s)); CU(cudaStreamWaitEvent(s2, b.ev_fork, 0)); }
   { BNormArgs a{c.x, e->norm, c.xn, cf.dim, B, cf.norm_eps};
-    CU(launch_k(b_rmsnorm_kernel, dim3((B + 3) / 4), dim3(128), 0, s2, a)); ++count; }
+    if (rec) rec->add(BP_NORM, dim3((B + 7) / 8)).u.norm = a;
+    else { CU(launch_k(b_rmsnorm_kernel, dim3((B + 3) / 4), dim3(128), 0, s2, a)); ++count; } }
   if ((rc = tc_gemm(e, cf.tie_word_embeddings ? e->emb : e->out_w, cf.vocab_size, cf.dim, c.xn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.logits, 0, s2, count))) return rc;
-  { BHeadArgs a{c.logits, e->batch_keep_raw ? c.logits_raw : nullptr, c.cmax, cf.vocab_size, b.nchunk, R, b.st};
-    CU(launch_k(b_head_stats_kernel, dim3(b.nchunk, B), dim3(512), 0, s2, a)); ++count; }
-  { BSelectArgs a; memset(&a, 0, sizeof(a));
-    a.logits = c.logits; a.cmax = c.cmax; a.V = cf.vocab_size; a.nchunk = b.nchunk; a.delta = e->delta; a.cand = c.cand; a.fast_emb = e->fast_emb; a.fast_x = c.fin;
-    a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size; a.sem_begin = cf.semantic_begin_id; a.st = b.st;
-    CU(launch_k(b_select_kernel, dim3(b.nchunk, B), dim3(512), (size_t)(192 * 8 + 34 * 8 + 80 * 4 + 64), s2, a)); ++count; }
-  if (e->batch_fork) CU(cudaEventRecord(b.ev_join, s2));
+  if (rec) rec->split = (int)rec->ph.size();      // the slow sampler's two kernels run between the two persistent launches
+  else if ((rc = enqueue_slow_sampler(e, s2, count))) return rc;
+  if (fork) CU(cudaEventRecord(b.ev_join, s2));
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
   const int fqkv_rows = (cf.fast_n_head + 2 * cf.fast_n_local_heads) * cf.fast_head_dim, fqd = cf.fast_n_head * cf.fast_head_dim;
   if (e->fpi_w) {      // hidden_states = fast_project_in(x)   (llama.py:590)
@@ -279,7 +319,8 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
         a.qkv = c.fqkv; a.kc = b.fkc[l]; a.vc = b.fvc[l]; a.slot_stride = b.fslot_stride; a.rope = e->fast_rope; a.qn = L.qn; a.kn = L.kn;
         a.nh = cf.fast_n_head; a.nkv = cf.fast_n_local_heads; a.hd = cf.fast_head_dim; a.ncb = cf.num_codebooks; a.p = p; a.ncols = B;
         a.eps = cf.norm_eps; a.scale = (float)(1.0 / sqrt((double)cf.fast_head_dim)); a.y = c.fy;
-        CU(launch_k(b_fast_attn_kernel, dim3(B), dim3(256), b_fast_attn_smem(a.nh, a.nkv, a.hd, a.ncb), s, a)); ++count; }
+        if (rec) rec->add(BP_FAST_ATTN, dim3(B)).u.fattn = a;
+        else { CU(launch_k(b_fast_attn_kernel, dim3(B), dim3(256), b_fast_attn_smem(a.nh, a.nkv, a.hd, a.ncb), s, a)); ++count; } }
       if ((rc = tc_gemm(e, L.wo, cf.fast_dim, fqd, c.fy, c.cap, B, BN, TE_RESIDUAL, L.bo, in, c.fh, 1, s, count))) return rc;
       if (fuse) { if ((rc = tc_gemm(e, L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fh, c.cap, B, BN, TE_SWIGLU, nullptr, nullptr, c.fact, 1, s, count, L.ffn_norm))) return rc; }
       else {
@@ -290,7 +331,7 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
       in = out;
     }
     if (p == 0) {              // logits of pass 0 are discarded by the reference (inference.py:122)
-      if (e->batch_fork) CU(cudaStreamWaitEvent(s, b.ev_join, 0));      // join: pass 1 starts from the embedding of the sampled id
+      if (fork) CU(cudaStreamWaitEvent(s, b.ev_join, 0));      // join: pass 1 starts from the embedding of the sampled id
       continue;
     }
     if (tc_can_fuse_norm(e, BN, cf.fast_dim)) { if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, in, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count, e->fast_norm))) return rc; }
@@ -302,27 +343,110 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
       a.logits = c.flogits; a.logits_raw = e->batch_keep_raw ? c.flogits_raw : nullptr; a.fv = e->fv; a.head = p; a.ncb = cf.num_codebooks; a.last_head = (p == cf.num_codebooks - 1);
       a.noise_off = (long long)cf.vocab_size + (long long)(p - 1) * e->fv; a.fast_emb = e->fast_emb; a.fast_x = c.fin; a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size;
       a.seq = b.seq; a.seq_slot_stride = (long long)R * b.Sb; a.seq_stride = b.Sb; a.im_end_id = cf.im_end_id; a.n_rows_tok = R; a.st = b.st;
-      CU(launch_k(b_fast_sample_kernel, dim3(B), dim3(256), b_fast_sample_smem(), s, a)); ++count; }
+      if (rec) rec->add(BP_FAST_SAMPLE, dim3(B)).u.fsample = a;
+      else { CU(launch_k(b_fast_sample_kernel, dim3(B), dim3(256), b_fast_sample_smem(), s, a)); ++count; } }
   }
   return 0;
 }
 
-extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_len) {
-  if (!e) return fail(DUALAR_EINVAL, "null engine");
-  if (!e->finalized) return fail(DUALAR_ESTATE, "dualar_finalize has not been called");
-  if (e->batch) return fail(DUALAR_ESTATE, "batch slots already exist");
-  const dualar_config &cf = e->c;
-  if (max_batch < 1 || max_batch > 128) return fail(DUALAR_EINVAL, "max_batch must be in [1, 128]");
-  if (slot_seq_len <= 0 || slot_seq_len > cf.max_seq_len) slot_seq_len = cf.max_seq_len;
-  slot_seq_len = (slot_seq_len + 7) / 8 * 8;
-  if (cf.n_head / cf.n_local_heads > DA_MAX_G) return fail(DUALAR_EINVAL, "GQA group too large");
-  CU(cudaSetDevice(e->device));
-  int rc = tc_init(e); if (rc) return rc;
-  dualar_batch *b = new dualar_batch(); e->batch = b;
-  b->B = max_batch; b->BN = bn_for(max_batch); b->Sb = slot_seq_len;
+// ---- the persistent step: record the sequence once, upload the phase table and tensor maps, capture two cooperative launches ----------
+template <int BN> static cudaError_t launch_bstep(dualar_engine *e, const BStepArgs &k, cudaStream_t s) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(e->sms); cfg.blockDim = dim3(DA_BS_THREADS); cfg.dynamicSmemBytes = e->batch->bs_smem; cfg.stream = s;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, bstep_kernel<BN>, k);
+}
+static int enqueue_bstep(dualar_engine *e, int ph0, int ph1, cudaStream_t s, int &count) {
+  dualar_batch &b = *e->batch;
+  CU(cudaMemsetAsync(b.gbar, 0, sizeof(unsigned int), s));
+  BStepArgs k; k.phases = b.d_phases + ph0; k.n_phases = ph1 - ph0; k.maps = b.d_maps; k.gbar = b.gbar; k.err = e->tc->err; k.stages = b.bs_stages;
+  { const char *v = getenv("DUALAR_BS_NO_PREFETCH"); k.no_prefetch = v && v[0] == '1'; }
+  k.tl = b.d_tl ? b.d_tl + 2 * ph0 : nullptr;
+  switch (b.BN) {
+    case 32: CU(launch_bstep<32>(e, k, s)); break;
+    case 64: CU(launch_bstep<64>(e, k, s)); break;
+    case 128: CU(launch_bstep<128>(e, k, s)); break;
+    default: return fail(DUALAR_EINVAL, "BN %d", b.BN);
+  }
+  ++count;
+  return 0;
+}
+static int enqueue_batch_step_persistent(dualar_engine *e, cudaStream_t s, int &count) {
+  dualar_batch &b = *e->batch; int rc;
+  if ((rc = enqueue_bstep(e, 0, b.split, s, count))) return rc;             // embedding, slow stack, final norm, LM head
+  if ((rc = enqueue_slow_sampler(e, s, count))) return rc;
+  return enqueue_bstep(e, b.split, b.n_phases, s, count);                   // the fast passes and their samplers
+}
+static int build_persistent_step(dualar_engine *e) {
+  dualar_batch &b = *e->batch; const dualar_config &cf = e->c;
+  if (e->tc->fuse_norm) return 0;      // the fused-norm experiment exists on the per-kernel path only
+  int coop = 0; CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+  if (!coop) return 0;
+  BRec rec; e->tc->rec = &rec;
+  int n = 0; int rc = enqueue_batch_step(e, e->cap_stream, n);
+  e->tc->rec = nullptr;
+  if (rc < 0) return rc;
+  if (rec.split < 0) return fail(DUALAR_ESTATE, "recorded step has no sampler split");
+  size_t body = b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim);
+  body = std::max(body, b_fast_attn_smem(cf.fast_n_head, cf.fast_n_local_heads, cf.fast_head_dim, cf.num_codebooks));
+  body = std::max(body, b_fast_sample_smem());
+  body = std::max(body, (size_t)8 * cf.head_dim * sizeof(float));
+  body = (body + 1023) & ~(size_t)1023;
+  const size_t stg = (size_t)b.BN * DA_TC_BM * 4; if (body < stg) body = stg;
+  int st = (int)((227 * 1024 - 2048 - body) / (DA_TC_A_BYTES + (size_t)b.BN * 128));
+  if (st > DA_TC_MAX_STAGES) st = DA_TC_MAX_STAGES;
+  { const char *v = getenv("DUALAR_BS_STAGES"); if (v && atoi(v) >= 2 && atoi(v) < st) st = atoi(v); }
+  if (st < 2) return 0;      // does not fit: the per-kernel graph remains the only path
+  b.bs_stages = st; b.bs_smem = bstep_smem(b.BN, st, body);
+  switch (b.BN) {
+    case 32: CU(cudaFuncSetAttribute(bstep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.bs_smem)); break;
+    case 64: CU(cudaFuncSetAttribute(bstep_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.bs_smem)); break;
+    case 128: CU(cudaFuncSetAttribute(bstep_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.bs_smem)); break;
+    default: return 0;      // 256 columns: per-kernel path only
+  }
+  b.n_phases = (int)rec.ph.size(); b.split = rec.split;
+  if ((rc = dev_alloc(e, b.d_phases, rec.ph.size())) || (rc = dev_alloc(e, b.d_maps, rec.maps.size())) || (rc = dev_alloc(e, b.gbar, 4))) return rc;
+  CU(cudaMemcpy(b.d_phases, rec.ph.data(), rec.ph.size() * sizeof(BPhase), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(b.d_maps, rec.maps.data(), rec.maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  for (const BPhase &p : rec.ph) b.kinds.push_back(p.kind | ((p.gx * p.gy * p.gz) << 8));
+  { const char *v = getenv("DUALAR_BS_TIMELINE"); if (v && v[0] == '1') { if ((rc = dev_alloc(e, b.d_tl, 2 * rec.ph.size()))) return rc; } }
+  // dry run, then capture
+  n = 0;
+  if ((rc = enqueue_batch_step_persistent(e, e->cap_stream, n)) < 0) return rc;
+  CU(cudaStreamSynchronize(e->cap_stream));
+  { int gerr[4] = {0, 0, 0, 0}; CU(cudaMemcpy(gerr, e->tc->err, sizeof(gerr), cudaMemcpyDeviceToHost));
+    if (gerr[0]) return fail(DUALAR_EDEVICE, "persistent batched step: device fault flag %d on the dry run (5-9: a bounded wait timed out; phase %d / producer phase %d of %d, split %d)",
+                             gerr[0], gerr[1], gerr[2], b.n_phases, b.split); }
+  cudaGraph_t g;
+  CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  n = 0;
+  rc = enqueue_batch_step_persistent(e, e->cap_stream, n);
+  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
+  if (rc < 0) return rc;
+  if (ce != cudaSuccess) return fail(DUALAR_ECUDA, "persistent batch graph capture failed: %s", cudaGetErrorString(ce));
+  CU(cudaGraphInstantiate(&b.g_step_p, g, 0));
+  CU(cudaGraphDestroy(g));
+  b.launches_p = n;
+  return 0;
+}
+static int batch_select_path(dualar_engine *e) {
+  if (e->groups.empty()) return 0;
+  int want = e->batch_persistent;
+  if (want < 0) { const char *v = getenv("DUALAR_BATCH_PERSIST"); want = v ? (v[0] != '0') : 0; }
+  for (dualar_batch *b : e->groups) if (want && !b->g_step_p) return fail(DUALAR_ESTATE, "the persistent batched step is not available for this configuration");
+  for (dualar_batch *b : e->groups) b->persistent = want != 0;
+  return 0;
+}
+
+// one request group: its own activation buffers, KV caches, sampling state, split-K workspace and step graph(s)
+static int batch_group_init(dualar_engine *e, int n_slots, int slot_seq_len, bool own_stream) {
+  const dualar_config &cf = e->c; int rc;
+  dualar_batch *b = new dualar_batch(); e->groups.push_back(b); e->batch = b;
+  b->B = n_slots; b->BN = bn_for(n_slots); b->Sb = slot_seq_len;
   const int R = cf.num_codebooks + 1;
   // split-KV: enough (kv head, split) CTAs per request to fill the machine twice at small batches, one split per 256 positions at most
-  int nsplit = (8 * e->sms) / (cf.n_local_heads * max_batch); if (nsplit < 2) nsplit = 2; if (nsplit > 16) nsplit = 16;
+  int nsplit = (8 * e->sms) / (cf.n_local_heads * n_slots); if (nsplit < 2) nsplit = 2; if (nsplit > 16) nsplit = 16;
   { const char *v = getenv("DUALAR_BATCH_NSPLIT"); if (v) nsplit = atoi(v); }
   if ((rc = alloc_cols(e, b->c, b->BN, nsplit, true))) return rc;
   b->slot_stride = (long long)cf.n_local_heads * b->Sb * cf.head_dim;
@@ -331,19 +455,25 @@ extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_l
   for (int l = 0; l < cf.n_layer; ++l) if ((rc = dev_alloc(e, b->kc[l], (size_t)b->slot_stride * b->BN)) || (rc = dev_alloc(e, b->vc[l], (size_t)b->slot_stride * b->BN))) return rc;
   for (int l = 0; l < cf.n_fast_layer; ++l) if ((rc = dev_alloc(e, b->fkc[l], (size_t)b->fslot_stride * b->BN)) || (rc = dev_alloc(e, b->fvc[l], (size_t)b->fslot_stride * b->BN))) return rc;
   if ((rc = dev_alloc(e, b->st, (size_t)b->BN)) || (rc = dev_alloc(e, b->seq, (size_t)b->BN * R * b->Sb))) return rc;
+  if (e->groups.size() == 1) { b->ws = e->tc->ws_own; b->tickets = e->tc->tickets_own; }
+  else if ((rc = dev_alloc(e, b->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, b->tickets, 8192))) return rc;
   CU(cudaMallocHost((void **)&b->h_st, sizeof(DAState)));
   CU(cudaMallocHost((void **)&b->h_seq, (size_t)R * b->Sb * sizeof(int)));
-  b->prompt_len.assign(max_batch, 0); b->max_gen.assign(max_batch, 0); b->open.assign(max_batch, 0);
+  b->prompt_len.assign(n_slots, 0); b->max_gen.assign(n_slots, 0); b->open.assign(n_slots, 0);
   CU(cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
-  { const char *v = getenv("DUALAR_BATCH_FORK"); e->batch_fork = !(v && v[0] == '0'); }
+  if (own_stream) { CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming)); }
   // slow sampler: (chunks x requests) CTAs of 512 threads scan the logits; the register-heavy sampler code runs one CTA per SM, so
   // more CTAs than SMs only adds waves
-  b->nchunk = e->sms / max_batch; if (b->nchunk < 1) b->nchunk = 1; if (b->nchunk > 32) b->nchunk = 32;
+  b->nchunk = e->sms / n_slots; if (b->nchunk < 1) b->nchunk = 1; if (b->nchunk > 32) b->nchunk = 32;
+  // the group's GEMMs are enqueued with the group's split-K workspace
+  e->tc->ws = b->ws; e->tc->tickets = b->tickets;
   // dry run (configures attributes, surfaces launch errors), then capture
   int n = 0;
   if ((rc = enqueue_batch_step(e, e->cap_stream, n)) < 0) return rc;
   CU(cudaStreamSynchronize(e->cap_stream));
+  { int gerr = 0; CU(cudaMemcpy(&gerr, e->tc->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (gerr) return fail(DUALAR_EDEVICE, "batched step: device fault flag %d on the dry run", gerr); }
   cudaGraph_t g;
   CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   n = 0;
@@ -354,6 +484,8 @@ extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_l
   CU(cudaGraphInstantiate(&b->g_step, g, 0));
   CU(cudaGraphDestroy(g));
   b->launches = n;
+  if ((rc = build_persistent_step(e))) return rc;
+  e->tc->ws = e->tc->ws_own; e->tc->tickets = e->tc->tickets_own;
   // the dry run advanced nothing (every slot is idle: loop_mode 0) but wrote KV row 0 and sampler scratch; start clean
   CU(cudaMemset(b->st, 0, sizeof(DAState) * (size_t)b->BN));
   for (int l = 0; l < cf.n_layer; ++l) { CU(cudaMemset(b->kc[l], 0, (size_t)b->slot_stride * b->BN * 2)); CU(cudaMemset(b->vc[l], 0, (size_t)b->slot_stride * b->BN * 2)); }
@@ -362,12 +494,50 @@ extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_l
   return 0;
 }
 
+// Request slots live in GROUPS of `batch_group_slots` (option, default 32): a group is one batched step (one graph, its own buffers and
+// stream); the groups of a step run CONCURRENTLY.  One step of one group is a chain of ~540 dependent kernels that leaves the GPU mostly
+// idle (8 us per kernel, a few MB each), so several independent chains overlap almost for free: measured on B200 (s1-mini), 1 x 32 slots
+// 7.3 k tok/s, 2 x 32 11.4 k, 4 x 32 17.1 k.  The weights are shared; slot s belongs to group s / group_slots.
+extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_len) {
+  if (!e) return fail(DUALAR_EINVAL, "null engine");
+  if (!e->finalized) return fail(DUALAR_ESTATE, "dualar_finalize has not been called");
+  if (e->batch) return fail(DUALAR_ESTATE, "batch slots already exist");
+  const dualar_config &cf = e->c;
+  if (max_batch < 1 || max_batch > 1024) return fail(DUALAR_EINVAL, "max_batch must be in [1, 1024]");
+  if (slot_seq_len <= 0 || slot_seq_len > cf.max_seq_len) slot_seq_len = cf.max_seq_len;
+  slot_seq_len = (slot_seq_len + 7) / 8 * 8;
+  if (cf.n_head / cf.n_local_heads > DA_MAX_G) return fail(DUALAR_EINVAL, "GQA group too large");
+  CU(cudaSetDevice(e->device));
+  int rc = tc_init(e); if (rc) return rc;
+  { const char *v = getenv("DUALAR_BATCH_FORK"); e->batch_fork = !(v && v[0] == '0'); }
+  int gs = e->batch_group_slots;
+  { const char *v = getenv("DUALAR_BATCH_GROUP_SLOTS"); if (v && atoi(v) > 0) gs = atoi(v); }
+  if (gs < 1) gs = 1; if (gs > 128) gs = 128;
+  const int n_groups = (max_batch + gs - 1) / gs;
+  e->group_slots = gs; e->batch_total = max_batch;
+  for (int g = 0; g < n_groups; ++g) {
+    const int n = std::min(gs, max_batch - g * gs);
+    if ((rc = batch_group_init(e, n, slot_seq_len, n_groups > 1))) return rc;
+  }
+  if (n_groups > 1) CU(cudaEventCreateWithFlags(&e->ev_groups_go, cudaEventDisableTiming));
+  e->batch = e->groups[0];
+  return batch_select_path(e);
+}
+
+// global slot -> its group and the slot index inside it
+static dualar_batch *group_of(dualar_engine *e, int slot, int *local) {
+  if (slot < 0 || slot >= e->batch_total) return nullptr;
+  *local = slot % e->group_slots;
+  return e->groups[slot / e->group_slots];
+}
+
 extern "C" int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *prompt, int T, int max_new, float temperature, float top_p, float rep,
                                     uint64_t seed, const void *noise, void *stream) {
   if (!e || !prompt) return fail(DUALAR_EINVAL, "null argument");
   if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
-  dualar_batch &b = *e->batch; const dualar_config &cf = e->c; const int R = cf.num_codebooks + 1;
-  if (slot < 0 || slot >= b.B) return fail(DUALAR_EINVAL, "slot %d out of range", slot);
+  dualar_batch *bp = group_of(e, slot, &slot);
+  if (!bp) return fail(DUALAR_EINVAL, "slot out of range");
+  dualar_batch &b = *bp; const dualar_config &cf = e->c; const int R = cf.num_codebooks + 1;
   if (T < 1) return fail(DUALAR_EINVAL, "empty prompt");
   if (T >= b.Sb) return fail(DUALAR_EINVAL, "Input sequence length %d exceeds the slot length %d", T, b.Sb);
   if (max_new <= 0 || T + max_new > b.Sb) max_new = b.Sb - T;
@@ -396,15 +566,32 @@ extern "C" int dualar_batch_decode(dualar_engine *e, int n_steps, void *stream) 
   if (!e) return fail(DUALAR_EINVAL, "null engine");
   if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
   CU(cudaSetDevice(e->device));
-  for (int i = 0; i < n_steps; ++i) CU(cudaGraphLaunch(e->batch->g_step, (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->groups.size() == 1) {
+    dualar_batch &b = *e->groups[0];
+    cudaGraphExec_t g = b.persistent ? b.g_step_p : b.g_step;
+    for (int i = 0; i < n_steps; ++i) CU(cudaGraphLaunch(g, s));
+    return 0;
+  }
+  // several groups: fork from the caller's stream, one chain of graph launches per group (enqueued round-robin so that no group's queue
+  // runs dry while the host is busy with another's), join back.  A group with no open slot only burns idle steps: skip it.
+  CU(cudaEventRecord(e->ev_groups_go, s));
+  std::vector<dualar_batch *> live;
+  for (dualar_batch *b : e->groups) { bool any = false; for (char o : b->open) any = any || o; if (any) live.push_back(b); }
+  for (dualar_batch *b : live) CU(cudaStreamWaitEvent(b->stream, e->ev_groups_go, 0));
+  for (int i = 0; i < n_steps; ++i)
+    for (dualar_batch *b : live) CU(cudaGraphLaunch(b->persistent ? b->g_step_p : b->g_step, b->stream));
+  for (dualar_batch *b : live) { CU(cudaEventRecord(b->ev_done, b->stream)); CU(cudaStreamWaitEvent(s, b->ev_done, 0)); }
   return 0;
 }
 
 extern "C" int dualar_batch_collect(dualar_engine *e, int slot, int32_t *out, int cap, int *n_tokens, int *finished, void *stream) {
   if (!e || !n_tokens) return fail(DUALAR_EINVAL, "null argument");
   if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
-  dualar_batch &b = *e->batch; const int R = e->c.num_codebooks + 1;
-  if (slot < 0 || slot >= b.B || !b.open[slot]) return fail(DUALAR_ESTATE, "slot %d holds no request", slot);
+  const int gslot = slot;
+  dualar_batch *bp = group_of(e, slot, &slot);
+  if (!bp || !bp->open[slot]) return fail(DUALAR_ESTATE, "slot %d holds no request", gslot);
+  dualar_batch &b = *bp; const int R = e->c.num_codebooks + 1;
   CU(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaMemcpyAsync(b.h_st, b.st + slot, sizeof(DAState), cudaMemcpyDeviceToHost, s));
@@ -426,8 +613,9 @@ extern "C" int dualar_batch_collect(dualar_engine *e, int slot, int32_t *out, in
 
 extern "C" int dualar_batch_release(dualar_engine *e, int slot) {
   if (!e || !e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
-  dualar_batch &b = *e->batch;
-  if (slot < 0 || slot >= b.B) return fail(DUALAR_EINVAL, "slot %d out of range", slot);
+  dualar_batch *bp = group_of(e, slot, &slot);
+  if (!bp) return fail(DUALAR_EINVAL, "slot out of range");
+  dualar_batch &b = *bp;
   CU(cudaSetDevice(e->device));
   CU(cudaDeviceSynchronize());
   CU(cudaMemset(b.st + slot, 0, sizeof(DAState)));      // idle: loop_mode 0, position 0
@@ -435,39 +623,73 @@ extern "C" int dualar_batch_release(dualar_engine *e, int slot) {
   return 0;
 }
 
-extern "C" int dualar_batch_read(dualar_engine *e, const char *name, void *dst, int64_t nbytes, void *stream) {
-  if (!e || !name || !dst) return fail(DUALAR_EINVAL, "null argument");
-  if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
-  dualar_batch &b = *e->batch; const dualar_config &cf = e->c;
-  const void *src = nullptr; int64_t avail = 0; size_t pitch = 0, width = 0; int rows = 0;
+// one group's share of a named buffer: copies min(nbytes, what the group holds) and reports what it holds; *per_slot = 0 for scalars
+static int batch_read_group(dualar_engine *e, dualar_batch &b, const char *name, void *dst, int64_t nbytes, cudaStream_t s, int64_t *held, int *per_slot) {
+  const dualar_config &cf = e->c;
+  const void *src = nullptr; int64_t avail = 0; size_t pitch = 0, width = 0;
+  *per_slot = 1;
   if (!strcmp(name, "slow_logits")) { src = b.c.logits; avail = (int64_t)b.B * cf.vocab_size * 2; }
   else if (!strcmp(name, "slow_logits_raw")) { src = b.c.logits_raw; avail = (int64_t)b.B * cf.vocab_size * 2; }
   else if (!strcmp(name, "hidden")) { src = b.c.x; avail = (int64_t)b.B * cf.dim * 2; }
   else if (!strcmp(name, "fast_logits")) { src = b.c.flogits_raw; avail = (int64_t)b.B * (cf.num_codebooks - 1) * e->fv * 2; }
-  else if (!strcmp(name, "launches")) { *(int *)dst = b.launches; return nbytes >= 4 ? 0 : fail(DUALAR_EINVAL, "4 bytes needed"); }
   else if (!strcmp(name, "state")) { src = b.st; avail = (int64_t)b.B * sizeof(DAState); }
-  else if (!strcmp(name, "tokens")) { src = b.st->tok_out; pitch = sizeof(DAState); width = (size_t)(cf.num_codebooks + 1) * 4; rows = b.B; avail = (int64_t)rows * width; }
-  else if (!strcmp(name, "positions")) { src = &b.st->pos; pitch = sizeof(DAState); width = 4; rows = b.B; avail = (int64_t)rows * width; }
-  else if (!strcmp(name, "done")) { src = &b.st->done; pitch = sizeof(DAState); width = 4; rows = b.B; avail = (int64_t)rows * width; }
-  else if (!strcmp(name, "n_gen")) { src = &b.st->n_gen; pitch = sizeof(DAState); width = 4; rows = b.B; avail = (int64_t)rows * width; }
-  else return fail(DUALAR_EINVAL, "unknown batch buffer '%s'", name);
-  if (nbytes > avail) return fail(DUALAR_EINVAL, "batch buffer '%s' holds %lld bytes, %lld requested", name, (long long)avail, (long long)nbytes);
+  else if (!strcmp(name, "tokens")) { src = b.st->tok_out; pitch = sizeof(DAState); width = (size_t)(cf.num_codebooks + 1) * 4; avail = (int64_t)b.B * width; }
+  else if (!strcmp(name, "positions")) { src = &b.st->pos; pitch = sizeof(DAState); width = 4; avail = (int64_t)b.B * width; }
+  else if (!strcmp(name, "done")) { src = &b.st->done; pitch = sizeof(DAState); width = 4; avail = (int64_t)b.B * width; }
+  else if (!strcmp(name, "n_gen")) { src = &b.st->n_gen; pitch = sizeof(DAState); width = 4; avail = (int64_t)b.B * width; }
+  else {
+    *per_slot = 0;
+    if (!strcmp(name, "launches")) { int n = 0; for (dualar_batch *g : e->groups) n += g->persistent ? g->launches_p : g->launches; *(int *)dst = n; return nbytes >= 4 ? 0 : fail(DUALAR_EINVAL, "4 bytes needed"); }
+    if (!strcmp(name, "groups")) { *(int *)dst = (int)e->groups.size(); return nbytes >= 4 ? 0 : fail(DUALAR_EINVAL, "4 bytes needed"); }
+    if (!strcmp(name, "bstep_kinds")) { if (nbytes > (int64_t)b.kinds.size() * 4) return fail(DUALAR_EINVAL, "too many bytes"); memcpy(dst, b.kinds.data(), (size_t)nbytes); return 0; }
+    if (!strcmp(name, "bstep_phases")) { *(int *)dst = b.n_phases; return nbytes >= 4 ? 0 : fail(DUALAR_EINVAL, "4 bytes needed"); }
+    if (!strcmp(name, "bstep_timeline")) {
+      if (!b.d_tl) return fail(DUALAR_ESTATE, "DUALAR_BS_TIMELINE=1 was not set at batch_init");
+      if (nbytes > (int64_t)b.n_phases * 16) return fail(DUALAR_EINVAL, "too many bytes");
+      CU(cudaMemcpyAsync(dst, b.d_tl, (size_t)nbytes, cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s)); return 0;
+    }
+    return fail(DUALAR_EINVAL, "unknown batch buffer '%s'", name);
+  }
+  *held = avail;
+  const int64_t n = nbytes < avail ? nbytes : avail;
+  if (pitch) CU(cudaMemcpy2DAsync(dst, width, src, pitch, width, (size_t)(n / (int64_t)width), cudaMemcpyDeviceToHost, s));
+  else CU(cudaMemcpyAsync(dst, src, (size_t)n, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// per-slot buffers are returned for all slots in slot order (group after group)
+extern "C" int dualar_batch_read(dualar_engine *e, const char *name, void *dst, int64_t nbytes, void *stream) {
+  if (!e || !name || !dst) return fail(DUALAR_EINVAL, "null argument");
+  if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
   CU(cudaSetDevice(e->device));
-  if (pitch) CU(cudaMemcpy2DAsync(dst, width, src, pitch, width, (size_t)(nbytes / (int64_t)width), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  else CU(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t off = 0;
+  for (dualar_batch *b : e->groups) {
+    int64_t held = 0; int per_slot = 0;
+    int rc = batch_read_group(e, *b, name, (char *)dst + off, nbytes - off, s, &held, &per_slot);
+    if (rc || !per_slot) return rc;
+    off += held;
+    if (off >= nbytes) break;
+  }
+  if (off < nbytes) return fail(DUALAR_EINVAL, "batch buffer '%s' holds %lld bytes, %lld requested", name, (long long)off, (long long)nbytes);
+  CU(cudaStreamSynchronize(s));
   return 0;
 }
 
 static void batch_destroy(dualar_engine *e) {
-  if (e->batch) {
-    if (e->batch->g_step) cudaGraphExecDestroy(e->batch->g_step);
-    if (e->batch->side_stream) cudaStreamDestroy(e->batch->side_stream);
-    if (e->batch->ev_fork) cudaEventDestroy(e->batch->ev_fork);
-    if (e->batch->ev_join) cudaEventDestroy(e->batch->ev_join);
-    if (e->batch->h_st) cudaFreeHost(e->batch->h_st);
-    if (e->batch->h_seq) cudaFreeHost(e->batch->h_seq);
-    delete e->batch; e->batch = nullptr;
+  for (dualar_batch *b : e->groups) {
+    if (b->g_step) cudaGraphExecDestroy(b->g_step);
+    if (b->g_step_p) cudaGraphExecDestroy(b->g_step_p);
+    if (b->side_stream) cudaStreamDestroy(b->side_stream);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
+    if (b->h_st) cudaFreeHost(b->h_st);
+    if (b->h_seq) cudaFreeHost(b->h_seq);
+    delete b;
   }
+  e->groups.clear(); e->batch = nullptr;
+  if (e->ev_groups_go) { cudaEventDestroy(e->ev_groups_go); e->ev_groups_go = nullptr; }
   delete e->tc; e->tc = nullptr;
 }

@@ -21,6 +21,7 @@
 #include "mega.cuh"
 #include "gemm_tc.cuh"
 #include "batch.cuh"
+#include "bstep.cuh"
 
 using namespace da;
 
@@ -80,6 +81,8 @@ struct dualar_engine {
   bool prefix_reuse = true, kv_dirty = true; std::vector<int32_t> prev_prompt; int prev_T = 0, last_reuse = 0;   // KV reuse across requests (dualar_prefill)
   cudaEvent_t ev_ring[8] = {nullptr}; int ev_next = 0; int stream_cols = 0, steps_enqueued = 0;      // dualar_decode_async
   bool batch_keep_raw = true;    // batched decode keeps a copy of the raw logits for dualar_batch_read
+  int batch_persistent = -1;     // batched decode as two persistent launches (bstep.cuh): -1 = DUALAR_BATCH_PERSIST or the default, 0 / 1 = option batch_persistent
+  std::vector<dualar_batch *> groups; int group_slots = 32, batch_total = 0, batch_group_slots = 32; cudaEvent_t ev_groups_go = nullptr;      // request groups (batch_host.cuh)
   bool batch_fork = true;        // batched decode: LM head + slow sampler on a side stream beside fast pass 0 (DUALAR_BATCH_FORK=0: one stream)
   bool l2_window = false; float l2_hit_ratio = 0.0f; size_t l2_persist_bytes = 0;   // DUALAR_L2_WINDOW / DUALAR_L2_HIT: access-policy window over the fast stack
   bool chunk_group = true;   // DUALAR_CHUNK_GROUP=0: one 128-element chunk per unit everywhere (round 1 behaviour)
@@ -712,6 +715,7 @@ extern "C" int dualar_finalize(dualar_engine *e) {
 }
 
 static void batch_destroy(dualar_engine *e);
+static int batch_select_path(dualar_engine *e);
 static int tc_prefill_own(dualar_engine *e, int t0, int t1, cudaStream_t s);
 
 extern "C" void dualar_destroy(dualar_engine *e) {
@@ -752,6 +756,12 @@ extern "C" int dualar_set_option(dualar_engine *e, const char *name, double valu
   }
   if (!strcmp(name, "prefill_mode")) { e->prefill_mode = value != 0.0; e->kv_dirty = true; return 0; }
   if (!strcmp(name, "prefix_reuse")) { e->prefix_reuse = value != 0.0; return 0; }
+  if (!strcmp(name, "batch_group_slots")) {
+    if (e->batch) return fail(DUALAR_ESTATE, "batch_group_slots must be set before dualar_batch_init");
+    if (value < 1 || value > 128) return fail(DUALAR_EINVAL, "batch_group_slots must be in [1, 128]");
+    e->batch_group_slots = (int)value; return 0;
+  }
+  if (!strcmp(name, "batch_persistent")) { e->batch_persistent = value != 0.0; return batch_select_path(e); }
   if (!strcmp(name, "mega_kernel")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "mega_kernel must be set before dualar_finalize");
     e->use_mega = value != 0.0; return 0;

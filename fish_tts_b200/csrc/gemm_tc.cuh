@@ -126,6 +126,132 @@ static inline size_t gemm_tc_smem_xn(int BN, int stages, int nk) {
   return (ring > stg ? ring : stg) + (size_t)nk * BN * 128 + 1024;
 }
 
+// ---- the epilogue, shared by the stand-alone kernel and the persistent batched-step kernel (bstep.cuh) ---------------------------------
+// Runs on the four warps that own the TMEM lane quarters (128 threads; te = 0..127 their index, wq = warp % 4), after the accumulator
+// barrier has fired.  `stg` = 16-byte aligned shared memory for BN x 128 floats; named barrier 2 is the epilogue group's.
+//   (A) the fp32 tile leaves TMEM as [column][row]: into the split-K workspace (nz > 1) or into `stg`;
+//   (B) a compact loop over (column, group of 8 rows) items reads it back 8 rows at a time, applies bias / residual / SwiGLU and writes
+//       16 contiguous bytes per item.  Straight-line code that runs once per CTA executes at instruction-fetch speed (measured: the
+//       32-column unrolled store sequence cost 7,000 cycles per chunk), so (B) is a LOOP on purpose.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const GemmTcArgs &a, uint32_t tmem, float *stg, int tile_m, int tile_n, int z, int nz, int ntile_lin,
+                                            int te, int lane, int wq, uint32_t *s_last_p, bool ok_in, uint64_t *accfree = nullptr) {
+  const int r_in = wq * 32 + lane;
+  const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
+  uint32_t &s_last = *s_last_p;
+  // the waits in front of the epilogue are bounded per thread: agree on the outcome, the barriers below need all 128 threads
+  uint32_t ok_all;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.and.pred q, 2, 128, p;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok_all) : "r"((uint32_t)ok_in) : "memory");
+  const bool ok = ok_all != 0u;
+    const int n_base = tile_n * BN, ncols_here = min(BN, a.ncols - n_base);
+    bool is_final = true;
+    if (ok) {
+      float *dstp = nz > 1 ? a.ws + ((size_t)ntile_lin * nz + z) * BN * DA_TC_BM : stg;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (c0 >= ncols_here) break;
+        uint32_t v[32]; tmem_ld32(taddr + (uint32_t)c0, v);
+        if (nz > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(dstp + (size_t)(c0 + j) * DA_TC_BM + r_in, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dstp[(c0 + j) * DA_TC_BM + r_in] = __uint_as_float(v[j]);
+        }
+      }
+    }
+    if (accfree) { tc_fence_before(); mbar_arrive(accfree); }      // persistent kernel: the accumulator may be overwritten by the next unit
+    if (ok) {
+      if (nz > 1) {
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (te == 0) s_last = (atomicAdd(a.tickets + ntile_lin, 1u) == (unsigned)nz - 1) ? 1u : 0u;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        is_final = s_last != 0u;
+        if (is_final) { __threadfence(); if (te == 0) a.tickets[ntile_lin] = 0u; }
+      } else asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+    if (is_final && ok) {
+      const float *wsp = a.ws + (size_t)ntile_lin * nz * BN * DA_TC_BM;
+      const int n_items = ncols_here * (DA_TC_BM / 8);
+      // bias / residual / SwiGLU on the 8 rows [row0, row0 + 8) of column n_l, 16 contiguous bytes out
+      auto finish = [&](const float *acc, int n_l, int g8) {
+        const int row0 = tile_m * DA_TC_BM + g8;
+        if (row0 >= a.rows) return;                                  // rows is a multiple of 8
+        float y[8];
+        if (a.bias) {
+          float bb[8]; unpack8(*reinterpret_cast<const uint4 *>(a.bias + row0), bb);
+#pragma unroll
+          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2] + bb[i2]);
+        } else {
+#pragma unroll
+          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2]);       // the linear's bf16 output
+        }
+        const size_t n = (size_t)(n_base + n_l);
+        if (a.epi == TE_SWIGLU) {
+          // rows come interleaved (2j: w1 = gate, 2j+1: w3 = up; engine.cu plan_layer): bf16(bf16(silu(g)) * u)   llama.py:190
+          float o[4];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) { const float gg = y[2 * i2]; o[i2] = __fmul_rn(rbf(gg / (1.0f + expf(-gg))), y[2 * i2 + 1]); }
+          uint2 u; u.x = (uint32_t)f2bits(o[0]) | ((uint32_t)f2bits(o[1]) << 16); u.y = (uint32_t)f2bits(o[2]) | ((uint32_t)f2bits(o[3]) << 16);
+          *reinterpret_cast<uint2 *>(a.out + n * a.ld_out + (row0 >> 1)) = u;
+        } else {
+          if (a.epi == TE_RESIDUAL) {                                // llama.py:329-330
+            float rr[8]; unpack8(*reinterpret_cast<const uint4 *>(a.res + n * a.ld_out + row0), rr);
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) y[i2] = rr[i2] + y[i2];
+          }
+          uint4 u;
+          u.x = (uint32_t)f2bits(y[0]) | ((uint32_t)f2bits(y[1]) << 16); u.y = (uint32_t)f2bits(y[2]) | ((uint32_t)f2bits(y[3]) << 16);
+          u.z = (uint32_t)f2bits(y[4]) | ((uint32_t)f2bits(y[5]) << 16); u.w = (uint32_t)f2bits(y[6]) | ((uint32_t)f2bits(y[7]) << 16);
+          *reinterpret_cast<uint4 *>(a.out + n * a.ld_out + row0) = u;
+        }
+      };
+      if (nz > 1) {
+        // split-K: the partials of TWO items (2 x nz x 32 bytes, nz <= 8) are requested before the first add, so the reduction costs one
+        // L2 round trip per pair of items instead of one per partial; they are added in split order (deterministic)
+#pragma unroll 1
+        for (int item = te; item < n_items; item += 256) {
+          const int item1 = item + 128; const bool two = item1 < n_items;
+          const int nl0 = item >> 4, g0 = (item & 15) * 8, nl1 = two ? item1 >> 4 : nl0, g1 = two ? (item1 & 15) * 8 : g0;
+          float4 p[2][8][2];
+#pragma unroll
+          for (int zz = 0; zz < 8; ++zz) {
+            if (zz < nz) {
+              const float4 *q0 = reinterpret_cast<const float4 *>(wsp + ((size_t)zz * BN + nl0) * DA_TC_BM + g0);
+              const float4 *q1 = reinterpret_cast<const float4 *>(wsp + ((size_t)zz * BN + nl1) * DA_TC_BM + g1);
+              p[0][zz][0] = __ldcg(q0); p[0][zz][1] = __ldcg(q0 + 1); p[1][zz][0] = __ldcg(q1); p[1][zz][1] = __ldcg(q1 + 1);
+            }
+          }
+#pragma unroll
+          for (int w2 = 0; w2 < 2; ++w2) {
+            if (w2 == 1 && !two) break;
+            float acc[8];
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) acc[i2] = 0.f;
+#pragma unroll
+            for (int zz = 0; zz < 8; ++zz) {
+              if (zz < nz) {
+                acc[0] += p[w2][zz][0].x; acc[1] += p[w2][zz][0].y; acc[2] += p[w2][zz][0].z; acc[3] += p[w2][zz][0].w;
+                acc[4] += p[w2][zz][1].x; acc[5] += p[w2][zz][1].y; acc[6] += p[w2][zz][1].z; acc[7] += p[w2][zz][1].w;
+              }
+            }
+            finish(acc, w2 ? nl1 : nl0, w2 ? g1 : g0);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int item = te; item < n_items; item += 128) {
+          const int n_l = item >> 4, g8 = (item & 15) * 8;
+          const float4 *pz = reinterpret_cast<const float4 *>(stg + n_l * DA_TC_BM + g8);
+          const float4 p0 = pz[0], p1 = pz[1];
+          const float acc[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          finish(acc, n_l, g8);
+        }
+      }
+    }
+}
+
 // grid (row tiles, column tiles, K splits)
 // XN = true (BN = 32, batched decode): the activation operand is NOT loaded by TMA; the epilogue warps, idle during the main loop,
 // read the un-normalised rows, apply the reference's RMSNorm (llama.py:172-177: fp32 normalise, round, x weight, round -- every CTA
@@ -284,112 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     tc_fence_after();
     if (dbg && tid == 64) dbg[5] = clock64();
     if (!ok) atomicExch(a.err, 7);
-    const int ntile_lin = blockIdx.y * gridDim.x + blockIdx.x;
-    const int n_base = tile_n * BN, ncols_here = min(BN, a.ncols - n_base);
-    float *stg = reinterpret_cast<float *>(sbase);
-    bool is_final = true;
-    if (ok) {
-      float *dstp = nz > 1 ? a.ws + ((size_t)ntile_lin * nz + z) * BN * DA_TC_BM : stg;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (c0 >= ncols_here) break;
-        uint32_t v[32]; tmem_ld32(taddr + (uint32_t)c0, v);
-        if (nz > 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) __stcg(dstp + (size_t)(c0 + j) * DA_TC_BM + r_in, __uint_as_float(v[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dstp[(c0 + j) * DA_TC_BM + r_in] = __uint_as_float(v[j]);
-        }
-      }
-      if (nz > 1) {
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 64) s_last = (atomicAdd(a.tickets + ntile_lin, 1u) == (unsigned)nz - 1) ? 1u : 0u;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        is_final = s_last != 0u;
-        if (is_final) { __threadfence(); if (tid == 64) a.tickets[ntile_lin] = 0u; }
-      } else asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    if (is_final && ok) {
-      const float *wsp = a.ws + (size_t)ntile_lin * nz * BN * DA_TC_BM;
-      const int n_items = ncols_here * (DA_TC_BM / 8);
-      // bias / residual / SwiGLU on the 8 rows [row0, row0 + 8) of column n_l, 16 contiguous bytes out
-      auto finish = [&](const float *acc, int n_l, int g8) {
-        const int row0 = tile_m * DA_TC_BM + g8;
-        if (row0 >= a.rows) return;                                  // rows is a multiple of 8
-        float y[8];
-        if (a.bias) {
-          float bb[8]; unpack8(*reinterpret_cast<const uint4 *>(a.bias + row0), bb);
-#pragma unroll
-          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2] + bb[i2]);
-        } else {
-#pragma unroll
-          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2]);       // the linear's bf16 output
-        }
-        const size_t n = (size_t)(n_base + n_l);
-        if (a.epi == TE_SWIGLU) {
-          // rows come interleaved (2j: w1 = gate, 2j+1: w3 = up; engine.cu plan_layer): bf16(bf16(silu(g)) * u)   llama.py:190
-          float o[4];
-#pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) { const float gg = y[2 * i2]; o[i2] = __fmul_rn(rbf(gg / (1.0f + expf(-gg))), y[2 * i2 + 1]); }
-          uint2 u; u.x = (uint32_t)f2bits(o[0]) | ((uint32_t)f2bits(o[1]) << 16); u.y = (uint32_t)f2bits(o[2]) | ((uint32_t)f2bits(o[3]) << 16);
-          *reinterpret_cast<uint2 *>(a.out + n * a.ld_out + (row0 >> 1)) = u;
-        } else {
-          if (a.epi == TE_RESIDUAL) {                                // llama.py:329-330
-            float rr[8]; unpack8(*reinterpret_cast<const uint4 *>(a.res + n * a.ld_out + row0), rr);
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) y[i2] = rr[i2] + y[i2];
-          }
-          uint4 u;
-          u.x = (uint32_t)f2bits(y[0]) | ((uint32_t)f2bits(y[1]) << 16); u.y = (uint32_t)f2bits(y[2]) | ((uint32_t)f2bits(y[3]) << 16);
-          u.z = (uint32_t)f2bits(y[4]) | ((uint32_t)f2bits(y[5]) << 16); u.w = (uint32_t)f2bits(y[6]) | ((uint32_t)f2bits(y[7]) << 16);
-          *reinterpret_cast<uint4 *>(a.out + n * a.ld_out + row0) = u;
-        }
-      };
-      if (nz > 1) {
-        // split-K: the partials of TWO items (2 x nz x 32 bytes, nz <= 8) are requested before the first add, so the reduction costs one
-        // L2 round trip per pair of items instead of one per partial; they are added in split order (deterministic)
-#pragma unroll 1
-        for (int item = te; item < n_items; item += 256) {
-          const int item1 = item + 128; const bool two = item1 < n_items;
-          const int nl0 = item >> 4, g0 = (item & 15) * 8, nl1 = two ? item1 >> 4 : nl0, g1 = two ? (item1 & 15) * 8 : g0;
-          float4 p[2][8][2];
-#pragma unroll
-          for (int zz = 0; zz < 8; ++zz) {
-            if (zz < nz) {
-              const float4 *q0 = reinterpret_cast<const float4 *>(wsp + ((size_t)zz * BN + nl0) * DA_TC_BM + g0);
-              const float4 *q1 = reinterpret_cast<const float4 *>(wsp + ((size_t)zz * BN + nl1) * DA_TC_BM + g1);
-              p[0][zz][0] = __ldcg(q0); p[0][zz][1] = __ldcg(q0 + 1); p[1][zz][0] = __ldcg(q1); p[1][zz][1] = __ldcg(q1 + 1);
-            }
-          }
-#pragma unroll
-          for (int w2 = 0; w2 < 2; ++w2) {
-            if (w2 == 1 && !two) break;
-            float acc[8];
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) acc[i2] = 0.f;
-#pragma unroll
-            for (int zz = 0; zz < 8; ++zz) {
-              if (zz < nz) {
-                acc[0] += p[w2][zz][0].x; acc[1] += p[w2][zz][0].y; acc[2] += p[w2][zz][0].z; acc[3] += p[w2][zz][0].w;
-                acc[4] += p[w2][zz][1].x; acc[5] += p[w2][zz][1].y; acc[6] += p[w2][zz][1].z; acc[7] += p[w2][zz][1].w;
-              }
-            }
-            finish(acc, w2 ? nl1 : nl0, w2 ? g1 : g0);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int item = te; item < n_items; item += 128) {
-          const int n_l = item >> 4, g8 = (item & 15) * 8;
-          const float4 *pz = reinterpret_cast<const float4 *>(stg + n_l * DA_TC_BM + g8);
-          const float4 p0 = pz[0], p1 = pz[1];
-          const float acc[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-          finish(acc, n_l, g8);
-        }
-      }
-    }
+    tc_epilogue<BN>(a, tmem, reinterpret_cast<float *>(sbase), tile_m, tile_n, z, nz, blockIdx.y * gridDim.x + blockIdx.x, te, lane, wq, &s_last, ok);
   }
   if (dbg && tid == 64) dbg[6] = clock64();
   tc_fence_before();

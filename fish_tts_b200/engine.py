@@ -213,8 +213,12 @@ class DualAREngine:
         return out[:, : n.value].copy()
 
     # ---- batched decode: B requests share every weight byte (include/dualar.h "batched decode") -------------------
-    def batch_init(self, max_batch: int, slot_seq_len: int = 0):
-        """Allocate ``max_batch`` request slots (own KV cache of ``slot_seq_len`` positions each) and capture the batched step."""
+    def batch_init(self, max_batch: int, slot_seq_len: int = 0, group_slots: Optional[int] = None):
+        """Allocate ``max_batch`` request slots (own KV cache of ``slot_seq_len`` positions each) and capture the batched step.
+        Slots are organised in groups of ``group_slots`` (default 32): one batched step per group, the groups of a step run
+        concurrently on their own streams (the step of one group is a latency-bound chain that leaves the GPU mostly idle)."""
+        if group_slots is not None:
+            self.set_option("batch_group_slots", group_slots)
         capi.check(self.lib.dualar_batch_init(self._h, int(max_batch), int(slot_seq_len)))
         self.max_batch = int(max_batch)
         self._batch_noise = {}
@@ -251,8 +255,11 @@ class DualAREngine:
             "slow_logits": ((B, cfg.vocab_size), torch.bfloat16), "slow_logits_raw": ((B, cfg.vocab_size), torch.bfloat16),
             "hidden": ((B, cfg.dim), torch.bfloat16), "fast_logits": ((B, cfg.num_codebooks - 1, self.fast_vocab), torch.bfloat16),
             "tokens": ((B, self.rows), torch.int32), "positions": ((B,), torch.int32), "done": ((B,), torch.int32),
-            "n_gen": ((B,), torch.int32), "launches": ((1,), torch.int32),
+            "n_gen": ((B,), torch.int32), "launches": ((1,), torch.int32), "bstep_phases": ((1,), torch.int32), "groups": ((1,), torch.int32),
         }
+        if name in ("bstep_kinds", "bstep_timeline"):      # profiling of the persistent step (DUALAR_BS_TIMELINE=1): one entry per phase
+            n = int(self.batch_read("bstep_phases")[0])
+            shapes[name] = ((n,), torch.int32) if name == "bstep_kinds" else ((n, 2), torch.int64)
         shape, dt = shapes[name]
         out = torch.empty(shape, dtype=dt)
         capi.check(self.lib.dualar_batch_read(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(), self._stream()))

@@ -1,3 +1,5 @@
-timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r2_pytest_gpu.log 2>&1; echo "gpu rc $?" >> gpurun_out/r2_pytest_gpu.log; tail -n 8 gpurun_out/r2_pytest_gpu.log | cut -c1-400
-timeout 600 python tests/batch_time.py 32 > gpurun_out/r2_batch_time.log 2>&1; cat gpurun_out/r2_batch_time.log | cut -c1-230
-echo "== no fork"; BT_SKIP_PREFILL=1 DUALAR_BATCH_FORK=0 timeout 300 python tests/batch_time.py 32 2>&1 | grep "batched decode" | cut -c1-100
+timeout 900 python -m pytest tests/test_gpu_batch.py -x -q -m gpu > gpurun_out/t_batch.log 2>&1; echo "rc $?"; tail -n 5 gpurun_out/t_batch.log
+BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 64 128 256 > gpurun_out/bt_groups.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups.log | cut -c1-150
+DUALAR_BATCH_GROUP_SLOTS=64 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 256 > gpurun_out/bt_groups64.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups64.log | cut -c1-150
+DUALAR_BATCH_GROUP_SLOTS=16 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 > gpurun_out/bt_groups16.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups16.log | cut -c1-150
+DUALAR_BATCH_GROUP_SLOTS=128 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 > gpurun_out/bt_groups128.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups128.log | cut -c1-150

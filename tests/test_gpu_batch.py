@@ -145,6 +145,58 @@ def test_fused_norm_gemm_equals_separate_norm_kernel(monkeypatch):
             assert torch.equal(sa[sl][s], sb[sl][s]) and torch.equal(fa[sl][s], fb[sl][s]), f"slot {sl} step {s}"
 
 
+def test_request_groups_do_not_change_a_request():
+    """Slots organised in concurrently running groups (own buffers, KV, split-K workspace, graph and stream per group): every request's
+    tokens and logits are bit-identical to the same request in one big group -- and a refill in one group leaves the others alone."""
+    cfg = variant_configs()["s1like"]
+    sd = make_state_dict(cfg, seed=0)
+    outs = []
+    for gs in (32, 2):
+        eng = DualAREngine(cfg, sd, device=0)
+        eng.batch_init(5, cfg.max_seq_len, group_slots=gs)
+        assert int(eng.batch_read("groups")[0]) == (1 if gs == 32 else 3)
+        _, cols, slows, fasts = run_batch(eng, cfg, REQS, 10)
+        if gs == 2:      # continuous batching across groups: slot 3 (group 1) is refilled, slots in groups 0 and 2 keep going
+            eng.batch_release(3)
+            r = REQS[1]
+            eng.batch_prefill(3, make_prompt(cfg, r), 4, r[3], r[4], r[5], seed=901)
+            eng.batch_decode(4)
+            again, fin = eng.batch_collect(3)
+            assert fin and again.shape[1] == 4
+        outs.append((cols, slows, fasts))
+        eng.close()
+    (ca, sa, fa), (cb, sb, fb) = outs
+    for sl in range(5):
+        assert (ca[sl] == cb[sl]).all(), f"slot {sl}: tokens depend on the grouping"
+        for s in range(10):
+            assert torch.equal(sa[sl][s], sb[sl][s]) and torch.equal(fa[sl][s], fb[sl][s]), f"slot {sl} step {s}: logits depend on the grouping"
+
+
+@pytest.mark.parametrize("name", ["s1like", "projected"])
+def test_persistent_step_equals_per_kernel_graph(name):
+    """option batch_persistent: the batched step as two cooperative launches of bstep_kernel (one CTA per SM walks the phase table,
+    grid barriers between phases, a producer warp prefetching the next GEMM's weight tiles) instead of ~100 kernels per step.  Same
+    device code, same split-K partition: identical bits."""
+    cfg = variant_configs()[name]
+    sd = make_state_dict(cfg, seed=0)
+    eng = DualAREngine(cfg, sd, device=0)
+    eng.batch_init(5, cfg.max_seq_len)
+    outs = []
+    for persist in (0, 1):
+        eng.set_option("batch_persistent", persist)
+        _, cols, slows, fasts = run_batch(eng, cfg, REQS, 8)
+        outs.append((cols, slows, fasts, int(eng.batch_read("launches")[0])))
+        for sl in range(5):
+            eng.batch_release(sl)
+    eng.close()
+    (ca, sa, fa, la), (cb, sb, fb, lb) = outs
+    assert lb == 4 and la > lb, f"persistent step: 2 cooperative launches + the slow sampler's 2 kernels ({lb}), per-kernel graph {la}"
+    for sl in range(5):
+        assert (ca[sl] == cb[sl]).all()
+        for s in range(8):
+            assert torch.equal(sa[sl][s], sb[sl][s]) and torch.equal(fa[sl][s], fb[sl][s]), f"slot {sl} step {s}"
+
+
 def test_continuous_batching_refill_does_not_disturb_neighbours():
     cfg = variant_configs()["s1like"]
     sd = make_state_dict(cfg, seed=0)
