@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) b_qkv_post_kernel(const BQkvPostArgs a) {
 struct BAttnArgs {
   const bf16 *qkv;           // [ncols][(nh + 2 nkv) * hd], q already normalised + rotated
   const bf16 *kc, *vc; long long slot_stride;
-  int nh, nkv, hd, S, ncols, nsplit_max; float sf;
+  int nh, nkv, hd, S, ncols, nsplit_max, tiles_per_split; float sf;
   float *part_o, *part_ml;   // [ncols][nkv][nsplit_max][G][hd], [...][G][2]
   unsigned int *tickets;     // [ncols][nkv], zero between launches
   bf16 *y;                   // [ncols][nh * hd]
@@ -167,6 +167,7 @@ struct BAttnArgs {
 // probabilities handed to all lanes for P@V where a lane owns hd/32 output dims -- and the warps meet ONCE, after the last tile
 // (the decode kernel's tile walk, mega.cuh).  One CTA barrier per tile instead of three, no idle warps during the softmax.
 #define DA_B_AWARPS (DA_ATTN_THREADS / 32)
+static_assert(DA_TILE == 8 * DA_B_AWARPS, "a warp owns 8 positions of a tile: 4 lanes each");
 static inline size_t b_attn_smem(int G, int hd) {
   size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t);
   f = (f + 127) & ~(size_t)127;
@@ -186,9 +187,9 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   if (pos < 0 || pos >= a.S) return;
   const int L = pos + 1;
   const int n_tiles = (L + DA_TILE - 1) / DA_TILE;
-  // a split is worth its partials / ticket / merge only from ~4 tiles (256 positions) on: measured at bs = 32, context ~360, one split
-  // per (request, kv head) beats four (4.48 vs 4.55 ms per step)
-  const int nsplit = max(1, min(a.nsplit_max, (n_tiles + 3) / 4));
+  // a split is worth its partials / ticket / merge only from tiles_per_split tiles on (8 = 512 positions by default): measured at
+  // 4 x 32 slots, context ~360, 6.73 ms per round with 8 tiles per split against 7.04 with 4
+  const int nsplit = max(1, min(a.nsplit_max, (n_tiles + a.tiles_per_split - 1) / a.tiles_per_split));
   const int tps = (n_tiles + nsplit - 1) / nsplit;
   const int nsplit_eff = (n_tiles + tps - 1) / tps;
   if (split >= nsplit_eff) return;
@@ -226,7 +227,15 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   }
   B::sync();
   bool ok = true;
-  const int psl = lane >> 3, dl = lane & 7;
+  // Per tile a warp owns the 8 positions w, w + 8, ...: scores with 4 lanes per position (lane = 4 * slot + dl; every lane walks its
+  // hd / 4 dims in 4-element chunks, the chunk order rotated by the slot so that the four positions of a half-warp hit different banks),
+  // ONE online-softmax update per tile and warp, then P@V with the 8 probabilities broadcast to all lanes (a lane owns hd / 32 output
+  // dims).  The query is pre-multiplied by sqrt(scale) and the dot product by sqrt(scale) again -- the reference scales q and k
+  // separately (llama.py:265-270 through the math SDPA backend); the difference is one fp32 rounding.  With G <= 2 (one head pair)
+  // the running (max, sum, output) stay in registers for the CTA's whole walk.
+  const int psl = lane >> 2, dl = lane & 3, nit = hd >> 4;
+  const bool single = G <= 2;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f}, o_acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   for (int t = t0; t < t1; ++t) {
     const int buf = (t - t0) & 1;
     const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
@@ -234,82 +243,83 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
     ok = mbar_wait(&bars[buf], phase[buf]) && ok; phase[buf] ^= 1u;
     const bf16 *kt = kbuf + (size_t)buf * DA_TILE * hd, *vt = vbuf + (size_t)buf * DA_TILE * hd;
     for (int h0 = 0; h0 < G; h0 += 2) {
-      float m_run[2], l_run[2], o_acc[2][4];
       const bool first = t == t0;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const bool hv = h0 + hh < G;
-        const int h = hv ? h0 + hh : h0;
-        m_run[hh] = first ? -INFINITY : pm[w * G + h]; l_run[hh] = first ? 0.f : pl[w * G + h];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o_acc[hh][i] = (hv && i < dpl && !first) ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
-      }
-      const float *q0 = q + (size_t)h0 * hd, *q1 = q + (size_t)(h0 + 1 < G ? h0 + 1 : h0) * hd;
-#pragma unroll 1
-      for (int half = 0; half < DA_TILE / (4 * DA_B_AWARPS); ++half) {      // 4 position slots per warp per round: rows w + 8 * (4 half + slot)
-        const int jme = w + DA_B_AWARPS * (4 * half + psl);
-        float s2[2] = {0.f, 0.f};
-        if (jme < nrow) {
-          const bf16 *krow = kt + (size_t)jme * hd;
-          for (int e = dl * 4; e < hd; e += 32) {
-            float kf[4];
-            { const uint2 u = *reinterpret_cast<const uint2 *>(krow + e);
-              kf[0] = __uint_as_float(u.x << 16); kf[1] = __uint_as_float(u.x & 0xffff0000u); kf[2] = __uint_as_float(u.y << 16); kf[3] = __uint_as_float(u.y & 0xffff0000u); }
-            const float4 qa = *reinterpret_cast<const float4 *>(q0 + e), qb = *reinterpret_cast<const float4 *>(q1 + e);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) kf[i] = __fmul_rn(kf[i], a.sf);
-            s2[0] = fmaf(qa.x, kf[0], s2[0]); s2[0] = fmaf(qa.y, kf[1], s2[0]); s2[0] = fmaf(qa.z, kf[2], s2[0]); s2[0] = fmaf(qa.w, kf[3], s2[0]);
-            s2[1] = fmaf(qb.x, kf[0], s2[1]); s2[1] = fmaf(qb.y, kf[1], s2[1]); s2[1] = fmaf(qb.z, kf[2], s2[1]); s2[1] = fmaf(qb.w, kf[3], s2[1]);
-          }
-        }
-        float pj[4][2];
+      if (!single) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          float sv = s2[hh];
-          sv += __shfl_xor_sync(0xffffffffu, sv, 1); sv += __shfl_xor_sync(0xffffffffu, sv, 2); sv += __shfl_xor_sync(0xffffffffu, sv, 4);
-          if (!(jme < nrow && h0 + hh < G)) sv = -INFINITY;
-          float mx = fmaxf(sv, __shfl_xor_sync(0xffffffffu, sv, 8));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-          const float m_new = fmaxf(m_run[hh], mx);
-          float pme = 0.f;
-          if (m_new != -INFINITY) {
-            const float sc_old = expf(m_run[hh] - m_new);      // exp(-inf) = 0 before the first position
-            l_run[hh] *= sc_old; m_run[hh] = m_new;
+          const bool hv = h0 + hh < G;
+          const int h = hv ? h0 + hh : h0;
+          m_run[hh] = first ? -INFINITY : pm[w * G + h]; l_run[hh] = first ? 0.f : pl[w * G + h];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o_acc[hh][i] *= sc_old;
-            pme = expf(sv - m_new);
-          }
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) pj[jj][hh] = __shfl_sync(0xffffffffu, pme, jj * 8);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = w + DA_B_AWARPS * (4 * half + jj);
-          if (j < nrow) {
-            float vf[4] = {0.f, 0.f, 0.f, 0.f};
-            const bf16 *vp = vt + (size_t)j * hd + lane * dpl;
-            if (dpl == 4) { const uint2 u = *reinterpret_cast<const uint2 *>(vp); vf[0] = __uint_as_float(u.x << 16); vf[1] = __uint_as_float(u.x & 0xffff0000u); vf[2] = __uint_as_float(u.y << 16); vf[3] = __uint_as_float(u.y & 0xffff0000u); }
-            else if (dpl == 2) { const uint32_t u = *reinterpret_cast<const uint32_t *>(vp); vf[0] = __uint_as_float(u << 16); vf[1] = __uint_as_float(u & 0xffff0000u); }
-            else vf[0] = bf2f(*vp);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              l_run[hh] += pj[jj][hh];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(pj[jj][hh], vf[i], o_acc[hh][i]);
-            }
-          }
+          for (int i = 0; i < 4; ++i) o_acc[hh][i] = (hv && i < dpl && !first) ? po[((size_t)w * G + h) * hd + lane * dpl + i] : 0.f;
         }
       }
+      const float *q0 = q + (size_t)h0 * hd, *q1 = q + (size_t)(h0 + 1 < G ? h0 + 1 : h0) * hd;
+      const int jme = w + DA_B_AWARPS * psl;
+      float s2[2] = {0.f, 0.f};
+      if (jme < nrow) {
+        const bf16 *krow = kt + (size_t)jme * hd;
+#pragma unroll 4
+        for (int i = 0; i < nit; ++i) {
+          const int e = dl * 4 + 16 * ((i + psl) & (nit - 1));
+          float kf[4];
+          { const uint2 u = *reinterpret_cast<const uint2 *>(krow + e);
+            kf[0] = __uint_as_float(u.x << 16); kf[1] = __uint_as_float(u.x & 0xffff0000u); kf[2] = __uint_as_float(u.y << 16); kf[3] = __uint_as_float(u.y & 0xffff0000u); }
+          const float4 qa = *reinterpret_cast<const float4 *>(q0 + e), qb = *reinterpret_cast<const float4 *>(q1 + e);
+          s2[0] = fmaf(qa.x, kf[0], s2[0]); s2[0] = fmaf(qa.y, kf[1], s2[0]); s2[0] = fmaf(qa.z, kf[2], s2[0]); s2[0] = fmaf(qa.w, kf[3], s2[0]);
+          s2[1] = fmaf(qb.x, kf[0], s2[1]); s2[1] = fmaf(qb.y, kf[1], s2[1]); s2[1] = fmaf(qb.z, kf[2], s2[1]); s2[1] = fmaf(qb.w, kf[3], s2[1]);
+        }
+      }
+      float pj[DA_B_AWARPS][2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        if (h0 + hh < G) {
-          const int h = h0 + hh;
-          if (lane == 0) { pm[w * G + h] = m_run[hh]; pl[w * G + h] = l_run[hh]; }
+        float sv = s2[hh];
+        sv += __shfl_xor_sync(0xffffffffu, sv, 1); sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+        sv = (jme < nrow && h0 + hh < G) ? __fmul_rn(sv, a.sf) : -INFINITY;
+        float mx = fmaxf(sv, __shfl_xor_sync(0xffffffffu, sv, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        const float m_new = fmaxf(m_run[hh], mx);
+        float pme = 0.f;
+        if (m_new != -INFINITY) {
+          const float sc_old = expf(m_run[hh] - m_new);      // exp(-inf) = 0 before the first position
+          l_run[hh] *= sc_old; m_run[hh] = m_new;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) if (i < dpl) po[((size_t)w * G + h) * hd + lane * dpl + i] = o_acc[hh][i];
+          for (int i = 0; i < 4; ++i) o_acc[hh][i] *= sc_old;
+          pme = expf(sv - m_new);
+        }
+#pragma unroll
+        for (int jj = 0; jj < DA_B_AWARPS; ++jj) pj[jj][hh] = __shfl_sync(0xffffffffu, pme, jj * 4);
+      }
+#pragma unroll
+      for (int jj = 0; jj < DA_B_AWARPS; ++jj) {
+        const int j = w + DA_B_AWARPS * jj;
+        if (j < nrow) {
+          float vf[4] = {0.f, 0.f, 0.f, 0.f};
+          const bf16 *vp = vt + (size_t)j * hd + lane * dpl;
+          if (dpl == 4) { const uint2 u = *reinterpret_cast<const uint2 *>(vp); vf[0] = __uint_as_float(u.x << 16); vf[1] = __uint_as_float(u.x & 0xffff0000u); vf[2] = __uint_as_float(u.y << 16); vf[3] = __uint_as_float(u.y & 0xffff0000u); }
+          else if (dpl == 2) { const uint32_t u = *reinterpret_cast<const uint32_t *>(vp); vf[0] = __uint_as_float(u << 16); vf[1] = __uint_as_float(u & 0xffff0000u); }
+          else vf[0] = bf2f(*vp);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            l_run[hh] += pj[jj][hh];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o_acc[hh][i] = fmaf(pj[jj][hh], vf[i], o_acc[hh][i]);
+          }
         }
       }
-      __syncwarp();
+      if (!single || t + 1 == t1) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (h0 + hh < G) {
+            const int h = h0 + hh;
+            if (lane == 0) { pm[w * G + h] = m_run[hh]; pl[w * G + h] = l_run[hh]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (i < dpl) po[((size_t)w * G + h) * hd + lane * dpl + i] = o_acc[hh][i];
+          }
+        }
+        __syncwarp();
+      }
     }
     B::sync();      // every warp is past its last read of the tile: its buffer may be refilled
   }

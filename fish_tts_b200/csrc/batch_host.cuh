@@ -43,6 +43,8 @@ struct dualar_batch {
   std::vector<int> prompt_len, max_gen; std::vector<char> open;
   float *ws = nullptr; unsigned int *tickets = nullptr;      // split-K workspace of THIS group's GEMMs (groups run concurrently)
   cudaStream_t stream = nullptr; cudaEvent_t ev_done = nullptr;      // the group's own stream when there are several groups
+  cudaEvent_t ev_pf = nullptr, ev_act = nullptr, ev_rel = nullptr; bool act_pending = false, rel_pending = false;      // asynchronous prefill: KV rows written / slot activated
+  DAState *st_idle = nullptr;      // device copy of the idle slot state (loop_mode 0, position -1: the step's KV write and attention skip the slot)
   // persistent step (bstep.cuh): two cooperative launches around the slow sampler's kernels
   bool persistent = false; BPhase *d_phases = nullptr; CUtensorMap *d_maps = nullptr; unsigned int *gbar = nullptr;
   int n_phases = 0, split = 0, bs_stages = 0; size_t bs_smem = 0; long long *d_tl = nullptr; std::vector<int> kinds;
@@ -54,6 +56,8 @@ struct dualar_tc {
   float *ws_own = nullptr; unsigned int *tickets_own = nullptr;
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
+  bool concurrent_groups = false;      // set while the steps of a multi-group engine are captured
+  int attn_tiles_per_split = 8;      // a KV split is worth its partials / ticket / merge only from this many 64-position tiles on (DUALAR_ATTN_TPS)
   BRec *rec = nullptr;        // non-null while the step is being recorded for the persistent kernel
   int ksplit_override = 0, stages_override = 0, bn_override = 0;
   bool fuse_norm = false;     // DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>) instead of a separate
@@ -117,10 +121,12 @@ static int tc_init(dualar_engine *e) {
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   e->tc->ws_own = e->tc->ws; e->tc->tickets_own = e->tc->tickets;
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
+  { const char *v = getenv("DUALAR_ATTN_TPS"); if (v && atoi(v) > 0) e->tc->attn_tiles_per_split = atoi(v); }
   { const char *v = getenv("DUALAR_TC_KSPLIT"); if (v) e->tc->ksplit_override = atoi(v); }
   { const char *v = getenv("DUALAR_TC_STAGES"); if (v) e->tc->stages_override = atoi(v); }
   { const char *v = getenv("DUALAR_TC_PREFILL_BN"); if (v) e->tc->bn_override = atoi(v); }
-  if (e->c.head_dim < 32) return fail(DUALAR_EINVAL, "the tensor-core path needs head_dim >= 32 (a lane owns head_dim / 32 output dims in the attention kernel)");
+  if (e->c.head_dim < 32 || e->c.head_dim > 128 || (e->c.head_dim & (e->c.head_dim - 1)))
+    return fail(DUALAR_EINVAL, "the tensor-core path needs head_dim 32, 64 or 128 (a lane owns head_dim / 32 output dims and head_dim / 4 score dims in the attention kernel)");
   CU(cudaFuncSetAttribute(b_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_attn_smem(e->c.n_head / e->c.n_local_heads, e->c.head_dim)));
   CU(cudaFuncSetAttribute(b_fast_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)b_fast_attn_smem(e->c.fast_n_head, e->c.fast_n_local_heads, e->c.fast_head_dim, e->c.num_codebooks)));
@@ -157,7 +163,10 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
   GemmTcArgs a; memset(&a, 0, sizeof(a));
   a.rows = rows; a.K = K; a.ncols = ncols; a.epi = epi; a.ld_out = epi == TE_SWIGLU ? rows / 2 : rows; a.w_keep = w_keep;
   a.bias = bias; a.res = res; a.out = out; a.ws = e->tc->ws; a.tickets = e->tc->tickets; a.err = e->tc->err;
-  int st = tiles > 2 * e->sms ? 4 : 8;      // many tiles: two CTAs per SM hide each other's set-up; few tiles: deep ring per CTA
+  // many tiles: two CTAs per SM hide each other's set-up; few tiles: deep ring per CTA -- unless several request groups run
+  // concurrently: then shared memory is better spent on co-resident CTAs of the other groups (4 x 32 slots: 7.02 ms per round with 4
+  // stages against 7.26 with 8; 8 x 32: 10.9 against 12.7)
+  int st = (tiles > 2 * e->sms || e->tc->concurrent_groups) ? 4 : 8;
   if (e->tc->stages_override > 0) st = e->tc->stages_override;
   const int mxs = tc_max_stages(BN); if (st > mxs) st = mxs;
   const int nk_per = (nkb + ks - 1) / ks; if (st > nk_per) st = nk_per < 2 ? 2 : nk_per;
@@ -227,7 +236,7 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
       else { CU(launch_k(b_qkv_post_kernel, g, dim3(256), (size_t)8 * cf.head_dim * sizeof(float), s, a)); ++count; } }
     { BAttnArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S;
-      a.ncols = ncols; a.nsplit_max = c.nsplit; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
+      a.ncols = ncols; a.nsplit_max = c.nsplit; a.tiles_per_split = e->tc->attn_tiles_per_split; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
       a.tickets = c.attn_tickets; a.y = c.y; a.pos = pos; a.err = e->tc->err;
       const dim3 g(c.nsplit, cf.n_local_heads, ncols);
       if (BRec *r = e->tc->rec) r->add(BP_ATTN, g).u.attn = a;
@@ -455,19 +464,25 @@ static int batch_group_init(dualar_engine *e, int n_slots, int slot_seq_len, boo
   for (int l = 0; l < cf.n_layer; ++l) if ((rc = dev_alloc(e, b->kc[l], (size_t)b->slot_stride * b->BN)) || (rc = dev_alloc(e, b->vc[l], (size_t)b->slot_stride * b->BN))) return rc;
   for (int l = 0; l < cf.n_fast_layer; ++l) if ((rc = dev_alloc(e, b->fkc[l], (size_t)b->fslot_stride * b->BN)) || (rc = dev_alloc(e, b->fvc[l], (size_t)b->fslot_stride * b->BN))) return rc;
   if ((rc = dev_alloc(e, b->st, (size_t)b->BN)) || (rc = dev_alloc(e, b->seq, (size_t)b->BN * R * b->Sb))) return rc;
-  if (e->groups.size() == 1) { b->ws = e->tc->ws_own; b->tickets = e->tc->tickets_own; }
+  if (!own_stream) { b->ws = e->tc->ws_own; b->tickets = e->tc->tickets_own; }      // a single group: its prefills run on the same stream as its steps
   else if ((rc = dev_alloc(e, b->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, b->tickets, 8192))) return rc;
   CU(cudaMallocHost((void **)&b->h_st, sizeof(DAState)));
   CU(cudaMallocHost((void **)&b->h_seq, (size_t)R * b->Sb * sizeof(int)));
   b->prompt_len.assign(n_slots, 0); b->max_gen.assign(n_slots, 0); b->open.assign(n_slots, 0);
   CU(cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
-  if (own_stream) { CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming)); }
+  if (own_stream) {
+    CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_pf, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_act, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_rel, cudaEventDisableTiming));
+  }
+  if ((rc = dev_alloc(e, b->st_idle, 1))) return rc;
+  { DAState idle; memset(&idle, 0, sizeof(idle)); idle.pos = -1; CU(cudaMemcpy(b->st_idle, &idle, sizeof(idle), cudaMemcpyHostToDevice)); }
   // slow sampler: (chunks x requests) CTAs of 512 threads scan the logits; the register-heavy sampler code runs one CTA per SM, so
   // more CTAs than SMs only adds waves
   b->nchunk = e->sms / n_slots; if (b->nchunk < 1) b->nchunk = 1; if (b->nchunk > 32) b->nchunk = 32;
   // the group's GEMMs are enqueued with the group's split-K workspace
-  e->tc->ws = b->ws; e->tc->tickets = b->tickets;
+  e->tc->ws = b->ws; e->tc->tickets = b->tickets; e->tc->concurrent_groups = own_stream;
   // dry run (configures attributes, surfaces launch errors), then capture
   int n = 0;
   if ((rc = enqueue_batch_step(e, e->cap_stream, n)) < 0) return rc;
@@ -485,9 +500,9 @@ static int batch_group_init(dualar_engine *e, int n_slots, int slot_seq_len, boo
   CU(cudaGraphDestroy(g));
   b->launches = n;
   if ((rc = build_persistent_step(e))) return rc;
-  e->tc->ws = e->tc->ws_own; e->tc->tickets = e->tc->tickets_own;
+  e->tc->ws = e->tc->ws_own; e->tc->tickets = e->tc->tickets_own; e->tc->concurrent_groups = false;
   // the dry run advanced nothing (every slot is idle: loop_mode 0) but wrote KV row 0 and sampler scratch; start clean
-  CU(cudaMemset(b->st, 0, sizeof(DAState) * (size_t)b->BN));
+  for (int i = 0; i < b->BN; ++i) CU(cudaMemcpy(b->st + i, b->st_idle, sizeof(DAState), cudaMemcpyDeviceToDevice));
   for (int l = 0; l < cf.n_layer; ++l) { CU(cudaMemset(b->kc[l], 0, (size_t)b->slot_stride * b->BN * 2)); CU(cudaMemset(b->vc[l], 0, (size_t)b->slot_stride * b->BN * 2)); }
   CU(cudaMemset(e->tc->err, 0, 4));
   CU(cudaDeviceSynchronize());
@@ -519,7 +534,7 @@ extern "C" int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_l
     const int n = std::min(gs, max_batch - g * gs);
     if ((rc = batch_group_init(e, n, slot_seq_len, n_groups > 1))) return rc;
   }
-  if (n_groups > 1) CU(cudaEventCreateWithFlags(&e->ev_groups_go, cudaEventDisableTiming));
+  if (n_groups > 1) { CU(cudaEventCreateWithFlags(&e->ev_groups_go, cudaEventDisableTiming)); CU(cudaStreamCreateWithFlags(&e->pf_stream, cudaStreamNonBlocking)); }
   e->batch = e->groups[0];
   return batch_select_path(e);
 }
@@ -542,8 +557,16 @@ extern "C" int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *p
   if (T >= b.Sb) return fail(DUALAR_EINVAL, "Input sequence length %d exceeds the slot length %d", T, b.Sb);
   if (max_new <= 0 || T + max_new > b.Sb) max_new = b.Sb - T;
   CU(cudaSetDevice(e->device));
-  cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaStreamSynchronize(s));      // staging buffers are reused
+  // Several groups: the prefill runs ASYNCHRONOUSLY on the engine's prefill stream while the other groups (and this group's other slots)
+  // keep decoding; the slot is switched on by a copy of its state on the GROUP's stream, behind an event -- i.e. between two steps of the
+  // group, never in the middle of one.  One group: everything on the caller's stream, synchronously.
+  const bool async = b.stream != nullptr;
+  cudaStream_t s = async ? e->pf_stream : (cudaStream_t)stream;
+  if (async) {
+    if (b.act_pending) { CU(cudaEventSynchronize(b.ev_act)); b.act_pending = false; }
+    if (b.rel_pending) CU(cudaStreamWaitEvent(s, b.ev_rel, 0));
+  }      // the group's pinned staging buffers are free again
+  else CU(cudaStreamSynchronize(s));
   int *seq = b.seq + (size_t)slot * R * b.Sb;
   for (int r = 0; r < R; ++r) memcpy(b.h_seq + (size_t)r * T, prompt + (size_t)r * T, (size_t)T * sizeof(int));
   CU(cudaMemcpy2DAsync(seq, (size_t)b.Sb * sizeof(int), b.h_seq, (size_t)T * sizeof(int), (size_t)T * sizeof(int), R, cudaMemcpyHostToDevice, s));
@@ -556,8 +579,16 @@ extern "C" int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *p
   h->pos = T - 1; h->max_gen = max_new; h->prompt_len = T; h->loop_mode = 1; h->temperature = temperature; h->top_p = top_p; h->rep_penalty = rep;
   h->seed = seed; h->cpu_sem = e->cpu_sem; h->noise = (const bf16 *)noise; h->noise_stride = (long long)cf.vocab_size + (long long)(cf.num_codebooks - 1) * e->fv;
   for (int r = 0; r < R; ++r) h->tok_in[r] = prompt[(size_t)r * T + (T - 1)];
-  CU(cudaMemcpyAsync(b.st + slot, h, sizeof(*h), cudaMemcpyHostToDevice, s));
-  CU(cudaStreamSynchronize(s));      // `kc` / `vc` / the staging state live on this stack frame / in pinned memory
+  if (async) {
+    CU(cudaEventRecord(b.ev_pf, s));
+    CU(cudaStreamWaitEvent(b.stream, b.ev_pf, 0));
+    CU(cudaMemcpyAsync(b.st + slot, h, sizeof(*h), cudaMemcpyHostToDevice, b.stream));
+    CU(cudaEventRecord(b.ev_act, b.stream));
+    b.act_pending = true;
+  } else {
+    CU(cudaMemcpyAsync(b.st + slot, h, sizeof(*h), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));      // the pinned staging buffers are reused by the next call
+  }
   b.prompt_len[slot] = T; b.max_gen[slot] = max_new; b.open[slot] = 1;
   return 0;
 }
@@ -594,6 +625,7 @@ extern "C" int dualar_batch_collect(dualar_engine *e, int slot, int32_t *out, in
   dualar_batch &b = *bp; const int R = e->c.num_codebooks + 1;
   CU(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (b.act_pending) { CU(cudaEventSynchronize(b.ev_act)); b.act_pending = false; }      // h_st is the prefill's staging buffer too
   CU(cudaMemcpyAsync(b.h_st, b.st + slot, sizeof(DAState), cudaMemcpyDeviceToHost, s));
   int gerr = 0; CU(cudaMemcpyAsync(&gerr, e->tc->err, sizeof(int), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -617,8 +649,15 @@ extern "C" int dualar_batch_release(dualar_engine *e, int slot) {
   if (!bp) return fail(DUALAR_EINVAL, "slot out of range");
   dualar_batch &b = *bp;
   CU(cudaSetDevice(e->device));
-  CU(cudaDeviceSynchronize());
-  CU(cudaMemset(b.st + slot, 0, sizeof(DAState)));      // idle: loop_mode 0, position 0
+  if (b.stream) {
+    // several groups: no device-wide synchronisation (other groups' prefills may be in flight); the idle state is written on the
+    // group's stream, i.e. after every step already enqueued for the group and before any later one
+    CU(cudaMemcpyAsync(b.st + slot, b.st_idle, sizeof(DAState), cudaMemcpyDeviceToDevice, b.stream));
+    CU(cudaEventRecord(b.ev_rel, b.stream)); b.rel_pending = true;      // a later prefill of the slot must not overtake steps that still see the old request
+  } else {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(b.st + slot, b.st_idle, sizeof(DAState), cudaMemcpyDeviceToDevice));      // idle: loop_mode 0, position -1
+  }
   b.open[slot] = 0;
   return 0;
 }
@@ -663,6 +702,7 @@ extern "C" int dualar_batch_read(dualar_engine *e, const char *name, void *dst, 
   if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
   CU(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
+  for (dualar_batch *b : e->groups) if (b->act_pending) CU(cudaStreamWaitEvent(s, b->ev_act, 0));
   int64_t off = 0;
   for (dualar_batch *b : e->groups) {
     int64_t held = 0; int per_slot = 0;
@@ -685,11 +725,15 @@ static void batch_destroy(dualar_engine *e) {
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
+    if (b->ev_pf) cudaEventDestroy(b->ev_pf);
+    if (b->ev_act) cudaEventDestroy(b->ev_act);
+    if (b->ev_rel) cudaEventDestroy(b->ev_rel);
     if (b->h_st) cudaFreeHost(b->h_st);
     if (b->h_seq) cudaFreeHost(b->h_seq);
     delete b;
   }
   e->groups.clear(); e->batch = nullptr;
   if (e->ev_groups_go) { cudaEventDestroy(e->ev_groups_go); e->ev_groups_go = nullptr; }
+  if (e->pf_stream) { cudaStreamDestroy(e->pf_stream); e->pf_stream = nullptr; }
   delete e->tc; e->tc = nullptr;
 }

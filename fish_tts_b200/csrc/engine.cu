@@ -82,7 +82,7 @@ struct dualar_engine {
   cudaEvent_t ev_ring[8] = {nullptr}; int ev_next = 0; int stream_cols = 0, steps_enqueued = 0;      // dualar_decode_async
   bool batch_keep_raw = true;    // batched decode keeps a copy of the raw logits for dualar_batch_read
   int batch_persistent = -1;     // batched decode as two persistent launches (bstep.cuh): -1 = DUALAR_BATCH_PERSIST or the default, 0 / 1 = option batch_persistent
-  std::vector<dualar_batch *> groups; int group_slots = 32, batch_total = 0, batch_group_slots = 32; cudaEvent_t ev_groups_go = nullptr;      // request groups (batch_host.cuh)
+  std::vector<dualar_batch *> groups; int group_slots = 32, batch_total = 0, batch_group_slots = 32; cudaEvent_t ev_groups_go = nullptr; cudaStream_t pf_stream = nullptr;      // request groups (batch_host.cuh)
   bool batch_fork = true;        // batched decode: LM head + slow sampler on a side stream beside fast pass 0 (DUALAR_BATCH_FORK=0: one stream)
   bool l2_window = false; float l2_hit_ratio = 0.0f; size_t l2_persist_bytes = 0;   // DUALAR_L2_WINDOW / DUALAR_L2_HIT: access-policy window over the fast stack
   bool chunk_group = true;   // DUALAR_CHUNK_GROUP=0: one 128-element chunk per unit everywhere (round 1 behaviour)

@@ -1,5 +1,5 @@
 timeout 900 python -m pytest tests/test_gpu_batch.py -x -q -m gpu > gpurun_out/t_batch.log 2>&1; echo "rc $?"; tail -n 5 gpurun_out/t_batch.log
-BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 64 128 256 > gpurun_out/bt_groups.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups.log | cut -c1-150
-DUALAR_BATCH_GROUP_SLOTS=64 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 256 > gpurun_out/bt_groups64.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups64.log | cut -c1-150
-DUALAR_BATCH_GROUP_SLOTS=16 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 > gpurun_out/bt_groups16.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups16.log | cut -c1-150
-DUALAR_BATCH_GROUP_SLOTS=128 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 > gpurun_out/bt_groups128.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_groups128.log | cut -c1-150
+timeout 900 python bench.py --workload utterances --utterances 1024 --batch 128 > gpurun_out/r2_bench_utt1024_b128_1gpu_async.json 2> gpurun_out/utt_b128.err; echo "rc $?"; python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_utt1024_b128_1gpu_async.json')); print(d['value'], d['seconds_max_rank'], d['total_tokens'])"; tail -n 3 gpurun_out/utt_b128.err
+timeout 900 python bench.py --workload utterances --utterances 1024 --batch 256 > gpurun_out/r2_bench_utt1024_b256_1gpu_async.json 2> gpurun_out/utt_b256.err; echo "rc $?"; python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_utt1024_b256_1gpu_async.json')); print(d['value'], d['seconds_max_rank'], d['total_tokens'])"; tail -n 3 gpurun_out/utt_b256.err
