@@ -19,7 +19,7 @@ HEADERS = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dualar.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # Blackwell B200 only; no PTX fallback for other archs
-    "-lineinfo", "-O3", "-std=c++17", *(["-DDA_DEBUG_ATTN"] if os.environ.get("DA_DEBUG_ATTN") else []),
+    "-lineinfo", "-O3", "-std=c++17", *os.environ.get("DUALAR_NVCC_DEFS", "").split(),      # experiment switches, e.g. DUALAR_NVCC_DEFS="-DDA_TC_MIN_BLOCKS=3"
     "-shared", "-Xcompiler", "-fPIC",
 ]
 

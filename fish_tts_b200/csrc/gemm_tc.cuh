@@ -42,6 +42,9 @@ enum { TE_STORE = 0, TE_RESIDUAL = 1, TE_SWIGLU = 2 };
 #define DA_TC_BK 64                       // k-block: 64 bf16 = one 128-byte swizzle row
 #define DA_TC_A_BYTES (DA_TC_BM * 128)    // 16 KB per stage
 #define DA_TC_MAX_STAGES 12
+#ifndef DA_TC_MIN_BLOCKS
+#define DA_TC_MIN_BLOCKS 1             // co-resident GEMM CTAs per SM the register allocation must allow (166 registers at 1: two fit)
+#endif
 
 struct GemmTcArgs {
   int rows, K, ncols;        // weight rows, contraction length, valid activation rows
@@ -258,7 +261,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmTcArgs &a, uint32_t tmem, 
 // recomputes the row statistics, 64 KB of L2 reads) and write the CTA's k-range into shared memory in the same 128-byte-swizzle
 // K-major layout TMA would have produced.  That removes one kernel (and one kernel boundary, ~5 us in a dependent chain) per norm.
 template <int BN, bool XN = false>
-__global__ void __launch_bounds__(DA_TC_THREADS, 1)
+__global__ void __launch_bounds__(DA_TC_THREADS, DA_TC_MIN_BLOCKS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmTcArgs a) {
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "TMEM allocations are powers of two >= 32 columns");
   static_assert(!XN || BN == 32, "the fused-norm operand staging deals 8 rows to each of the four epilogue warps");

@@ -137,18 +137,27 @@ int dualar_generate(dualar_engine *e, const int32_t *prompt, int prompt_len, int
  * The reference is batch 1 only (inference.py:73 reads `logits[0, -1]`, :355 views the prompt as (1, C+1, T)), so there is
  * no reference entry point to mirror: these calls are the loop API above with a `slot` argument.  A slot is one request:
  * its own KV cache (`slot_seq_len` positions), position, repetition window, sampling parameters and Philox stream, so its
- * tokens are those of the same request run alone.  One decode step streams every weight byte ONCE for all slots: the
- * linears are tcgen05 GEMMs (csrc/gemm_tc.cuh) with the requests as the N dimension.
- *   dualar_batch_init     after dualar_finalize: allocates `max_batch` slots and captures the batched step as a CUDA graph
+ * tokens are those of the same request run alone.  The linears are tcgen05 GEMMs (csrc/gemm_tc.cuh) with the requests as
+ * the N dimension: one decode step of a GROUP of slots streams every weight byte once for the whole group.
+ * Slots live in groups of `batch_group_slots` (dualar_set_option, default 32, <= 128): slot s belongs to group
+ * s / batch_group_slots; every group has its own buffers, graph and stream and the groups of a step run concurrently (one
+ * group's step is a latency-bound chain of ~540 kernels that leaves the GPU mostly idle).  Options (dualar_set_option):
+ * "batch_group_slots" (before dualar_batch_init), "batch_persistent" (1: the step as two persistent cooperative launches,
+ * csrc/bstep.cuh -- identical results, measured slower, an experiment switch).
+ *   dualar_batch_init     after dualar_finalize: allocates `max_batch` slots (<= 1024) and captures one CUDA graph per group
  *   dualar_batch_prefill  HOST prompt (num_codebooks+1, prompt_len) int32 -> KV rows of the slot through the tensor-core
  *                         prefill; the slot then joins the batch and the NEXT dualar_batch_decode step produces its first
- *                         token.  `noise`: optional explicit Exp(1) draws (device, layout of dualar_set_noise), NULL = Philox(seed)
- *   dualar_batch_decode   n_steps batched steps, no host round trip; finished or empty slots ride along as no-ops
+ *                         token.  `noise`: optional explicit Exp(1) draws (device, layout of dualar_set_noise), NULL = Philox(seed).
+ *                         With several groups the prefill runs asynchronously on the engine's own stream beside the decoding
+ *                         groups and the call returns at once; with one group it is synchronous on `stream`
+ *   dualar_batch_decode   n_steps batched steps of every group that holds a request, no host round trip; returns at once, the
+ *                         caller's stream waits for all groups; finished or empty slots ride along as no-ops
  *   dualar_batch_collect  like dualar_collect, for one slot
  *   dualar_batch_release  frees the slot for the next request (continuous batching)
  *   dualar_batch_read     introspection (tests, bench): "slow_logits_raw" / "slow_logits" (B x vocab bf16), "hidden" (B x dim),
  *                         "fast_logits" (B x (num_codebooks-1) x fast_vocab), "tokens" (B x (num_codebooks+1) int32),
- *                         "positions" / "done" / "n_gen" (B int32), "launches" (1 int32: kernels per batched step) */
+ *                         "positions" / "done" / "n_gen" (B int32) -- all in slot order over all groups; "launches" (1 int32:
+ *                         kernels per step, summed over the groups), "groups" (1 int32) */
 int dualar_batch_init(dualar_engine *e, int max_batch, int slot_seq_len);
 int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *prompt, int prompt_len, int max_new_tokens,
                          float temperature, float top_p, float repetition_penalty, uint64_t seed, const void *noise,

@@ -1,5 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_batch.py -x -q -m gpu > gpurun_out/t_batch.log 2>&1; echo "rc $?"; tail -n 5 gpurun_out/t_batch.log
-timeout 900 python bench.py --workload utterances --utterances 1024 --batch 128 > gpurun_out/r2_bench_utt1024_b128_1gpu_async.json 2> gpurun_out/utt_b128.err; echo "rc $?"; python -c "
-import json; d=json.load(open('gpurun_out/r2_bench_utt1024_b128_1gpu_async.json')); print(d['value'], d['seconds_max_rank'], d['total_tokens'])"; tail -n 3 gpurun_out/utt_b128.err
-timeout 900 python bench.py --workload utterances --utterances 1024 --batch 256 > gpurun_out/r2_bench_utt1024_b256_1gpu_async.json 2> gpurun_out/utt_b256.err; echo "rc $?"; python -c "
-import json; d=json.load(open('gpurun_out/r2_bench_utt1024_b256_1gpu_async.json')); print(d['value'], d['seconds_max_rank'], d['total_tokens'])"; tail -n 3 gpurun_out/utt_b256.err
+BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 32 128 256 > gpurun_out/bt_mb3.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_mb3.log | cut -c1-100
+DUALAR_TC_STAGES=3 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 256 > gpurun_out/bt_mb3_st3.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_mb3_st3.log | cut -c1-100
+DUALAR_TC_STAGES=2 BT_SKIP_PREFILL=1 timeout 600 python tests/batch_time.py 128 256 > gpurun_out/bt_mb3_st2.log 2>&1; echo "rc $?"; grep "batched decode" gpurun_out/bt_mb3_st2.log | cut -c1-100
