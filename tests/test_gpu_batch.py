@@ -197,6 +197,37 @@ def test_persistent_step_equals_per_kernel_graph(name):
             assert torch.equal(sa[sl][s], sb[sl][s]) and torch.equal(fa[sl][s], fb[sl][s]), f"slot {sl} step {s}"
 
 
+def test_continuous_batching_over_groups_equals_one_request_at_a_time():
+    """The whole serving loop under churn: 36 short utterances through `replicas.run_rank_batched` on 8 slots in 4 groups of 2
+    (asynchronous prefills beside the decoding groups, releases without a device synchronisation, slots refilled many times) --
+    every utterance's codes must be those of the same request run alone in a one-slot engine."""
+    from fish_tts_b200 import replicas
+    cfg = variant_configs()["s1like"]
+    sd = make_state_dict(cfg, seed=0)
+    rng = np.random.default_rng(11)
+    utts = []
+    for i in range(36):
+        T = int(rng.integers(10, 60))
+        utts.append(replicas.Utterance(uid=i, prompt=synthetic_prompt(cfg, 3, T - 7, 4, seed=500 + i).numpy(), max_new_tokens=int(rng.integers(3, 40)),
+                                       temperature=0.7, top_p=0.8, repetition_penalty=1.1))
+    eng = DualAREngine(cfg, sd, device=0)
+    eng.batch_init(8, cfg.max_seq_len, group_slots=2)
+    assert int(eng.batch_read("groups")[0]) == 4
+    res = replicas.run_rank_batched(eng, utts, 0, 1, 8, poll_steps=5, sync=torch.cuda.synchronize, seed_base=7000)
+    eng.close()
+    assert sorted(res.uids) == list(range(36))
+    alone = DualAREngine(cfg, sd, device=0)
+    alone.batch_init(1, cfg.max_seq_len)
+    for u in utts:
+        alone.batch_prefill(0, u.prompt, u.max_new_tokens, u.temperature, u.top_p, u.repetition_penalty, seed=7000 + u.uid)
+        alone.batch_decode(u.max_new_tokens + 1)
+        ref, fin = alone.batch_collect(0)
+        alone.batch_release(0)
+        assert fin and ref.shape == res.codes[u.uid].shape, f"utterance {u.uid}: {ref.shape} vs {res.codes[u.uid].shape}"
+        assert (ref == res.codes[u.uid]).all(), f"utterance {u.uid} differs between the serving loop and a solitary run"
+    alone.close()
+
+
 def test_continuous_batching_refill_does_not_disturb_neighbours():
     cfg = variant_configs()["s1like"]
     sd = make_state_dict(cfg, seed=0)
