@@ -9,6 +9,8 @@
 
 namespace {
 
+#define DA_SSQ_LD 64      // row tiles per column a statistics buffer has room for (rows <= 8192)
+
 struct MapKey { const void *p; int rows, K, box; bool operator<(const MapKey &o) const { return std::tie(p, rows, K, box) < std::tie(o.p, o.rows, o.K, o.box); } };
 
 // activation buffers for up to `cap` columns
@@ -21,6 +23,9 @@ struct ColBufs {
   bf16 *logits = nullptr, *logits_raw = nullptr, *fin = nullptr, *fx[2] = {nullptr, nullptr}, *fh = nullptr, *fqkv = nullptr, *fy = nullptr, *fact = nullptr,
        *fxn = nullptr, *flogits = nullptr, *flogits_raw = nullptr, *fpi = nullptr;
   float *cmax = nullptr; unsigned long long *cand = nullptr;
+  // DUALAR_TC_FUSE_NORM=2: per activation buffer that feeds an RMSNorm, the partial sums of squares its producing GEMM leaves ([cap][DA_SSQ_LD]);
+  // `ssq_valid` tracks, while a step is being enqueued, which buffers were last written by such a GEMM
+  std::map<const bf16 *, float *> ssq; std::set<const bf16 *> ssq_valid;
 };
 
 // the step's kernel sequence recorded as phases of the persistent kernel (bstep.cuh) instead of being launched
@@ -60,7 +65,7 @@ struct dualar_tc {
   int attn_tiles_per_split = 8;      // a KV split is worth its partials / ticket / merge only from this many 64-position tiles on (DUALAR_ATTN_TPS)
   BRec *rec = nullptr;        // non-null while the step is being recorded for the persistent kernel
   int ksplit_override = 0, stages_override = 0, bn_override = 0;
-  bool fuse_norm = false;     // DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>) instead of a separate
+  int fuse_norm = 0;          // DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>) instead of a separate
                               // RMSNorm kernel in front of them.  Bit-identical (tests/test_gpu_batch.py), 145 kernels fewer per step -- and measured
                               // SLOWER on B200 (5.45 vs 4.83 ms per bs-32 step): every CTA re-reads the full rows for the statistics and stages the
                               // operand behind the dependency wait, which costs more than the ~3 us a separate 8-CTA kernel adds to the chain
@@ -96,6 +101,9 @@ static int alloc_cols(dualar_engine *e, ColBufs &c, int cap, int nsplit, bool de
       (rc = dev_alloc(e, c.part_o, (size_t)cap * cf.n_local_heads * nsplit * G * cf.head_dim)) || (rc = dev_alloc(e, c.part_ml, (size_t)cap * cf.n_local_heads * nsplit * G * 2)) ||
       (rc = dev_alloc(e, c.attn_tickets, (size_t)cap * cf.n_local_heads)))
     return rc;
+  if (decode && e->tc->fuse_norm == 2) {
+    for (bf16 *p : {c.x, c.h}) { float *q = nullptr; if ((rc = dev_alloc(e, q, (size_t)cap * DA_SSQ_LD))) return rc; c.ssq[p] = q; }
+  }
   if (!decode) return 0;
   if ((rc = dev_alloc(e, c.logits, (size_t)cap * cf.vocab_size)) || (rc = dev_alloc(e, c.logits_raw, (size_t)cap * cf.vocab_size)) ||
       (rc = dev_alloc(e, c.fin, (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fx[0], (size_t)cap * cf.fast_dim)) || (rc = dev_alloc(e, c.fx[1], (size_t)cap * cf.fast_dim)) ||
@@ -105,6 +113,9 @@ static int alloc_cols(dualar_engine *e, ColBufs &c, int cap, int nsplit, bool de
       (rc = dev_alloc(e, c.flogits, (size_t)cap * e->fv)) || (rc = dev_alloc(e, c.flogits_raw, (size_t)cap * (cf.num_codebooks - 1) * e->fv)) ||
       (rc = dev_alloc(e, c.cmax, (size_t)cap * 64)) || (rc = dev_alloc(e, c.cand, (size_t)cap * DA_CAND_CAP)))
     return rc;
+  if (e->tc->fuse_norm == 2) {
+    for (bf16 *p : {c.fx[0], c.fx[1], c.fh, c.fpi}) { float *q = nullptr; if ((rc = dev_alloc(e, q, (size_t)cap * DA_SSQ_LD))) return rc; c.ssq[p] = q; }
+  }
   return 0;
 }
 
@@ -116,7 +127,7 @@ static int tc_init(dualar_engine *e) {
   int rc;
   if ((rc = tc_configure<32>()) || (rc = tc_configure<64>()) || (rc = tc_configure<128>()) || (rc = tc_configure<256>())) return rc;
   CU(cudaFuncSetAttribute(gemm_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  { const char *v = getenv("DUALAR_TC_FUSE_NORM"); e->tc->fuse_norm = v && v[0] == '1'; }
+  { const char *v = getenv("DUALAR_TC_FUSE_NORM"); e->tc->fuse_norm = v ? atoi(v) : 0; }      // 2: statistics from the producing GEMM's epilogue (see ColBufs::ssq)
   e->tc->ws_bytes = (size_t)48 << 20;
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   e->tc->ws_own = e->tc->ws; e->tc->tickets_own = e->tc->tickets;
@@ -137,8 +148,19 @@ static int tc_init(dualar_engine *e) {
 // Y[n][r] = W[r][:] . X[n][:] on the tensor cores (gemm_tc.cuh); xcap = rows of the X buffer
 // norm_w != nullptr: X is the UN-normalised activation and the kernel applies RMSNorm(norm_w) itself (BN = 32 only, see tc_can_fuse_norm)
 static bool tc_can_fuse_norm(const dualar_engine *e, int BN, int K) { return e->tc->fuse_norm && BN == 32 && K % 256 == 0 && K <= 4096; }
+// mode 2: the GEMM that writes `out` leaves the RMSNorm statistics of its output; the consumer's operand staging reads them
+static float *ssq_out_for(dualar_engine *e, ColBufs &c, int BN, int rows, int epi, const bf16 *out) {
+  if (e->tc->fuse_norm != 2 || BN != 32 || epi == TE_SWIGLU || rows % DA_TC_BM || rows / DA_TC_BM > DA_SSQ_LD) return nullptr;
+  auto it = c.ssq.find(out); if (it == c.ssq.end()) return nullptr;
+  c.ssq_valid.insert(out); return it->second;
+}
+static const float *ssq_in_for(dualar_engine *e, ColBufs &c, int BN, int K, const bf16 *x) {
+  if (e->tc->fuse_norm != 2 || !tc_can_fuse_norm(e, BN, K) || !c.ssq_valid.count(x)) return nullptr;
+  return c.ssq.at(x);
+}
 static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 *X, int xcap, int ncols, int BN, int epi, const bf16 *bias,
-                   const bf16 *res, bf16 *out, int w_keep, cudaStream_t s, int &count, const bf16 *norm_w = nullptr, bool prefill = false) {
+                   const bf16 *res, bf16 *out, int w_keep, cudaStream_t s, int &count, const bf16 *norm_w = nullptr, bool prefill = false,
+                   const float *ssq_in = nullptr, float *ssq_out = nullptr) {
   const CUtensorMap *mw, *mx; int rc;
   if (prefill) {
     // prefill: parallelism comes from COLUMN tiles, never from split-K -- a K split of a 256-column tile writes and re-reads
@@ -163,6 +185,7 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
   GemmTcArgs a; memset(&a, 0, sizeof(a));
   a.rows = rows; a.K = K; a.ncols = ncols; a.epi = epi; a.ld_out = epi == TE_SWIGLU ? rows / 2 : rows; a.w_keep = w_keep;
   a.bias = bias; a.res = res; a.out = out; a.ws = e->tc->ws; a.tickets = e->tc->tickets; a.err = e->tc->err;
+  a.ssq_out = ssq_out; a.ssq_ld = rows / DA_TC_BM; a.ssq_in = ssq_in; a.ssq_n = K / DA_TC_BM;
   // many tiles: two CTAs per SM hide each other's set-up; few tiles: deep ring per CTA -- unless several request groups run
   // concurrently: then shared memory is better spent on co-resident CTAs of the other groups (4 x 32 slots: 7.02 ms per round with 4
   // stages against 7.26 with 8; 8 x 32: 10.9 against 12.7)
@@ -220,14 +243,19 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
     BNormArgs a{x, w, out, K, ncols, cf.norm_eps};
     if (BRec *r = e->tc->rec) { r->add(BP_NORM, dim3((ncols + 7) / 8)).u.norm = a; return 0; }      // one warp per column, 8 compute warps
     CU(launch_k(b_rmsnorm_kernel, dim3((ncols + 3) / 4), dim3(128), 0, s, a)); ++count; return 0; };
+  c.ssq_valid.clear();      // the embedding kernel leaves no statistics; nothing carries over from the previous step
+  // y = W . RMSNorm(x): a separate norm kernel in front of a TMA-fed GEMM (default), or the GEMM normalises its own operand
+  // (DUALAR_TC_FUSE_NORM=1: statistics recomputed by every CTA; =2: statistics left by the GEMM that produced x, where there is one)
+  auto normed_gemm = [&](const bf16 *W, int rows, int K, const bf16 *x, const bf16 *nw, bf16 *xn, int epi, const bf16 *bias, bf16 *out, int w_keep) -> int {
+    const int mode = (prefill || e->tc->rec) ? 0 : e->tc->fuse_norm;
+    if (mode == 1 && tc_can_fuse_norm(e, BN, K)) return tc_gemm(e, W, rows, K, x, c.cap, ncols, BN, epi, bias, nullptr, out, w_keep, s, count, nw);
+    if (mode == 2) { if (const float *sq = ssq_in_for(e, c, BN, K, x)) return tc_gemm(e, W, rows, K, x, c.cap, ncols, BN, epi, bias, nullptr, out, w_keep, s, count, nw, false, sq); }
+    int r2 = norm(x, nw, xn, K); if (r2) return r2;
+    return tc_gemm(e, W, rows, K, xn, c.cap, ncols, BN, epi, bias, nullptr, out, w_keep, s, count, nullptr, prefill);
+  };
   for (int l = 0; l < cf.n_layer; ++l) {
     LayerW &L = e->slow[l];
-    const bool fuse = !prefill && tc_can_fuse_norm(e, BN, cf.dim);      // decode (optional): the GEMM normalises its own operand
-    if (fuse) { if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.x, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count, L.attn_norm))) return rc; }
-    else {
-      if ((rc = norm(c.x, L.attn_norm, c.xn, cf.dim))) return rc;
-      if ((rc = tc_gemm(e, L.wqkv, qkv_rows, cf.dim, c.xn, c.cap, ncols, BN, TE_STORE, L.bqkv, nullptr, c.qkv, 0, s, count, nullptr, prefill))) return rc;
-    }
+    if ((rc = normed_gemm(L.wqkv, qkv_rows, cf.dim, c.x, L.attn_norm, c.xn, TE_STORE, L.bqkv, c.qkv, 0))) return rc;
     { BQkvPostArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn;
       a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S; a.ncols = ncols; a.eps = cf.norm_eps; a.pos = pos;
@@ -241,13 +269,12 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
       const dim3 g(c.nsplit, cf.n_local_heads, ncols);
       if (BRec *r = e->tc->rec) r->add(BP_ATTN, g).u.attn = a;
       else { CU(launch_k(b_attn_kernel, g, dim3(DA_ATTN_THREADS), b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; } }
-    if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count, nullptr, prefill))) return rc;
-    if (fuse) { if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.h, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count, L.ffn_norm))) return rc; }
-    else {
-      if ((rc = norm(c.h, L.ffn_norm, c.xn, cf.dim))) return rc;
-      if ((rc = tc_gemm(e, L.w13, 2 * cf.intermediate_size, cf.dim, c.xn, c.cap, ncols, BN, TE_SWIGLU, nullptr, nullptr, c.act, 0, s, count, nullptr, prefill))) return rc;
-    }
-    if ((rc = tc_gemm(e, L.w2, cf.dim, cf.intermediate_size, c.act, c.cap, ncols, BN, TE_RESIDUAL, nullptr, c.h, c.x, 0, s, count, nullptr, prefill))) return rc;
+    const bool emit = !prefill && !e->tc->rec;
+    if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count, nullptr, prefill, nullptr,
+                      emit ? ssq_out_for(e, c, BN, cf.dim, TE_RESIDUAL, c.h) : nullptr))) return rc;
+    if ((rc = normed_gemm(L.w13, 2 * cf.intermediate_size, cf.dim, c.h, L.ffn_norm, c.xn, TE_SWIGLU, nullptr, c.act, 0))) return rc;
+    if ((rc = tc_gemm(e, L.w2, cf.dim, cf.intermediate_size, c.act, c.cap, ncols, BN, TE_RESIDUAL, nullptr, c.h, c.x, 0, s, count, nullptr, prefill, nullptr,
+                      emit ? ssq_out_for(e, c, BN, cf.dim, TE_RESIDUAL, c.x) : nullptr))) return rc;
   }
   return 0;
 }
@@ -310,44 +337,43 @@ static int enqueue_batch_step(dualar_engine *e, cudaStream_t s, int &count) {
   if (fork) CU(cudaEventRecord(b.ev_join, s2));
   // fast AR: pass 0 consumes the slow hidden state, pass k >= 1 the embedding of codebook k-1 (inference.py:121-149)
   const int fqkv_rows = (cf.fast_n_head + 2 * cf.fast_n_local_heads) * cf.fast_head_dim, fqd = cf.fast_n_head * cf.fast_head_dim;
+  const bool emit = !rec;
+  c.ssq_valid.erase(c.fin);      // written by the samplers (an embedding row): no statistics
+  auto normed_gemm = [&](const bf16 *W, int rows, int K, const bf16 *x, const bf16 *nw, bf16 *xn, int epi, const bf16 *bias, bf16 *out) -> int {
+    const int mode = rec ? 0 : e->tc->fuse_norm;
+    if (mode == 1 && tc_can_fuse_norm(e, BN, K)) return tc_gemm(e, W, rows, K, x, c.cap, B, BN, epi, bias, nullptr, out, 1, s, count, nw);
+    if (mode == 2) { if (const float *sq = ssq_in_for(e, c, BN, K, x)) return tc_gemm(e, W, rows, K, x, c.cap, B, BN, epi, bias, nullptr, out, 1, s, count, nw, false, sq); }
+    int r2 = norm(x, nw, xn, K); if (r2) return r2;
+    return tc_gemm(e, W, rows, K, xn, c.cap, B, BN, epi, bias, nullptr, out, 1, s, count);
+  };
   if (e->fpi_w) {      // hidden_states = fast_project_in(x)   (llama.py:590)
-    if ((rc = tc_gemm(e, e->fpi_w, cf.fast_dim, cf.dim, c.x, c.cap, B, BN, TE_STORE, e->fpi_b, nullptr, c.fpi, 1, s, count))) return rc;
+    if ((rc = tc_gemm(e, e->fpi_w, cf.fast_dim, cf.dim, c.x, c.cap, B, BN, TE_STORE, e->fpi_b, nullptr, c.fpi, 1, s, count, nullptr, false, nullptr,
+                      emit ? ssq_out_for(e, c, BN, cf.fast_dim, TE_STORE, c.fpi) : nullptr))) return rc;
   }
   for (int p = 0; p < cf.num_codebooks; ++p) {
     const bf16 *in = p == 0 ? (e->fpi_w ? c.fpi : c.x) : c.fin;
     for (int l = 0; l < cf.n_fast_layer; ++l) {
       LayerW &L = e->fast[l];
       bf16 *out = c.fx[l & 1];
-      const bool fuse = tc_can_fuse_norm(e, BN, cf.fast_dim);
-      if (fuse) { if ((rc = tc_gemm(e, L.wqkv, fqkv_rows, cf.fast_dim, in, c.cap, B, BN, TE_STORE, L.bqkv, nullptr, c.fqkv, 1, s, count, L.attn_norm))) return rc; }
-      else {
-        if ((rc = norm(in, L.attn_norm, c.fxn, cf.fast_dim))) return rc;
-        if ((rc = tc_gemm(e, L.wqkv, fqkv_rows, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, L.bqkv, nullptr, c.fqkv, 1, s, count))) return rc;
-      }
+      if ((rc = normed_gemm(L.wqkv, fqkv_rows, cf.fast_dim, in, L.attn_norm, c.fxn, TE_STORE, L.bqkv, c.fqkv))) return rc;
       { BFastAttnArgs a; memset(&a, 0, sizeof(a));
         a.qkv = c.fqkv; a.kc = b.fkc[l]; a.vc = b.fvc[l]; a.slot_stride = b.fslot_stride; a.rope = e->fast_rope; a.qn = L.qn; a.kn = L.kn;
         a.nh = cf.fast_n_head; a.nkv = cf.fast_n_local_heads; a.hd = cf.fast_head_dim; a.ncb = cf.num_codebooks; a.p = p; a.ncols = B;
         a.eps = cf.norm_eps; a.scale = (float)(1.0 / sqrt((double)cf.fast_head_dim)); a.y = c.fy;
         if (rec) rec->add(BP_FAST_ATTN, dim3(B)).u.fattn = a;
         else { CU(launch_k(b_fast_attn_kernel, dim3(B), dim3(256), b_fast_attn_smem(a.nh, a.nkv, a.hd, a.ncb), s, a)); ++count; } }
-      if ((rc = tc_gemm(e, L.wo, cf.fast_dim, fqd, c.fy, c.cap, B, BN, TE_RESIDUAL, L.bo, in, c.fh, 1, s, count))) return rc;
-      if (fuse) { if ((rc = tc_gemm(e, L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fh, c.cap, B, BN, TE_SWIGLU, nullptr, nullptr, c.fact, 1, s, count, L.ffn_norm))) return rc; }
-      else {
-        if ((rc = norm(c.fh, L.ffn_norm, c.fxn, cf.fast_dim))) return rc;
-        if ((rc = tc_gemm(e, L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fxn, c.cap, B, BN, TE_SWIGLU, nullptr, nullptr, c.fact, 1, s, count))) return rc;
-      }
-      if ((rc = tc_gemm(e, L.w2, cf.fast_dim, cf.fast_intermediate_size, c.fact, c.cap, B, BN, TE_RESIDUAL, nullptr, c.fh, out, 1, s, count))) return rc;
+      if ((rc = tc_gemm(e, L.wo, cf.fast_dim, fqd, c.fy, c.cap, B, BN, TE_RESIDUAL, L.bo, in, c.fh, 1, s, count, nullptr, false, nullptr,
+                        emit ? ssq_out_for(e, c, BN, cf.fast_dim, TE_RESIDUAL, c.fh) : nullptr))) return rc;
+      if ((rc = normed_gemm(L.w13, 2 * cf.fast_intermediate_size, cf.fast_dim, c.fh, L.ffn_norm, c.fxn, TE_SWIGLU, nullptr, c.fact))) return rc;
+      if ((rc = tc_gemm(e, L.w2, cf.fast_dim, cf.fast_intermediate_size, c.fact, c.cap, B, BN, TE_RESIDUAL, nullptr, c.fh, out, 1, s, count, nullptr, false, nullptr,
+                        emit ? ssq_out_for(e, c, BN, cf.fast_dim, TE_RESIDUAL, out) : nullptr))) return rc;
       in = out;
     }
     if (p == 0) {              // logits of pass 0 are discarded by the reference (inference.py:122)
       if (fork) CU(cudaStreamWaitEvent(s, b.ev_join, 0));      // join: pass 1 starts from the embedding of the sampled id
       continue;
     }
-    if (tc_can_fuse_norm(e, BN, cf.fast_dim)) { if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, in, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count, e->fast_norm))) return rc; }
-    else {
-      if ((rc = norm(in, e->fast_norm, c.fxn, cf.fast_dim))) return rc;
-      if ((rc = tc_gemm(e, e->fast_out, e->fv, cf.fast_dim, c.fxn, c.cap, B, BN, TE_STORE, nullptr, nullptr, c.flogits, 1, s, count))) return rc;
-    }
+    if ((rc = normed_gemm(e->fast_out, e->fv, cf.fast_dim, in, e->fast_norm, c.fxn, TE_STORE, nullptr, c.flogits))) return rc;
     { BFastSampleArgs a; memset(&a, 0, sizeof(a));
       a.logits = c.flogits; a.logits_raw = e->batch_keep_raw ? c.flogits_raw : nullptr; a.fv = e->fv; a.head = p; a.ncb = cf.num_codebooks; a.last_head = (p == cf.num_codebooks - 1);
       a.noise_off = (long long)cf.vocab_size + (long long)(p - 1) * e->fv; a.fast_emb = e->fast_emb; a.fast_x = c.fin; a.fast_dim = cf.fast_dim; a.codebook_size = cf.codebook_size;

@@ -58,6 +58,10 @@ struct GemmTcArgs {
   const bf16 *xraw;          // XN kernels: un-normalised activations [ncols][K]; the kernel applies the custom RMSNorm itself
   const bf16 *norm_w;        //             norm weight [K]
   float eps;
+  const float *ssq_in;       // XN kernels, optional: per column ssq_n partial sums of squares of xraw's row (written by the producing GEMM)
+  int ssq_n;
+  float *ssq_out;            // optional: this GEMM's epilogue writes, per column and row tile, the sum of squares of the bf16 outputs: [col][ssq_ld]
+  int ssq_ld;
   float *ws;                 // split-K partials [tile][split][BN][128]
   unsigned int *tickets;     // split-K arrival counters, one per tile, zero between launches
   int *err;                  // device fault flag (DAState::err or a stand-alone word)
@@ -208,6 +212,16 @@ __device__ __forceinline__ void tc_epilogue(const GemmTcArgs &a, uint32_t tmem, 
           u.x = (uint32_t)f2bits(y[0]) | ((uint32_t)f2bits(y[1]) << 16); u.y = (uint32_t)f2bits(y[2]) | ((uint32_t)f2bits(y[3]) << 16);
           u.z = (uint32_t)f2bits(y[4]) | ((uint32_t)f2bits(y[5]) << 16); u.w = (uint32_t)f2bits(y[6]) | ((uint32_t)f2bits(y[7]) << 16);
           *reinterpret_cast<uint4 *>(a.out + n * a.ld_out + row0) = u;
+          if (a.ssq_out) {
+            // statistics for the RMSNorm that consumes this output (llama.py:172-177 squares the bf16 values in fp32): the 16 items of a
+            // column in this 128-row tile sit in the 16 lanes of a half-warp -- fixed-order butterfly, one partial per (column, row tile)
+            float ss = 0.f;
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) { const float r = rbf(y[i2]); ss = fmaf(r, r, ss); }
+            const unsigned hm = 0xFFFFu << (lane & 16);
+            ss += __shfl_xor_sync(hm, ss, 8); ss += __shfl_xor_sync(hm, ss, 4); ss += __shfl_xor_sync(hm, ss, 2); ss += __shfl_xor_sync(hm, ss, 1);
+            if ((lane & 15) == 0) a.ssq_out[n * a.ssq_ld + tile_m] = ss;
+          }
         }
       };
       if (nz > 1) {
@@ -261,7 +275,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmTcArgs &a, uint32_t tmem, 
 // recomputes the row statistics, 64 KB of L2 reads) and write the CTA's k-range into shared memory in the same 128-byte-swizzle
 // K-major layout TMA would have produced.  That removes one kernel (and one kernel boundary, ~5 us in a dependent chain) per norm.
 template <int BN, bool XN = false>
-__global__ void __launch_bounds__(DA_TC_THREADS, DA_TC_MIN_BLOCKS)
+__global__ void __launch_bounds__(DA_TC_THREADS, XN ? 2 : DA_TC_MIN_BLOCKS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmTcArgs a) {
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "TMEM allocations are powers of two >= 32 columns");
   static_assert(!XN || BN == 32, "the fused-norm operand staging deals 8 rows to each of the four epilogue warps");
@@ -356,6 +370,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       // row statistics: warp wq owns rows wq, wq + 4, ...; per lane the chunks lane, lane + 32, ... in ascending order, then a butterfly
       // (the summation order of b_rmsnorm_kernel, so fused and unfused paths agree bit for bit)
       const int K = a.K, cpl = K >> 8;      // 16-byte chunks per lane
+      if (a.ssq_in) {
+        // the producing GEMM's epilogue left ssq_n partial sums of squares per column: add them in tile order
+        if (te < BN) {
+          float t = 0.f;
+          if (te < a.ncols) for (int j = 0; j < a.ssq_n; ++j) t += a.ssq_in[(size_t)te * a.ssq_n + j];
+          s_inv[te] = rsqrtf(t * (1.0f / (float)K) + a.eps);
+        }
+      } else {
       float ss[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) ss[r] = 0.f;
@@ -386,25 +408,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const float tot = warp_sum(ss[r]);
         if (lane == 0) s_inv[wq + 4 * r] = rsqrtf(tot * (1.0f / (float)K) + a.eps);
       }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       // transform + swizzled store: 16-byte chunk c16 of row n of k-block kb goes to  sB + kb * BN * 128 + n * 128 + ((c16 ^ (n & 7)) << 4)
       const int per_row = nk * 8, total = BN * per_row;
-#pragma unroll 2
-      for (int c = te; c < total; c += 128) {
-        const int n = c / per_row, kc = c - n * per_row, kb = kc >> 3, c16 = kc & 7;
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (n < a.ncols) {
-          const size_t k0 = (size_t)(kb0 + kb) * DA_TC_BK + (size_t)c16 * 8;
-          float f[8], g[8];
-          unpack8(*reinterpret_cast<const uint4 *>(a.xraw + (size_t)n * K + k0), f);
-          unpack8(*reinterpret_cast<const uint4 *>(a.norm_w + k0), g);
-          const float inv = s_inv[n];
+      // eight chunks per thread and round: all sixteen 16-byte loads (activations + norm weights) are in flight before the first is
+      // used, so a round costs one L2 round trip instead of eight dependent ones
+#pragma unroll 1
+      for (int c0 = te; c0 < total; c0 += 8 * 128) {
+        uint4 xv[8], gv[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = rbf(__fmul_rn(rbf(__fmul_rn(f[q], inv)), g[q]));      // .type_as(x), then * weight
-          u.x = (uint32_t)f2bits(f[0]) | ((uint32_t)f2bits(f[1]) << 16); u.y = (uint32_t)f2bits(f[2]) | ((uint32_t)f2bits(f[3]) << 16);
-          u.z = (uint32_t)f2bits(f[4]) | ((uint32_t)f2bits(f[5]) << 16); u.w = (uint32_t)f2bits(f[6]) | ((uint32_t)f2bits(f[7]) << 16);
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j * 128;
+          xv[j] = make_uint4(0u, 0u, 0u, 0u); gv[j] = xv[j];
+          if (c < total) {
+            const int n = c / per_row, kc = c - n * per_row;
+            const size_t k0 = (size_t)(kb0 + (kc >> 3)) * DA_TC_BK + (size_t)(kc & 7) * 8;
+            if (n < a.ncols) { xv[j] = *reinterpret_cast<const uint4 *>(a.xraw + (size_t)n * K + k0); gv[j] = *reinterpret_cast<const uint4 *>(a.norm_w + k0); }
+          }
         }
-        *reinterpret_cast<uint4 *>(sB + (size_t)kb * BN * 128 + (size_t)n * 128 + (size_t)((c16 ^ (n & 7)) << 4)) = u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j * 128;
+          if (c < total) {
+            const int n = c / per_row, kc = c - n * per_row, kb = kc >> 3, c16 = kc & 7;
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (n < a.ncols) {
+              float f[8], g[8];
+              unpack8(xv[j], f); unpack8(gv[j], g);
+              const float inv = s_inv[n];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] = rbf(__fmul_rn(rbf(__fmul_rn(f[q], inv)), g[q]));      // .type_as(x), then * weight
+              u.x = (uint32_t)f2bits(f[0]) | ((uint32_t)f2bits(f[1]) << 16); u.y = (uint32_t)f2bits(f[2]) | ((uint32_t)f2bits(f[3]) << 16);
+              u.z = (uint32_t)f2bits(f[4]) | ((uint32_t)f2bits(f[5]) << 16); u.w = (uint32_t)f2bits(f[6]) | ((uint32_t)f2bits(f[7]) << 16);
+            }
+            *reinterpret_cast<uint4 *>(sB + (size_t)kb * BN * 128 + (size_t)n * 128 + (size_t)((c16 ^ (n & 7)) << 4)) = u;
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's async proxy
       mbar_arrive(&xready_bar);

@@ -228,6 +228,33 @@ def test_continuous_batching_over_groups_equals_one_request_at_a_time():
     alone.close()
 
 
+@pytest.mark.parametrize("name", ["s1like", "projected"])
+def test_producer_side_norm_statistics_against_oracle(name, monkeypatch):
+    """DUALAR_TC_FUSE_NORM=2: the GEMM that produces an activation leaves the RMSNorm's sums of squares (per column and 128-row tile, from
+    its epilogue), the consuming GEMM normalises its own operand with them -- no norm kernel between the two.  The fp32 order of the
+    sum of squares differs from the norm kernel's, so the check is the oracle replay with the usual tolerance, and the kernel count."""
+    monkeypatch.setenv("DUALAR_TC_FUSE_NORM", "2")
+    cfg = variant_configs()[name]
+    sd = make_state_dict(cfg, seed=0)
+    m = orc.OracleModel.build(cfg, sd, device="cuda:0")
+    eng = DualAREngine(cfg, sd, device=0)
+    eng.batch_init(5, cfg.max_seq_len)
+    n = 10
+    prompts, cols, slows, fasts = run_batch(eng, cfg, REQS, n)
+    launches = int(eng.batch_read("launches")[0])
+    same = 0
+    for sl, r in enumerate(REQS):
+        same += replay_slot(cfg, m, eng, prompts[sl], cols[sl], slows[sl], fasts[sl], r[3], r[4], r[5], 100 + sl, f"{name} fused slot {sl}")
+    eng.close()
+    monkeypatch.setenv("DUALAR_TC_FUSE_NORM", "0")
+    eng = DualAREngine(cfg, sd, device=0)
+    eng.batch_init(5, cfg.max_seq_len)
+    plain = int(eng.batch_read("launches")[0])
+    eng.close()
+    print(f"\n[{name}] {launches} kernels per step with producer-side statistics, {plain} without; {same}/{n * len(REQS)} (slot, step) pairs identical to the oracle")
+    assert launches < plain - cfg.n_layer and same >= int(0.8 * n * len(REQS))
+
+
 def test_continuous_batching_refill_does_not_disturb_neighbours():
     cfg = variant_configs()["s1like"]
     sd = make_state_dict(cfg, seed=0)
