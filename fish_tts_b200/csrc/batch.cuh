@@ -167,18 +167,19 @@ struct BAttnArgs {
 // probabilities handed to all lanes for P@V where a lane owns hd/32 output dims -- and the warps meet ONCE, after the last tile
 // (the decode kernel's tile walk, mega.cuh).  One CTA barrier per tile instead of three, no idle warps during the softmax.
 #define DA_B_AWARPS (DA_ATTN_THREADS / 32)
+#define DA_B_NBUF 3      // K/V tile buffers: two tiles are in flight while one is being consumed (a tile's HBM latency is ~2x its compute time)
 static_assert(DA_TILE == 8 * DA_B_AWARPS, "a warp owns 8 positions of a tile: 4 lanes each");
 static inline size_t b_attn_smem(int G, int hd) {
   size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t);
   f = (f + 127) & ~(size_t)127;
-  return f + 128 + 4 * (size_t)DA_TILE * hd * sizeof(bf16);
+  return f + 128 + 2 * DA_B_NBUF * (size_t)DA_TILE * hd * sizeof(bf16);
 }
-// `bars`: two mbarriers in STATIC shared memory; `phase`: their parities as this thread has seen them.  The stand-alone kernel
+// `bars`: DA_B_NBUF mbarriers in STATIC shared memory; `phase`: their parities as this thread has seen them.  The stand-alone kernel
 // initialises them per launch (init = true); the persistent kernel initialises them once and carries the parities from unit to unit --
 // re-initialising an mbarrier in the middle of a kernel (through a per-thread address: a plain 64-bit store + a sync-unit cache
 // invalidate in SASS) lost the transaction that followed on B200.
 template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm,
-                                                               uint64_t *bars, uint32_t (&phase)[2], bool init) {
+                                                               uint64_t *bars, uint32_t (&phase)[DA_B_NBUF], bool init) {
   (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
   unsigned char *smraw_b = dsm;
   const int g = by, split = bx, n = bz;
@@ -200,11 +201,11 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   size_t off = (size_t)((unsigned char *)(po + (size_t)DA_B_AWARPS * G * hd) - smraw_b) + 16;
   off = (off + 127) & ~(size_t)127;
   bf16 *kbuf = reinterpret_cast<bf16 *>(smraw_b + off);
-  bf16 *vbuf = kbuf + 2 * DA_TILE * hd;
+  bf16 *vbuf = kbuf + DA_B_NBUF * DA_TILE * hd;
   const bf16 *kc = a.kc + (size_t)n * a.slot_stride, *vc = a.vc + (size_t)n * a.slot_stride;
   const uint64_t pol = policy_evict_first();
   if (init && threadIdx.x == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    for (int i = 0; i < DA_B_NBUF; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   B::sync();
@@ -216,7 +217,7 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
     bulk_g2s(kbuf + (size_t)buf * DA_TILE * hd, kc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
     bulk_g2s(vbuf + (size_t)buf * DA_TILE * hd, vc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
   };
-  if (threadIdx.x == 0) issue(t0, 0);
+  if (threadIdx.x == 0) { issue(t0, 0); if (t0 + 1 < t1) issue(t0 + 1, 1); }
   {
     const bf16 *qsrc = a.qkv + (size_t)n * (a.nh + 2 * a.nkv) * hd + (size_t)g * G * hd;
     for (int c = threadIdx.x; c * 8 < G * hd; c += DA_ATTN_THREADS) {
@@ -237,9 +238,9 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   const bool single = G <= 2;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f}, o_acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   for (int t = t0; t < t1; ++t) {
-    const int buf = (t - t0) & 1;
+    const int buf = (t - t0) % DA_B_NBUF;
     const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
-    if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);
+    if (threadIdx.x == 0 && t + 2 < t1) issue(t + 2, (t - t0 + 2) % DA_B_NBUF);      // into the buffer of tile t - 1, released by the barrier that ended it
     ok = mbar_wait(&bars[buf], phase[buf]) && ok; phase[buf] ^= 1u;
     const bf16 *kt = kbuf + (size_t)buf * DA_TILE * hd, *vt = vbuf + (size_t)buf * DA_TILE * hd;
     for (int h0 = 0; h0 < G; h0 += 2) {
@@ -372,8 +373,8 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
   extern __shared__ __align__(128) unsigned char dsm_b_attn_body[];
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ __align__(8) uint64_t s_bars[2];
-  uint32_t phase[2] = {0u, 0u};
+  __shared__ __align__(8) uint64_t s_bars[DA_B_NBUF];
+  uint32_t phase[DA_B_NBUF] = {};
   b_attn_body<BlockAll>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_attn_body, s_bars, phase, true);
 }
 

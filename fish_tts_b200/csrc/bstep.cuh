@@ -69,7 +69,7 @@ template <int BN>
 __global__ void __launch_bounds__(DA_BS_THREADS, 1) bstep_kernel(const BStepArgs k) {
   static_assert(BN == 32 || BN == 64 || BN == 128, "TMEM allocations are powers of two >= 32 columns");
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[DA_TC_MAX_STAGES], empty_bar[DA_TC_MAX_STAGES], accum_bar, accfree_bar, attn_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[DA_TC_MAX_STAGES], empty_bar[DA_TC_MAX_STAGES], accum_bar, accfree_bar, attn_bar[DA_B_NBUF];
   __shared__ uint32_t s_tmem, s_last;
   __shared__ int s_abort, s_go;
   __shared__ __align__(16) BPhase s_ph[2];
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(DA_BS_THREADS, 1) bstep_kernel(const BStepArgs
 
   if (tid == 0) {
     for (int i = 0; i < ST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&accum_bar, 1); mbar_init(&accfree_bar, 128); mbar_init(&attn_bar[0], 1); mbar_init(&attn_bar[1], 1);
+    mbar_init(&accum_bar, 1); mbar_init(&accfree_bar, 128); for (int i = 0; i < DA_B_NBUF; ++i) mbar_init(&attn_bar[i], 1);
     s_abort = 0; s_go = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(DA_BS_THREADS, 1) bstep_kernel(const BStepArgs
   } else {
     // ===== compute warps =====
     uint32_t it = 0, uc = 0;      // running k-block / unit counters: the mbarrier parities continue across units and phases
-    uint32_t attn_phase[2] = {0u, 0u};
+    uint32_t attn_phase[DA_B_NBUF] = {};
     for (int p = 0; p < k.n_phases; ++p) {
       const BPhase &ph = s_ph[p & 1];
       if (k.tl && cta == 0 && tid == 0) k.tl[2 * p] = clock64();
