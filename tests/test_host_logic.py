@@ -152,3 +152,23 @@ def test_token_ids_from_model_dir(tmp_path):
         rh.fabricate_model_dir(cfg, {}, d)
         ids = TokenIds.from_model_dir(d)
         assert (ids.semantic_begin_id, ids.semantic_end_id, ids.im_end_id) == (cfg.semantic_begin_id, cfg.semantic_end_id, cfg.im_end_id)
+
+
+def test_pack_prompt_layout():
+    """row 0 = token ids (VQ positions: code 0 + semantic_begin_id), rows 1.. = codes at VQ positions, 0 elsewhere (inference.py:611-640)"""
+    import numpy as np
+
+    from fish_tts_b200.prompt import pack_prompt, pack_prompts
+    C, sb = 4, 1000
+    text = np.array([5, 6, 7])
+    codes = np.arange(C * 2).reshape(C, 2)
+    out = pack_prompt([text, codes, [9]], C, sb)
+    assert out.dtype == np.int32 and out.shape == (C + 1, 6)
+    assert out[0].tolist() == [5, 6, 7, sb + 0, sb + 1, 9]
+    assert (out[1:, :3] == 0).all() and (out[1:, 3:5] == codes).all() and (out[1:, 5] == 0).all()
+    batch, lens = pack_prompts([[text], [codes, text]], C, sb)
+    assert lens.tolist() == [3, 5] and batch[1].shape == (C + 1, 5)
+    assert pack_prompt([], C, sb).shape == (C + 1, 0)
+    import pytest
+    with pytest.raises(ValueError):
+        pack_prompt([np.zeros((C, 2)) + 99], C, sb, codebook_size=16)

@@ -53,3 +53,38 @@ def test_reference_rng_path_is_reproduced():
     torch.manual_seed(77)
     y2 = orc.generate(orc.OracleModel.build(cfg, sd), prompt.clone(), 16, 0.7, 0.8, 1.1)
     assert torch.equal(y, y2)
+
+
+def test_prompt_packing_equals_encode_for_inference():
+    """fish_tts_b200.prompt.pack_prompt (numpy, whole arrays) == ContentSequence.encode_for_inference (inference.py:611-640, one
+    .item() per code) on mixed text / VQ parts, for one request and for a ragged batch"""
+    import numpy as np
+
+    from fish_tts_b200.prompt import pack_prompt, pack_prompts
+    cfg = variant_configs()["s1like"]
+    sd = make_state_dict(cfg, seed=3)
+    _, inf = rh.import_reference()
+    with tempfile.TemporaryDirectory() as d:
+        model, _ = rh.load_reference_model(cfg, sd, d)
+    tok = model.tokenizer
+    rng = np.random.default_rng(0)
+    reqs = []
+    for n_parts in (1, 2, 5, 4):
+        parts = []
+        for i in range(n_parts):
+            if i % 2 == 0:
+                parts.append(rng.integers(0, 200, size=int(rng.integers(1, 9))).astype(np.int64))
+            else:
+                parts.append(rng.integers(0, cfg.codebook_size, size=(cfg.num_codebooks, int(rng.integers(1, 30)))).astype(np.int64))
+        reqs.append(parts)
+    for parts in reqs:
+        seq = inf.ContentSequence()
+        for p in parts:
+            seq.append(inf.TextPart(tokens=p.tolist()) if p.ndim == 1 else inf.VQPart(codes=torch.from_numpy(p)), add_end=False)
+        ref, masks, audio = seq.encode_for_inference(tok, cfg.num_codebooks)
+        mine = pack_prompt(parts, cfg.num_codebooks, tok.semantic_begin_id, cfg.codebook_size)
+        assert mine.dtype == np.int32 and mine.shape == tuple(ref.shape) and (torch.from_numpy(mine) == ref).all()
+    batch, lens = pack_prompts(reqs, cfg.num_codebooks, tok.semantic_begin_id)
+    assert [b.shape[1] for b in batch] == lens.tolist() and all((b == pack_prompt(r, cfg.num_codebooks, tok.semantic_begin_id)).all() for b, r in zip(batch, reqs))
+    with pytest.raises(ValueError):
+        pack_prompt([np.zeros((cfg.num_codebooks + 1, 3))], cfg.num_codebooks, tok.semantic_begin_id)
