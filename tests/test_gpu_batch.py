@@ -352,3 +352,31 @@ def test_s1_mini_batched_decode_against_oracle():
     eng.close()
     print(f"\n[s1-mini batched] {launches} kernels per step; semantic-logit max |ours - oracle| = {worst:.4f}; {same}/{n * 4} (slot, step) pairs identical in all rows")
     assert same >= int(0.6 * n * 4)
+
+
+def test_s1_mini_serving_loop_is_deterministic_and_group_invariant():
+    """BASELINE-size property test of the serving loop: 48 mixed utterances (prompts 64..200, 16..48 tokens) on the full-size model
+    through 64 request slots in two concurrent groups, twice -- identical codes (no race between groups, asynchronous prefills and
+    refills) -- and once more through ONE group of 32 slots: the grouping does not change a single code either.  Ids in range."""
+    from fish_tts_b200 import replicas
+    cfg = s1_mini_config()
+    sd = make_state_dict(cfg, seed=0)
+    rng = np.random.default_rng(5)
+    utts = []
+    for i in range(48):
+        T = int(rng.integers(64, 201))
+        utts.append(replicas.Utterance(uid=i, prompt=synthetic_prompt(cfg, 3, T - 8, 5, seed=2000 + i).numpy(), max_new_tokens=int(rng.integers(16, 49))))
+    runs = []
+    for max_batch, gs in ((64, 32), (64, 32), (32, 32)):
+        eng = DualAREngine(cfg, sd, device=0)
+        eng.batch_init(max_batch, 320, group_slots=gs)
+        res = replicas.run_rank_batched(eng, utts, 0, 1, max_batch, poll_steps=8, sync=torch.cuda.synchronize, seed_base=9000)
+        eng.close()
+        assert sorted(res.uids) == list(range(48)) and res.tokens == sum(u.max_new_tokens for u in utts)
+        runs.append(res.codes)
+    for u in utts:
+        a, b, c = (r[u.uid] for r in runs)
+        assert a.shape == (cfg.num_codebooks + 1, u.max_new_tokens)
+        assert (a == b).all(), f"utterance {u.uid}: two identical runs differ"
+        assert (a == c).all(), f"utterance {u.uid}: two groups of 32 and one group of 32 differ"
+        assert ((a[0] >= cfg.semantic_begin_id) & (a[0] <= cfg.semantic_end_id)).all() and ((a[1:] >= 0) & (a[1:] < cfg.codebook_size)).all()
