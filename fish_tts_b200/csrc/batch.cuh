@@ -153,8 +153,11 @@ __global__ void __launch_bounds__(256) b_qkv_post_kernel(const BQkvPostArgs a) {
 
 // ---- slow attention: split-KV flash-decode, one query per column ----------------------------------------------------------------
 struct BAttnArgs {
-  const bf16 *qkv;           // [ncols][(nh + 2 nkv) * hd], q already normalised + rotated
-  const bf16 *kc, *vc; long long slot_stride;
+  const bf16 *qkv;           // [ncols][(nh + 2 nkv) * hd]; fuse_post = 0: q already normalised + rotated (b_qkv_post_kernel ran)
+  bf16 *kc, *vc; long long slot_stride;
+  // fuse_post = 1 (batched decode; one cache per column): the raw wqkv output comes in and the CTA applies q/k nn.RMSNorm + RoPE itself
+  // (llama.py:246-251); the CTA whose tiles contain the new position writes the K / V row into the cache (KVCache.update, :142-149)
+  int fuse_post; const bf16 *rope, *qn, *kn; float eps;
   int nh, nkv, hd, S, ncols, nsplit_max, tiles_per_split; float sf;
   float *part_o, *part_ml;   // [ncols][nkv][nsplit_max][G][hd], [...][G][2]
   unsigned int *tickets;     // [ncols][nkv], zero between launches
@@ -170,7 +173,7 @@ struct BAttnArgs {
 #define DA_B_NBUF 3      // K/V tile buffers: two tiles are in flight while one is being consumed (a tile's HBM latency is ~2x its compute time)
 static_assert(DA_TILE == 8 * DA_B_AWARPS, "a warp owns 8 positions of a tile: 4 lanes each");
 static inline size_t b_attn_smem(int G, int hd) {
-  size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t);
+  size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t) + (size_t)hd * (sizeof(float) + 2 * sizeof(bf16));
   f = (f + 127) & ~(size_t)127;
   return f + 128 + 2 * DA_B_NBUF * (size_t)DA_TILE * hd * sizeof(bf16);
 }
@@ -198,7 +201,9 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float *q = reinterpret_cast<float *>(smraw_b);
   float *pm = q + G * hd, *pl = pm + DA_B_AWARPS * G, *po = pl + DA_B_AWARPS * G;      // per-warp partials: [8][G], [8][G], [8][G][hd]
-  size_t off = (size_t)((unsigned char *)(po + (size_t)DA_B_AWARPS * G * hd) - smraw_b) + 16;
+  float *knew_f = po + (size_t)DA_B_AWARPS * G * hd;      // fuse_post: the new K row while it is normalised (fp32), then the new K and V rows (bf16)
+  bf16 *krow_new = reinterpret_cast<bf16 *>(knew_f + hd), *vrow_new = krow_new + hd;
+  size_t off = (size_t)((unsigned char *)(vrow_new + hd) - smraw_b) + 16;
   off = (off + 127) & ~(size_t)127;
   bf16 *kbuf = reinterpret_cast<bf16 *>(smraw_b + off);
   bf16 *vbuf = kbuf + DA_B_NBUF * DA_TILE * hd;
@@ -218,12 +223,32 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
     bulk_g2s(vbuf + (size_t)buf * DA_TILE * hd, vc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
   };
   if (threadIdx.x == 0) { issue(t0, 0); if (t0 + 1 < t1) issue(t0 + 1, 1); }
+  const int t_new = pos / DA_TILE;
+  const bool owns_new = a.fuse_post && t_new >= t0 && t_new < t1;      // this CTA's tiles contain the position being decoded
   {
-    const bf16 *qsrc = a.qkv + (size_t)n * (a.nh + 2 * a.nkv) * hd + (size_t)g * G * hd;
+    const bf16 *row = a.qkv + (size_t)n * (a.nh + 2 * a.nkv) * hd;
+    const bf16 *qsrc = row + (size_t)g * G * hd;
     for (int c = threadIdx.x; c * 8 < G * hd; c += DA_ATTN_THREADS) {
       float t[8]; unpack8(*reinterpret_cast<const uint4 *>(qsrc + c * 8), t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[c * 8 + j] = __fmul_rn(t[j], a.sf);      // q * sqrt(scale), fp32 (math SDPA)
+      for (int j = 0; j < 8; ++j) q[c * 8 + j] = a.fuse_post ? t[j] : __fmul_rn(t[j], a.sf);      // q * sqrt(scale), fp32 (math SDPA)
+    }
+    if (a.fuse_post) {
+      if (owns_new) for (int d = threadIdx.x; d < hd; d += DA_ATTN_THREADS) knew_f[d] = bf2f(row[(size_t)(a.nh + g) * hd + d]);
+      B::sync();
+      // tasks 0 .. G-1: the query heads of this kv head; G: the new K row; G + 1: the new V row -- one warp each
+      const bf16 *rope_row = a.rope + (size_t)pos * hd;
+      for (int task = w; task < G + (owns_new ? 2 : 0); task += DA_B_AWARPS) {
+        if (task < G) {
+          head_norm_rope(q + (size_t)task * hd, hd, a.qn, a.eps, rope_row, lane);
+          for (int d = lane; d < hd; d += 32) q[(size_t)task * hd + d] = __fmul_rn(q[(size_t)task * hd + d], a.sf);
+        } else if (task == G) {
+          head_norm_rope(knew_f, hd, a.kn, a.eps, rope_row, lane);
+          for (int d = lane; d < hd; d += 32) { const bf16 kv = f2bf(knew_f[d]); krow_new[d] = kv; a.kc[(size_t)n * a.slot_stride + ((size_t)g * a.S + pos) * hd + d] = kv; }
+        } else {
+          for (int d = lane; d < hd; d += 32) { const bf16 vv = row[(size_t)(a.nh + a.nkv + g) * hd + d]; vrow_new[d] = vv; a.vc[(size_t)n * a.slot_stride + ((size_t)g * a.S + pos) * hd + d] = vv; }
+        }
+      }
     }
   }
   B::sync();
@@ -242,7 +267,16 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
     const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
     if (threadIdx.x == 0 && t + 2 < t1) issue(t + 2, (t - t0 + 2) % DA_B_NBUF);      // into the buffer of tile t - 1, released by the barrier that ended it
     ok = mbar_wait(&bars[buf], phase[buf]) && ok; phase[buf] ^= 1u;
-    const bf16 *kt = kbuf + (size_t)buf * DA_TILE * hd, *vt = vbuf + (size_t)buf * DA_TILE * hd;
+    bf16 *kt = kbuf + (size_t)buf * DA_TILE * hd, *vt = vbuf + (size_t)buf * DA_TILE * hd;
+    if (owns_new && t == t_new) {
+      // the bulk copy brought whatever the cache held at row `pos`; the warp that owns that row of the tile (rows w, w + 8, ...) replaces
+      // it with the row computed above -- only this warp reads it, in Q.K and in P@V, so a warp-level fence is all it takes
+      const int jrow = pos - r0;
+      if ((jrow & (DA_B_AWARPS - 1)) == w) {
+        for (int d = lane; d < hd; d += 32) { kt[(size_t)jrow * hd + d] = krow_new[d]; vt[(size_t)jrow * hd + d] = vrow_new[d]; }
+        __syncwarp();
+      }
+    }
     for (int h0 = 0; h0 < G; h0 += 2) {
       const bool first = t == t0;
       if (!single) {

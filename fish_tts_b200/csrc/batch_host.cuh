@@ -61,6 +61,7 @@ struct dualar_tc {
   float *ws_own = nullptr; unsigned int *tickets_own = nullptr;
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
+  bool attn_fuse_post = true;      // DUALAR_ATTN_FUSE_POST=0: b_qkv_post_kernel in front of the decode attention, as in prefill
   bool concurrent_groups = false;      // set while the steps of a multi-group engine are captured
   int attn_tiles_per_split = 8;      // a KV split is worth its partials / ticket / merge only from this many 64-position tiles on (DUALAR_ATTN_TPS)
   BRec *rec = nullptr;        // non-null while the step is being recorded for the persistent kernel
@@ -132,6 +133,7 @@ static int tc_init(dualar_engine *e) {
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   e->tc->ws_own = e->tc->ws; e->tc->tickets_own = e->tc->tickets;
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
+  { const char *v = getenv("DUALAR_ATTN_FUSE_POST"); e->tc->attn_fuse_post = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_TPS"); if (v && atoi(v) > 0) e->tc->attn_tiles_per_split = atoi(v); }
   { const char *v = getenv("DUALAR_TC_KSPLIT"); if (v) e->tc->ksplit_override = atoi(v); }
   { const char *v = getenv("DUALAR_TC_STAGES"); if (v) e->tc->stages_override = atoi(v); }
@@ -256,7 +258,10 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
   for (int l = 0; l < cf.n_layer; ++l) {
     LayerW &L = e->slow[l];
     if ((rc = normed_gemm(L.wqkv, qkv_rows, cf.dim, c.x, L.attn_norm, c.xn, TE_STORE, L.bqkv, c.qkv, 0))) return rc;
-    { BQkvPostArgs a; memset(&a, 0, sizeof(a));
+    // decode: q/k-norm + RoPE + the KV row write happen inside the attention kernel (one cache per column); prefill: the columns are
+    // positions of ONE request that read each other's rows, so those must be in the cache before the attention kernel starts
+    const bool fuse_post = !prefill && e->tc->attn_fuse_post;
+    if (!fuse_post) { BQkvPostArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn;
       a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S; a.ncols = ncols; a.eps = cf.norm_eps; a.pos = pos;
       const dim3 g(ncols, (cf.n_head + 2 * cf.n_local_heads + 7) / 8);
@@ -266,6 +271,7 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S;
       a.ncols = ncols; a.nsplit_max = c.nsplit; a.tiles_per_split = e->tc->attn_tiles_per_split; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
       a.tickets = c.attn_tickets; a.y = c.y; a.pos = pos; a.err = e->tc->err;
+      a.fuse_post = fuse_post; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn; a.eps = cf.norm_eps;
       const dim3 g(c.nsplit, cf.n_local_heads, ncols);
       if (BRec *r = e->tc->rec) r->add(BP_ATTN, g).u.attn = a;
       else { CU(launch_k(b_attn_kernel, g, dim3(DA_ATTN_THREADS), b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; } }
