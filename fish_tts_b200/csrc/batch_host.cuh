@@ -61,6 +61,7 @@ struct dualar_tc {
   float *ws_own = nullptr; unsigned int *tickets_own = nullptr;
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
+  bool cluster_reduce = true;      // DUALAR_TC_CLUSTER=0: split-K through the global workspace + ticket (the prefill path's way)
   bool attn_fuse_post = true;      // DUALAR_ATTN_FUSE_POST=0: b_qkv_post_kernel in front of the decode attention, as in prefill
   bool concurrent_groups = false;      // set while the steps of a multi-group engine are captured
   int attn_tiles_per_split = 8;      // a KV split is worth its partials / ticket / merge only from this many 64-position tiles on (DUALAR_ATTN_TPS)
@@ -128,11 +129,14 @@ static int tc_init(dualar_engine *e) {
   int rc;
   if ((rc = tc_configure<32>()) || (rc = tc_configure<64>()) || (rc = tc_configure<128>()) || (rc = tc_configure<256>())) return rc;
   CU(cudaFuncSetAttribute(gemm_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_tc_smem_cl(32, tc_max_stages(32) > 10 ? 10 : tc_max_stages(32))));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_tc_smem_cl(64, tc_max_stages(64) > 8 ? 8 : tc_max_stages(64))));
   { const char *v = getenv("DUALAR_TC_FUSE_NORM"); e->tc->fuse_norm = v ? atoi(v) : 0; }      // 2: statistics from the producing GEMM's epilogue (see ColBufs::ssq)
   e->tc->ws_bytes = (size_t)48 << 20;
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   e->tc->ws_own = e->tc->ws; e->tc->tickets_own = e->tc->tickets;
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
+  { const char *v = getenv("DUALAR_TC_CLUSTER"); e->tc->cluster_reduce = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_FUSE_POST"); e->tc->attn_fuse_post = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_TPS"); if (v && atoi(v) > 0) e->tc->attn_tiles_per_split = atoi(v); }
   { const char *v = getenv("DUALAR_TC_KSPLIT"); if (v) e->tc->ksplit_override = atoi(v); }
@@ -211,6 +215,20 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
     if (smx > 200 * 1024) return fail(DUALAR_EINVAL, "fused-norm operand does not fit shared memory (K %d, splits %d)", K, ks);
     a.stages = st;
     CU(launch_k(gemm_tc_kernel<32, true>, grid, block, smx, s, *mw, *mx, a)); ++count;
+    return 0;
+  }
+  // K splits of a tile as a thread-block cluster reducing through distributed shared memory (decode; power-of-two splits; no
+  // statistics emission, whose butterfly assumes the 16 row groups of a tile in one CTA)
+  if (!prefill && e->tc->cluster_reduce && (ks == 2 || ks == 4 || ks == 8) && (BN == 32 || BN == 64) && !ssq_out) {
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = gemm_tc_smem_cl(BN, st); cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)ks;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
+    if (BN == 32) CU(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32, false, true>, *mw, *mx, a));
+    else CU(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, false, true>, *mw, *mx, a));
+    ++count;
     return 0;
   }
   const size_t smem = gemm_tc_smem(BN, st);

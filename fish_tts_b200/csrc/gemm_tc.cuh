@@ -127,10 +127,56 @@ static inline size_t gemm_tc_smem(int BN, int stages) {
   const size_t ring = (size_t)stages * (DA_TC_A_BYTES + (size_t)BN * 128), stg = (size_t)BN * DA_TC_BM * 4;
   return (ring > stg ? ring : stg) + 1024;
 }
+// CL kernels: the ring, then the receive buffer of the cluster reduction (BN x 128 floats however many splits)
+static inline size_t gemm_tc_smem_cl(int BN, int stages) { return (size_t)stages * (DA_TC_A_BYTES + (size_t)BN * 128) + (size_t)BN * DA_TC_BM * 4 + 1024; }
 // XN kernels: a ring of weight tiles only, then the resident activation operand of the CTA's nk k-blocks
 static inline size_t gemm_tc_smem_xn(int BN, int stages, int nk) {
   const size_t ring = (size_t)stages * DA_TC_A_BYTES, stg = (size_t)BN * DA_TC_BM * 4;
   return (ring > stg ? ring : stg) + (size_t)nk * BN * 128 + 1024;
+}
+
+// bias / residual / SwiGLU on the 8 rows [row0, row0 + 8) of column n_base + n_l, 16 contiguous bytes out (shared by all epilogues)
+__device__ __forceinline__ void tc_finish(const GemmTcArgs &a, const float *acc, int tile_m, int n_base, int n_l, int g8, int lane) {
+        const int row0 = tile_m * DA_TC_BM + g8;
+        if (row0 >= a.rows) return;                                  // rows is a multiple of 8
+        float y[8];
+        if (a.bias) {
+          float bb[8]; unpack8(*reinterpret_cast<const uint4 *>(a.bias + row0), bb);
+#pragma unroll
+          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2] + bb[i2]);
+        } else {
+#pragma unroll
+          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2]);       // the linear's bf16 output
+        }
+        const size_t n = (size_t)(n_base + n_l);
+        if (a.epi == TE_SWIGLU) {
+          // rows come interleaved (2j: w1 = gate, 2j+1: w3 = up; engine.cu plan_layer): bf16(bf16(silu(g)) * u)   llama.py:190
+          float o[4];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) { const float gg = y[2 * i2]; o[i2] = __fmul_rn(rbf(gg / (1.0f + expf(-gg))), y[2 * i2 + 1]); }
+          uint2 u; u.x = (uint32_t)f2bits(o[0]) | ((uint32_t)f2bits(o[1]) << 16); u.y = (uint32_t)f2bits(o[2]) | ((uint32_t)f2bits(o[3]) << 16);
+          *reinterpret_cast<uint2 *>(a.out + n * a.ld_out + (row0 >> 1)) = u;
+        } else {
+          if (a.epi == TE_RESIDUAL) {                                // llama.py:329-330
+            float rr[8]; unpack8(*reinterpret_cast<const uint4 *>(a.res + n * a.ld_out + row0), rr);
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) y[i2] = rr[i2] + y[i2];
+          }
+          uint4 u;
+          u.x = (uint32_t)f2bits(y[0]) | ((uint32_t)f2bits(y[1]) << 16); u.y = (uint32_t)f2bits(y[2]) | ((uint32_t)f2bits(y[3]) << 16);
+          u.z = (uint32_t)f2bits(y[4]) | ((uint32_t)f2bits(y[5]) << 16); u.w = (uint32_t)f2bits(y[6]) | ((uint32_t)f2bits(y[7]) << 16);
+          *reinterpret_cast<uint4 *>(a.out + n * a.ld_out + row0) = u;
+          if (a.ssq_out) {
+            // statistics for the RMSNorm that consumes this output (llama.py:172-177 squares the bf16 values in fp32): the 16 items of a
+            // column in this 128-row tile sit in the 16 lanes of a half-warp -- fixed-order butterfly, one partial per (column, row tile)
+            float ss = 0.f;
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) { const float r = rbf(y[i2]); ss = fmaf(r, r, ss); }
+            const unsigned hm = 0xFFFFu << (lane & 16);
+            ss += __shfl_xor_sync(hm, ss, 8); ss += __shfl_xor_sync(hm, ss, 4); ss += __shfl_xor_sync(hm, ss, 2); ss += __shfl_xor_sync(hm, ss, 1);
+            if ((lane & 15) == 0) a.ssq_out[n * a.ssq_ld + tile_m] = ss;
+          }
+        }
 }
 
 // ---- the epilogue, shared by the stand-alone kernel and the persistent batched-step kernel (bstep.cuh) ---------------------------------
@@ -181,49 +227,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmTcArgs &a, uint32_t tmem, 
     if (is_final && ok) {
       const float *wsp = a.ws + (size_t)ntile_lin * nz * BN * DA_TC_BM;
       const int n_items = ncols_here * (DA_TC_BM / 8);
-      // bias / residual / SwiGLU on the 8 rows [row0, row0 + 8) of column n_l, 16 contiguous bytes out
-      auto finish = [&](const float *acc, int n_l, int g8) {
-        const int row0 = tile_m * DA_TC_BM + g8;
-        if (row0 >= a.rows) return;                                  // rows is a multiple of 8
-        float y[8];
-        if (a.bias) {
-          float bb[8]; unpack8(*reinterpret_cast<const uint4 *>(a.bias + row0), bb);
-#pragma unroll
-          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2] + bb[i2]);
-        } else {
-#pragma unroll
-          for (int i2 = 0; i2 < 8; ++i2) y[i2] = rbf(acc[i2]);       // the linear's bf16 output
-        }
-        const size_t n = (size_t)(n_base + n_l);
-        if (a.epi == TE_SWIGLU) {
-          // rows come interleaved (2j: w1 = gate, 2j+1: w3 = up; engine.cu plan_layer): bf16(bf16(silu(g)) * u)   llama.py:190
-          float o[4];
-#pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) { const float gg = y[2 * i2]; o[i2] = __fmul_rn(rbf(gg / (1.0f + expf(-gg))), y[2 * i2 + 1]); }
-          uint2 u; u.x = (uint32_t)f2bits(o[0]) | ((uint32_t)f2bits(o[1]) << 16); u.y = (uint32_t)f2bits(o[2]) | ((uint32_t)f2bits(o[3]) << 16);
-          *reinterpret_cast<uint2 *>(a.out + n * a.ld_out + (row0 >> 1)) = u;
-        } else {
-          if (a.epi == TE_RESIDUAL) {                                // llama.py:329-330
-            float rr[8]; unpack8(*reinterpret_cast<const uint4 *>(a.res + n * a.ld_out + row0), rr);
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) y[i2] = rr[i2] + y[i2];
-          }
-          uint4 u;
-          u.x = (uint32_t)f2bits(y[0]) | ((uint32_t)f2bits(y[1]) << 16); u.y = (uint32_t)f2bits(y[2]) | ((uint32_t)f2bits(y[3]) << 16);
-          u.z = (uint32_t)f2bits(y[4]) | ((uint32_t)f2bits(y[5]) << 16); u.w = (uint32_t)f2bits(y[6]) | ((uint32_t)f2bits(y[7]) << 16);
-          *reinterpret_cast<uint4 *>(a.out + n * a.ld_out + row0) = u;
-          if (a.ssq_out) {
-            // statistics for the RMSNorm that consumes this output (llama.py:172-177 squares the bf16 values in fp32): the 16 items of a
-            // column in this 128-row tile sit in the 16 lanes of a half-warp -- fixed-order butterfly, one partial per (column, row tile)
-            float ss = 0.f;
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) { const float r = rbf(y[i2]); ss = fmaf(r, r, ss); }
-            const unsigned hm = 0xFFFFu << (lane & 16);
-            ss += __shfl_xor_sync(hm, ss, 8); ss += __shfl_xor_sync(hm, ss, 4); ss += __shfl_xor_sync(hm, ss, 2); ss += __shfl_xor_sync(hm, ss, 1);
-            if ((lane & 15) == 0) a.ssq_out[n * a.ssq_ld + tile_m] = ss;
-          }
-        }
-      };
+      auto finish = [&](const float *acc, int n_l, int g8) { tc_finish(a, acc, tile_m, n_base, n_l, g8, lane); };
       if (nz > 1) {
         // split-K: the partials of TWO items (2 x nz x 32 bytes, nz <= 8) are requested before the first add, so the reduction costs one
         // L2 round trip per pair of items instead of one per partial; they are added in split order (deterministic)
@@ -274,11 +278,12 @@ __device__ __forceinline__ void tc_epilogue(const GemmTcArgs &a, uint32_t tmem, 
 // read the un-normalised rows, apply the reference's RMSNorm (llama.py:172-177: fp32 normalise, round, x weight, round -- every CTA
 // recomputes the row statistics, 64 KB of L2 reads) and write the CTA's k-range into shared memory in the same 128-byte-swizzle
 // K-major layout TMA would have produced.  That removes one kernel (and one kernel boundary, ~5 us in a dependent chain) per norm.
-template <int BN, bool XN = false>
+template <int BN, bool XN = false, bool CL = false>
 __global__ void __launch_bounds__(DA_TC_THREADS, XN ? 2 : DA_TC_MIN_BLOCKS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmTcArgs a) {
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "TMEM allocations are powers of two >= 32 columns");
   static_assert(!XN || BN == 32, "the fused-norm operand staging deals 8 rows to each of the four epilogue warps");
+  static_assert(!(XN && CL), "the cluster reduction is for the plain TMA-fed GEMM");
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[DA_TC_MAX_STAGES], empty_bar[DA_TC_MAX_STAGES], accum_bar, xready_bar;
   __shared__ uint32_t s_tmem, s_last;
@@ -309,6 +314,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const uint32_t tmem = s_tmem;
   bool ok = true;
   if (dbg && tid == 0) dbg[1] = clock64();
+  // CL: the K splits of a tile form a thread-block cluster (cluster dims (1, 1, gridDim.z)) and reduce through distributed shared memory
+  // instead of a global workspace + ticket.  Barrier 1 (arrive here, wait before the first remote store) only proves that every CTA of
+  // the cluster has started; barrier 2 publishes the partials.  All 192 threads take part in both.
+  if (CL) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
   if (warp == 0) {
     // ===== producer =====
@@ -453,7 +462,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     tc_fence_after();
     if (dbg && tid == 64) dbg[5] = clock64();
     if (!ok) atomicExch(a.err, 7);
-    tc_epilogue<BN>(a, tmem, reinterpret_cast<float *>(sbase), tile_m, tile_n, z, nz, blockIdx.y * gridDim.x + blockIdx.x, te, lane, wq, &s_last, ok);
+    if (!CL) tc_epilogue<BN>(a, tmem, reinterpret_cast<float *>(sbase), tile_m, tile_n, z, nz, blockIdx.y * gridDim.x + blockIdx.x, te, lane, wq, &s_last, ok);
+    else {
+      // ---- reduce-scatter over the cluster: CTA r finishes rows [r * RPC, (r + 1) * RPC) of the tile.  Every thread holds one row of the
+      // CTA's partial (its TMEM lane); it stores the row's BN values into the owner's receive buffer [source z][column][row in slice]
+      // (remote shared memory; a warp's 32 rows are 32 consecutive floats there).  After barrier 2 every CTA adds its ks slices in split
+      // order -- the order of the workspace path, so both give the same bits -- and runs the usual bias / residual / SwiGLU finish.
+      const int RPC = DA_TC_BM / nz, n_base = tile_n * BN, ncols_here = min(BN, a.ncols - n_base);
+      float *recv = reinterpret_cast<float *>(sbase + (size_t)stages * (DA_TC_A_BYTES + BN * 128));      // [nz][BN][RPC], behind the ring
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      const int r_in = wq * 32 + lane, owner = r_in / RPC, r_sl = r_in - owner * RPC;
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(recv)), "r"(owner));
+      const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (c0 >= ncols_here) break;
+        uint32_t v[32]; tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + (uint32_t)((((size_t)z * BN + c0 + j) * RPC + r_sl) * 4)), "r"(v[j]) : "memory");
+      }
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      const int groups = RPC / 8, n_items = ncols_here * groups;      // (column, 8 rows of this CTA's slice)
+#pragma unroll 1
+      for (int item = te; item < n_items; item += 128) {
+        const int n_l = item / groups, g = item - n_l * groups;
+        float acc[8];
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) acc[i2] = 0.f;
+#pragma unroll 1
+        for (int zz = 0; zz < nz; ++zz) {
+          const float4 *pz = reinterpret_cast<const float4 *>(recv + ((size_t)zz * BN + n_l) * RPC + g * 8);
+          const float4 p0 = pz[0], p1 = pz[1];
+          acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w; acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
+        }
+        tc_finish(a, acc, tile_m, n_base, n_l, z * RPC + g * 8, lane);
+      }
+    }
+  }
+  if (CL && warp < 2) {      // producer and MMA warps: their share of the two cluster barriers
+    __syncwarp();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
   if (dbg && tid == 64) dbg[6] = clock64();
   tc_fence_before();
