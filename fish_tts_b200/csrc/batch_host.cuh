@@ -61,6 +61,7 @@ struct dualar_tc {
   float *ws_own = nullptr; unsigned int *tickets_own = nullptr;
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
+  int target_ctas = 0, min_kb = 0;      // decode split-K heuristic: CTAs aimed at per GEMM, least k-blocks per CTA (0 = by mode; DUALAR_TC_CTAS, DUALAR_TC_MINKB)
   bool cluster_reduce = true;      // DUALAR_TC_CLUSTER=0: split-K through the global workspace + ticket (the prefill path's way)
   bool attn_fuse_post = true;      // DUALAR_ATTN_FUSE_POST=0: b_qkv_post_kernel in front of the decode attention, as in prefill
   bool concurrent_groups = false;      // set while the steps of a multi-group engine are captured
@@ -136,6 +137,8 @@ static int tc_init(dualar_engine *e) {
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   e->tc->ws_own = e->tc->ws; e->tc->tickets_own = e->tc->tickets;
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
+  { const char *v = getenv("DUALAR_TC_CTAS"); if (v && atoi(v) > 0) e->tc->target_ctas = atoi(v); }
+  { const char *v = getenv("DUALAR_TC_MINKB"); if (v && atoi(v) > 0) e->tc->min_kb = atoi(v); }
   { const char *v = getenv("DUALAR_TC_CLUSTER"); e->tc->cluster_reduce = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_FUSE_POST"); e->tc->attn_fuse_post = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_TPS"); if (v && atoi(v) > 0) e->tc->attn_tiles_per_split = atoi(v); }
@@ -181,7 +184,15 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
   if ((rc = tc_map(e, W, rows, K, DA_TC_BM, &mw)) || (rc = tc_map(e, X, xcap, K, BN, &mx))) return rc;
   const int rt = (rows + DA_TC_BM - 1) / DA_TC_BM, ct = (ncols + BN - 1) / BN, tiles = rt * ct, nkb = K / DA_TC_BK;
   int ks = 1;
-  if (!prefill && tiles < 64) { ks = 128 / tiles; if (ks > nkb / 4) ks = nkb / 4; if (ks > 8) ks = 8; if (ks < 1) ks = 1; }
+  if (!prefill && tiles < 64) {
+    // with the cluster reduction a split is cheap: down to 2 k-blocks per CTA.  Measured (ms per step, 32 slots / 4 x 32 slots):
+    // 128 CTAs of >= 4 k-blocks 3.44 / 5.74, 128 of >= 2: 3.38 / 5.77, 192 of >= 2: 3.26 / 6.05.  ONE rule for every mode: the K
+    // partition fixes the summation order, and a request's bits must not depend on how many groups run beside it
+    const int want = e->tc->target_ctas ? e->tc->target_ctas : 128;
+    const int min_kb = e->tc->min_kb ? e->tc->min_kb : (e->tc->cluster_reduce ? 2 : 4);
+    ks = want / tiles; if (ks > nkb / min_kb) ks = nkb / min_kb; if (ks > 8) ks = 8; if (ks < 1) ks = 1;
+    if (e->tc->cluster_reduce) while (ks & (ks - 1)) --ks;      // the cluster reduction deals 128 / ks rows to every split
+  }
   // prefill: a K split only for the matrices with very few row tiles (wo, w2: 8), chosen from the MATRIX alone so that a position's
   // summation order does not depend on how the prompt was chunked
   if (prefill && rt < 16 && nkb >= 16) ks = 4;
