@@ -158,6 +158,9 @@ struct BAttnArgs {
   // fuse_post = 1 (batched decode; one cache per column): the raw wqkv output comes in and the CTA applies q/k nn.RMSNorm + RoPE itself
   // (llama.py:246-251); the CTA whose tiles contain the new position writes the K / V row into the cache (KVCache.update, :142-149)
   int fuse_post; const bf16 *rope, *qn, *kn; float eps;
+  // cluster_merge = 1: the KV splits of a (column, kv head) are a thread-block cluster (cluster dims (nsplit_max, 1, 1)); their partial
+  // (max, sum, output) meet in the first split's shared memory instead of a global buffer + ticket
+  int cluster_merge;
   int nh, nkv, hd, S, ncols, nsplit_max, tiles_per_split; float sf;
   float *part_o, *part_ml;   // [ncols][nkv][nsplit_max][G][hd], [...][G][2]
   unsigned int *tickets;     // [ncols][nkv], zero between launches
@@ -170,10 +173,12 @@ struct BAttnArgs {
 // probabilities handed to all lanes for P@V where a lane owns hd/32 output dims -- and the warps meet ONCE, after the last tile
 // (the decode kernel's tile walk, mega.cuh).  One CTA barrier per tile instead of three, no idle warps during the softmax.
 #define DA_B_AWARPS (DA_ATTN_THREADS / 32)
+#define DA_B_MAXSPLIT 4   // KV splits per (column, kv head) at most (a cluster; the receive buffer must leave room for two CTAs per SM)
 #define DA_B_NBUF 3      // K/V tile buffers: two tiles are in flight while one is being consumed (a tile's HBM latency is ~2x its compute time)
 static_assert(DA_TILE == 8 * DA_B_AWARPS, "a warp owns 8 positions of a tile: 4 lanes each");
 static inline size_t b_attn_smem(int G, int hd) {
-  size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t) + (size_t)hd * (sizeof(float) + 2 * sizeof(bf16));
+  size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t) + (size_t)hd * (sizeof(float) + 2 * sizeof(bf16)) +
+             (size_t)DA_B_MAXSPLIT * G * (hd + 2) * sizeof(float);
   f = (f + 127) & ~(size_t)127;
   return f + 128 + 2 * DA_B_NBUF * (size_t)DA_TILE * hd * sizeof(bf16);
 }
@@ -196,14 +201,23 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   const int nsplit = max(1, min(a.nsplit_max, (n_tiles + a.tiles_per_split - 1) / a.tiles_per_split));
   const int tps = (n_tiles + nsplit - 1) / nsplit;
   const int nsplit_eff = (n_tiles + tps - 1) / tps;
-  if (split >= nsplit_eff) return;
+  const bool cl = a.cluster_merge != 0;
+  // cluster barrier 1 (arrive here, wait before the first remote store) proves that the first split's CTA is running; barrier 2 publishes
+  // the partials.  A CTA without tiles takes part in both and leaves; a column without a request is skipped by its whole cluster alike.
+  if (cl) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  if (split >= nsplit_eff) {
+    if (cl) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+    return;
+  }
   const int t0 = split * tps, t1 = min(n_tiles, t0 + tps);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float *q = reinterpret_cast<float *>(smraw_b);
   float *pm = q + G * hd, *pl = pm + DA_B_AWARPS * G, *po = pl + DA_B_AWARPS * G;      // per-warp partials: [8][G], [8][G], [8][G][hd]
   float *knew_f = po + (size_t)DA_B_AWARPS * G * hd;      // fuse_post: the new K row while it is normalised (fp32), then the new K and V rows (bf16)
   bf16 *krow_new = reinterpret_cast<bf16 *>(knew_f + hd), *vrow_new = krow_new + hd;
-  size_t off = (size_t)((unsigned char *)(vrow_new + hd) - smraw_b) + 16;
+  float *recv = reinterpret_cast<float *>(vrow_new + hd);      // cluster merge: [split][G * hd outputs | G x (max, sum)]
+  const int rstride = G * (hd + 2);
+  size_t off = (size_t)((unsigned char *)(recv + (size_t)DA_B_MAXSPLIT * rstride) - smraw_b) + 16;
   off = (off + 127) & ~(size_t)127;
   bf16 *kbuf = reinterpret_cast<bf16 *>(smraw_b + off);
   bf16 *vbuf = kbuf + DA_B_NBUF * DA_TILE * hd;
@@ -359,6 +373,7 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
     B::sync();      // every warp is past its last read of the tile: its buffer may be refilled
   }
   if (!ok && threadIdx.x == 0) atomicExch(a.err, 2);
+  if (cl) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // barrier 1: every CTA of the cluster is running
   // fold the 8 warps' partials in warp order: thread e = (h, d)
   const size_t pbase = ((size_t)n * a.nkv + g) * a.nsplit_max;
   float *pog = a.part_o + ((pbase + split) * G) * hd;
@@ -377,7 +392,36 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
       o = fmaf(po[((size_t)ww * G + h) * hd + dd], sc_w, o);
     }
     if (nsplit_eff == 1) a.y[(size_t)n * a.nh * hd + (size_t)g * G * hd + e] = f2bf(o / l);      // single split: no partials, no ticket
-    else { pog[e] = o; if (dd == 0) { pml[h * 2] = m; pml[h * 2 + 1] = l; } }
+    else if (!cl) { pog[e] = o; if (dd == 0) { pml[h * 2] = m; pml[h * 2 + 1] = l; } }
+    else {
+      // into split 0's receive buffer (its own for split 0)
+      uint32_t dst;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_u32(recv + (size_t)split * rstride)), "r"(0));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + (uint32_t)e * 4u), "f"(o) : "memory");
+      if (dd == 0) {
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + (uint32_t)(G * hd + h * 2) * 4u), "f"(m) : "memory");
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + (uint32_t)(G * hd + h * 2 + 1) * 4u), "f"(l) : "memory");
+      }
+    }
+  }
+  if (cl) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (nsplit_eff == 1 || split != 0) return;
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    for (int e = threadIdx.x; e < G * hd; e += DA_ATTN_THREADS) {      // merge in split order: the arithmetic of the ticket path below
+      const int h = e / hd;
+      float m = -INFINITY;
+      for (int s = 0; s < nsplit_eff; ++s) m = fmaxf(m, recv[(size_t)s * rstride + G * hd + h * 2]);
+      float l = 0.f, o = 0.f;
+      for (int s = 0; s < nsplit_eff; ++s) {
+        const float *rs = recv + (size_t)s * rstride;
+        const float sc_s = expf(rs[G * hd + h * 2] - m);
+        l = fmaf(rs[G * hd + h * 2 + 1], sc_s, l);
+        o = fmaf(rs[e], sc_s, o);
+      }
+      a.y[(size_t)n * a.nh * hd + (size_t)g * G * hd + e] = f2bf(o / l);
+    }
+    return;
   }
   if (nsplit_eff == 1) return;
   __shared__ unsigned int s_last;

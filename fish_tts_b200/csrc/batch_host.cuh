@@ -62,10 +62,11 @@ struct dualar_tc {
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
   int target_ctas = 0, min_kb = 0;      // decode split-K heuristic: CTAs aimed at per GEMM, least k-blocks per CTA (0 = by mode; DUALAR_TC_CTAS, DUALAR_TC_MINKB)
+  bool attn_cluster = true;        // DUALAR_ATTN_CLUSTER=0: KV splits merged through a global buffer + ticket
   bool cluster_reduce = true;      // DUALAR_TC_CLUSTER=0: split-K through the global workspace + ticket (the prefill path's way)
   bool attn_fuse_post = true;      // DUALAR_ATTN_FUSE_POST=0: b_qkv_post_kernel in front of the decode attention, as in prefill
   bool concurrent_groups = false;      // set while the steps of a multi-group engine are captured
-  int attn_tiles_per_split = 8;      // a KV split is worth its partials / ticket / merge only from this many 64-position tiles on (DUALAR_ATTN_TPS)
+  int attn_tiles_per_split = 0;      // 0 = by mode (see enqueue_slow_cols);      // a KV split is worth its partials / ticket / merge only from this many 64-position tiles on (DUALAR_ATTN_TPS)
   BRec *rec = nullptr;        // non-null while the step is being recorded for the persistent kernel
   int ksplit_override = 0, stages_override = 0, bn_override = 0;
   int fuse_norm = 0;          // DUALAR_TC_FUSE_NORM=1: the decode GEMMs normalise their own operand (gemm_tc_kernel<32, true>) instead of a separate
@@ -139,6 +140,7 @@ static int tc_init(dualar_engine *e) {
   if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
   { const char *v = getenv("DUALAR_TC_CTAS"); if (v && atoi(v) > 0) e->tc->target_ctas = atoi(v); }
   { const char *v = getenv("DUALAR_TC_MINKB"); if (v && atoi(v) > 0) e->tc->min_kb = atoi(v); }
+  { const char *v = getenv("DUALAR_ATTN_CLUSTER"); e->tc->attn_cluster = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_TC_CLUSTER"); e->tc->cluster_reduce = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_FUSE_POST"); e->tc->attn_fuse_post = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_TPS"); if (v && atoi(v) > 0) e->tc->attn_tiles_per_split = atoi(v); }
@@ -298,11 +300,27 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
       else { CU(launch_k(b_qkv_post_kernel, g, dim3(256), (size_t)8 * cf.head_dim * sizeof(float), s, a)); ++count; } }
     { BAttnArgs a; memset(&a, 0, sizeof(a));
       a.qkv = c.qkv; a.kc = kv.kc[l]; a.vc = kv.vc[l]; a.slot_stride = kv.slot_stride; a.nh = cf.n_head; a.nkv = cf.n_local_heads; a.hd = cf.head_dim; a.S = kv.S;
-      a.ncols = ncols; a.nsplit_max = c.nsplit; a.tiles_per_split = e->tc->attn_tiles_per_split; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
+      a.ncols = ncols; a.nsplit_max = c.nsplit; a.sf = (float)sqrt(1.0 / sqrt((double)cf.head_dim)); a.part_o = c.part_o; a.part_ml = c.part_ml;
       a.tickets = c.attn_tickets; a.y = c.y; a.pos = pos; a.err = e->tc->err;
       a.fuse_post = fuse_post; a.rope = e->rope; a.qn = L.qn; a.kn = L.kn; a.eps = cf.norm_eps;
       const dim3 g(c.nsplit, cf.n_local_heads, ncols);
+      // KV splits as a cluster merging through distributed shared memory: pays when the GPU is nearly empty (8 slots: 2.81 against 3.01 ms
+      // per step, a split per tile) and costs when it is not (32 slots: 3.68 against 3.40; 4 x 32: 7.1 against 5.8 -- four co-scheduled CTAs
+      // per (request, kv head), most of them idle).  So: engines with at most 8 slots only; everything larger splits from 8 tiles on and
+      // merges through the ticket, whatever the grouping (the partition fixes the merge order, hence the bits)
+      const bool small = e->tc->attn_cluster && e->batch_total > 0 && e->batch_total <= 8 && c.nsplit > 1 && c.nsplit <= DA_B_MAXSPLIT && !prefill;
+      a.tiles_per_split = e->tc->attn_tiles_per_split ? e->tc->attn_tiles_per_split : (small ? 1 : 8);
+      a.cluster_merge = small && !e->tc->rec;
       if (BRec *r = e->tc->rec) r->add(BP_ATTN, g).u.attn = a;
+      else if (a.cluster_merge) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = g; cfg.blockDim = dim3(DA_ATTN_THREADS); cfg.dynamicSmemBytes = b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim); cfg.stream = s;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)c.nsplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
+        CU(cudaLaunchKernelEx(&cfg, b_attn_kernel, a)); ++count;
+      }
       else { CU(launch_k(b_attn_kernel, g, dim3(DA_ATTN_THREADS), b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; } }
     const bool emit = !prefill && !e->tc->rec;
     if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count, nullptr, prefill, nullptr,
@@ -515,8 +533,9 @@ static int batch_group_init(dualar_engine *e, int n_slots, int slot_seq_len, boo
   dualar_batch *b = new dualar_batch(); e->groups.push_back(b); e->batch = b;
   b->B = n_slots; b->BN = bn_for(n_slots); b->Sb = slot_seq_len;
   const int R = cf.num_codebooks + 1;
-  // split-KV: enough (kv head, split) CTAs per request to fill the machine twice at small batches, one split per 256 positions at most
-  int nsplit = (8 * e->sms) / (cf.n_local_heads * n_slots); if (nsplit < 2) nsplit = 2; if (nsplit > 16) nsplit = 16;
+  // split-KV: up to 4 splits per (request, kv head), whatever the group size -- the partition fixes the order of the softmax merge, and
+  // a request's bits must not depend on the grouping.  With the cluster merge a split costs about a microsecond, so even two tiles are split
+  int nsplit = 4;
   { const char *v = getenv("DUALAR_BATCH_NSPLIT"); if (v) nsplit = atoi(v); }
   if ((rc = alloc_cols(e, b->c, b->BN, nsplit, true))) return rc;
   b->slot_stride = (long long)cf.n_local_heads * b->Sb * cf.head_dim;
