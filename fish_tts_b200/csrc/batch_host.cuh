@@ -230,9 +230,10 @@ static int tc_gemm(dualar_engine *e, const bf16 *W, int rows, int K, const bf16 
     CU(launch_k(gemm_tc_kernel<32, true>, grid, block, smx, s, *mw, *mx, a)); ++count;
     return 0;
   }
-  // K splits of a tile as a thread-block cluster reducing through distributed shared memory (decode; power-of-two splits; no
+  // K splits of a tile as a thread-block cluster reducing through distributed shared memory (tiles of <= 64 columns: the receive buffer
+  // sits behind the ring; power-of-two splits; same bits as the workspace path, so prefill chunking stays irrelevant; no
   // statistics emission, whose butterfly assumes the 16 row groups of a tile in one CTA)
-  if (!prefill && e->tc->cluster_reduce && (ks == 2 || ks == 4 || ks == 8) && (BN == 32 || BN == 64) && !ssq_out) {
+  if (e->tc->cluster_reduce && (ks == 2 || ks == 4 || ks == 8) && (BN == 32 || BN == 64) && !ssq_out) {
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = gemm_tc_smem_cl(BN, st); cfg.stream = s;
     cudaLaunchAttribute at[2];
