@@ -516,6 +516,7 @@ def run_utterances(args, cfg, eng, dist, rank, world, local):
                                                    f"{'continuous batching over ' + str(B) + ' request slots per GPU' if B > 1 else 'one request at a time per GPU (batch-1 kernel)'}, "
                                                    "prefill included, longest-first partition"),
                 "total_tokens": agg["tokens"], "seconds_max_rank": agg["seconds"], "seconds_per_rank": per_rank,
+                "host_blocked_on_gpu_s_rank0": getattr(res, "wait_seconds", None),
                 "imbalance": (max(per_rank) - min(per_rank)) / max(per_rank) if per_rank else 0.0, "clocks": clocks.summary()}
         print(json.dumps(line), flush=True)
     if dist:

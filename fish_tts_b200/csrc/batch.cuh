@@ -739,7 +739,7 @@ template <class B> __device__ __forceinline__ void b_fast_sample_body(const BFas
   if (threadIdx.x == 0) {
     st->tok_out[a.head + 1] = (int)tok;
     if (a.last_head && !st->done) {
-      GemvArgs g; g.st = st; g.seq = a.seq + (size_t)n * a.seq_slot_stride; g.seq_stride = a.seq_stride; g.im_end_id = a.im_end_id; g.n_rows_tok = a.n_rows_tok;
+      GemvArgs g; g.st = st; g.seq = a.seq + (size_t)n * a.seq_slot_stride; g.seq_stride = a.seq_stride; g.im_end_id = a.im_end_id; g.n_rows_tok = a.n_rows_tok; g.park_on_done = 1;
       finish_step(g);
     }
   }

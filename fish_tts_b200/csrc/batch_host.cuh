@@ -41,7 +41,9 @@ struct BRec {
 struct dualar_batch {
   int B = 0, BN = 32, Sb = 0, nchunk = 32;
   ColBufs c;
-  DAState *st = nullptr, *h_st = nullptr; int *seq = nullptr, *h_seq = nullptr;
+  DAState *st = nullptr, *h_st = nullptr; int *seq = nullptr, *h_seq = nullptr;      // h_st / h_seq: pinned staging of dualar_batch_collect
+  DAState *h_act = nullptr; int *h_prompt = nullptr;      // pinned staging of dualar_batch_prefill: one state per slot, one prompt buffer
+  cudaEvent_t ev_prompt = nullptr; bool prompt_pending = false, decode_pending = false; std::vector<char> known_done;
   std::vector<bf16 *> kc, vc, fkc, fvc; long long slot_stride = 0, fslot_stride = 0;
   cudaGraphExec_t g_step = nullptr, g_step_p = nullptr; int launches = 0, launches_p = 0;      // per-kernel graph / persistent graph
   cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;      // LM head + slow sampler run beside fast pass 0
@@ -137,7 +139,7 @@ static int tc_init(dualar_engine *e) {
   e->tc->ws_bytes = (size_t)48 << 20;
   if ((rc = dev_alloc(e, e->tc->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, e->tc->tickets, 8192)) || (rc = dev_alloc(e, e->tc->err, 4))) return rc;
   e->tc->ws_own = e->tc->ws; e->tc->tickets_own = e->tc->tickets;
-  if ((rc = alloc_cols(e, e->tc->pf, 256, 1, false))) return rc;
+  if ((rc = alloc_cols(e, e->tc->pf, 512, 1, false))) return rc;      // columns per prefill chunk: one chain of ~225 kernels per chunk, so prompts of up to 512 positions take one
   { const char *v = getenv("DUALAR_TC_CTAS"); if (v && atoi(v) > 0) e->tc->target_ctas = atoi(v); }
   { const char *v = getenv("DUALAR_TC_MINKB"); if (v && atoi(v) > 0) e->tc->min_kb = atoi(v); }
   { const char *v = getenv("DUALAR_ATTN_CLUSTER"); e->tc->attn_cluster = !(v && v[0] == '0'); }
@@ -549,7 +551,10 @@ static int batch_group_init(dualar_engine *e, int n_slots, int slot_seq_len, boo
   else if ((rc = dev_alloc(e, b->ws, e->tc->ws_bytes / 4)) || (rc = dev_alloc(e, b->tickets, 8192))) return rc;
   CU(cudaMallocHost((void **)&b->h_st, sizeof(DAState)));
   CU(cudaMallocHost((void **)&b->h_seq, (size_t)R * b->Sb * sizeof(int)));
-  b->prompt_len.assign(n_slots, 0); b->max_gen.assign(n_slots, 0); b->open.assign(n_slots, 0);
+  CU(cudaMallocHost((void **)&b->h_act, sizeof(DAState) * (size_t)n_slots));
+  CU(cudaMallocHost((void **)&b->h_prompt, (size_t)R * b->Sb * sizeof(int)));
+  CU(cudaEventCreateWithFlags(&b->ev_prompt, cudaEventDisableTiming));
+  b->prompt_len.assign(n_slots, 0); b->max_gen.assign(n_slots, 0); b->open.assign(n_slots, 0); b->known_done.assign(n_slots, 0);
   CU(cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
   if (own_stream) {
@@ -643,20 +648,23 @@ extern "C" int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *p
   // group, never in the middle of one.  One group: everything on the caller's stream, synchronously.
   const bool async = b.stream != nullptr;
   cudaStream_t s = async ? e->pf_stream : (cudaStream_t)stream;
+  // the prompt staging buffer is free once the previous prompt's copy has run (it runs on the prefill stream, not behind decode steps); a
+  // finished request parks its slot (position -1), so the steps still in flight for the group do not touch the cache being filled
   if (async) {
-    if (b.act_pending) { CU(cudaEventSynchronize(b.ev_act)); b.act_pending = false; }
-    if (b.rel_pending) CU(cudaStreamWaitEvent(s, b.ev_rel, 0));
-  }      // the group's pinned staging buffers are free again
+    if (b.prompt_pending) { CU(cudaEventSynchronize(b.ev_prompt)); b.prompt_pending = false; }
+    if (b.rel_pending) { CU(cudaStreamWaitEvent(s, b.ev_rel, 0)); b.rel_pending = false; }
+  }
   else CU(cudaStreamSynchronize(s));
   int *seq = b.seq + (size_t)slot * R * b.Sb;
-  for (int r = 0; r < R; ++r) memcpy(b.h_seq + (size_t)r * T, prompt + (size_t)r * T, (size_t)T * sizeof(int));
-  CU(cudaMemcpy2DAsync(seq, (size_t)b.Sb * sizeof(int), b.h_seq, (size_t)T * sizeof(int), (size_t)T * sizeof(int), R, cudaMemcpyHostToDevice, s));
+  for (int r = 0; r < R; ++r) memcpy(b.h_prompt + (size_t)r * T, prompt + (size_t)r * T, (size_t)T * sizeof(int));
+  CU(cudaMemcpy2DAsync(seq, (size_t)b.Sb * sizeof(int), b.h_prompt, (size_t)T * sizeof(int), (size_t)T * sizeof(int), R, cudaMemcpyHostToDevice, s));
+  if (async) { CU(cudaEventRecord(b.ev_prompt, s)); b.prompt_pending = true; }
   std::vector<bf16 *> kc(cf.n_layer), vc(cf.n_layer);
   for (int l = 0; l < cf.n_layer; ++l) { kc[l] = b.kc[l] + (size_t)slot * b.slot_stride; vc[l] = b.vc[l] + (size_t)slot * b.slot_stride; }
   KvTarget kv{kc.data(), vc.data(), 0, b.Sb};
   int rc = tc_prefill(e, kv, seq, b.Sb, 0, T - 1, s); if (rc) return rc;
   // the slot joins the batch at the LAST prompt position: the next batched step produces its first token (no penalty, inference.py:353-362)
-  DAState *h = b.h_st; memset(h, 0, sizeof(*h));
+  DAState *h = b.h_act + slot; memset(h, 0, sizeof(*h));      // per slot: the copy below may sit behind a burst of decode steps
   h->pos = T - 1; h->max_gen = max_new; h->prompt_len = T; h->loop_mode = 1; h->temperature = temperature; h->top_p = top_p; h->rep_penalty = rep;
   h->seed = seed; h->cpu_sem = e->cpu_sem; h->noise = (const bf16 *)noise; h->noise_stride = (long long)cf.vocab_size + (long long)(cf.num_codebooks - 1) * e->fv;
   for (int r = 0; r < R; ++r) h->tok_in[r] = prompt[(size_t)r * T + (T - 1)];
@@ -670,7 +678,7 @@ extern "C" int dualar_batch_prefill(dualar_engine *e, int slot, const int32_t *p
     CU(cudaMemcpyAsync(b.st + slot, h, sizeof(*h), cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));      // the pinned staging buffers are reused by the next call
   }
-  b.prompt_len[slot] = T; b.max_gen[slot] = max_new; b.open[slot] = 1;
+  b.prompt_len[slot] = T; b.max_gen[slot] = max_new; b.open[slot] = 1; b.known_done[slot] = 0;
   return 0;
 }
 
@@ -693,7 +701,9 @@ extern "C" int dualar_batch_decode(dualar_engine *e, int n_steps, void *stream) 
   for (dualar_batch *b : live) CU(cudaStreamWaitEvent(b->stream, e->ev_groups_go, 0));
   for (int i = 0; i < n_steps; ++i)
     for (dualar_batch *b : live) CU(cudaGraphLaunch(b->persistent ? b->g_step_p : b->g_step, b->stream));
-  for (dualar_batch *b : live) { CU(cudaEventRecord(b->ev_done, b->stream)); CU(cudaStreamWaitEvent(s, b->ev_done, 0)); }
+  // no join here: dualar_batch_read and dualar_batch_collect make the caller's stream wait for the groups they look at -- so the host
+  // can collect finished requests and enqueue prefills while the next burst of steps is already running
+  for (dualar_batch *b : live) { CU(cudaEventRecord(b->ev_done, b->stream)); b->decode_pending = true; }
   return 0;
 }
 
@@ -706,7 +716,11 @@ extern "C" int dualar_batch_collect(dualar_engine *e, int slot, int32_t *out, in
   dualar_batch &b = *bp; const int R = e->c.num_codebooks + 1;
   CU(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (b.act_pending) { CU(cudaEventSynchronize(b.ev_act)); b.act_pending = false; }      // h_st is the prefill's staging buffer too
+  // a request the host has SEEN finished (dualar_batch_read "done") is stable: no need to wait for the steps enqueued since
+  if (!b.known_done[slot]) {
+    if (b.act_pending) CU(cudaStreamWaitEvent(s, b.ev_act, 0));
+    if (b.decode_pending) CU(cudaStreamWaitEvent(s, b.ev_done, 0));
+  }
   CU(cudaMemcpyAsync(b.h_st, b.st + slot, sizeof(DAState), cudaMemcpyDeviceToHost, s));
   int gerr = 0; CU(cudaMemcpyAsync(&gerr, e->tc->err, sizeof(int), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -734,7 +748,9 @@ extern "C" int dualar_batch_release(dualar_engine *e, int slot) {
     // several groups: no device-wide synchronisation (other groups' prefills may be in flight); the idle state is written on the
     // group's stream, i.e. after every step already enqueued for the group and before any later one
     CU(cudaMemcpyAsync(b.st + slot, b.st_idle, sizeof(DAState), cudaMemcpyDeviceToDevice, b.stream));
-    CU(cudaEventRecord(b.ev_rel, b.stream)); b.rel_pending = true;      // a later prefill of the slot must not overtake steps that still see the old request
+    // an UNFINISHED request released early may still be writing its KV rows in steps already enqueued: a later prefill of the slot waits
+    // for them; a finished one is parked (position -1) and needs no such wait
+    if (!b.known_done[slot]) { CU(cudaEventRecord(b.ev_rel, b.stream)); b.rel_pending = true; }
   } else {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(b.st + slot, b.st_idle, sizeof(DAState), cudaMemcpyDeviceToDevice));      // idle: loop_mode 0, position -1
@@ -783,7 +799,10 @@ extern "C" int dualar_batch_read(dualar_engine *e, const char *name, void *dst, 
   if (!e->batch) return fail(DUALAR_ESTATE, "dualar_batch_init has not been called");
   CU(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
-  for (dualar_batch *b : e->groups) if (b->act_pending) CU(cudaStreamWaitEvent(s, b->ev_act, 0));
+  for (dualar_batch *b : e->groups) {
+    if (b->act_pending) CU(cudaStreamWaitEvent(s, b->ev_act, 0));
+    if (b->decode_pending) CU(cudaStreamWaitEvent(s, b->ev_done, 0));
+  }
   int64_t off = 0;
   for (dualar_batch *b : e->groups) {
     int64_t held = 0; int per_slot = 0;
@@ -794,6 +813,11 @@ extern "C" int dualar_batch_read(dualar_engine *e, const char *name, void *dst, 
   }
   if (off < nbytes) return fail(DUALAR_EINVAL, "batch buffer '%s' holds %lld bytes, %lld requested", name, (long long)off, (long long)nbytes);
   CU(cudaStreamSynchronize(s));
+  for (dualar_batch *b : e->groups) { b->decode_pending = false; b->act_pending = false; }      // everything enqueued so far has run
+  if (!strcmp(name, "done")) {      // remember which requests the host has seen finished (dualar_batch_collect / release rely on it)
+    const int32_t *d = (const int32_t *)dst; int64_t i = 0, n = nbytes / 4;
+    for (dualar_batch *b : e->groups) for (int sl = 0; sl < b->B && i < n; ++sl, ++i) if (d[i]) b->known_done[sl] = 1;
+  }
   return 0;
 }
 
@@ -811,6 +835,9 @@ static void batch_destroy(dualar_engine *e) {
     if (b->ev_rel) cudaEventDestroy(b->ev_rel);
     if (b->h_st) cudaFreeHost(b->h_st);
     if (b->h_seq) cudaFreeHost(b->h_seq);
+    if (b->h_act) cudaFreeHost(b->h_act);
+    if (b->h_prompt) cudaFreeHost(b->h_prompt);
+    if (b->ev_prompt) cudaEventDestroy(b->ev_prompt);
     delete b;
   }
   e->groups.clear(); e->batch = nullptr;

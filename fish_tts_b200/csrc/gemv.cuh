@@ -56,6 +56,8 @@ struct GemvArgs {
   bf16 *fast_x;           // next fast pass input [fast_dim]
   int fast_dim, last_head, codebook_size;
   int *seq; int seq_stride; int im_end_id; int n_rows_tok;  // finish_step
+  int park_on_done;       // request slots: a finished request's position becomes -1, so the steps it still rides along in skip its KV cache
+                          // (the slot may already be receiving the next request's prefill)
   DAState *st;
   Timeline tl;
 };
@@ -296,7 +298,7 @@ __device__ __forceinline__ void finish_step(const GemvArgs &a) {
   if (st->noise) st->noise += st->noise_stride;
   // the reference tests for <|im_end|> only inside decode_n_tokens (inference.py:210): the column produced by the
   // prefill call is never checked, so an EOS there is followed by one more step
-  if ((n_gen > 1 && st->tok_out[0] == a.im_end_id) || n_gen >= st->max_gen) st->done = 1;
+  if ((n_gen > 1 && st->tok_out[0] == a.im_end_id) || n_gen >= st->max_gen) { st->done = 1; if (a.park_on_done) st->pos = -1; }
   // previous_tokens[:, j] = generated column j+1 (the prefill-produced column 0 is never recorded)
   int i = n_gen - 1, T = st->prompt_len;
   for (int c = 0; c < DA_WIN; ++c) {

@@ -1278,7 +1278,7 @@ __global__ void __launch_bounds__(DA_M_THREADS, 1) mega_kernel(const __grid_cons
         st->pos = np;
         for (int r = 0; r < a.n_rows_tok; ++r) st->tok_in[r] = a.seq[(size_t)r * a.seq_stride + np];
       } else {
-        GemvArgs g; g.st = st; g.seq = a.seq; g.seq_stride = a.seq_stride; g.im_end_id = a.im_end_id; g.n_rows_tok = a.n_rows_tok;
+        GemvArgs g; g.st = st; g.seq = a.seq; g.seq_stride = a.seq_stride; g.im_end_id = a.im_end_id; g.n_rows_tok = a.n_rows_tok; g.park_on_done = 0;
         finish_step(g);
       }
     }

@@ -54,6 +54,7 @@ class RankResult:
     codes: dict = field(default_factory=dict)     # uid -> (num_codebooks + 1, n) int32
     tokens: int = 0
     seconds: float = 0.0
+    wait_seconds: float = 0.0
 
 
 def run_rank(generate_fn: Callable[[Utterance], np.ndarray], utterances: Sequence[Utterance], rank: int, world: int,
@@ -78,29 +79,50 @@ def run_rank(generate_fn: Callable[[Utterance], np.ndarray], utterances: Sequenc
 
 
 def run_rank_batched(engine, utterances: Sequence[Utterance], rank: int, world: int, max_batch: int, poll_steps: int = 16,
-                     sync: Optional[Callable[[], None]] = None, seed_base: int = 0) -> RankResult:
+                     sync: Optional[Callable[[], None]] = None, seed_base: int = 0, pipeline: Optional[bool] = None) -> RankResult:
     """This rank's share through the engine's request slots with CONTINUOUS BATCHING: every free slot is refilled from the queue
     (tensor-core prefill), ``poll_steps`` batched decode steps run without a host round trip, finished slots are collected and
     released.  ``engine`` is a DualAREngine on which ``batch_init(max_batch, ...)`` has been called.  Longest-first within the
-    rank keeps the tail short.  One device -> host read of the ``done`` flags per ``poll_steps`` steps."""
+    rank keeps the tail short.  One device -> host read of the ``done`` flags per ``poll_steps`` steps.
+
+    ``pipeline`` (default: on when the engine runs several request groups): as soon as the ``done`` flags of burst k are on the host,
+    burst k+1 is enqueued, and only THEN are the finished requests collected, their slots released and refilled -- the host work
+    (D2H of the codes, ~230 kernel launches per prefill) overlaps the GPU's next burst instead of leaving it idle.  A refilled slot
+    joins at burst k+2; its prefill runs beside burst k+1 on the engine's prefill stream (finished requests park their slot, so the
+    steps in flight do not touch the cache being filled)."""
     mine = partition_longest_first([u.cost for u in utterances], world)[rank]
     queue = sorted(mine, key=lambda i: (-utterances[i].cost, i))
     res = RankResult(rank=rank)
     slots: dict[int, int] = {}          # slot -> utterance index
     free = list(range(max_batch))
-    if sync:
-        sync()
-    t0 = time.perf_counter()
-    while queue or slots:
+    if pipeline is None:
+        pipeline = int(engine.batch_read("groups")[0]) > 1
+
+    def refill():
         while free and queue:
             i = queue.pop(0)
             u = utterances[i]
             sl = free.pop()
             engine.batch_prefill(sl, u.prompt, u.max_new_tokens, u.temperature, u.top_p, u.repetition_penalty, seed=seed_base + u.uid)
             slots[sl] = i
-        engine.batch_decode(poll_steps)
-        done = engine.batch_read("done").numpy()
-        for sl in [s for s in slots if done[s]]:
+
+    if sync:
+        sync()
+    t0 = time.perf_counter()
+    t_wait = 0.0
+    in_flight = False
+    refill()
+    while queue or slots:
+        if not in_flight:
+            engine.batch_decode(poll_steps)
+        tw = time.perf_counter()
+        done = engine.batch_read("done").numpy()          # waits for every burst enqueued so far
+        t_wait += time.perf_counter() - tw
+        finished = [s for s in slots if done[s]]
+        in_flight = pipeline and len(slots) > len(finished)
+        if in_flight:
+            engine.batch_decode(poll_steps)               # the GPU goes on while the host collects and refills
+        for sl in finished:
             u = utterances[slots.pop(sl)]
             out, fin = engine.batch_collect(sl)
             assert fin
@@ -109,9 +131,11 @@ def run_rank_batched(engine, utterances: Sequence[Utterance], rank: int, world: 
             res.uids.append(u.uid)
             res.codes[u.uid] = out
             res.tokens += int(out.shape[1])
+        refill()
     if sync:
         sync()
     res.seconds = time.perf_counter() - t0
+    res.wait_seconds = t_wait          # host blocked on the GPU (the rest of `seconds` is host work: collects, releases, prefill enqueues)
     return res
 
 

@@ -380,3 +380,23 @@ def test_s1_mini_serving_loop_is_deterministic_and_group_invariant():
         assert (a == b).all(), f"utterance {u.uid}: two identical runs differ"
         assert (a == c).all(), f"utterance {u.uid}: two groups of 32 and one group of 32 differ"
         assert ((a[0] >= cfg.semantic_begin_id) & (a[0] <= cfg.semantic_end_id)).all() and ((a[1:] >= 0) & (a[1:] < cfg.codebook_size)).all()
+
+
+@pytest.mark.parametrize("max_batch", [9, 3])
+def test_long_context_slots_split_kv_paths(max_batch):
+    """Contexts of many 64-position tiles: with more than 8 slots the KV range is split from 8 tiles on and merged through partials + a
+    ticket (the last split owns the new position: it computes, writes and patches the K / V row); with at most 8 slots every tile is a
+    split of a 4-CTA cluster merging through distributed shared memory.  Both against the oracle replay, next to short requests."""
+    cfg = tiny_config(max_seq_len=2048)
+    sd = make_state_dict(cfg, seed=0)
+    m = orc.OracleModel.build(cfg, sd, device="cuda:0")
+    eng = DualAREngine(cfg, sd, device=0)
+    eng.batch_init(max_batch, 2048)
+    reqs = [(5, 1200, 1, 0.7, 0.8, 1.1), (3, 30, 2, 0.7, 1e-9, 1.0), (4, 600, 4, 0.3, 0.5, 1.2)]
+    n = 6
+    prompts, cols, slows, fasts = run_batch(eng, cfg, reqs, n)
+    same = 0
+    for sl, r in enumerate(reqs):
+        same += replay_slot(cfg, m, eng, prompts[sl], cols[sl], slows[sl], fasts[sl], r[3], r[4], r[5], 100 + sl, f"long slot {sl} ({max_batch} slots)")
+    eng.close()
+    assert same >= int(0.8 * n * len(reqs))

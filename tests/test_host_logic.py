@@ -172,3 +172,65 @@ def test_pack_prompt_layout():
     import pytest
     with pytest.raises(ValueError):
         pack_prompt([np.zeros((C, 2)) + 99], C, sb, codebook_size=16)
+
+
+class _FakeSlots:
+    """host-side stand-in for the request-slot API: a request produces `max_new` columns, one per step it is switched on for"""
+    def __init__(self, n, groups):
+        import numpy as np
+        self.np, self.n, self.groups = np, n, groups
+        self.left = [0] * n; self.total = [0] * n; self.open = [False] * n; self.seen_done = [False] * n
+        self.pending = {}            # slot -> (max_new, uid): prefilled, joins at the next decode call (asynchronous prefill)
+        self.log = []
+    def batch_prefill(self, slot, prompt, max_new, *a, seed=0):
+        assert not self.open[slot], "prefill into an occupied slot"
+        self.open[slot] = True; self.seen_done[slot] = False; self.pending[slot] = (max_new, seed)
+        self.left[slot] = -1
+    def batch_decode(self, n):
+        for sl, (mx, seed) in list(self.pending.items()):
+            self.left[sl] = mx; self.total[sl] = mx; del self.pending[sl]
+        for sl in range(self.n):
+            if self.open[sl] and self.left[sl] > 0:
+                self.left[sl] = max(0, self.left[sl] - n)
+        self.log.append("decode")
+    def batch_read(self, name):
+        import torch
+        if name == "groups":
+            return torch.tensor([self.groups], dtype=torch.int32)
+        assert name == "done"
+        d = [int(self.open[sl] and self.left[sl] == 0) for sl in range(self.n)]
+        for sl in range(self.n):
+            self.seen_done[sl] = self.seen_done[sl] or bool(d[sl])
+        self.log.append("read")
+        return torch.tensor(d, dtype=torch.int32)
+    def batch_collect(self, slot):
+        assert self.seen_done[slot], "collected before the host saw the request finished"
+        self.log.append("collect")
+        return self.np.zeros((3, self.total[slot]), dtype=self.np.int32), True
+    def batch_release(self, slot):
+        self.open[slot] = False; self.log.append("release")
+
+
+def test_serving_loop_host_logic_with_fake_slots():
+    """run_rank_batched: every utterance exactly once and complete, never more requests than slots, and in pipelined mode the next
+    burst is enqueued BEFORE the finished requests are collected"""
+    import numpy as np
+
+    from fish_tts_b200 import replicas
+    rng = np.random.default_rng(0)
+    utts = [replicas.Utterance(uid=i, prompt=np.zeros((3, int(rng.integers(4, 40))), dtype=np.int32), max_new_tokens=int(rng.integers(1, 50))) for i in range(37)]
+    for groups in (1, 3):
+        eng = _FakeSlots(5, groups)
+        res = replicas.run_rank_batched(eng, utts, 0, 1, 5, poll_steps=4)
+        assert sorted(res.uids) == list(range(37)) and res.tokens == sum(u.max_new_tokens for u in utts)
+        assert all(res.codes[u.uid].shape[1] == u.max_new_tokens for u in utts)
+        log = eng.log
+        first_collect = log.index("collect")
+        if groups > 1:
+            assert log[first_collect - 1] == "decode" and log[first_collect - 2] == "read", "pipelined: read, decode, then collect"
+        else:
+            assert log[first_collect - 1] == "read"
+    # two ranks split the work without overlap
+    a = replicas.run_rank_batched(_FakeSlots(4, 2), utts, 0, 2, 4)
+    b = replicas.run_rank_batched(_FakeSlots(4, 2), utts, 1, 2, 4)
+    assert sorted(a.uids + b.uids) == list(range(37))
