@@ -15,6 +15,7 @@
 #pragma once
 #include "attention.cuh"
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "sampler.cuh"
 
@@ -161,6 +162,7 @@ struct BAttnArgs {
   // cluster_merge = 1: the KV splits of a (column, kv head) are a thread-block cluster (cluster dims (nsplit_max, 1, 1)); their partial
   // (max, sum, output) meet in the first split's shared memory instead of a global buffer + ticket
   int cluster_merge;
+  int use_mma;               // Q.K^T and P@V on the tensor cores (b_attn_body<B, true>)
   int nh, nkv, hd, S, ncols, nsplit_max, tiles_per_split; float sf;
   float *part_o, *part_ml;   // [ncols][nkv][nsplit_max][G][hd], [...][G][2]
   unsigned int *tickets;     // [ncols][nkv], zero between launches
@@ -186,8 +188,34 @@ static inline size_t b_attn_smem(int G, int hd) {
 // initialises them per launch (init = true); the persistent kernel initialises them once and carries the parities from unit to unit --
 // re-initialising an mbarrier in the middle of a kernel (through a per-thread address: a plain 64-bit store + a sync-unit cache
 // invalidate in SASS) lost the transaction that followed on B200.
-template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm,
-                                                               uint64_t *bars, uint32_t (&phase)[DA_B_NBUF], bool init) {
+// MMA = true: Q.K^T and P@V on the tensor cores (mma.sync m16n8k16, bf16 in, fp32 accumulate).  The G <= 8 query heads of the kv head are
+// rows 0 .. G-1 of the 16-row A operand.  Q and K are bf16 values, so every product q_d * k_d is exact in fp32 and the dot product times
+// scale (= sqrt(scale)^2) differs from the reference's sum of (q_d sqrt(scale)) (k_d sqrt(scale)) by fp32 roundings only.  P is fp32: it
+// is split EXACTLY into three bf16 terms (24 significant bits = 3 x 8) that accumulate into the same fp32 output registers, so P@V is the
+// fp32 product as well.  K / V tiles come in by 2-D TMA (cp.async.bulk.tensor) as boxes of 64 positions x 64 dims with the 128-byte
+// swizzle, so the 32-bit fragment loads of K and the transposing ldmatrix of V are bank-conflict free (one bulk copy PER ROW at a padded
+// stride was tried first: 128 small copies per tile cost more than the arithmetic they saved).  A warp owns 16 positions of a 64-position
+// tile (w % 4) and half of the output dims (w / 4); the two warps of a position block compute the same scores.  hd = 64 or 128.
+#define DA_BM_NBUF 3
+static inline size_t b_attn_mma_smem(int G, int hd) {
+  size_t f = ((size_t)G * hd + (size_t)DA_B_AWARPS * G * (2 + hd)) * sizeof(float) + 2 * sizeof(uint64_t) + (size_t)hd * (sizeof(float) + 2 * sizeof(bf16)) +
+             (size_t)DA_B_MAXSPLIT * G * (hd + 2) * sizeof(float);
+  f = (f + 127) & ~(size_t)127;
+  return f + 1024 + 2 * DA_BM_NBUF * (size_t)DA_TILE * hd * sizeof(bf16);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { return (uint32_t)f2bits(lo) | ((uint32_t)f2bits(hi) << 16); }
+// element (row r, dim d) of a tile made of 64-dim boxes [64 rows][128 bytes] with the 128-byte swizzle: byte offset
+__device__ __forceinline__ uint32_t sw128_off(int r, int d) {
+  return (uint32_t)((d >> 6) * (DA_TILE * 128) + r * 128 + ((((d & 63) >> 3) ^ (r & 7)) << 4) + (d & 7) * 2);
+}
+template <class B, bool MMA = false> __device__ __forceinline__ void b_attn_body(const BAttnArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm,
+                                                               uint64_t *bars, uint32_t (&phase)[DA_B_NBUF], bool init,
+                                                               const CUtensorMap *mk = nullptr, const CUtensorMap *mv = nullptr) {
+  constexpr int NBUF = MMA ? DA_BM_NBUF : DA_B_NBUF;
   (void)bx; (void)by; (void)bz; (void)gy; (void)dsm;
   unsigned char *smraw_b = dsm;
   const int g = by, split = bx, n = bz;
@@ -218,23 +246,35 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   float *recv = reinterpret_cast<float *>(vrow_new + hd);      // cluster merge: [split][G * hd outputs | G x (max, sum)]
   const int rstride = G * (hd + 2);
   size_t off = (size_t)((unsigned char *)(recv + (size_t)DA_B_MAXSPLIT * rstride) - smraw_b) + 16;
-  off = (off + 127) & ~(size_t)127;
+  if (MMA) off += (1024u - ((smem_u32(smraw_b) + (uint32_t)off) & 1023u)) & 1023u;      // swizzled boxes are 1024-byte aligned
+  else off = (off + 127) & ~(size_t)127;
   bf16 *kbuf = reinterpret_cast<bf16 *>(smraw_b + off);
-  bf16 *vbuf = kbuf + DA_B_NBUF * DA_TILE * hd;
+  const int rs = hd;
+  bf16 *vbuf = kbuf + (size_t)NBUF * DA_TILE * rs;
   const bf16 *kc = a.kc + (size_t)n * a.slot_stride, *vc = a.vc + (size_t)n * a.slot_stride;
   const uint64_t pol = policy_evict_first();
   if (init && threadIdx.x == 0) {
-    for (int i = 0; i < DA_B_NBUF; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < NBUF; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   B::sync();
-  auto issue = [&](int t, int buf) {
+  auto issue = [&](int t, int buf) {      // scalar path: thread 0; MMA path: every lane of warp 0 (one bulk copy per row, padded stride)
     const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE);
     const uint32_t bytes = (uint32_t)(r1 - r0) * hd * sizeof(bf16);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bars[buf], 2 * bytes);
-    bulk_g2s(kbuf + (size_t)buf * DA_TILE * hd, kc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
-    bulk_g2s(vbuf + (size_t)buf * DA_TILE * hd, vc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
+    if (!MMA) {
+      mbar_expect_tx(&bars[buf], 2 * bytes);
+      bulk_g2s(kbuf + (size_t)buf * DA_TILE * hd, kc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
+      bulk_g2s(vbuf + (size_t)buf * DA_TILE * hd, vc + ((size_t)g * a.S + r0) * hd, bytes, &bars[buf], pol);
+    } else {
+      // whole 64-row boxes (rows past the context are other positions' finite values or zero fill: masked below), hd / 64 boxes per tile
+      mbar_expect_tx(&bars[buf], 2u * DA_TILE * (uint32_t)hd * sizeof(bf16));
+      const int grow = (int)(((long long)n * a.slot_stride) / hd) + g * a.S + r0;
+      for (int bxi = 0; bxi < (hd >> 6); ++bxi) {
+        tma_load_2d(reinterpret_cast<unsigned char *>(kbuf + (size_t)buf * DA_TILE * hd) + bxi * (DA_TILE * 128), mk, bxi * 64, grow, &bars[buf], pol);
+        tma_load_2d(reinterpret_cast<unsigned char *>(vbuf + (size_t)buf * DA_TILE * hd) + bxi * (DA_TILE * 128), mv, bxi * 64, grow, &bars[buf], pol);
+      }
+    }
   };
   if (threadIdx.x == 0) { issue(t0, 0); if (t0 + 1 < t1) issue(t0 + 1, 1); }
   const int t_new = pos / DA_TILE;
@@ -245,7 +285,7 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
     for (int c = threadIdx.x; c * 8 < G * hd; c += DA_ATTN_THREADS) {
       float t[8]; unpack8(*reinterpret_cast<const uint4 *>(qsrc + c * 8), t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[c * 8 + j] = a.fuse_post ? t[j] : __fmul_rn(t[j], a.sf);      // q * sqrt(scale), fp32 (math SDPA)
+      for (int j = 0; j < 8; ++j) q[c * 8 + j] = (a.fuse_post || MMA) ? t[j] : __fmul_rn(t[j], a.sf);      // q * sqrt(scale), fp32 (math SDPA)
     }
     if (a.fuse_post) {
       if (owns_new) for (int d = threadIdx.x; d < hd; d += DA_ATTN_THREADS) knew_f[d] = bf2f(row[(size_t)(a.nh + g) * hd + d]);
@@ -255,7 +295,7 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
       for (int task = w; task < G + (owns_new ? 2 : 0); task += DA_B_AWARPS) {
         if (task < G) {
           head_norm_rope(q + (size_t)task * hd, hd, a.qn, a.eps, rope_row, lane);
-          for (int d = lane; d < hd; d += 32) q[(size_t)task * hd + d] = __fmul_rn(q[(size_t)task * hd + d], a.sf);
+          if (!MMA) for (int d = lane; d < hd; d += 32) q[(size_t)task * hd + d] = __fmul_rn(q[(size_t)task * hd + d], a.sf);
         } else if (task == G) {
           head_norm_rope(knew_f, hd, a.kn, a.eps, rope_row, lane);
           for (int d = lane; d < hd; d += 32) { const bf16 kv = f2bf(knew_f[d]); krow_new[d] = kv; a.kc[(size_t)n * a.slot_stride + ((size_t)g * a.S + pos) * hd + d] = kv; }
@@ -267,6 +307,7 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   }
   B::sync();
   bool ok = true;
+  if constexpr (!MMA) {
   // Per tile a warp owns the 8 positions w, w + 8, ...: scores with 4 lanes per position (lane = 4 * slot + dl; every lane walks its
   // hd / 4 dims in 4-element chunks, the chunk order rotated by the slot so that the four positions of a half-warp hit different banks),
   // ONE online-softmax update per tile and warp, then P@V with the 8 probabilities broadcast to all lanes (a lane owns hd / 32 output
@@ -372,6 +413,115 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
     }
     B::sync();      // every warp is past its last read of the tile: its buffer may be refilled
   }
+  } else {
+    // ---- tensor-core tile walk ----------------------------------------------------------------------------------------------------
+    const int pb = w & 3, dh = w >> 2, hh = hd >> 1, nkk = hd >> 4, nnt = hd >> 4;      // position block, dim half, dims per half, k-steps, n-tiles per half
+    const int hrow = lane >> 2, qc = (lane & 3) * 2;                                       // this lane's head row / column pair inside a fragment
+    const float scale = __fmul_rn(a.sf, a.sf);
+    uint32_t qa0[8], qa2[8];      // A fragments of Q for up to 8 k-steps (hd <= 128): rows >= G are zero
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      qa0[kk] = 0u; qa2[kk] = 0u;
+      if (kk < nkk && hrow < G) {
+        const float *qr = q + (size_t)hrow * hd + kk * 16 + qc;
+        qa0[kk] = pack_bf16x2(qr[0], qr[1]); qa2[kk] = pack_bf16x2(qr[8], qr[9]);
+      }
+    }
+    float m_run = -INFINITY, l_run = 0.f, o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    for (int t = t0; t < t1; ++t) {
+      const int buf = (t - t0) % NBUF;
+      const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
+      if (threadIdx.x == 0 && t + 2 < t1) issue(t + 2, (t - t0 + 2) % NBUF);      // into the buffer of tile t - 1, released by the barrier that ended it
+      ok = mbar_wait(&bars[buf], phase[buf]) && ok; phase[buf] ^= 1u;
+      unsigned char *kt = reinterpret_cast<unsigned char *>(kbuf + (size_t)buf * DA_TILE * hd), *vt = reinterpret_cast<unsigned char *>(vbuf + (size_t)buf * DA_TILE * hd);
+      const int p0 = pb * 16;      // this warp's 16 positions of the tile
+      // the new position's row is not in the cache yet when the tile is fetched: both warps of its position block patch it in (same values)
+      if (owns_new && t == t_new) {
+        const int jrow = pos - r0;
+        if (jrow >= p0 && jrow < p0 + 16)
+          for (int d = lane; d < hd; d += 32) {
+            *reinterpret_cast<bf16 *>(kt + sw128_off(jrow, d)) = krow_new[d]; *reinterpret_cast<bf16 *>(vt + sw128_off(jrow, d)) = vrow_new[d];
+          }
+      }
+      __syncwarp();
+      // S = Q K^T for the two 8-position n-tiles of the block
+      float sacc[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+        const int krow = p0 + j * 8 + hrow;      // B fragment: position = lane / 4, dims (lane % 4) * 2 + {0, 1} (+ 8)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          if (kk < nkk) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(kt + sw128_off(krow, kk * 16 + qc)), b1 = *reinterpret_cast<const uint32_t *>(kt + sw128_off(krow, kk * 16 + 8 + qc));
+            mma_bf16_16816(sacc[j], qa0[kk], 0u, qa2[kk], 0u, b0, b1);
+          }
+        }
+      }
+      // online softmax for head row `hrow` over this warp's 16 positions: the lane holds 4 of them, its 3 neighbours the rest
+      float sv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pcol = p0 + (i >> 1) * 8 + qc + (i & 1);
+        sv[i] = (pcol < nrow && hrow < G) ? __fmul_rn(sacc[i >> 1][i & 1], scale) : -INFINITY;
+      }
+      float mx = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run, mx);
+      float pr[4] = {0.f, 0.f, 0.f, 0.f}, sc_old = 1.f;
+      if (m_new != -INFINITY) {
+        sc_old = expf(m_run - m_new);      // exp(-inf) = 0 before the first position
+        m_run = m_new;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pr[i] = expf(sv[i] - m_new);
+      }
+      float rsum = (pr[0] + pr[1]) + (pr[2] + pr[3]);
+      rsum += __shfl_xor_sync(0xffffffffu, rsum, 1); rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+      l_run = fmaf(l_run, sc_old, rsum);
+      // P as three exact bf16 terms; A fragments: a0 = columns of n-tile 0 (k 0..7), a2 = n-tile 1 (k 8..15)
+      uint32_t pa0[3], pa2[3];
+      {
+        float r0f[4], hi;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r0f[i] = pr[i];
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+          float tt[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { hi = rbf(r0f[i]); tt[i] = hi; r0f[i] = r0f[i] - hi; }
+          pa0[s3] = pack_bf16x2(tt[0], tt[1]); pa2[s3] = pack_bf16x2(tt[2], tt[3]);
+        }
+      }
+      // O = O * sc_old + P V over this warp's dim half: V^T fragments by transposing ldmatrix (two n-tiles per instruction)
+      const int vrow = p0 + ((lane >> 3) & 1) * 8 + (lane & 7), vd0 = dh * hh + (lane >> 4) * 8;      // this lane's row address for ldmatrix
+      const uint32_t vt_s = smem_u32(vt);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        if (j < nnt) {
+          uint32_t b00, b01, b10, b11;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b00), "=r"(b01), "=r"(b10), "=r"(b11) : "r"(vt_s + sw128_off(vrow, vd0 + j * 8)));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { o[j][i] *= sc_old; o[j + 1][i] *= sc_old; }
+#pragma unroll
+          for (int s3 = 0; s3 < 3; ++s3) {
+            mma_bf16_16816(o[j], pa0[s3], 0u, pa2[s3], 0u, b00, b01);
+            if (j + 1 < nnt) mma_bf16_16816(o[j + 1], pa0[s3], 0u, pa2[s3], 0u, b10, b11);
+          }
+        }
+      }
+      B::sync();      // every warp is past its last read of the tile: its buffer may be refilled
+    }
+    // per-warp partials for the fold: (max, sum) per head, output for this warp's dim half
+    if (hrow < G) {
+      if ((lane & 3) == 0) { pm[w * G + hrow] = m_run; pl[w * G + hrow] = l_run; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nnt) { po[((size_t)w * G + hrow) * hd + dh * hh + j * 8 + qc] = o[j][0]; po[((size_t)w * G + hrow) * hd + dh * hh + j * 8 + qc + 1] = o[j][1]; }
+    }
+    B::sync();
+  }
   if (!ok && threadIdx.x == 0) atomicExch(a.err, 2);
   if (cl) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // barrier 1: every CTA of the cluster is running
   // fold the 8 warps' partials in warp order: thread e = (h, d)
@@ -380,12 +530,12 @@ template <class B> __device__ __forceinline__ void b_attn_body(const BAttnArgs &
   float *pml = a.part_ml + ((pbase + split) * G) * 2;
   for (int e = threadIdx.x; e < G * hd; e += DA_ATTN_THREADS) {
     const int h = e / hd, dd = e - h * hd;
+    // scalar path: all 8 warps hold partials of every dim; tensor-core path: the 4 warps (position blocks) of this dim's half
+    const int w_lo = MMA ? (dd >= (hd >> 1) ? 4 : 0) : 0, w_hi = MMA ? w_lo + 4 : DA_B_AWARPS;
     float m = -INFINITY;
-#pragma unroll
-    for (int ww = 0; ww < DA_B_AWARPS; ++ww) m = fmaxf(m, pm[ww * G + h]);
+    for (int ww = w_lo; ww < w_hi; ++ww) m = fmaxf(m, pm[ww * G + h]);
     float l = 0.f, o = 0.f;
-#pragma unroll
-    for (int ww = 0; ww < DA_B_AWARPS; ++ww) {
+    for (int ww = w_lo; ww < w_hi; ++ww) {
       const float v = pm[ww * G + h];
       const float sc_w = v == -INFINITY ? 0.f : expf(v - m);
       l = fmaf(pl[ww * G + h], sc_w, l);
@@ -454,6 +604,14 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_kernel(const BAttnA
   __shared__ __align__(8) uint64_t s_bars[DA_B_NBUF];
   uint32_t phase[DA_B_NBUF] = {};
   b_attn_body<BlockAll>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_attn_body, s_bars, phase, true);
+}
+__global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_mma_kernel(const __grid_constant__ CUtensorMap mk, const __grid_constant__ CUtensorMap mv, const BAttnArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm_b_attn_mma[];
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __align__(8) uint64_t s_bars[DA_B_NBUF];
+  uint32_t phase[DA_B_NBUF] = {};
+  b_attn_body<BlockAll, true>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_attn_mma, s_bars, phase, true, &mk, &mv);
 }
 
 // ---- fast-layer attention for codebook position p, one CTA per column ---------------------------------------------------------------

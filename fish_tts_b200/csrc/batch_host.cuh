@@ -64,6 +64,7 @@ struct dualar_tc {
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
   int target_ctas = 0, min_kb = 0;      // decode split-K heuristic: CTAs aimed at per GEMM, least k-blocks per CTA (0 = by mode; DUALAR_TC_CTAS, DUALAR_TC_MINKB)
+  bool attn_mma = false;           // DUALAR_ATTN_MMA=1: Q.K^T and P@V of the decode attention on the tensor cores (b_attn_body<B, true>): parity-green, not faster yet
   bool attn_cluster = true;        // DUALAR_ATTN_CLUSTER=0: KV splits merged through a global buffer + ticket
   bool cluster_reduce = true;      // DUALAR_TC_CLUSTER=0: split-K through the global workspace + ticket (the prefill path's way)
   bool attn_fuse_post = true;      // DUALAR_ATTN_FUSE_POST=0: b_qkv_post_kernel in front of the decode attention, as in prefill
@@ -142,6 +143,7 @@ static int tc_init(dualar_engine *e) {
   if ((rc = alloc_cols(e, e->tc->pf, 512, 1, false))) return rc;      // columns per prefill chunk: one chain of ~225 kernels per chunk, so prompts of up to 512 positions take one
   { const char *v = getenv("DUALAR_TC_CTAS"); if (v && atoi(v) > 0) e->tc->target_ctas = atoi(v); }
   { const char *v = getenv("DUALAR_TC_MINKB"); if (v && atoi(v) > 0) e->tc->min_kb = atoi(v); }
+  { const char *v = getenv("DUALAR_ATTN_MMA"); e->tc->attn_mma = v && v[0] == '1'; }
   { const char *v = getenv("DUALAR_ATTN_CLUSTER"); e->tc->attn_cluster = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_TC_CLUSTER"); e->tc->cluster_reduce = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_FUSE_POST"); e->tc->attn_fuse_post = !(v && v[0] == '0'); }
@@ -152,6 +154,7 @@ static int tc_init(dualar_engine *e) {
   if (e->c.head_dim < 32 || e->c.head_dim > 128 || (e->c.head_dim & (e->c.head_dim - 1)))
     return fail(DUALAR_EINVAL, "the tensor-core path needs head_dim 32, 64 or 128 (a lane owns head_dim / 32 output dims and head_dim / 4 score dims in the attention kernel)");
   CU(cudaFuncSetAttribute(b_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_attn_smem(e->c.n_head / e->c.n_local_heads, e->c.head_dim)));
+  CU(cudaFuncSetAttribute(b_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_attn_mma_smem(e->c.n_head / e->c.n_local_heads, e->c.head_dim)));
   CU(cudaFuncSetAttribute(b_fast_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)b_fast_attn_smem(e->c.fast_n_head, e->c.fast_n_local_heads, e->c.fast_head_dim, e->c.num_codebooks)));
   e->tc->ready = true;
@@ -314,17 +317,35 @@ static int enqueue_slow_cols(dualar_engine *e, ColBufs &c, int ncols, int BN, co
       const bool small = e->tc->attn_cluster && e->batch_total > 0 && e->batch_total <= 8 && c.nsplit > 1 && c.nsplit <= DA_B_MAXSPLIT && !prefill;
       a.tiles_per_split = e->tc->attn_tiles_per_split ? e->tc->attn_tiles_per_split : (small ? 1 : 8);
       a.cluster_merge = small && !e->tc->rec;
-      if (BRec *r = e->tc->rec) r->add(BP_ATTN, g).u.attn = a;
+      const int Gq = cf.n_head / cf.n_local_heads;
+      // tensor-core attention: decode only (one tensor map per layer over the group's whole cache; prefill targets one slot's cache)
+      a.use_mma = !prefill && kv.slot_stride > 0 && e->tc->attn_mma && Gq <= 8 && (cf.head_dim == 64 || cf.head_dim == 128);
+      const size_t asmem = a.use_mma ? b_attn_mma_smem(Gq, cf.head_dim) : b_attn_smem(Gq, cf.head_dim);
+      const CUtensorMap *mkp = nullptr, *mvp = nullptr;
+      if (a.use_mma) {
+        const long long rows_total = (long long)c.cap * (kv.slot_stride / cf.head_dim);
+        if ((rc = tc_map(e, kv.kc[l], (int)rows_total, cf.head_dim, DA_TILE, &mkp)) || (rc = tc_map(e, kv.vc[l], (int)rows_total, cf.head_dim, DA_TILE, &mvp))) return rc;
+      }
+      auto launch_attn = [&](cudaLaunchConfig_t &cfg) -> cudaError_t {
+        return a.use_mma ? cudaLaunchKernelEx(&cfg, b_attn_mma_kernel, *mkp, *mvp, a) : cudaLaunchKernelEx(&cfg, b_attn_kernel, a);
+      };
+      if (BRec *r = e->tc->rec) { BPhase &ph = r->add(BP_ATTN, g); ph.u.attn = a; if (a.use_mma) { ph.map_w = r->map_index(mkp); ph.map_x = r->map_index(mvp); } }
       else if (a.cluster_merge) {
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = g; cfg.blockDim = dim3(DA_ATTN_THREADS); cfg.dynamicSmemBytes = b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim); cfg.stream = s;
+        cfg.gridDim = g; cfg.blockDim = dim3(DA_ATTN_THREADS); cfg.dynamicSmemBytes = asmem; cfg.stream = s;
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)c.nsplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
-        CU(cudaLaunchKernelEx(&cfg, b_attn_kernel, a)); ++count;
+        CU(launch_attn(cfg)); ++count;
       }
-      else { CU(launch_k(b_attn_kernel, g, dim3(DA_ATTN_THREADS), b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), s, a)); ++count; } }
+      else {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = g; cfg.blockDim = dim3(DA_ATTN_THREADS); cfg.dynamicSmemBytes = asmem; cfg.stream = s;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+        CU(launch_attn(cfg)); ++count;
+      } }
     const bool emit = !prefill && !e->tc->rec;
     if ((rc = tc_gemm(e, L.wo, cf.dim, qd, c.y, c.cap, ncols, BN, TE_RESIDUAL, L.bo, c.x, c.h, 0, s, count, nullptr, prefill, nullptr,
                       emit ? ssq_out_for(e, c, BN, cf.dim, TE_RESIDUAL, c.h) : nullptr))) return rc;
@@ -701,9 +722,12 @@ extern "C" int dualar_batch_decode(dualar_engine *e, int n_steps, void *stream) 
   for (dualar_batch *b : live) CU(cudaStreamWaitEvent(b->stream, e->ev_groups_go, 0));
   for (int i = 0; i < n_steps; ++i)
     for (dualar_batch *b : live) CU(cudaGraphLaunch(b->persistent ? b->g_step_p : b->g_step, b->stream));
-  // no join here: dualar_batch_read and dualar_batch_collect make the caller's stream wait for the groups they look at -- so the host
-  // can collect finished requests and enqueue prefills while the next burst of steps is already running
-  for (dualar_batch *b : live) { CU(cudaEventRecord(b->ev_done, b->stream)); b->decode_pending = true; }
+  // option batch_decode_join = 0 (the pipelined serving loop): no join here -- dualar_batch_read and dualar_batch_collect make the caller's
+  // stream wait for the groups they look at, so the host can collect finished requests and enqueue prefills while the next burst runs
+  for (dualar_batch *b : live) {
+    CU(cudaEventRecord(b->ev_done, b->stream)); b->decode_pending = true;
+    if (e->batch_decode_join) CU(cudaStreamWaitEvent(s, b->ev_done, 0));
+  }
   return 0;
 }
 

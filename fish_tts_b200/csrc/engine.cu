@@ -84,6 +84,7 @@ struct dualar_engine {
   bool batch_keep_raw = true;    // batched decode keeps a copy of the raw logits for dualar_batch_read
   int batch_persistent = -1;     // batched decode as two persistent launches (bstep.cuh): -1 = DUALAR_BATCH_PERSIST or the default, 0 / 1 = option batch_persistent
   std::vector<dualar_batch *> groups; int group_slots = 32, batch_total = 0, batch_group_slots = 32; cudaEvent_t ev_groups_go = nullptr; cudaStream_t pf_stream = nullptr;      // request groups (batch_host.cuh)
+  bool batch_decode_join = true; // dualar_batch_decode makes the caller's stream wait for every group's steps (option batch_decode_join)
   bool batch_fork = true;        // batched decode: LM head + slow sampler on a side stream beside fast pass 0 (DUALAR_BATCH_FORK=0: one stream)
   bool l2_window = false; float l2_hit_ratio = 0.0f; size_t l2_persist_bytes = 0;   // DUALAR_L2_WINDOW / DUALAR_L2_HIT: access-policy window over the fast stack
   bool chunk_group = true;   // DUALAR_CHUNK_GROUP=0: one 128-element chunk per unit everywhere (round 1 behaviour)
@@ -762,6 +763,7 @@ extern "C" int dualar_set_option(dualar_engine *e, const char *name, double valu
     if (value < 1 || value > 128) return fail(DUALAR_EINVAL, "batch_group_slots must be in [1, 128]");
     e->batch_group_slots = (int)value; return 0;
   }
+  if (!strcmp(name, "batch_decode_join")) { e->batch_decode_join = value != 0.0; return 0; }
   if (!strcmp(name, "batch_persistent")) { e->batch_persistent = value != 0.0; return batch_select_path(e); }
   if (!strcmp(name, "mega_kernel")) {
     if (e->finalized) return fail(DUALAR_ESTATE, "mega_kernel must be set before dualar_finalize");

@@ -97,6 +97,8 @@ def run_rank_batched(engine, utterances: Sequence[Utterance], rank: int, world: 
     free = list(range(max_batch))
     if pipeline is None:
         pipeline = int(engine.batch_read("groups")[0]) > 1
+    if pipeline and hasattr(engine, "set_option"):
+        engine.set_option("batch_decode_join", 0)      # batch_read / batch_collect wait for what they need; decode itself returns at once
 
     def refill():
         while free and queue:
@@ -132,6 +134,8 @@ def run_rank_batched(engine, utterances: Sequence[Utterance], rank: int, world: 
             res.codes[u.uid] = out
             res.tokens += int(out.shape[1])
         refill()
+    if pipeline and hasattr(engine, "set_option"):
+        engine.set_option("batch_decode_join", 1)
     if sync:
         sync()
     res.seconds = time.perf_counter() - t0

@@ -143,7 +143,9 @@ int dualar_generate(dualar_engine *e, const int32_t *prompt, int prompt_len, int
  * s / batch_group_slots; every group has its own buffers, graph and stream and the groups of a step run concurrently (one
  * group's step is a latency-bound chain of ~540 kernels that leaves the GPU mostly idle).  Options (dualar_set_option):
  * "batch_group_slots" (before dualar_batch_init), "batch_persistent" (1: the step as two persistent cooperative launches,
- * csrc/bstep.cuh -- identical results, measured slower, an experiment switch).
+ * csrc/bstep.cuh -- identical results, measured slower, an experiment switch), "batch_decode_join" (default 1; 0: dualar_batch_decode
+ * does not make the caller's stream wait for the groups -- dualar_batch_read / dualar_batch_collect wait for what they read -- so a
+ * serving loop can collect finished requests and enqueue prefills while the next burst of steps runs).
  *   dualar_batch_init     after dualar_finalize: allocates `max_batch` slots (<= 1024) and captures one CUDA graph per group
  *   dualar_batch_prefill  HOST prompt (num_codebooks+1, prompt_len) int32 -> KV rows of the slot through the tensor-core
  *                         prefill; the slot then joins the batch and the NEXT dualar_batch_decode step produces its first

@@ -255,6 +255,29 @@ def test_producer_side_norm_statistics_against_oracle(name, monkeypatch):
     assert launches < plain - cfg.n_layer and same >= int(0.8 * n * len(REQS))
 
 
+def test_tensor_core_attention_against_oracle(monkeypatch):
+    """DUALAR_ATTN_MMA=1: Q.K^T and P@V of the decode attention as mma.sync m16n8k16 (bf16 x bf16 products are exact in fp32; P split
+    exactly into three bf16 terms), K / V tiles by 2-D TMA with the 128-byte swizzle.  Oracle replay with the usual tolerance, next to
+    the scalar kernel's result on the same requests (same tokens unless the oracle itself is near a tie)."""
+    cfg = variant_configs()["s1like"]
+    sd = make_state_dict(cfg, seed=0)
+    m = orc.OracleModel.build(cfg, sd, device="cuda:0")
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DUALAR_ATTN_MMA", flag)
+        eng = DualAREngine(cfg, sd, device=0)
+        eng.batch_init(5, cfg.max_seq_len)
+        prompts, cols, slows, fasts = run_batch(eng, cfg, REQS, 10)
+        if flag == "1":
+            same = sum(replay_slot(cfg, m, eng, prompts[sl], cols[sl], slows[sl], fasts[sl], r[3], r[4], r[5], 100 + sl, f"mma slot {sl}") for sl, r in enumerate(REQS))
+            assert same >= int(0.8 * 10 * len(REQS))
+        outs[flag] = (cols, slows)
+        eng.close()
+    worst = max(float((outs["1"][1][sl][s].float() - outs["0"][1][sl][s].float()).abs().max()) for sl in range(5) for s in range(10))
+    print(f"\n[tensor-core attention] max |slow logit (mma) - slow logit (scalar)| over 5 slots x 10 steps: {worst:.4f}")
+    assert worst < 0.13      # one bf16 ulp at |x| <= 16 is 0.125 ... 0.0625: accumulation-order noise
+
+
 def test_continuous_batching_refill_does_not_disturb_neighbours():
     cfg = variant_configs()["s1like"]
     sd = make_state_dict(cfg, seed=0)
