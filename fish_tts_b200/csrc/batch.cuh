@@ -212,7 +212,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { return (ui
 __device__ __forceinline__ uint32_t sw128_off(int r, int d) {
   return (uint32_t)((d >> 6) * (DA_TILE * 128) + r * 128 + ((((d & 63) >> 3) ^ (r & 7)) << 4) + (d & 7) * 2);
 }
-template <class B, bool MMA = false> __device__ __forceinline__ void b_attn_body(const BAttnArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm,
+template <class B, bool MMA = false, int HD = 128> __device__ __forceinline__ void b_attn_body(const BAttnArgs &a, int bx, int by, int bz, int gy, unsigned char *dsm,
                                                                uint64_t *bars, uint32_t (&phase)[DA_B_NBUF], bool init,
                                                                const CUtensorMap *mk = nullptr, const CUtensorMap *mv = nullptr) {
   constexpr int NBUF = MMA ? DA_BM_NBUF : DA_B_NBUF;
@@ -415,21 +415,26 @@ template <class B, bool MMA = false> __device__ __forceinline__ void b_attn_body
   }
   } else {
     // ---- tensor-core tile walk ----------------------------------------------------------------------------------------------------
-    const int pb = w & 3, dh = w >> 2, hh = hd >> 1, nkk = hd >> 4, nnt = hd >> 4;      // position block, dim half, dims per half, k-steps, n-tiles per half
+    constexpr int hh = HD / 2, nkk = HD / 16, nnt = HD / 16;      // dims per half, k-steps, n-tiles per half (HD = head_dim, 64 or 128)
+    const int pb = w & 3, dh = w >> 2;                           // position block, dim half
     const int hrow = lane >> 2, qc = (lane & 3) * 2;                                       // this lane's head row / column pair inside a fragment
     const float scale = __fmul_rn(a.sf, a.sf);
-    uint32_t qa0[8], qa2[8];      // A fragments of Q for up to 8 k-steps (hd <= 128): rows >= G are zero
+    uint32_t qa0[nkk], qa2[nkk];      // A fragments of Q: rows >= G are zero
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
+    for (int kk = 0; kk < nkk; ++kk) {
       qa0[kk] = 0u; qa2[kk] = 0u;
-      if (kk < nkk && hrow < G) {
+      if (hrow < G) {
         const float *qr = q + (size_t)hrow * hd + kk * 16 + qc;
         qa0[kk] = pack_bf16x2(qr[0], qr[1]); qa2[kk] = pack_bf16x2(qr[8], qr[9]);
       }
     }
-    float m_run = -INFINITY, l_run = 0.f, o[8][4];
+    float m_run = -INFINITY, l_run = 0.f, o[nnt][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    for (int j = 0; j < nnt; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    // swizzled fragment addresses: element (row r, dim d) lives at box (d / 64), row r, 16-byte chunk ((d % 64) / 8) ^ (r % 8).  The rows a
+    // lane touches keep r % 8 for the whole walk (K: lane / 4, V: lane % 8), so the XOR term is a per-lane constant and a chunk index that
+    // is known at compile time costs one LOP3
+    const uint32_t kx = (uint32_t)(hrow & 7) << 4, vx = (uint32_t)(lane & 7) << 4;
     for (int t = t0; t < t1; ++t) {
       const int buf = (t - t0) % NBUF;
       const int r0 = t * DA_TILE, r1 = min(L, r0 + DA_TILE), nrow = r1 - r0;
@@ -451,13 +456,12 @@ template <class B, bool MMA = false> __device__ __forceinline__ void b_attn_body
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
-        const int krow = p0 + j * 8 + hrow;      // B fragment: position = lane / 4, dims (lane % 4) * 2 + {0, 1} (+ 8)
+        const unsigned char *kr = kt + (p0 + j * 8 + hrow) * 128 + qc * 2;      // B fragment: position = lane / 4, dims (lane % 4) * 2 + {0, 1} (+ 8)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          if (kk < nkk) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(kt + sw128_off(krow, kk * 16 + qc)), b1 = *reinterpret_cast<const uint32_t *>(kt + sw128_off(krow, kk * 16 + 8 + qc));
-            mma_bf16_16816(sacc[j], qa0[kk], 0u, qa2[kk], 0u, b0, b1);
-          }
+        for (int kk = 0; kk < nkk; ++kk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t *>(kr + (kk >> 2) * (DA_TILE * 128) + ((uint32_t)(((2 * kk) & 7) << 4) ^ kx));
+          const uint32_t b1 = *reinterpret_cast<const uint32_t *>(kr + (kk >> 2) * (DA_TILE * 128) + ((uint32_t)(((2 * kk + 1) & 7) << 4) ^ kx));
+          mma_bf16_16816(sacc[j], qa0[kk], 0u, qa2[kk], 0u, b0, b1);
         }
       }
       // online softmax for head row `hrow` over this warp's 16 positions: the lane holds 4 of them, its 3 neighbours the rest
@@ -495,20 +499,19 @@ template <class B, bool MMA = false> __device__ __forceinline__ void b_attn_body
         }
       }
       // O = O * sc_old + P V over this warp's dim half: V^T fragments by transposing ldmatrix (two n-tiles per instruction)
-      const int vrow = p0 + ((lane >> 3) & 1) * 8 + (lane & 7), vd0 = dh * hh + (lane >> 4) * 8;      // this lane's row address for ldmatrix
-      const uint32_t vt_s = smem_u32(vt);
+      // this lane's row address for ldmatrix: row p0 + (lane / 8 % 2) * 8 + lane % 8, dims dh * hh + (lane / 16) * 8 + j * 8
+      const int vd0 = dh * hh + (lane >> 4) * 8;
+      const uint32_t vr = smem_u32(vt) + (uint32_t)((p0 + ((lane >> 3) & 1) * 8 + (lane & 7)) * 128 + (vd0 >> 6) * (DA_TILE * 128));
+      const uint32_t vc0 = (uint32_t)((vd0 & 63) >> 3);      // chunk of n-tile 0 inside its box; n-tile j adds j (hh <= 64: never leaves the box)
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        if (j < nnt) {
-          uint32_t b00, b01, b10, b11;
-          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b00), "=r"(b01), "=r"(b10), "=r"(b11) : "r"(vt_s + sw128_off(vrow, vd0 + j * 8)));
+      for (int j = 0; j < nnt; j += 2) {
+        uint32_t b00, b01, b10, b11;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b00), "=r"(b01), "=r"(b10), "=r"(b11) : "r"(vr + ((((vc0 + (uint32_t)j) & 7u) << 4) ^ vx)));
+        o[j][0] *= sc_old; o[j][1] *= sc_old; o[j + 1][0] *= sc_old; o[j + 1][1] *= sc_old;      // rows 8 .. 15 of the fragments stay zero
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { o[j][i] *= sc_old; o[j + 1][i] *= sc_old; }
-#pragma unroll
-          for (int s3 = 0; s3 < 3; ++s3) {
-            mma_bf16_16816(o[j], pa0[s3], 0u, pa2[s3], 0u, b00, b01);
-            if (j + 1 < nnt) mma_bf16_16816(o[j + 1], pa0[s3], 0u, pa2[s3], 0u, b10, b11);
-          }
+        for (int s3 = 0; s3 < 3; ++s3) {
+          mma_bf16_16816(o[j], pa0[s3], 0u, pa2[s3], 0u, b00, b01);
+          mma_bf16_16816(o[j + 1], pa0[s3], 0u, pa2[s3], 0u, b10, b11);
         }
       }
       B::sync();      // every warp is past its last read of the tile: its buffer may be refilled
@@ -517,8 +520,7 @@ template <class B, bool MMA = false> __device__ __forceinline__ void b_attn_body
     if (hrow < G) {
       if ((lane & 3) == 0) { pm[w * G + hrow] = m_run; pl[w * G + hrow] = l_run; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nnt) { po[((size_t)w * G + hrow) * hd + dh * hh + j * 8 + qc] = o[j][0]; po[((size_t)w * G + hrow) * hd + dh * hh + j * 8 + qc + 1] = o[j][1]; }
+      for (int j = 0; j < nnt; ++j) { po[((size_t)w * G + hrow) * hd + dh * hh + j * 8 + qc] = o[j][0]; po[((size_t)w * G + hrow) * hd + dh * hh + j * 8 + qc + 1] = o[j][1]; }
     }
     B::sync();
   }
@@ -611,7 +613,8 @@ __global__ void __launch_bounds__(DA_ATTN_THREADS, 2) b_attn_mma_kernel(const __
   pdl_wait();
   __shared__ __align__(8) uint64_t s_bars[DA_B_NBUF];
   uint32_t phase[DA_B_NBUF] = {};
-  b_attn_body<BlockAll, true>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_attn_mma, s_bars, phase, true, &mk, &mv);
+  if (a.hd == 128) b_attn_body<BlockAll, true, 128>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_attn_mma, s_bars, phase, true, &mk, &mv);
+  else b_attn_body<BlockAll, true, 64>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, dsm_b_attn_mma, s_bars, phase, true, &mk, &mv);
 }
 
 // ---- fast-layer attention for codebook position p, one CTA per column ---------------------------------------------------------------

@@ -64,7 +64,7 @@ struct dualar_tc {
   ColBufs pf;                 // prefill columns (cap 256)
   bool ready = false;
   int target_ctas = 0, min_kb = 0;      // decode split-K heuristic: CTAs aimed at per GEMM, least k-blocks per CTA (0 = by mode; DUALAR_TC_CTAS, DUALAR_TC_MINKB)
-  bool attn_mma = false;           // DUALAR_ATTN_MMA=1: Q.K^T and P@V of the decode attention on the tensor cores (b_attn_body<B, true>): parity-green, not faster yet
+  bool attn_mma = true;            // DUALAR_ATTN_MMA=0: the scalar fp32 walk instead of Q.K^T and P@V on the tensor cores (b_attn_body<B, true>) in decode
   bool attn_cluster = true;        // DUALAR_ATTN_CLUSTER=0: KV splits merged through a global buffer + ticket
   bool cluster_reduce = true;      // DUALAR_TC_CLUSTER=0: split-K through the global workspace + ticket (the prefill path's way)
   bool attn_fuse_post = true;      // DUALAR_ATTN_FUSE_POST=0: b_qkv_post_kernel in front of the decode attention, as in prefill
@@ -143,7 +143,7 @@ static int tc_init(dualar_engine *e) {
   if ((rc = alloc_cols(e, e->tc->pf, 512, 1, false))) return rc;      // columns per prefill chunk: one chain of ~225 kernels per chunk, so prompts of up to 512 positions take one
   { const char *v = getenv("DUALAR_TC_CTAS"); if (v && atoi(v) > 0) e->tc->target_ctas = atoi(v); }
   { const char *v = getenv("DUALAR_TC_MINKB"); if (v && atoi(v) > 0) e->tc->min_kb = atoi(v); }
-  { const char *v = getenv("DUALAR_ATTN_MMA"); e->tc->attn_mma = v && v[0] == '1'; }
+  { const char *v = getenv("DUALAR_ATTN_MMA"); e->tc->attn_mma = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_CLUSTER"); e->tc->attn_cluster = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_TC_CLUSTER"); e->tc->cluster_reduce = !(v && v[0] == '0'); }
   { const char *v = getenv("DUALAR_ATTN_FUSE_POST"); e->tc->attn_fuse_post = !(v && v[0] == '0'); }

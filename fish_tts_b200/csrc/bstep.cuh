@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(DA_BS_THREADS, 1) bstep_kernel(const BStepArgs
               case BP_NORM: b_rmsnorm_body<BsBlock>(ph.u.norm, bx, by, bz, gy, body); break;
               case BP_QKV_POST: b_qkv_post_body<BsBlock>(ph.u.post, bx, by, bz, gy, body); break;
               case BP_ATTN:
-                if (ph.u.attn.use_mma) b_attn_body<BsBlock, true>(ph.u.attn, bx, by, bz, gy, body, attn_bar, attn_phase, false, k.maps + ph.map_w, k.maps + ph.map_x);
+                if (ph.u.attn.use_mma && ph.u.attn.hd == 128) b_attn_body<BsBlock, true, 128>(ph.u.attn, bx, by, bz, gy, body, attn_bar, attn_phase, false, k.maps + ph.map_w, k.maps + ph.map_x);
+                else if (ph.u.attn.use_mma) b_attn_body<BsBlock, true, 64>(ph.u.attn, bx, by, bz, gy, body, attn_bar, attn_phase, false, k.maps + ph.map_w, k.maps + ph.map_x);
                 else b_attn_body<BsBlock>(ph.u.attn, bx, by, bz, gy, body, attn_bar, attn_phase, false);
                 break;
               case BP_FAST_ATTN: b_fast_attn_body<BsBlock>(ph.u.fattn, bx, by, bz, gy, body); break;

@@ -256,9 +256,9 @@ def test_producer_side_norm_statistics_against_oracle(name, monkeypatch):
 
 
 def test_tensor_core_attention_against_oracle(monkeypatch):
-    """DUALAR_ATTN_MMA=1: Q.K^T and P@V of the decode attention as mma.sync m16n8k16 (bf16 x bf16 products are exact in fp32; P split
-    exactly into three bf16 terms), K / V tiles by 2-D TMA with the 128-byte swizzle.  Oracle replay with the usual tolerance, next to
-    the scalar kernel's result on the same requests (same tokens unless the oracle itself is near a tie)."""
+    """The decode attention's Q.K^T and P@V as mma.sync m16n8k16 (default; bf16 x bf16 products are exact in fp32, P split exactly into
+    three bf16 terms, K / V tiles by 2-D TMA with the 128-byte swizzle) against the scalar fp32 walk (DUALAR_ATTN_MMA=0): oracle replay
+    with the usual tolerance, and the two kernels' logits next to each other."""
     cfg = variant_configs()["s1like"]
     sd = make_state_dict(cfg, seed=0)
     m = orc.OracleModel.build(cfg, sd, device="cuda:0")
