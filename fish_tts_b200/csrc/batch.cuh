@@ -8,8 +8,9 @@
 //
 //   b_embed_kernel       llama.py:409-429    token + codebook embedding per column
 //   b_rmsnorm_kernel     llama.py:172-177    custom RMSNorm (round before the weight multiply), one warp per column
-//   b_qkv_post_kernel    llama.py:246-251, 142-149   q/k nn.RMSNorm + RoPE in place, K/V rows into the column's cache
-//   b_attn_kernel        llama.py:258-274    split-KV flash-decode per (column, kv head), fp32 like the math SDPA backend
+//   b_qkv_post_kernel    llama.py:246-251, 142-149   q/k nn.RMSNorm + RoPE in place, K/V rows into the column's cache (prefill; decode does it in attention)
+//   b_attn_kernel        llama.py:258-274    split-KV flash-decode per (column, kv head), fp32 like the math SDPA backend (scalar walk)
+//   b_attn_mma_kernel    the same with Q.K^T and P@V on the tensor cores (decode, head_dim 64 / 128)
 //   b_fast_attn_kernel   llama.py:285-309    the fast layers' bf16 attention over <= num_codebooks positions
 //   b_head_stats_kernel / b_select_kernel / b_fast_sample_kernel    inference.py:30-80, 103-149    penalty, exact nucleus, Exp(1) race
 #pragma once

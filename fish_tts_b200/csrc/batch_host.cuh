@@ -3,8 +3,17 @@
 //
 // One schedule serves both uses: a COLUMN is a prompt position (prefill: T columns of one request, KV rows written for all of
 // them, no LM head) or a request slot (batched decode: B columns, one per slot, each with its own KV cache, position, sampling
-// state and Philox stream).  Per slow layer: RMSNorm -> wqkv GEMM -> q/k norm + RoPE + KV write -> split-KV attention -> wo GEMM
-// (+ residual) -> RMSNorm -> w1/w3 GEMM (SwiGLU epilogue) -> w2 GEMM (+ residual); all GEMMs are gemm_tc_kernel (tcgen05).
+// state and Philox stream).  Per slow layer: RMSNorm -> wqkv GEMM -> q/k norm + RoPE + KV write (a kernel of its own in prefill,
+// inside the attention kernel in decode) -> split-KV attention -> wo GEMM (+ residual) -> RMSNorm -> w1/w3 GEMM (SwiGLU epilogue)
+// -> w2 GEMM (+ residual); all GEMMs are gemm_tc_kernel (tcgen05), their K splits a thread-block cluster.
+// Request slots live in GROUPS (one graph, stream and set of buffers each; the groups of a step run concurrently), prefills run on
+// the engine's own stream beside them; see dualar_batch_init.  Experiment switches (environment, read once per engine):
+//   DUALAR_TC_CLUSTER=0        split-K through a global workspace + ticket instead of the cluster reduction
+//   DUALAR_TC_CTAS / _MINKB    split heuristic: CTAs aimed at per GEMM, least k-blocks per CTA;  DUALAR_TC_STAGES: ring depth
+//   DUALAR_TC_FUSE_NORM=1 / 2  RMSNorm inside the consuming GEMM (own statistics / statistics from the producing GEMM) -- slower
+//   DUALAR_ATTN_MMA=0          scalar fp32 attention walk instead of the tensor-core one;  DUALAR_ATTN_FUSE_POST=0: separate q/k-norm kernel
+//   DUALAR_ATTN_CLUSTER=0, DUALAR_ATTN_TPS     KV-split merge through a ticket for small engines too; least tiles per split
+//   DUALAR_BATCH_GROUP_SLOTS, DUALAR_BATCH_FORK, DUALAR_BATCH_PERSIST, DUALAR_BS_*   group size, LM-head fork, persistent step (bstep.cuh)
 #pragma once
 
 namespace {
