@@ -107,3 +107,23 @@ def test_where_the_three_nucleus_definitions_can_differ():
                         assert abs(n_k - n_orc) <= 2 and gap <= V * 2.0 ** -23 + float(p[min(j, V - 1)]), \
                             f"nucleus sizes {n_k} vs {n_orc} differ away from the rounding boundary (gap {gap:.3e})"
     assert differ <= 0.05 * total, f"{differ}/{total} vectors with a boundary disagreement"
+
+
+def test_three_way_bf16_split_of_fp32_is_exact():
+    """The tensor-core attention feeds P (fp32 probabilities) to bf16 MMAs as hi + mid + lo, each the round-to-nearest bf16 of what is
+    left (batch.cuh, b_attn_body<B, true>): 24 significant bits = 3 x 8, so the three terms add up to P exactly and the products with
+    bf16 V values are the fp32 products.  Checked on random values, on the edges of binades and on tiny / subnormal-adjacent inputs."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.rand(200_000, generator=g), torch.rand(50_000, generator=g) * 1e-6,
+                   torch.tensor([1.0, 0.5, 0.99999994, 0.50000006, 2.0 ** -20, 3.0 * 2.0 ** -30, 1.0 - 2.0 ** -9, 1.0 - 2.0 ** -17]),
+                   torch.exp(-torch.rand(100_000, generator=g) * 30.0)]).to(torch.float32)
+
+    def rbf(t):
+        return t.to(torch.bfloat16).to(torch.float32)
+    hi = rbf(x); r1 = x - hi
+    mid = rbf(r1); r2 = r1 - mid
+    lo = rbf(r2)
+    assert torch.equal(r2, lo), "the third term must capture the remainder exactly"
+    assert torch.equal((hi.double() + mid.double() + lo.double()).to(torch.float32), x)
+    assert torch.equal(hi.double() + mid.double() + lo.double(), x.double())
