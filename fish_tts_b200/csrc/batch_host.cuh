@@ -509,7 +509,7 @@ static int build_persistent_step(dualar_engine *e) {
   e->tc->rec = nullptr;
   if (rc < 0) return rc;
   if (rec.split < 0) return fail(DUALAR_ESTATE, "recorded step has no sampler split");
-  size_t body = b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim);
+  size_t body = std::max(b_attn_smem(cf.n_head / cf.n_local_heads, cf.head_dim), b_attn_mma_smem(cf.n_head / cf.n_local_heads, cf.head_dim));
   body = std::max(body, b_fast_attn_smem(cf.fast_n_head, cf.fast_n_local_heads, cf.fast_head_dim, cf.num_codebooks));
   body = std::max(body, b_fast_sample_smem());
   body = std::max(body, (size_t)8 * cf.head_dim * sizeof(float));
